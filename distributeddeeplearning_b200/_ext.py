@@ -1,0 +1,168 @@
+"""In-tree build + loader of the native module ``distributeddeeplearning_b200._C``.
+
+* ``build()``  compiles every ``csrc/**/*.cu`` with
+  ``nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo`` (cross-compiles without a GPU),
+  every ``csrc/**/*.cpp`` with g++, and links ``_C.so`` next to this file (so the artefact
+  travels with the source tree and shows up as an in-tree native module).
+* ``load()``   imports ``_C``; (re)builds first when the sources are newer than the artefact.
+  There is no eager-PyTorch fallback for GPU execution: if a CUDA device is present and the module
+  cannot be loaded, ``load()`` raises.
+"""
+from __future__ import annotations
+
+import hashlib
+import importlib
+import os
+import subprocess
+import sys
+import sysconfig
+import threading
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+_BUILD = os.path.join(_HERE, "csrc", "build")
+_SO = os.path.join(_HERE, "_C.so")
+_STAMP = os.path.join(_BUILD, "sources.sha")
+_LOCK = threading.Lock()
+_MODULE = None
+
+NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CUDA_HOME = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+
+
+def _sources() -> List[str]:
+    out = []
+    for root, _dirs, files in os.walk(_CSRC):
+        if os.path.abspath(root).startswith(os.path.abspath(_BUILD)):
+            continue
+        for f in sorted(files):
+            if f.endswith((".cu", ".cpp")):
+                out.append(os.path.join(root, f))
+    return sorted(out)
+
+
+def _all_inputs() -> List[str]:
+    out = []
+    for root, _dirs, files in os.walk(_CSRC):
+        if os.path.abspath(root).startswith(os.path.abspath(_BUILD)):
+            continue
+        for f in sorted(files):
+            if f.endswith((".cu", ".cpp", ".cuh", ".h")):
+                out.append(os.path.join(root, f))
+    return sorted(out)
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for p in _all_inputs():
+        h.update(os.path.relpath(p, _CSRC).encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    if not os.path.isfile(_SO) or not os.path.isfile(_STAMP):
+        return True
+    try:
+        with open(_STAMP) as f:
+            return f.read().strip() != _digest()
+    except OSError:
+        return True
+
+
+def _pybind_include() -> str:
+    import pybind11
+
+    return pybind11.get_include()
+
+
+def _run(cmd: List[str], verbose: bool) -> None:
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("build command failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    if verbose and (r.stdout or r.stderr):
+        print(r.stdout + r.stderr, flush=True)
+
+
+def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) -> str:
+    """Compile and link ``_C.so``; returns its path."""
+    with _LOCK:
+        if not force and not is_stale():
+            return _SO
+        nvcc = os.path.join(CUDA_HOME, "bin", "nvcc")
+        if not os.path.isfile(nvcc):
+            raise RuntimeError(f"nvcc not found at {nvcc}; cannot build the native module")
+        os.makedirs(_BUILD, exist_ok=True)
+        py_inc = sysconfig.get_paths()["include"]
+        common_inc = ["-I", _CSRC, "-I", os.path.join(CUDA_HOME, "include"), "-I", py_inc, "-I", _pybind_include()]
+        objs, jobs = [], []
+        for src in _sources():
+            rel = os.path.relpath(src, _CSRC).replace(os.sep, "_")
+            obj = os.path.join(_BUILD, rel + ".o")
+            objs.append(obj)
+            if src.endswith(".cu"):
+                cmd = [nvcc, "-c", src, "-o", obj, "-O3", "-std=c++17", "-lineinfo", *NVCC_ARCH,
+                       "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xcompiler", "-fvisibility=hidden",
+                       *common_inc]
+                if ptxas_info:
+                    cmd += ["-Xptxas", "-v"]
+            else:
+                cmd = ["g++", "-c", src, "-o", obj, "-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden",
+                       "-pthread", *common_inc]
+            jobs.append(cmd)
+        with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+            list(ex.map(lambda c: _run(c, verbose), jobs))
+        link = ["g++", "-shared", "-o", _SO + ".tmp", *objs, "-L", os.path.join(CUDA_HOME, "lib64"), "-lcudart",
+                "-ldl", "-lpthread", "-Wl,-rpath," + os.path.join(CUDA_HOME, "lib64")]
+        _run(link, verbose)
+        os.replace(_SO + ".tmp", _SO)
+        with open(_STAMP, "w") as f:
+            f.write(_digest())
+        return _SO
+
+
+def load(auto_build: bool = True):
+    """Import the native module (building it first if needed)."""
+    global _MODULE
+    if _MODULE is not None:
+        return _MODULE
+    if auto_build and is_stale():
+        nvcc = os.path.join(CUDA_HOME, "bin", "nvcc")
+        if os.path.isfile(nvcc):
+            build()
+        elif not os.path.isfile(_SO):
+            raise RuntimeError("native module _C.so is missing and nvcc is unavailable to build it")
+    import torch  # noqa: F401  (loads libcudart.so.12 that _C.so links against)
+
+    _MODULE = importlib.import_module("distributeddeeplearning_b200._C")
+    return _MODULE
+
+
+def available() -> bool:
+    try:
+        load()
+        return True
+    except Exception:
+        return False
+
+
+def sass(pattern: Optional[str] = None) -> str:
+    """cuobjdump -sass of the built module (profiling evidence helper)."""
+    cuobjdump = os.path.join(CUDA_HOME, "bin", "cuobjdump")
+    r = subprocess.run([cuobjdump, "-sass", _SO], capture_output=True, text=True)
+    txt = r.stdout
+    if pattern:
+        import re
+
+        txt = "\n".join(line for line in txt.splitlines() if re.search(pattern, line))
+    return txt
+
+
+if __name__ == "__main__":
+    path = build(verbose=True, force="--force" in sys.argv, ptxas_info="--ptxas" in sys.argv)
+    print("built", path)

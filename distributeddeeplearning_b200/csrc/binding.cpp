@@ -1,0 +1,310 @@
+// pybind11 bindings of the b200-ddl native runtime and kernels.
+//
+// Deliberately torch-header-free: tensors cross the boundary as raw device pointers
+// (tensor.data_ptr()) and a stream handle (torch.cuda.current_stream().cuda_stream); shape /
+// dtype / contiguity checks live in the Python wrappers (ops/*.py, parallel/engine.py).  This keeps
+// the build to seconds and the module importable on a GPU-less box.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+
+#include "comm/comm.h"
+#include "ops/conv_gemm.cuh"
+#include "ops/ops.h"
+#include "runtime/host_runtime.h"
+
+namespace py = pybind11;
+using ddl::BnBwdArgs;
+using ddl::BnFwdArgs;
+using ddl::BucketArgs;
+using ddl::CommCtx;
+using ddl::ConvArgs;
+using ddl::PoolArgs;
+using ddl::SgdHyper;
+using ddl::WgradArgs;
+using ddl::XentArgs;
+
+namespace ddl {
+cudaError_t launch_conv_gemm(int mode, const ConvArgs& a, const void* w, int w_rows, int w_cols, int n_total,
+                             const void* a_matrix, int a_cols, cudaStream_t stream);
+cudaError_t launch_conv_wgrad(const WgradArgs& a, const void* dy, const void* x_matrix, int splits,
+                              cudaStream_t stream);
+}  // namespace ddl
+
+namespace {
+
+using ptr_t = uintptr_t;
+
+template <class T>
+T* P(ptr_t p) { return reinterpret_cast<T*>(p); }
+cudaStream_t S(ptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+void check(cudaError_t e, const char* what) {
+  if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+struct PyCommCtx {
+  CommCtx c{};
+};
+
+PoolArgs pool_args(int N, int H, int W, int C, int Pq, int Q, int k, int stride, int pad) {
+  PoolArgs p;
+  p.N = N; p.H = H; p.W = W; p.C = C; p.P = Pq; p.Q = Q; p.k = k; p.stride = stride; p.pad = pad;
+  return p;
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "b200-ddl native runtime + sm_100a kernels";
+  m.attr("MAX_COMM_BLOCKS") = ddl::kMaxCommBlocks;
+  m.attr("COMM_CHANNELS") = ddl::kCommChannels;
+  m.attr("SIGNAL_PAD_BYTES") = ddl::kSignalPadBytes;
+  m.attr("SGD_HYPER_BYTES") = sizeof(SgdHyper);
+  m.attr("CONV_FWD") = static_cast<int>(ddl::kConvFwd);
+  m.attr("CONV_DGRAD") = static_cast<int>(ddl::kConvDgrad);
+  m.attr("CONV_GEMM") = static_cast<int>(ddl::kConvGemm);
+  m.attr("CONV_STEM") = static_cast<int>(ddl::kConvStem);
+
+  // ------------------------------------------------------------------ host runtime
+  m.def("driver_available", &ddl::driver_available);
+  m.def("plan_buckets",
+        [](const std::vector<int64_t>& numels, int64_t first_cap, int64_t cap, int64_t align, int64_t slice) {
+          ddl::BucketPlan p = ddl::plan_buckets(numels, first_cap, cap, align, slice);
+          py::dict d;
+          d["param_bucket"] = p.param_bucket;
+          d["param_offset"] = p.param_offset;
+          d["bucket_start"] = p.bucket_start;
+          d["bucket_numel"] = p.bucket_numel;
+          d["bucket_last_param"] = p.bucket_last_param;
+          d["bucket_param_count"] = p.bucket_param_count;
+          d["total_elems"] = p.total_elems;
+          d["hash"] = p.hash;
+          return d;
+        },
+        py::arg("numels"), py::arg("first_cap_elems"), py::arg("cap_elems"), py::arg("align_elems"),
+        py::arg("slice_elems"));
+  m.def("exchange_fds",
+        [](int rank, int world, int fd, const std::string& session, int timeout_ms) {
+          py::gil_scoped_release rel;
+          return ddl::exchange_fds(rank, world, fd, session, timeout_ms);
+        });
+  m.def("broadcast_fd", [](int rank, int world, int root, int fd, const std::string& session, int timeout_ms) {
+    py::gil_scoped_release rel;
+    return ddl::broadcast_fd(rank, world, root, fd, session, timeout_ms);
+  });
+
+  py::class_<ddl::SymmArena>(m, "SymmArena")
+      .def(py::init<int, int, int, size_t>(), py::arg("rank"), py::arg("world"), py::arg("device"), py::arg("bytes"))
+      .def("alloc", &ddl::SymmArena::alloc)
+      .def("exchange", &ddl::SymmArena::exchange, py::call_guard<py::gil_scoped_release>())
+      .def("multicast_supported", &ddl::SymmArena::multicast_supported)
+      .def("mc_create", &ddl::SymmArena::mc_create, py::call_guard<py::gil_scoped_release>())
+      .def("mc_bind", &ddl::SymmArena::mc_bind)
+      .def("release", &ddl::SymmArena::release)
+      .def_property_readonly("bytes", &ddl::SymmArena::bytes)
+      .def_property_readonly("local_ptr", &ddl::SymmArena::local_ptr)
+      .def_property_readonly("peer_ptrs", &ddl::SymmArena::peer_ptrs)
+      .def_property_readonly("mc_ptr", &ddl::SymmArena::mc_ptr)
+      .def_property_readonly("last_error", &ddl::SymmArena::last_error);
+
+  // ------------------------------------------------------------------ comm
+  py::class_<PyCommCtx>(m, "CommCtx")
+      .def(py::init([](const std::vector<uint64_t>& peers, uint64_t mc_base, int rank, int world, uint64_t flag_off,
+                       uint64_t grad_off, uint64_t weight_off, uint64_t wbf16_off, uint64_t stage_off,
+                       ptr_t epoch_ctr, ptr_t error_flag, uint64_t timeout_ns) {
+             if (world < 1 || world > ddl::kCommMaxWorld || static_cast<int>(peers.size()) < world)
+               throw std::invalid_argument("CommCtx: bad world / peers");
+             PyCommCtx x;
+             for (int i = 0; i < ddl::kCommMaxWorld; ++i) x.c.peer_base[i] = i < world ? peers[i] : 0;
+             x.c.mc_base = mc_base;
+             x.c.rank = rank;
+             x.c.world = world;
+             x.c.flag_off = flag_off;
+             x.c.grad_off = grad_off;
+             x.c.weight_off = weight_off;
+             x.c.wbf16_off = wbf16_off;
+             x.c.stage_off = stage_off;
+             x.c.epoch_ctr = P<uint32_t>(epoch_ctr);
+             x.c.error_flag = P<uint32_t>(error_flag);
+             x.c.timeout_ns = timeout_ns;
+             return x;
+           }),
+           py::arg("peers"), py::arg("mc_base"), py::arg("rank"), py::arg("world"), py::arg("flag_off"),
+           py::arg("grad_off"), py::arg("weight_off"), py::arg("wbf16_off"), py::arg("stage_off"),
+           py::arg("epoch_ctr"), py::arg("error_flag"), py::arg("timeout_ns"))
+      .def_property_readonly("has_multicast", [](const PyCommCtx& x) { return x.c.mc_base != 0; });
+
+  m.def("pack_sgd_hyper", [](float lr, float momentum, float dampening, float wd, float grad_scale, bool nesterov,
+                             bool first_step) {
+    SgdHyper h{lr, momentum, dampening, wd, grad_scale, nesterov ? 1 : 0, first_step ? 1 : 0, 0};
+    return py::bytes(reinterpret_cast<const char*>(&h), sizeof(h));
+  });
+  m.def("fused_sgd_local", [](ptr_t w, ptr_t g, ptr_t mom, ptr_t wb, ptr_t hyper, int64_t numel, int blocks,
+                              ptr_t stream) {
+    check(ddl::launch_fused_sgd_local(P<float>(w), P<float>(g), P<float>(mom), P<void>(wb), P<const SgdHyper>(hyper),
+                                      numel, blocks, S(stream)), "fused_sgd_local");
+  });
+  m.def("fused_allreduce_sgd", [](const PyCommCtx& c, int64_t start, int64_t numel, ptr_t momentum, ptr_t hyper,
+                                  int channel, bool use_mc, bool wire_bf16, int blocks, ptr_t stream) {
+    BucketArgs b;
+    b.start = start; b.numel = numel; b.momentum = P<float>(momentum); b.hyper = P<const SgdHyper>(hyper);
+    b.channel = channel;
+    check(ddl::launch_fused_allreduce_sgd(c.c, b, use_mc, wire_bf16, blocks, S(stream)), "fused_allreduce_sgd");
+  });
+  m.def("allreduce", [](const PyCommCtx& c, int channel, uint64_t off, int64_t numel, bool bf16, float scale,
+                        bool use_mc, bool oneshot, int blocks, ptr_t stream) {
+    check(ddl::launch_allreduce(c.c, channel, off, numel, bf16, scale, use_mc, oneshot, blocks, S(stream)), "allreduce");
+  });
+  m.def("broadcast", [](const PyCommCtx& c, int channel, uint64_t off, int64_t bytes, int root, bool use_mc,
+                        int blocks, ptr_t stream) {
+    check(ddl::launch_broadcast(c.c, channel, off, bytes, root, use_mc, blocks, S(stream)), "broadcast");
+  });
+  m.def("barrier", [](const PyCommCtx& c, int channel, ptr_t stream) {
+    check(ddl::launch_barrier(c.c, channel, S(stream)), "barrier");
+  });
+  m.def("allgather_slices", [](const PyCommCtx& c, int channel, ptr_t src, uint64_t dst_off, int64_t start,
+                               int64_t numel, bool use_mc, int blocks, ptr_t stream) {
+    check(ddl::launch_allgather_slices(c.c, channel, P<const float>(src), dst_off, start, numel, use_mc, blocks,
+                                       S(stream)), "allgather_slices");
+  });
+
+  // ------------------------------------------------------------------ conv / GEMM
+  m.def("conv_gemm",
+        [](int mode, ptr_t src, ptr_t out, ptr_t add, ptr_t bias, ptr_t sum, ptr_t sumsq, int M, int KB, int ldc,
+           int srcH, int srcW, int srcC, int dstH, int dstW, int R, int Sx, int stride, int pad, int dil,
+           int cchunks, int relu, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
+           ptr_t stream) {
+          ConvArgs a;
+          a.src = P<const __nv_bfloat16>(src); a.out = P<__nv_bfloat16>(out); a.add = P<const __nv_bfloat16>(add);
+          a.bias = P<const float>(bias); a.sum = P<float>(sum); a.sumsq = P<float>(sumsq);
+          a.M = M; a.KB = KB; a.ldc = ldc; a.srcH = srcH; a.srcW = srcW; a.srcC = srcC; a.dstH = dstH; a.dstW = dstW;
+          a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil; a.cchunks = cchunks; a.relu = relu;
+          check(ddl::launch_conv_gemm(mode, a, P<const void>(w), w_rows, w_cols, n_total, P<const void>(a_matrix),
+                                      a_cols, S(stream)), "conv_gemm");
+        });
+  m.def("conv_wgrad",
+        [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int ldw, int ncols, int H, int W, int C, int Pq,
+           int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, ptr_t stream) {
+          WgradArgs a;
+          a.x = P<const __nv_bfloat16>(x); a.dw = P<float>(dw); a.M = M; a.Cout = Cout; a.ldw = ldw; a.ncols = ncols;
+          a.H = H; a.W = W; a.C = C; a.P = Pq; a.Q = Q; a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil;
+          a.cchunks = cchunks; a.kb_per_split = 0; a.total_kb = 0; a.mode = mode;
+          check(ddl::launch_conv_wgrad(a, P<const void>(dy), P<const void>(x), splits, S(stream)), "conv_wgrad");
+        });
+
+  // ------------------------------------------------------------------ BN / activation
+  m.def("bn_act_fwd", [](ptr_t x, ptr_t residual, ptr_t z, ptr_t sum, ptr_t sumsq, ptr_t gamma, ptr_t beta,
+                         ptr_t mean, ptr_t invstd, ptr_t rmean, ptr_t rvar, float eps, float momentum, int M, int C,
+                         int relu, bool train, int sms, ptr_t stream) {
+    BnFwdArgs a;
+    a.x = P<const __nv_bfloat16>(x); a.residual = P<const __nv_bfloat16>(residual); a.z = P<__nv_bfloat16>(z);
+    a.sum = P<const float>(sum); a.sumsq = P<const float>(sumsq); a.gamma = P<const float>(gamma);
+    a.beta = P<const float>(beta); a.mean = P<float>(mean); a.invstd = P<float>(invstd);
+    a.running_mean = P<float>(rmean); a.running_var = P<float>(rvar); a.eps = eps; a.momentum = momentum;
+    a.M = M; a.C = C; a.relu = relu;
+    check(ddl::launch_bn_act_fwd(a, train, sms, S(stream)), "bn_act_fwd");
+  });
+  m.def("bn_act_bwd", [](ptr_t dz, ptr_t z, ptr_t x, ptr_t dx, ptr_t dres, ptr_t mean, ptr_t invstd, ptr_t gamma,
+                         ptr_t dgamma, ptr_t dbeta, ptr_t gamma_grad, ptr_t beta_grad, int M, int C, int relu,
+                         int sms, ptr_t stream) {
+    BnBwdArgs a;
+    a.dz = P<const __nv_bfloat16>(dz); a.z = P<const __nv_bfloat16>(z); a.x = P<const __nv_bfloat16>(x);
+    a.dx = P<__nv_bfloat16>(dx); a.dres = P<__nv_bfloat16>(dres); a.mean = P<const float>(mean);
+    a.invstd = P<const float>(invstd); a.gamma = P<const float>(gamma); a.dgamma = P<float>(dgamma);
+    a.dbeta = P<float>(dbeta); a.gamma_grad = P<float>(gamma_grad); a.beta_grad = P<float>(beta_grad);
+    a.M = M; a.C = C; a.relu = relu;
+    check(ddl::launch_bn_act_bwd(a, sms, S(stream)), "bn_act_bwd");
+  });
+  m.def("channel_stats", [](ptr_t x, ptr_t sum, ptr_t sumsq, int M, int C, int sms, ptr_t stream) {
+    check(ddl::launch_channel_stats(P<const __nv_bfloat16>(x), P<float>(sum), P<float>(sumsq), M, C, sms, S(stream)),
+          "channel_stats");
+  });
+
+  // ------------------------------------------------------------------ pooling
+  m.def("maxpool_fwd", [](ptr_t x, ptr_t y, ptr_t argmax, int N, int H, int W, int C, int Pq, int Q, int k,
+                          int stride, int pad, ptr_t stream) {
+    check(ddl::launch_maxpool_fwd(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), P<uint8_t>(argmax),
+                                  pool_args(N, H, W, C, Pq, Q, k, stride, pad), S(stream)), "maxpool_fwd");
+  });
+  m.def("maxpool_bwd", [](ptr_t dy, ptr_t argmax, ptr_t dx, int N, int H, int W, int C, int Pq, int Q, int k,
+                          int stride, int pad, ptr_t stream) {
+    check(ddl::launch_maxpool_bwd(P<const __nv_bfloat16>(dy), P<const uint8_t>(argmax), P<__nv_bfloat16>(dx),
+                                  pool_args(N, H, W, C, Pq, Q, k, stride, pad), S(stream)), "maxpool_bwd");
+  });
+  m.def("avgpool_fwd", [](ptr_t x, ptr_t y, int N, int H, int W, int C, int Pq, int Q, int k, int stride, int pad,
+                          int count_include_pad, ptr_t stream) {
+    check(ddl::launch_avgpool_fwd(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y),
+                                  pool_args(N, H, W, C, Pq, Q, k, stride, pad), count_include_pad, S(stream)),
+          "avgpool_fwd");
+  });
+  m.def("avgpool_bwd", [](ptr_t dy, ptr_t dx, int N, int H, int W, int C, int Pq, int Q, int k, int stride, int pad,
+                          int count_include_pad, ptr_t stream) {
+    check(ddl::launch_avgpool_bwd(P<const __nv_bfloat16>(dy), P<__nv_bfloat16>(dx),
+                                  pool_args(N, H, W, C, Pq, Q, k, stride, pad), count_include_pad, S(stream)),
+          "avgpool_bwd");
+  });
+  m.def("global_avgpool_fwd", [](ptr_t x, ptr_t y, int N, int HW, int C, ptr_t stream) {
+    check(ddl::launch_global_avgpool_fwd(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), N, HW, C, S(stream)),
+          "global_avgpool_fwd");
+  });
+  m.def("global_avgpool_bwd", [](ptr_t dy, ptr_t dx, int N, int HW, int C, ptr_t stream) {
+    check(ddl::launch_global_avgpool_bwd(P<const __nv_bfloat16>(dy), P<__nv_bfloat16>(dx), N, HW, C, S(stream)),
+          "global_avgpool_bwd");
+  });
+
+  // ------------------------------------------------------------------ loss / data / misc
+  m.def("softmax_xent", [](ptr_t logits, ptr_t labels, ptr_t dlogits, ptr_t loss_sum, ptr_t per_sample,
+                           ptr_t correct, float loss_scale, float grad_scale, int B, int classes, int ld,
+                           ptr_t stream) {
+    XentArgs a;
+    a.logits = P<const __nv_bfloat16>(logits); a.labels = P<const int64_t>(labels);
+    a.dlogits = P<__nv_bfloat16>(dlogits); a.loss_sum = P<float>(loss_sum); a.per_sample = P<float>(per_sample);
+    a.correct = P<int32_t>(correct); a.loss_scale = loss_scale; a.grad_scale = grad_scale; a.B = B;
+    a.classes = classes; a.ld = ld;
+    check(ddl::launch_softmax_xent(a, S(stream)), "softmax_xent");
+  });
+  m.def("philox_normal_nhwc", [](ptr_t out, int64_t pixels, int c_valid, int cpad, uint64_t seed, uint64_t offset,
+                                 ptr_t stream) {
+    check(ddl::launch_philox_normal_nhwc(P<__nv_bfloat16>(out), pixels, c_valid, cpad, seed, offset, S(stream)),
+          "philox_normal_nhwc");
+  });
+  m.def("philox_labels", [](ptr_t out, int64_t n, int classes, uint64_t seed, uint64_t offset, ptr_t stream) {
+    check(ddl::launch_philox_labels(P<int64_t>(out), n, classes, seed, offset, S(stream)), "philox_labels");
+  });
+  m.def("nchw_to_nhwc_norm", [](ptr_t in, ptr_t out, int N, int C, int H, int W, int cpad, ptr_t mean, ptr_t stdv,
+                                ptr_t stream) {
+    check(ddl::launch_nchw_to_nhwc_norm(P<const float>(in), P<__nv_bfloat16>(out), N, C, H, W, cpad,
+                                        P<const float>(mean), P<const float>(stdv), S(stream)), "nchw_to_nhwc_norm");
+  });
+  m.def("cast_f32_bf16", [](ptr_t in, ptr_t out, int64_t n, ptr_t stream) {
+    check(ddl::launch_cast_f32_bf16(P<const float>(in), P<__nv_bfloat16>(out), n, S(stream)), "cast_f32_bf16");
+  });
+  m.def("pack_stem_weight", [](ptr_t w, ptr_t packed, int Cout, int R, int Sx, int Cin, int RP, int SP,
+                               ptr_t stream) {
+    check(ddl::launch_pack_stem_weight(P<const float>(w), P<__nv_bfloat16>(packed), Cout, R, Sx, Cin, RP, SP,
+                                       S(stream)), "pack_stem_weight");
+  });
+  m.def("unpack_stem_grad", [](ptr_t packed, ptr_t gw, int Cout, int R, int Sx, int Cin, int RP, int SP,
+                               ptr_t stream) {
+    check(ddl::launch_unpack_stem_grad(P<const float>(packed), P<float>(gw), Cout, R, Sx, Cin, RP, SP, S(stream)),
+          "unpack_stem_grad");
+  });
+  m.def("bias_relu_bwd", [](ptr_t dy, ptr_t z, ptr_t dx, ptr_t dbias, int M, int C, int relu, int sms,
+                            ptr_t stream) {
+    check(ddl::launch_bias_relu_bwd(P<const __nv_bfloat16>(dy), P<const __nv_bfloat16>(z), P<__nv_bfloat16>(dx),
+                                    P<float>(dbias), M, C, relu, sms, S(stream)), "bias_relu_bwd");
+  });
+  m.def("dropout", [](ptr_t x, ptr_t y, int64_t n, float p, uint64_t seed, uint64_t offset, ptr_t stream) {
+    check(ddl::launch_dropout(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), n, p, seed, offset, S(stream)),
+          "dropout");
+  });
+  m.def("add_bf16", [](ptr_t a, ptr_t b, ptr_t y, int64_t n, ptr_t stream) {
+    check(ddl::launch_add_bf16(P<const __nv_bfloat16>(a), P<const __nv_bfloat16>(b), P<__nv_bfloat16>(y), n,
+                               S(stream)), "add_bf16");
+  });
+}

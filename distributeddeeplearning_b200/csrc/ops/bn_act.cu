@@ -1,0 +1,246 @@
+// Fused BatchNorm(train) + ReLU (+ residual add) forward / backward on NHWC bf16 activations.
+//
+// Replaces cuDNN BN fwd/bwd + ATen ReLU + ATen add of the reference step.
+// The batch statistics (sum, sum of squares per channel) arrive from the conv epilogue
+// (conv_gemm.cu, STATS) — the activation tensor is never re-read just to reduce it.
+//
+//   forward   z = relu( (x - mean) * invstd * gamma + beta  (+ residual) )          1 read (+1), 1 write
+//   backward  pass 1: dbeta = sum dy, dgamma = sum dy * xhat   with dy = dz * (z > 0)
+//             pass 2: dx = gamma*invstd * (dy - dbeta/M - xhat*dgamma/M),  dres = dy
+//
+// Thread mapping: a thread owns 8 consecutive channels (one 16-byte vector) of a FIXED channel
+// group and walks rows with a grid stride, so per-channel constants live in registers.
+#include "../common.cuh"
+#include "ops.h"
+
+namespace ddl {
+
+namespace {
+
+constexpr int kBnThreads = 256;
+
+struct Vec8 {
+  float v[8];
+};
+DDL_DEVICE Vec8 load8_bf16(const __nv_bfloat16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  Vec8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+DDL_DEVICE void store8_bf16(__nv_bfloat16* p, const Vec8& r) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]),
+                                            pack_bf16x2(r.v[4], r.v[5]), pack_bf16x2(r.v[6], r.v[7]));
+}
+DDL_DEVICE Vec8 load8_f32(const float* p) {
+  const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  Vec8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// ---- forward --------------------------------------------------------------------------------
+// TRAIN: scale/shift derived from (sum, sumsq); also emits mean/invstd (saved for backward) and
+// updates running stats.  EVAL: scale/shift from running stats.
+template <bool TRAIN>
+__global__ void __launch_bounds__(kBnThreads) bn_act_fwd_kernel(BnFwdArgs a) {
+  const int groups = a.C / 8;                       // channel groups per row
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = tid % groups;
+  const int row0 = tid / groups;
+  const int row_stride = (gridDim.x * blockDim.x) / groups;
+  const int c0 = g * 8;
+  float scale[8], shift[8];
+  {
+    Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
+    if (TRAIN) {
+      Vec8 s = load8_f32(a.sum + c0), ss = load8_f32(a.sumsq + c0);
+      const float inv_n = 1.f / static_cast<float>(a.M);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mean = s.v[i] * inv_n;
+        const float var = fmaxf(ss.v[i] * inv_n - mean * mean, 0.f);
+        const float invstd = rsqrtf(var + a.eps);
+        scale[i] = gam.v[i] * invstd;
+        shift[i] = bet.v[i] - mean * scale[i];
+        if (row0 == 0) {
+          a.mean[c0 + i] = mean;
+          a.invstd[c0 + i] = invstd;
+          if (a.running_mean) {
+            const float unbiased = a.M > 1 ? var * static_cast<float>(a.M) / static_cast<float>(a.M - 1) : var;
+            a.running_mean[c0 + i] = (1.f - a.momentum) * a.running_mean[c0 + i] + a.momentum * mean;
+            a.running_var[c0 + i] = (1.f - a.momentum) * a.running_var[c0 + i] + a.momentum * unbiased;
+          }
+        }
+      }
+    } else {
+      Vec8 rm = load8_f32(a.running_mean + c0), rv = load8_f32(a.running_var + c0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        scale[i] = gam.v[i] * rsqrtf(rv.v[i] + a.eps);
+        shift[i] = bet.v[i] - rm.v[i] * scale[i];
+      }
+    }
+  }
+  for (int r = row0; r < a.M; r += row_stride) {
+    const size_t off = static_cast<size_t>(r) * a.C + c0;
+    Vec8 x = load8_bf16(a.x + off);
+    Vec8 z;
+    if (a.residual) {
+      Vec8 res = load8_bf16(a.residual + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z.v[i] = fmaf(x.v[i], scale[i], shift[i]) + res.v[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z.v[i] = fmaf(x.v[i], scale[i], shift[i]);
+    }
+    if (a.relu) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) z.v[i] = fmaxf(z.v[i], 0.f);
+    }
+    store8_bf16(a.z + off, z);
+  }
+}
+
+// ---- backward pass 1: per-channel reductions ----------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads) bn_act_bwd_reduce_kernel(BnBwdArgs a) {
+  const int groups = a.C / 8;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = tid % groups;
+  const int row0 = tid / groups;
+  const int row_stride = (gridDim.x * blockDim.x) / groups;
+  const int c0 = g * 8;
+  Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0);
+  float sdy[8], sdyx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sdy[i] = 0.f; sdyx[i] = 0.f; }
+  for (int r = row0; r < a.M; r += row_stride) {
+    const size_t off = static_cast<size_t>(r) * a.C + c0;
+    Vec8 dz = load8_bf16(a.dz + off);
+    Vec8 x = load8_bf16(a.x + off);
+    if (a.relu) {
+      Vec8 z = load8_bf16(a.z + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sdy[i] += dz.v[i];
+      sdyx[i] = fmaf(dz.v[i], (x.v[i] - mean.v[i]) * invstd.v[i], sdyx[i]);
+    }
+  }
+  // threads of a block that share a channel group: blockDim / groups (>= 1 when groups <= 256)
+  __shared__ float red[2][kBnThreads][8 + 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = sdy[i]; red[1][threadIdx.x][i] = sdyx[i]; }
+  __syncthreads();
+  const int per_block = blockDim.x >= groups ? blockDim.x / groups : 1;
+  const int lg = threadIdx.x % groups;
+  if (threadIdx.x < groups && threadIdx.x < blockDim.x) {
+    // first thread of each channel group in this block folds its siblings, then 16 atomics
+    float t0[8], t1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0[i] = 0.f; t1[i] = 0.f; }
+    for (int k = 0; k < per_block; ++k) {
+      const int t = lg + k * groups;
+      if (t < blockDim.x) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { t0[i] += red[0][t][i]; t1[i] += red[1][t][i]; }
+      }
+    }
+    const int gc = ((blockIdx.x * blockDim.x + threadIdx.x) % groups) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(a.dbeta + gc + i, t0[i]);
+      atomicAdd(a.dgamma + gc + i, t1[i]);
+    }
+  }
+}
+
+// ---- backward pass 2: elementwise ----------------------------------------------------------------
+__global__ void __launch_bounds__(kBnThreads) bn_act_bwd_apply_kernel(BnBwdArgs a) {
+  const int groups = a.C / 8;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = tid % groups;
+  const int row0 = tid / groups;
+  const int row_stride = (gridDim.x * blockDim.x) / groups;
+  const int c0 = g * 8;
+  Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0), gam = load8_f32(a.gamma + c0);
+  Vec8 db = load8_f32(a.dbeta + c0), dg = load8_f32(a.dgamma + c0);
+  const float inv_n = 1.f / static_cast<float>(a.M);
+  if (row0 == 0 && a.gamma_grad) {   // exactly one thread per channel group: accumulate parameter grads
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      a.gamma_grad[c0 + i] += dg.v[i];
+      a.beta_grad[c0 + i] += db.v[i];
+    }
+  }
+  float k1[8], k2[8], k3[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    k1[i] = gam.v[i] * invstd.v[i];
+    k2[i] = db.v[i] * inv_n;
+    k3[i] = dg.v[i] * inv_n;
+  }
+  for (int r = row0; r < a.M; r += row_stride) {
+    const size_t off = static_cast<size_t>(r) * a.C + c0;
+    Vec8 dz = load8_bf16(a.dz + off);
+    Vec8 x = load8_bf16(a.x + off);
+    if (a.relu) {
+      Vec8 z = load8_bf16(a.z + off);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
+    }
+    if (a.dres) store8_bf16(a.dres + off, dz);
+    Vec8 dx;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xhat = (x.v[i] - mean.v[i]) * invstd.v[i];
+      dx.v[i] = k1[i] * (dz.v[i] - k2[i] - xhat * k3[i]);
+    }
+    store8_bf16(a.dx + off, dx);
+  }
+}
+
+// grid: every block must hold a whole number of channel groups AND total threads % groups == 0
+inline int bn_grid(int M, int C, int sms) {
+  const int groups = C / 8;
+  const long long total_vec = static_cast<long long>(M) * groups;
+  long long blocks = (total_vec + kBnThreads - 1) / kBnThreads;
+  const long long cap = static_cast<long long>(sms) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (groups > kBnThreads) {
+    // total threads must be a multiple of groups
+    const int need = groups / kBnThreads;
+    blocks = (blocks + need - 1) / need * need;
+  }
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream) {
+  if (a.C % 8 != 0) return cudaErrorInvalidValue;
+  const int groups = a.C / 8;
+  if (!((kBnThreads % groups == 0) || (groups % kBnThreads == 0))) return cudaErrorInvalidValue;
+  const int grid = bn_grid(a.M, a.C, sms);
+  if (train) bn_act_fwd_kernel<true><<<grid, kBnThreads, 0, stream>>>(a);
+  else bn_act_fwd_kernel<false><<<grid, kBnThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) {
+  if (a.C % 8 != 0) return cudaErrorInvalidValue;
+  const int groups = a.C / 8;
+  if (kBnThreads % groups != 0) return cudaErrorInvalidValue;   // groups <= 256 (C <= 2048), power of two
+  const int grid = bn_grid(a.M, a.C, sms);
+  bn_act_bwd_reduce_kernel<<<grid, kBnThreads, 0, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  bn_act_bwd_apply_kernel<<<grid, kBnThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace ddl

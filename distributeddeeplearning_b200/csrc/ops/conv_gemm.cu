@@ -1,0 +1,604 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 in, fp32 accumulate).
+//
+// Replaces the cuDNN conv fwd / bwd-data / bwd-filter and cuBLAS FC calls of the reference's
+// training step (N4, N5).  All three passes are GEMMs on NHWC data:
+//
+//   fwd    Y[m][co]  = sum_k  im2col(X)[m][k]  * W[co][k]          k = (r, s, ci)
+//   dgrad  dX[m][ci] = sum_k  im2colT(dY)[m][k] * W[co][(r,s,ci)]   k = (r, s, co)   (B is MN-major)
+//   wgrad  dW[co][k] = sum_m  dY[m][co]        * im2col(X)[m][k]    (A and B are MN-major, split-K)
+//
+// One CTA = 6 warps:
+//   warps 0-3  gather producers: each thread owns one 128-byte row of the operand tile and fills it
+//              with 16-byte cp.async (zero-fill = padding / tails) straight into the 128B-swizzled
+//              image tcgen05 expects; afterwards the same warps run the epilogue (TMEM -> registers
+//              -> smem -> coalesced global stores, fused BN statistics / bias / ReLU / residual add)
+//   warp 4     TMA producer (weights, and the activation operand when it is a plain matrix)
+//   warp 5     TMEM allocator + the single thread that issues tcgen05.mma and tcgen05.commit
+// Stages are handed over with mbarriers (full/empty ring + one accumulator-ready barrier).
+// Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns), so one CTA's epilogue overlaps the
+// other's main loop without a persistent scheduler.
+#include "conv_gemm.cuh"
+#include "tc_utils.cuh"
+
+#include <dlfcn.h>
+
+namespace ddl {
+using namespace tc;
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int kATileBytes = kBlockM * 128;        // 16 KB
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 192;
+constexpr int kLag = 2;                           // cp.async groups kept in flight per producer
+
+template <int BLOCK_N>
+struct FwdCfg {
+  static constexpr int kBTileBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (BLOCK_N <= 64) ? 4 : (BLOCK_N <= 128 ? 3 : 4);
+  static constexpr int kPitch = BLOCK_N * 2 + 16;                 // epilogue staging row pitch (bytes)
+  static constexpr int kStageTotal = kStages * kStageBytes;
+  static constexpr int kEpiBytes = kBlockM * kPitch;
+  static_assert(kEpiBytes <= kStageTotal, "epilogue staging must fit in the pipeline buffers");
+  static constexpr int kSmemBytes = kStageTotal + 256 /*barriers*/ + 1024 /*alignment slack*/;
+};
+
+DDL_DEVICE void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// fwd / dgrad / plain-GEMM / stem kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, int MODE, bool STATS>
+__global__ void __launch_bounds__(kThreads, (BLOCK_N <= 128) ? 2 : 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA, ConvArgs a) {
+  using Cfg = FwdCfg<BLOCK_N>;
+  constexpr bool kATma = (MODE == kConvGemm);
+  constexpr bool kBMn = (MODE == kConvDgrad);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStageTotal);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* acc_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * BLOCK_N;
+  const int m0 = blockIdx.y * kBlockM;
+  const int KB = a.KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], kATma ? 1u : (kProducerThreads + 1u));
+      mbar_init(&empty[s], 1u);
+    }
+    mbar_init(acc_full, 1u);
+    fence_mbar_init();
+  }
+  if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tmB);
+    if (kATma) tma_prefetch_desc(&tmA);
+  }
+  if (warp == 5) tmem_alloc<BLOCK_N>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // =============================== gather producers ===================================
+    if (!kATma) {
+      const int row = threadIdx.x;
+      const int m = m0 + row;
+      const bool row_ok = m < a.M;
+      int img = 0, dh = 0, dw = 0;
+      if (row_ok) {
+        const int hw = a.dstH * a.dstW;
+        img = m / hw;
+        const int rem = m - img * hw;
+        dh = rem / a.dstW;
+        dw = rem - dh * a.dstW;
+      }
+      // base coordinates in the gather source
+      int hb, wb;
+      if (MODE == kConvDgrad) { hb = dh + a.pad; wb = dw + a.pad; }
+      else { hb = dh * a.stride - a.pad; wb = dw * a.stride - a.pad; }
+      const __nv_bfloat16* img_base = a.src + static_cast<size_t>(img) * a.srcH * a.srcW * a.srcC;
+      const uint32_t row_off = row * 128u;
+      const uint32_t sw = row & 7u;
+      int tap_r = 0, tap_s = 0, cc = 0;   // incremental decode of kb -> (r, s, channel chunk)
+      for (int kb = 0; kb < KB; ++kb) {
+        const int stage = kb % Cfg::kStages;
+        const uint32_t phase = (kb / Cfg::kStages) & 1u;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        const uint32_t dst = smem_u32(smem + stage * Cfg::kStageBytes) + row_off;
+        if (MODE == kConvStem) {
+          // k-block = RPK filter rows x SP taps x 4 channels, SP = a.cchunks (padded taps per row)
+          const int SP = a.cchunks;
+          const int RPK = 16 / SP;           // 64 elements / (SP * 4)
+          int e = 0;                          // 8-byte element index within the 128-byte row (0..15)
+          for (int rr = 0; rr < RPK; ++rr) {
+            const int r = kb * RPK + rr;
+            const int h = hb + r * a.dil;
+            const bool h_ok = row_ok && r < a.R && h >= 0 && h < a.srcH;
+            for (int s = 0; s < SP; ++s, ++e) {
+              const int w = wb + s * a.dil;
+              const bool ok = h_ok && s < a.S && w >= 0 && w < a.srcW;
+              const __nv_bfloat16* src = ok ? img_base + (static_cast<size_t>(h) * a.srcW + w) * 4 : a.src;
+              const uint32_t chunk = (e >> 1) ^ sw;
+              cp_async_8(dst + (chunk << 4) + ((e & 1) << 3), src, ok);
+            }
+          }
+        } else {
+          bool ok;
+          int sh, swd;
+          if (MODE == kConvDgrad) {
+            const int th = hb - tap_r * a.dil, tw = wb - tap_s * a.dil;
+            if (a.stride == 1) {
+              sh = th; swd = tw;
+              ok = row_ok && th >= 0 && th < a.srcH && tw >= 0 && tw < a.srcW;
+            } else {
+              sh = th / a.stride; swd = tw / a.stride;
+              ok = row_ok && th >= 0 && tw >= 0 && (th - sh * a.stride) == 0 && (tw - swd * a.stride) == 0 &&
+                   sh < a.srcH && swd < a.srcW;
+            }
+          } else {
+            sh = hb + tap_r * a.dil; swd = wb + tap_s * a.dil;
+            ok = row_ok && sh >= 0 && sh < a.srcH && swd >= 0 && swd < a.srcW;
+          }
+          const __nv_bfloat16* src =
+              ok ? img_base + (static_cast<size_t>(sh) * a.srcW + swd) * a.srcC + cc * 64 : a.src;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cp_async_16(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), src + j * 8, ok);
+          if (++cc == a.cchunks) { cc = 0; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
+        }
+        cp_async_commit();
+        if (kb >= kLag) {
+          cp_async_wait<kLag>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full[(kb - kLag) % Cfg::kStages]);
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (int kb = (KB > kLag ? KB - kLag : 0); kb < KB; ++kb) mbar_arrive(&full[kb % Cfg::kStages]);
+    }
+
+    // =================================== epilogue ========================================
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint8_t* stg = smem;  // pipeline buffers are free: every MMA that read them has completed
+    const int row = threadIdx.x;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+        if (a.bias) { x0 += a.bias[n0 + c0 + 2 * j]; x1 += a.bias[n0 + c0 + 2 * j + 1]; }
+        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+        packed[j] = pack_bf16x2(x0, x1);
+      }
+      uint4* dstp = reinterpret_cast<uint4*>(stg + row * Cfg::kPitch + c0 * 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dstp[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+    }
+    tc_fence_before();
+    named_bar_sync(1, kProducerThreads);
+    if (STATS) {
+      // per-channel sum / sum of squares of the bf16-rounded outputs of this tile (rows >= M are 0)
+      constexpr int kGroups = (BLOCK_N >= 128) ? 1 : 128 / BLOCK_N;   // row groups sharing a column
+      constexpr int kColsPerThread = (BLOCK_N > 128) ? BLOCK_N / 128 : 1;
+#pragma unroll
+      for (int cidx = 0; cidx < kColsPerThread; ++cidx) {
+        const int col = (threadIdx.x % (BLOCK_N >= 128 ? 128 : BLOCK_N)) + cidx * 128;
+        const int grp = (BLOCK_N >= 128) ? 0 : threadIdx.x / BLOCK_N;
+        const int rows_per = kBlockM / kGroups;
+        float s = 0.f, ss = 0.f;
+        const uint8_t* colp = stg + col * 2 + grp * rows_per * Cfg::kPitch;
+#pragma unroll 8
+        for (int r = 0; r < rows_per; ++r) {
+          const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + r * Cfg::kPitch));
+          s += x;
+          ss = fmaf(x, x, ss);
+        }
+        atomicAdd(a.sum + n0 + col, s);
+        atomicAdd(a.sumsq + n0 + col, ss);
+      }
+    }
+    // coalesced stores: 16 bytes per thread, a row of the tile is BLOCK_N*2 contiguous bytes
+    constexpr int kVecPerRow = BLOCK_N / 8;
+    for (int idx = threadIdx.x; idx < kBlockM * kVecPerRow; idx += kProducerThreads) {
+      const int r = idx / kVecPerRow, ch = idx - r * kVecPerRow;
+      const int m = m0 + r;
+      if (m < a.M) {
+        uint4 val = *reinterpret_cast<const uint4*>(stg + r * Cfg::kPitch + ch * 16);
+        const size_t off = static_cast<size_t>(m) * a.ldc + n0 + ch * 8;
+        if (a.add) {
+          const uint4 o = *reinterpret_cast<const uint4*>(a.add + off);
+          float2 p, q;
+          p = unpack_bf16x2(val.x); q = unpack_bf16x2(o.x); val.x = pack_bf16x2(p.x + q.x, p.y + q.y);
+          p = unpack_bf16x2(val.y); q = unpack_bf16x2(o.y); val.y = pack_bf16x2(p.x + q.x, p.y + q.y);
+          p = unpack_bf16x2(val.z); q = unpack_bf16x2(o.z); val.z = pack_bf16x2(p.x + q.x, p.y + q.y);
+          p = unpack_bf16x2(val.w); q = unpack_bf16x2(o.w); val.w = pack_bf16x2(p.x + q.x, p.y + q.y);
+        }
+        *reinterpret_cast<uint4*>(a.out + off) = val;
+      }
+    }
+  } else if (warp == 4) {
+    // ================================== TMA producer =====================================
+    if (elect_one()) {
+      int tap = 0, cc = 0;
+      for (int kb = 0; kb < KB; ++kb) {
+        const int stage = kb % Cfg::kStages;
+        const uint32_t phase = (kb / Cfg::kStages) & 1u;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        uint8_t* sA = smem + stage * Cfg::kStageBytes;
+        const uint32_t sB = smem_u32(sA + kATileBytes);
+        mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + (kATma ? kATileBytes : 0));
+        if (kBMn) {
+          // weights W[co][(r,s,ci)]: K rows = 64 output channels, N = input channels (contiguous)
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_2d(sB + j * 8192, &tmB, tap * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
+          if (++cc == a.cchunks) { cc = 0; ++tap; }
+        } else {
+          tma_load_2d(sB, &tmB, kb * kBlockK, n0, &full[stage]);
+        }
+        if (kATma) tma_load_2d(smem_u32(sA), &tmA, kb * kBlockK, m0, &full[stage]);
+      }
+    }
+  } else {
+    // =================================== MMA issuer =======================================
+    constexpr uint32_t idesc = idesc_bf16(kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    for (int kb = 0; kb < KB; ++kb) {
+      const int stage = kb % Cfg::kStages;
+      const uint32_t phase = (kb / Cfg::kStages) & 1u;
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sB = sA + kATileBytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
+          const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (kb == KB - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<BLOCK_N>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad kernel: dW[co][k] += sum over a pixel range of dY[m][co] * im2col(X)[m][k]
+// ---------------------------------------------------------------------------------------------
+constexpr int kWgStages = 3;
+constexpr int kWgStageBytes = 32768;           // A: 2 x [64 pix][64 co], B: 2 x [64 pix][64 k]
+constexpr int kWgPitch = 132;                  // fp32 staging pitch (floats)
+constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 256 + 1024;
+static_assert(kBlockM * kWgPitch * 4 <= kWgStages * kWgStageBytes, "wgrad staging must fit");
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, WgradArgs a) {
+  constexpr bool kXTma = (MODE == kConvGemm);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+  uint64_t* empty = full + kWgStages;
+  uint64_t* acc_full = empty + kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int col0 = blockIdx.x * 128;          // first k column of this tile
+  const int co0 = blockIdx.y * 128;           // first output channel of this tile
+  const int kb_begin = blockIdx.z * a.kb_per_split;
+  const int kb_end = min(kb_begin + a.kb_per_split, a.total_kb);
+  const int KB = kb_end - kb_begin;
+  if (KB <= 0) return;                         // uniform per CTA
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kWgStages; ++s) {
+      mbar_init(&full[s], kXTma ? 1u : (kProducerThreads + 1u));
+      mbar_init(&empty[s], 1u);
+    }
+    mbar_init(acc_full, 1u);
+    fence_mbar_init();
+  }
+  if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tmDy);
+    if (kXTma) tma_prefetch_desc(&tmX);
+  }
+  if (warp == 5) tmem_alloc<128>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    if (!kXTma) {
+      const int chunk = threadIdx.x >> 6;      // which 64-column half of the B tile
+      const int row = threadIdx.x & 63;        // pixel row inside the k-block
+      const int colc = col0 + chunk * 64;      // first k column of my chunk
+      const bool col_ok = colc < a.ncols;
+      int tap_r = 0, tap_s = 0, c_off = 0;
+      if (MODE != kConvStem) {
+        const int tap = colc / a.C;
+        c_off = colc - tap * a.C;
+        tap_r = tap / a.S;
+        tap_s = tap - tap_r * a.S;
+      }
+      const uint32_t row_off = 16384u + chunk * 8192u + row * 128u;
+      const uint32_t sw = row & 7u;
+      const int pq = a.P * a.Q;
+      for (int i = 0; i < KB; ++i) {
+        const int stage = i % kWgStages;
+        const uint32_t phase = (i / kWgStages) & 1u;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        const uint32_t dst = smem_u32(smem + stage * kWgStageBytes) + row_off;
+        const int m = (kb_begin + i) * 64 + row;
+        const bool m_ok = col_ok && m < a.M;
+        int img = 0, p = 0, q = 0;
+        if (m_ok) {
+          img = m / pq;
+          const int rem = m - img * pq;
+          p = rem / a.Q;
+          q = rem - p * a.Q;
+        }
+        const int hb = p * a.stride - a.pad, wb = q * a.stride - a.pad;
+        const __nv_bfloat16* img_base = a.x + static_cast<size_t>(img) * a.H * a.W * a.C;
+        if (MODE == kConvStem) {
+          const int SP = a.cchunks, RPK = 16 / SP;
+          const int kbk = colc / 64;            // which k-block of the stem's packed K
+          int e = 0;
+          for (int rr = 0; rr < RPK; ++rr) {
+            const int r = kbk * RPK + rr;
+            const int h = hb + r * a.dil;
+            const bool h_ok = m_ok && r < a.R && h >= 0 && h < a.H;
+            for (int s = 0; s < SP; ++s, ++e) {
+              const int w = wb + s * a.dil;
+              const bool ok = h_ok && s < a.S && w >= 0 && w < a.W;
+              const __nv_bfloat16* src = ok ? img_base + (static_cast<size_t>(h) * a.W + w) * 4 : a.x;
+              cp_async_8(dst + (((e >> 1) ^ sw) << 4) + ((e & 1) << 3), src, ok);
+            }
+          }
+        } else {
+          const int h = hb + tap_r * a.dil, w = wb + tap_s * a.dil;
+          const bool ok = m_ok && h >= 0 && h < a.H && w >= 0 && w < a.W;
+          const __nv_bfloat16* src = ok ? img_base + (static_cast<size_t>(h) * a.W + w) * a.C + c_off : a.x;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) cp_async_16(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), src + j * 8, ok);
+        }
+        cp_async_commit();
+        if (i >= kLag) {
+          cp_async_wait<kLag>();
+          fence_proxy_async_smem();
+          mbar_arrive(&full[(i - kLag) % kWgStages]);
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      for (int i = (KB > kLag ? KB - kLag : 0); i < KB; ++i) mbar_arrive(&full[i % kWgStages]);
+    }
+
+    // epilogue: TMEM -> fp32 staging -> coalesced vector reductions into the gradient arena
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem);
+    const int row = threadIdx.x;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      float4* d = reinterpret_cast<float4*>(stg + row * kWgPitch + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                           __uint_as_float(v[4 * j + 3]));
+    }
+    tc_fence_before();
+    named_bar_sync(1, kProducerThreads);
+    const int lane = threadIdx.x & 31;
+    const int c = col0 + lane * 4;
+    if (c < a.ncols) {
+      for (int r = warp; r < 128; r += 4) {
+        const int co = co0 + r;
+        if (co < a.Cout) {
+          const float4 val = *reinterpret_cast<const float4*>(stg + r * kWgPitch + lane * 4);
+          red_add_f32x4(a.dw + static_cast<size_t>(co) * a.ldw + c, val.x, val.y, val.z, val.w);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (elect_one()) {
+      for (int i = 0; i < KB; ++i) {
+        const int stage = i % kWgStages;
+        const uint32_t phase = (i / kWgStages) & 1u;
+        mbar_wait(&empty[stage], phase ^ 1u);
+        const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
+        const int m = (kb_begin + i) * 64;
+        mbar_arrive_expect_tx(&full[stage], 16384u + (kXTma ? 16384u : 0u));
+        tma_load_2d(sA, &tmDy, co0, m, &full[stage]);
+        tma_load_2d(sA + 8192, &tmDy, co0 + 64, m, &full[stage]);
+        if (kXTma) {
+          tma_load_2d(sA + 16384, &tmX, col0, m, &full[stage]);
+          tma_load_2d(sA + 24576, &tmX, col0 + 64, m, &full[stage]);
+        }
+      }
+    }
+  } else {
+    constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);
+    for (int i = 0; i < KB; ++i) {
+      const int stage = i % kWgStages;
+      const uint32_t phase = (i / kWgStages) & 1u;
+      mbar_wait(&full[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
+        const uint32_t sB = sA + 16384;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = smem_desc_sw128(sA + k * 2048, 8192, 1024);
+          const uint64_t db = smem_desc_sw128(sB + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (i | k) != 0);
+        }
+        umma_commit(&empty[stage]);
+        if (i == KB - 1) umma_commit(acc_full);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<128>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launchers
+// ---------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* lib = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(dlsym(lib, "cuTensorMapEncodeTiled"));
+  }();
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [rows][cols] (cols contiguous), box = {box_cols, box_rows}, 128B swizzle.
+bool make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
+                 uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BLOCK_N, int MODE, bool STATS>
+cudaError_t launch_fwd_t(const CUtensorMap& tmB, const CUtensorMap& tmA, const ConvArgs& a, int n_total,
+                         cudaStream_t stream) {
+  using Cfg = FwdCfg<BLOCK_N>;
+  auto kern = conv_gemm_kernel<BLOCK_N, MODE, STATS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid(n_total / BLOCK_N, (a.M + kBlockM - 1) / kBlockM);
+  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmB, tmA, a);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmA, const ConvArgs& a, int n_total,
+                            bool stats, cudaStream_t stream) {
+  if (n_total % 128 == 0) {
+    return stats ? launch_fwd_t<128, MODE, true>(tmB, tmA, a, n_total, stream)
+                 : launch_fwd_t<128, MODE, false>(tmB, tmA, a, n_total, stream);
+  }
+  if (n_total % 64 == 0) {
+    return stats ? launch_fwd_t<64, MODE, true>(tmB, tmA, a, n_total, stream)
+                 : launch_fwd_t<64, MODE, false>(tmB, tmA, a, n_total, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+// `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad).
+cudaError_t launch_conv_gemm(int mode, const ConvArgs& a, const void* w, int w_rows, int w_cols, int n_total,
+                             const void* a_matrix, int a_cols, cudaStream_t stream) {
+  CUtensorMap tmB, tmA;
+  const int bn = (n_total % 128 == 0) ? 128 : 64;
+  if (n_total % 64 != 0) return cudaErrorInvalidValue;
+  if (mode == kConvDgrad) {
+    if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, 64)) return cudaErrorUnknown;
+  } else {
+    if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, bn)) return cudaErrorUnknown;
+  }
+  if (mode == kConvGemm) {
+    if (!make_map_2d(&tmA, a_matrix, a.M, a_cols, a_cols, 64, 128)) return cudaErrorUnknown;
+  } else {
+    tmA = tmB;
+  }
+  const bool stats = a.sum != nullptr;
+  switch (mode) {
+    case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmA, a, n_total, stats, stream);
+    case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmA, a, n_total, stats, stream);
+    case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmA, a, n_total, stats, stream);
+    case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmA, a, n_total, stats, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void* x_matrix, int splits,
+                              cudaStream_t stream) {
+  WgradArgs a = a_in;
+  CUtensorMap tmDy, tmX;
+  if (!make_map_2d(&tmDy, dy, a.M, a.Cout, a.Cout, 64, 64)) return cudaErrorUnknown;
+  if (a.mode == kConvGemm) {
+    if (!make_map_2d(&tmX, x_matrix, a.M, a.ncols, a.ncols, 64, 64)) return cudaErrorUnknown;
+  } else {
+    tmX = tmDy;
+  }
+  a.total_kb = (a.M + 63) / 64;
+  if (splits < 1) splits = 1;
+  if (splits > a.total_kb) splits = a.total_kb;
+  a.kb_per_split = (a.total_kb + splits - 1) / splits;
+  splits = (a.total_kb + a.kb_per_split - 1) / a.kb_per_split;
+  dim3 grid((a.ncols + 127) / 128, (a.Cout + 127) / 128, splits);
+  static bool configured[4] = {false, false, false, false};
+#define DDL_WG(MODE)                                                                                          \
+  do {                                                                                                        \
+    auto kern = conv_wgrad_kernel<MODE>;                                                                      \
+    if (!configured[MODE]) {                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);  \
+      if (e != cudaSuccess) return e;                                                                         \
+      configured[MODE] = true;                                                                                \
+    }                                                                                                         \
+    kern<<<grid, kThreads, kWgSmemBytes, stream>>>(tmDy, tmX, a);                                             \
+  } while (0)
+  switch (a.mode) {
+    case kConvFwd: DDL_WG(kConvFwd); break;
+    case kConvGemm: DDL_WG(kConvGemm); break;
+    case kConvStem: DDL_WG(kConvStem); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef DDL_WG
+  return cudaGetLastError();
+}
+
+}  // namespace ddl

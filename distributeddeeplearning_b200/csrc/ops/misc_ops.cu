@@ -1,0 +1,588 @@
+// Memory-bound support kernels (NHWC bf16): pooling, fused softmax-cross-entropy(+top-k), Philox
+// synthetic data, layout/dtype conversion, bias/ReLU backward, dropout.
+// Reference op inventory: SURVEY.md K1 (synthetic batch), K8 (max-pool), K9 (avg-pool), K11
+// (cross-entropy), K17 (accuracy), K20 (bias / dropout), K21 (normalise + layout convert).
+#include "../common.cuh"
+#include "ops.h"
+
+namespace ddl {
+namespace {
+
+DDL_DEVICE void unpack8(const uint4& u, float (&v)[8]) {
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+}
+DDL_DEVICE uint4 pack8(const float (&v)[8]) {
+  return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+// ---------------------------------------------------------------------------------------------
+// channel statistics (fallback when the producer did not fuse them)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ x, float* sum,
+                                                            float* sumsq, int M, int C) {
+  const int groups = C / 8;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = tid % groups, row0 = tid / groups;
+  const int row_stride = (gridDim.x * blockDim.x) / groups;
+  float s[8], ss[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+  for (int r = row0; r < M; r += row_stride) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * C + g * 8), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] = fmaf(v[i], v[i], ss[i]); }
+  }
+  __shared__ float red[2][256][9];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s[i]; red[1][threadIdx.x][i] = ss[i]; }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int per_block = blockDim.x / groups;
+    float t0[8], t1[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t0[i] = 0.f; t1[i] = 0.f; }
+    for (int k = 0; k < per_block; ++k) {
+      const int t = threadIdx.x + k * groups;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { t0[i] += red[0][t][i]; t1[i] += red[1][t][i]; }
+    }
+    const int gc = ((blockIdx.x * blockDim.x + threadIdx.x) % groups) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(sum + gc + i, t0[i]); atomicAdd(sumsq + gc + i, t1[i]); }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling: one thread = one output (or input) pixel x 8 channels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* y,
+                                                          uint8_t* argmax, PoolArgs p) {
+  const int groups = p.C / 8;
+  const int64_t total = static_cast<int64_t>(p.N) * p.P * p.Q * groups;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    int64_t pix = idx / groups;
+    const int q = pix % p.Q; pix /= p.Q;
+    const int pp = pix % p.P;
+    const int n = pix / p.P;
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; bi[i] = 0; }
+    for (int r = 0; r < p.k; ++r) {
+      const int h = pp * p.stride - p.pad + r;
+      if (h < 0 || h >= p.H) continue;
+      for (int s = 0; s < p.k; ++s) {
+        const int w = q * p.stride - p.pad + s;
+        if (w < 0 || w >= p.W) continue;
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.C + g * 8), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (v[i] > best[i]) { best[i] = v[i]; bi[i] = r * p.k + s; }
+      }
+    }
+    const size_t o = ((static_cast<size_t>(n) * p.P + pp) * p.Q + q) * p.C + g * 8;
+    *reinterpret_cast<uint4*>(y + o) = pack8(best);
+    if (argmax) {
+      uint2 a;
+      a.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      a.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + o) = a;
+    }
+  }
+}
+
+// gather formulation: each INPUT pixel sums the dy of the windows whose arg-max it is (no atomics)
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                          const uint8_t* __restrict__ argmax, __nv_bfloat16* dx,
+                                                          PoolArgs p) {
+  const int groups = p.C / 8;
+  const int64_t total = static_cast<int64_t>(p.N) * p.H * p.W * groups;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    int64_t pix = idx / groups;
+    const int w = pix % p.W; pix /= p.W;
+    const int h = pix % p.H;
+    const int n = pix / p.H;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    // windows (pp, q) covering (h, w): pp*stride - pad + r == h
+    for (int r = 0; r < p.k; ++r) {
+      const int th = h + p.pad - r;
+      if (th < 0 || th % p.stride != 0) continue;
+      const int pp = th / p.stride;
+      if (pp >= p.P) continue;
+      for (int s = 0; s < p.k; ++s) {
+        const int tw = w + p.pad - s;
+        if (tw < 0 || tw % p.stride != 0) continue;
+        const int q = tw / p.stride;
+        if (q >= p.Q) continue;
+        const size_t o = ((static_cast<size_t>(n) * p.P + pp) * p.Q + q) * p.C + g * 8;
+        const uint2 am = *reinterpret_cast<const uint2*>(argmax + o);
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + o), v);
+        const int code = r * p.k + s;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int a = ((i < 4 ? am.x : am.y) >> (8 * (i & 3))) & 0xff;
+          if (a == code) acc[i] += v[i];
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.C + g * 8) = pack8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* y,
+                                                          PoolArgs p, int count_include_pad) {
+  const int groups = p.C / 8;
+  const int64_t total = static_cast<int64_t>(p.N) * p.P * p.Q * groups;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    int64_t pix = idx / groups;
+    const int q = pix % p.Q; pix /= p.Q;
+    const int pp = pix % p.P;
+    const int n = pix / p.P;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    int cnt = 0;
+    for (int r = 0; r < p.k; ++r) {
+      const int h = pp * p.stride - p.pad + r;
+      if (h < 0 || h >= p.H) continue;
+      for (int s = 0; s < p.k; ++s) {
+        const int w = q * p.stride - p.pad + s;
+        if (w < 0 || w >= p.W) continue;
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.C + g * 8), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        ++cnt;
+      }
+    }
+    const float inv = 1.f / static_cast<float>(count_include_pad ? p.k * p.k : max(cnt, 1));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    *reinterpret_cast<uint4*>(y + ((static_cast<size_t>(n) * p.P + pp) * p.Q + q) * p.C + g * 8) = pack8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* dx,
+                                                          PoolArgs p, int count_include_pad) {
+  const int groups = p.C / 8;
+  const int64_t total = static_cast<int64_t>(p.N) * p.H * p.W * groups;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    int64_t pix = idx / groups;
+    const int w = pix % p.W; pix /= p.W;
+    const int h = pix % p.H;
+    const int n = pix / p.H;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int r = 0; r < p.k; ++r) {
+      const int th = h + p.pad - r;
+      if (th < 0 || th % p.stride != 0) continue;
+      const int pp = th / p.stride;
+      if (pp >= p.P) continue;
+      for (int s = 0; s < p.k; ++s) {
+        const int tw = w + p.pad - s;
+        if (tw < 0 || tw % p.stride != 0) continue;
+        const int q = tw / p.stride;
+        if (q >= p.Q) continue;
+        float inv;
+        if (count_include_pad) {
+          inv = 1.f / static_cast<float>(p.k * p.k);
+        } else {
+          const int h0 = max(pp * p.stride - p.pad, 0), h1 = min(pp * p.stride - p.pad + p.k, p.H);
+          const int w0 = max(q * p.stride - p.pad, 0), w1 = min(q * p.stride - p.pad + p.k, p.W);
+          inv = 1.f / static_cast<float>(max((h1 - h0) * (w1 - w0), 1));
+        }
+        float v[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + ((static_cast<size_t>(n) * p.P + pp) * p.Q + q) * p.C + g * 8), v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], inv, acc[i]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dx + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * p.C + g * 8) = pack8(acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) global_avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                 __nv_bfloat16* y, int N, int HW, int C) {
+  const int groups = C / 8;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * groups) return;
+  const int g = idx % groups, n = idx / groups;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const __nv_bfloat16* base = x + static_cast<size_t>(n) * HW * C + g * 8;
+  for (int t = 0; t < HW; ++t) {
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(base + static_cast<size_t>(t) * C), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] += v[i];
+  }
+  const float inv = 1.f / static_cast<float>(HW);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] *= inv;
+  *reinterpret_cast<uint4*>(y + static_cast<size_t>(n) * C + g * 8) = pack8(acc);
+}
+
+__global__ void __launch_bounds__(256) global_avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                                 __nv_bfloat16* dx, int N, int HW, int C) {
+  const int groups = C / 8;
+  const int64_t total = static_cast<int64_t>(N) * HW * groups;
+  const float inv = 1.f / static_cast<float>(HW);
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    const int64_t pix = idx / groups;
+    const int n = pix / HW;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + static_cast<size_t>(n) * C + g * 8), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= inv;
+    *reinterpret_cast<uint4*>(dx + static_cast<size_t>(pix) * C + g * 8) = pack8(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused softmax cross-entropy forward + backward + top-1/top-5: one warp per sample
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_xent_kernel(XentArgs a) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= a.B) return;
+  const __nv_bfloat16* row = a.logits + static_cast<size_t>(warp) * a.ld;
+  const int label = static_cast<int>(a.labels[warp]);
+  float mx = -INFINITY;
+  for (int c = lane; c < a.classes; c += 32) mx = fmaxf(mx, __bfloat162float(row[c]));
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int c = lane; c < a.classes; c += 32) se += __expf(__bfloat162float(row[c]) - mx);
+  se = warp_sum(se);
+  const float xl = __bfloat162float(row[label]);
+  const float lse = mx + __logf(se);
+  const float loss = lse - xl;
+  if (a.correct) {
+    // rank of the label logit: number of classes with a strictly larger logit (ties: lower index wins)
+    int larger = 0;
+    for (int c = lane; c < a.classes; c += 32) {
+      const float v = __bfloat162float(row[c]);
+      larger += (v > xl) || (v == xl && c < label);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) larger += __shfl_xor_sync(0xffffffffu, larger, o);
+    if (lane == 0) {
+      if (larger < 1) atomicAdd(a.correct, 1);
+      if (larger < 5) atomicAdd(a.correct + 1, 1);
+    }
+  }
+  if (lane == 0) {
+    if (a.per_sample) a.per_sample[warp] = loss;
+    if (a.loss_sum) atomicAdd(a.loss_sum, loss * a.loss_scale);
+  }
+  if (a.dlogits) {
+    __nv_bfloat16* drow = a.dlogits + static_cast<size_t>(warp) * a.ld;
+    const float inv = 1.f / se;
+    for (int c = lane; c < a.ld; c += 32) {
+      float g = 0.f;
+      if (c < a.classes) {
+        g = __expf(__bfloat162float(row[c]) - mx) * inv;
+        if (c == label) g -= 1.f;
+        g *= a.grad_scale;
+      }
+      drow[c] = __float2bfloat16_rn(g);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox synthetic data (K1): normal(0,1) NHWC images, uniform labels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) philox_normal_nhwc_kernel(__nv_bfloat16* out, int64_t pixels, int c_valid,
+                                                                 int cpad, uint64_t seed, uint64_t offset) {
+  // one Philox block (4 normals) per pixel; channels beyond c_valid are zero (cpad <= 4)
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pixels;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t ctr = offset + static_cast<uint64_t>(i);
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0x4e48u, 0), key);
+    const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+    float v[4] = {n0.x, n0.y, n1.x, n1.y};
+    for (int c = 0; c < cpad; ++c) out[i * cpad + c] = __float2bfloat16_rn(c < c_valid ? v[c] : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) philox_labels_kernel(int64_t* out, int64_t n, int classes, uint64_t seed,
+                                                            uint64_t offset) {
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t ctr = offset + static_cast<uint64_t>(i);
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0x4c42u, 0), key);
+  out[i] = static_cast<int64_t>(r.x % static_cast<uint32_t>(classes));
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout / dtype
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_norm_kernel(const float* __restrict__ in, __nv_bfloat16* out,
+                                                                int N, int C, int H, int W, int cpad,
+                                                                const float* mean, const float* stdv) {
+  const int64_t total = static_cast<int64_t>(N) * H * W;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t hw = i % (static_cast<int64_t>(H) * W);
+    const int64_t n = i / (static_cast<int64_t>(H) * W);
+    for (int c = 0; c < cpad; ++c) {
+      float v = 0.f;
+      if (c < C) {
+        v = in[(n * C + c) * static_cast<int64_t>(H) * W + hw];
+        if (mean) v = (v - mean[c]) / stdv[c];
+      }
+      out[i * cpad + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* out,
+                                                            int64_t n) {
+  const int64_t n4 = n / 4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) out[n4 * 4 + threadIdx.x] = __float2bfloat16_rn(in[n4 * 4 + threadIdx.x]);
+}
+
+// w: fp32 KRSC [Cout][R][S][Cin] ; packed: bf16 [Cout][RP][SP][4], zero padded (RP >= R, SP >= S)
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* packed, int Cout, int R, int S,
+                                        int Cin, int RP, int SP) {
+  const int total = Cout * RP * SP * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 3;
+    int t = i >> 2;
+    const int s = t % SP; t /= SP;
+    const int r = t % RP;
+    const int co = t / RP;
+    float v = 0.f;
+    if (c < Cin && s < S && r < R) v = w[((co * R + r) * S + s) * Cin + c];
+    packed[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void unpack_stem_grad_kernel(const float* __restrict__ packed, float* gw, int Cout, int R, int S, int Cin,
+                                        int RP, int SP) {
+  const int total = Cout * R * S * Cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i % Cin;
+    int t = i / Cin;
+    const int s = t % S; t /= S;
+    const int r = t % R;
+    const int co = t / R;
+    gw[i] += packed[((co * RP + r) * SP + s) * 4 + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bias / relu backward, dropout, add
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bias_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
+                                                            const __nv_bfloat16* __restrict__ z, __nv_bfloat16* dx,
+                                                            float* dbias, int M, int C, int relu) {
+  const int groups = C / 8;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = tid % groups, row0 = tid / groups;
+  const int row_stride = (gridDim.x * blockDim.x) / groups;
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int r = row0; r < M; r += row_stride) {
+    const size_t off = static_cast<size_t>(r) * C + g * 8;
+    float v[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + off), v);
+    if (relu) {
+      float zz[8];
+      unpack8(*reinterpret_cast<const uint4*>(z + off), zz);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = zz[i] > 0.f ? v[i] : 0.f;
+      *reinterpret_cast<uint4*>(dx + off) = pack8(v);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] += v[i];
+  }
+  if (dbias) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(dbias + g * 8 + i, s[i]);
+  }
+}
+
+__global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* y,
+                                                      int64_t n8, float p, uint64_t seed, uint64_t offset) {
+  // mask is a pure function of (seed, offset, element index): backward recomputes it (no mask tensor)
+  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const float scale = 1.f / (1.f - p);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t ctr = offset + static_cast<uint64_t>(i);
+    const uint4 r0 = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0x4450u, 0), key);
+    const uint4 r1 = philox4x32_10(make_uint4(static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0x4450u, 1), key);
+    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    float v[8];
+    unpack8(reinterpret_cast<const uint4*>(x)[i], v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = (u32_to_unit(rr[k]) > p) ? v[k] * scale : 0.f;
+    reinterpret_cast<uint4*>(y)[i] = pack8(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) add_bf16_kernel(const __nv_bfloat16* __restrict__ a,
+                                                       const __nv_bfloat16* __restrict__ b, __nv_bfloat16* y,
+                                                       int64_t n8) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float u[8], v[8];
+    unpack8(reinterpret_cast<const uint4*>(a)[i], u);
+    unpack8(reinterpret_cast<const uint4*>(b)[i], v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) u[k] += v[k];
+    reinterpret_cast<uint4*>(y)[i] = pack8(u);
+  }
+}
+
+inline int grid_for(int64_t work, int per_block = 256, int cap = 148 * 16) {
+  int64_t b = (work + per_block - 1) / per_block;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return static_cast<int>(b);
+}
+
+}  // namespace
+
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, float* sum, float* sumsq, int M, int C, int sms,
+                                 cudaStream_t stream) {
+  const int groups = C / 8;
+  if (C % 8 != 0 || 256 % groups != 0) return cudaErrorInvalidValue;
+  int blocks = grid_for(static_cast<int64_t>(M) * groups, 256, sms * 8);
+  channel_stats_kernel<<<blocks, 256, 0, stream>>>(x, sum, sumsq, M, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* argmax, const PoolArgs& p,
+                               cudaStream_t stream) {
+  if (p.C % 8 != 0) return cudaErrorInvalidValue;
+  maxpool_fwd_kernel<<<grid_for(static_cast<int64_t>(p.N) * p.P * p.Q * (p.C / 8)), 256, 0, stream>>>(x, y, argmax, p);
+  return cudaGetLastError();
+}
+cudaError_t launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* argmax, __nv_bfloat16* dx, const PoolArgs& p,
+                               cudaStream_t stream) {
+  if (p.C % 8 != 0) return cudaErrorInvalidValue;
+  maxpool_bwd_kernel<<<grid_for(static_cast<int64_t>(p.N) * p.H * p.W * (p.C / 8)), 256, 0, stream>>>(dy, argmax, dx, p);
+  return cudaGetLastError();
+}
+cudaError_t launch_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, const PoolArgs& p, int count_include_pad,
+                               cudaStream_t stream) {
+  if (p.C % 8 != 0) return cudaErrorInvalidValue;
+  avgpool_fwd_kernel<<<grid_for(static_cast<int64_t>(p.N) * p.P * p.Q * (p.C / 8)), 256, 0, stream>>>(x, y, p, count_include_pad);
+  return cudaGetLastError();
+}
+cudaError_t launch_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, const PoolArgs& p, int count_include_pad,
+                               cudaStream_t stream) {
+  if (p.C % 8 != 0) return cudaErrorInvalidValue;
+  avgpool_bwd_kernel<<<grid_for(static_cast<int64_t>(p.N) * p.H * p.W * (p.C / 8)), 256, 0, stream>>>(dy, dx, p, count_include_pad);
+  return cudaGetLastError();
+}
+cudaError_t launch_global_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int N, int HW, int C,
+                                      cudaStream_t stream) {
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  const int total = N * (C / 8);
+  global_avgpool_fwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(x, y, N, HW, C);
+  return cudaGetLastError();
+}
+cudaError_t launch_global_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, int N, int HW, int C,
+                                      cudaStream_t stream) {
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  global_avgpool_bwd_kernel<<<grid_for(static_cast<int64_t>(N) * HW * (C / 8)), 256, 0, stream>>>(dy, dx, N, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_softmax_xent(const XentArgs& a, cudaStream_t stream) {
+  const int warps_per_block = 8;
+  softmax_xent_kernel<<<(a.B + warps_per_block - 1) / warps_per_block, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_philox_normal_nhwc(__nv_bfloat16* out, int64_t pixels, int c_valid, int cpad, uint64_t seed,
+                                      uint64_t offset, cudaStream_t stream) {
+  if (cpad > 4 || c_valid > cpad) return cudaErrorInvalidValue;
+  philox_normal_nhwc_kernel<<<grid_for(pixels), 256, 0, stream>>>(out, pixels, c_valid, cpad, seed, offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_philox_labels(int64_t* out, int64_t n, int classes, uint64_t seed, uint64_t offset,
+                                 cudaStream_t stream) {
+  philox_labels_kernel<<<static_cast<int>((n + 255) / 256), 256, 0, stream>>>(out, n, classes, seed, offset);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nchw_to_nhwc_norm(const float* in, __nv_bfloat16* out, int N, int C, int H, int W, int cpad,
+                                     const float* mean, const float* stdv, cudaStream_t stream) {
+  nchw_to_nhwc_norm_kernel<<<grid_for(static_cast<int64_t>(N) * H * W), 256, 0, stream>>>(in, out, N, C, H, W, cpad, mean, stdv);
+  return cudaGetLastError();
+}
+cudaError_t launch_cast_f32_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t stream) {
+  cast_f32_bf16_kernel<<<grid_for(n / 4 + 1), 256, 0, stream>>>(in, out, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_pack_stem_weight(const float* w, __nv_bfloat16* packed, int Cout, int R, int S, int Cin, int RP,
+                                    int SP, cudaStream_t stream) {
+  pack_stem_weight_kernel<<<grid_for(static_cast<int64_t>(Cout) * RP * SP * 4), 256, 0, stream>>>(w, packed, Cout, R, S, Cin, RP, SP);
+  return cudaGetLastError();
+}
+cudaError_t launch_unpack_stem_grad(const float* packed, float* gw, int Cout, int R, int S, int Cin, int RP, int SP,
+                                    cudaStream_t stream) {
+  unpack_stem_grad_kernel<<<grid_for(static_cast<int64_t>(Cout) * R * S * Cin), 256, 0, stream>>>(packed, gw, Cout, R, S, Cin, RP, SP);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z, __nv_bfloat16* dx, float* dbias,
+                                 int M, int C, int relu, int sms, cudaStream_t stream) {
+  const int groups = C / 8;
+  if (C % 8 != 0) return cudaErrorInvalidValue;
+  // total threads must be a multiple of `groups`
+  int64_t threads = static_cast<int64_t>(M) * groups;
+  int64_t cap = static_cast<int64_t>(sms) * 4 * 256;
+  if (threads > cap) threads = cap;
+  int64_t unit = 256;                       // lcm(256, groups) / 256 blocks granularity
+  int64_t l = groups;
+  while (l % 256 != 0) l += groups;         // smallest multiple of groups divisible by 256
+  unit = l / 256;
+  int64_t blocks = (threads + 255) / 256;
+  blocks = (blocks + unit - 1) / unit * unit;
+  bias_relu_bwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dy, z, dx, dbias, M, C, relu);
+  return cudaGetLastError();
+}
+cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,
+                           uint64_t offset, cudaStream_t stream) {
+  if (n % 8 != 0) return cudaErrorInvalidValue;
+  dropout_kernel<<<grid_for(n / 8), 256, 0, stream>>>(x, y, n / 8, p, seed, offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, int64_t n,
+                            cudaStream_t stream) {
+  if (n % 8 != 0) return cudaErrorInvalidValue;
+  add_bf16_kernel<<<grid_for(n / 8), 256, 0, stream>>>(a, b, y, n / 8);
+  return cudaGetLastError();
+}
+
+}  // namespace ddl

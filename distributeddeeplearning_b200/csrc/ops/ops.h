@@ -1,0 +1,109 @@
+// Host-visible launchers of the memory-bound sm_100a kernels (NHWC bf16 activations).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ddl {
+
+struct BnFwdArgs {
+  const __nv_bfloat16* x;         // [M][C] conv output
+  const __nv_bfloat16* residual;  // optional [M][C]
+  __nv_bfloat16* z;               // [M][C]
+  const float* sum;               // [C] (train)
+  const float* sumsq;             // [C] (train)
+  const float* gamma;
+  const float* beta;
+  float* mean;                    // [C] out (train)
+  float* invstd;                  // [C] out (train)
+  float* running_mean;            // [C] in/out (may be null in train)
+  float* running_var;
+  float eps, momentum;
+  int M, C, relu;
+};
+
+struct BnBwdArgs {
+  const __nv_bfloat16* dz;        // [M][C] gradient wrt z
+  const __nv_bfloat16* z;         // [M][C] saved output (ReLU mask)
+  const __nv_bfloat16* x;         // [M][C] saved conv output
+  __nv_bfloat16* dx;              // [M][C] gradient wrt x
+  __nv_bfloat16* dres;            // optional [M][C] gradient wrt residual (= masked dz)
+  const float* mean;
+  const float* invstd;
+  const float* gamma;
+  float* dgamma;                  // [C] scratch, zeroed by the caller; receives this call's sums
+  float* dbeta;                   // [C] scratch
+  float* gamma_grad;              // optional accumulate targets (parameter gradients)
+  float* beta_grad;
+  int M, C, relu;
+};
+
+cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream);
+cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream);
+
+// per-channel sum / sumsq of a bf16 [M][C] tensor (used when the producer had no fused stats)
+cudaError_t launch_channel_stats(const __nv_bfloat16* x, float* sum, float* sumsq, int M, int C, int sms,
+                                 cudaStream_t stream);
+
+// ---- pooling -------------------------------------------------------------------------------------
+struct PoolArgs {
+  int N, H, W, C, P, Q, k, stride, pad;
+};
+cudaError_t launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* argmax, const PoolArgs& p,
+                               cudaStream_t stream);
+cudaError_t launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* argmax, __nv_bfloat16* dx, const PoolArgs& p,
+                               cudaStream_t stream);
+cudaError_t launch_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, const PoolArgs& p, int count_include_pad,
+                               cudaStream_t stream);
+cudaError_t launch_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, const PoolArgs& p, int count_include_pad,
+                               cudaStream_t stream);
+// global average pool: [N][HW][C] -> [N][C] and its backward
+cudaError_t launch_global_avgpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, int N, int HW, int C,
+                                      cudaStream_t stream);
+cudaError_t launch_global_avgpool_bwd(const __nv_bfloat16* dy, __nv_bfloat16* dx, int N, int HW, int C,
+                                      cudaStream_t stream);
+
+// ---- loss ----------------------------------------------------------------------------------------
+struct XentArgs {
+  const __nv_bfloat16* logits;  // [B][ld] (first `classes` columns valid)
+  const int64_t* labels;        // [B]
+  __nv_bfloat16* dlogits;       // [B][ld] or null ; = (softmax - onehot) * grad_scale, padded cols = 0
+  float* loss_sum;              // scalar accumulator: += sum_b loss_b * loss_scale
+  float* per_sample;            // optional [B]
+  int32_t* correct;             // optional [2]: top-1, top-5 hit counters (+=)
+  float loss_scale;             // usually 1/B
+  float grad_scale;             // usually 1/B
+  int B, classes, ld;
+};
+cudaError_t launch_softmax_xent(const XentArgs& a, cudaStream_t stream);
+
+// ---- synthetic data ------------------------------------------------------------------------------
+// Philox4x32-10 normal(0,1) image batch, NHWC with `cpad` channels (channels >= c_valid are zero)
+cudaError_t launch_philox_normal_nhwc(__nv_bfloat16* out, int64_t pixels, int c_valid, int cpad, uint64_t seed,
+                                      uint64_t offset, cudaStream_t stream);
+cudaError_t launch_philox_labels(int64_t* out, int64_t n, int classes, uint64_t seed, uint64_t offset,
+                                 cudaStream_t stream);
+
+// ---- layout / dtype helpers -----------------------------------------------------------------------
+// NCHW fp32 -> NHWC(cpad) bf16 with per-channel (x - mean) / std   (real-image input path, K21)
+cudaError_t launch_nchw_to_nhwc_norm(const float* in, __nv_bfloat16* out, int N, int C, int H, int W, int cpad,
+                                     const float* mean, const float* stdv, cudaStream_t stream);
+cudaError_t launch_cast_f32_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t stream);
+// stem weights: fp32 [Cout][R][S][Cin<=4] (KRSC) <-> packed bf16 [Cout][KBR][SP][4] (zero padded)
+cudaError_t launch_pack_stem_weight(const float* w, __nv_bfloat16* packed, int Cout, int R, int S, int Cin, int RP,
+                                    int SP, cudaStream_t stream);
+cudaError_t launch_unpack_stem_grad(const float* packed, float* gw, int Cout, int R, int S, int Cin, int RP, int SP,
+                                    cudaStream_t stream);
+
+// ---- bias / activation / dropout (VGG / AlexNet classifier paths) ---------------------------------
+// dy_masked = dy * (z > 0) ; dbias[c] += sum_m dy_masked    (z = relu(conv + bias) saved output)
+cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z, __nv_bfloat16* dx, float* dbias,
+                                 int M, int C, int relu, int sms, cudaStream_t stream);
+cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,
+                           uint64_t offset, cudaStream_t stream);
+// y = a + b (bf16)
+cudaError_t launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, int64_t n,
+                            cudaStream_t stream);
+
+}  // namespace ddl
