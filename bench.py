@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Headline benchmark: ResNet-50 synthetic-ImageNet training throughput (images/sec, device-timed,
+max over ranks) — the metric/config BASELINE.json names ("PyTorch_benchmark ResNet-50 bf16 synthetic,
+batch 256/GPU").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (N>1: run under torchrun, or
+                                                             #  bench.py re-launches itself with the local launcher)
+    python bench.py --impl reference --gpus N ...            # the reference's unmodified script (baseline/_ref)
+
+Prints ONE JSON line on rank 0.  Timed region = exactly K full training steps (forward, loss,
+backward, fused allreduce + SGD update) between barrier + cuda.synchronize on both sides, CUDA events
+on the launching stream, max over ranks.  Per-step working set (>5 GB of activations at batch 256)
+exceeds the 126 MB L2, so no explicit L2 flush is needed ("l2": "working_set_exceeds_l2").
+``e2e`` repeats the measurement through the public API with, every step, a host->device copy of that
+step's inputs from pinned memory (uint8 NHWC images, the decoded-JPEG format, + int64 labels) and a
+device->host read of the step's loss.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+REF_SCRIPT = os.path.join(HERE, "baseline", "_ref", "PyTorch_benchmark", "src", "pytorch_synthetic_benchmark.py")
+METRIC = "resnet50_synthetic_train_images_per_sec"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=30)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    p.add_argument("--model", default="resnet50")
+    p.add_argument("--batch-size", type=int, default=256, help="per-GPU batch (BASELINE config: 256)")
+    p.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (H2D/D2H per step) measurement")
+    p.add_argument("--fp16-allreduce", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clock sampling during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/ddl_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()          # exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+
+    from distributeddeeplearning_b200 import _ext
+    from distributeddeeplearning_b200.ops import native
+    from distributeddeeplearning_b200.parallel import dist
+    from distributeddeeplearning_b200.workloads.benchmark import BenchmarkSession
+
+    dist.init()
+    rank, world = dist.rank(), dist.size()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (use workloads.benchmark --no-cuda for the CPU plumbing mode)")
+    session = BenchmarkSession(a.model, a.batch_size, True, a.fp16_allreduce)
+    B, dev = a.batch_size, session.device
+
+    def region(step_fn, steps, warmup):
+        for _ in range(warmup):
+            step_fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = _ext.launch_count()
+        start.record()
+        for _ in range(steps):
+            step_fn()
+        stop.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = dist.allreduce_scalar(start.elapsed_time(stop), op="max")
+        return ms, _ext.launch_count() - launches0
+
+    # ---- device-timed headline ------------------------------------------------------------------
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    ms, launches = region(session.step, a.steps, a.warmup)
+    clocks = sampler.stop() if rank == 0 else {}
+    loss = float(session.last_loss)
+    value = world * B * a.steps / (ms / 1e3)
+
+    # ---- end to end: per-step H2D of the inputs from pinned memory + D2H of the loss --------------
+    e2e = None
+    if not a.no_e2e:
+        size = 224 if not a.model.startswith("inception") else 299
+        pool = 4
+        g = torch.Generator().manual_seed(1234 + rank)
+        host_x = [torch.randint(0, 256, (B, size, size, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(pool)]
+        host_y = [torch.randint(0, 1000, (B,), dtype=torch.int64, generator=g).pin_memory() for _ in range(pool)]
+        mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
+        std = torch.tensor([0.229, 0.224, 0.225], device=dev)
+        copy_stream = torch.cuda.Stream()
+        host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        state = {"i": 0, "next": None, "losses": []}
+
+        def prefetch(i):
+            with torch.cuda.stream(copy_stream):
+                xd = host_x[i % pool].to(dev, non_blocking=True)
+                yd = host_y[i % pool].to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return xd, yd, ev
+
+        def e2e_step():
+            i = state["i"]
+            if state["next"] is None:
+                state["next"] = prefetch(i)
+            xd, yd, ev = state["next"]
+            torch.cuda.current_stream().wait_event(ev)
+            state["next"] = prefetch(i + 1)            # overlaps this step's compute
+            x = native.u8_nhwc_to_nhwc4(xd, mean, std)
+            xd.record_stream(torch.cuda.current_stream())
+            yd.record_stream(torch.cuda.current_stream())
+            l = session.step(x, yd)
+            host_loss.copy_(l.reshape(1), non_blocking=False)   # D2H read of this step's result
+            state["losses"].append(float(host_loss[0]))
+            state["i"] = i + 1
+
+        ms_e, _ = region(e2e_step, a.steps, max(3, a.warmup // 2))
+        e2e = {"value": world * B * a.steps / (ms_e / 1e3), "unit": "images/sec",
+               "h2d_bytes_per_step": world * (B * size * size * 3 + B * 8), "d2h_bytes_per_step": world * 4,
+               "ms_per_step": ms_e / a.steps}
+    if hasattr(session.optimizer, "check_errors"):
+        session.optimizer.check_errors()
+
+    if rank == 0:
+        base = None
+        try:
+            with open(os.path.join(HERE, "BASELINE.json")) as f:
+                pub = json.load(f).get("published", {})
+            base = pub.get("value") if isinstance(pub, dict) else None
+        except Exception:
+            pass
+        out = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": a.steps,
+               "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": (value / base) if base else None, "dtype": "bf16", "data": "synthetic",
+               "impl": "ours", "final_loss": loss,
+               "config": {"model": a.model, "global_batch": world * B, "per_gpu_batch": B, "image": "224x224x3",
+                          "seq_len": None, "parallelism": f"dp{world}", "optimizer": "sgd lr=0.01 (fused allreduce+update)",
+                          "weights": "random-init, fp32 master + bf16 compute", "l2": "working_set_exceeds_l2",
+                          "engine": session.optimizer.describe() if hasattr(session.optimizer, "describe") else "generic"},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
+        print(json.dumps(out), flush=True)
+    dist.shutdown()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own script, unmodified, through its own CLI
+# ------------------------------------------------------------------------------------------------
+def run_reference(a):
+    def unavailable(why):
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
+        return 0
+
+    if not os.path.isfile(REF_SCRIPT):
+        inst = os.path.join(HERE, "baseline", "install_reference.py")
+        if int(os.environ.get("RANK", "0")) == 0 and os.path.isfile(inst):
+            subprocess.run([sys.executable, inst], capture_output=True)
+        time.sleep(1.0)
+    if not os.path.isfile(REF_SCRIPT):
+        return unavailable("reference is a cookiecutter template (not pip-installable) and baseline/_ref scripts are absent")
+    try:
+        import torch
+        import torchvision  # noqa: F401
+    except Exception as e:  # pragma: no cover
+        return unavailable(f"torch/torchvision import failed: {e}")
+    if not torch.cuda.is_available():
+        return unavailable("no CUDA device")
+    sys.path.insert(0, os.path.join(HERE, "baseline", "hvd_shim"))
+    import runpy
+
+    import horovod.torch as hvd
+
+    hvd.init()
+    rank, world = hvd.rank(), hvd.size()
+    argv = [REF_SCRIPT, "--model", a.model, "--batch-size", str(a.batch_size), "--num-warmup-batches", str(a.warmup),
+            "--num-batches-per-iter", str(a.steps), "--num-iters", "1"]
+    if a.fp16_allreduce:
+        argv.append("--fp16-allreduce")
+    old_argv, sys.argv = sys.argv, argv
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()
+    import contextlib
+    import io
+
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            runpy.run_path(REF_SCRIPT, run_name="__main__")      # the reference's own code path, start to finish
+    finally:
+        sys.argv = old_argv
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else {}
+    ev = hvd.STEP_EVENTS
+    if len(ev) < a.warmup + a.steps:
+        return unavailable(f"reference ran {len(ev)} steps, expected {a.warmup + a.steps}")
+    first = ev[a.warmup - 1] if a.warmup > 0 else ev[0]
+    ms = first.elapsed_time(ev[a.warmup + a.steps - 1])
+    steps = a.steps if a.warmup > 0 else a.steps - 1
+    t = torch.tensor([ms], device="cuda")
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank == 0:
+        value = world * a.batch_size * steps / (ms / 1e3)
+        print(json.dumps({"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": a.steps,
+                          "warmup": a.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "fp32 (cuDNN TF32 convs: torch default)", "data": "synthetic",
+                          "impl": "reference",
+                          "config": {"model": a.model, "global_batch": world * a.batch_size, "parallelism": f"dp{world}",
+                                     "script": "PyTorch_benchmark/src/pytorch_synthetic_benchmark.py (unmodified)",
+                                     "stack": f"torch {torch.__version__} + torchvision + cuDNN + NCCL via horovod shim",
+                                     "stdout_tail": buf.getvalue().strip().splitlines()[-3:]},
+                          "clocks": clocks}), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    launched = "RANK" in os.environ and "WORLD_SIZE" in os.environ
+    if a.gpus > 1 and not launched:
+        # convenience: re-launch ourselves on N ranks with the repo's own launcher
+        from distributeddeeplearning_b200.cli.launcher import free_port
+
+        port = free_port()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__), *sys.argv[1:]]
+        return subprocess.call(cmd)
+    if a.impl == "reference":
+        return run_reference(a)
+    run_ours(a)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

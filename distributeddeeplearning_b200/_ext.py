@@ -126,6 +126,46 @@ def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) 
         return _SO
 
 
+# kernels launched per call of each binding (everything not listed launches none)
+KERNEL_LAUNCHES = {
+    "fused_sgd_local": 1, "fused_allreduce_sgd": 1, "allreduce": 1, "broadcast": 1, "barrier": 1,
+    "allgather_slices": 1, "conv_gemm": 1, "conv_wgrad": 1, "bn_act_fwd": 1, "bn_act_bwd": 2, "channel_stats": 1,
+    "maxpool_fwd": 1, "maxpool_bwd": 1, "avgpool_fwd": 1, "avgpool_bwd": 1, "global_avgpool_fwd": 1,
+    "global_avgpool_bwd": 1, "softmax_xent": 1, "philox_normal_nhwc": 1, "philox_labels": 1, "nchw_to_nhwc_norm": 1,
+    "nhwc_u8_to_nhwc4": 1, "cast_f32_bf16": 1, "pack_stem_weight": 1, "unpack_stem_grad": 1, "bias_relu_bwd": 1,
+    "dropout": 1, "add_bf16": 1,
+}
+LAUNCH_COUNT = [0]          # kernels of THIS repo launched so far (bench.py reports the per-region delta)
+
+
+class _Counting:
+    """Thin proxy over ``_C`` that counts kernel launches of this repo's own kernels."""
+
+    def __init__(self, mod):
+        self._mod = mod
+        for name in dir(mod):
+            if name.startswith("__"):
+                continue
+            obj = getattr(mod, name)
+            n = KERNEL_LAUNCHES.get(name)
+            if n and callable(obj):
+                setattr(self, name, self._wrap(obj, n))
+            else:
+                setattr(self, name, obj)
+
+    @staticmethod
+    def _wrap(fn, n):
+        def call(*a):
+            LAUNCH_COUNT[0] += n
+            return fn(*a)
+        call.__name__ = getattr(fn, "__name__", "kernel")
+        return call
+
+
+def launch_count() -> int:
+    return LAUNCH_COUNT[0]
+
+
 def load(auto_build: bool = True):
     """Import the native module (building it first if needed)."""
     global _MODULE
@@ -139,7 +179,7 @@ def load(auto_build: bool = True):
             raise RuntimeError("native module _C.so is missing and nvcc is unavailable to build it")
     import torch  # noqa: F401  (loads libcudart.so.12 that _C.so links against)
 
-    _MODULE = importlib.import_module("distributeddeeplearning_b200._C")
+    _MODULE = _Counting(importlib.import_module("distributeddeeplearning_b200._C"))
     return _MODULE
 
 

@@ -177,21 +177,21 @@ PYBIND11_MODULE(_C, m) {
   m.def("conv_gemm",
         [](int mode, ptr_t src, ptr_t out, ptr_t add, ptr_t bias, ptr_t sum, ptr_t sumsq, int M, int KB, int ldc,
            int srcH, int srcW, int srcC, int dstH, int dstW, int R, int Sx, int stride, int pad, int dil,
-           int cchunks, int relu, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
+           int cchunks, int relu, int n_valid, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
            ptr_t stream) {
           ConvArgs a;
           a.src = P<const __nv_bfloat16>(src); a.out = P<__nv_bfloat16>(out); a.add = P<const __nv_bfloat16>(add);
           a.bias = P<const float>(bias); a.sum = P<float>(sum); a.sumsq = P<float>(sumsq);
           a.M = M; a.KB = KB; a.ldc = ldc; a.srcH = srcH; a.srcW = srcW; a.srcC = srcC; a.dstH = dstH; a.dstW = dstW;
-          a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil; a.cchunks = cchunks; a.relu = relu;
+          a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil; a.cchunks = cchunks; a.relu = relu; a.n_valid = n_valid;
           check(ddl::launch_conv_gemm(mode, a, P<const void>(w), w_rows, w_cols, n_total, P<const void>(a_matrix),
                                       a_cols, S(stream)), "conv_gemm");
         });
   m.def("conv_wgrad",
-        [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int ldw, int ncols, int H, int W, int C, int Pq,
+        [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int dy_ld, int ldw, int ncols, int H, int W, int C, int Pq,
            int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, ptr_t stream) {
           WgradArgs a;
-          a.x = P<const __nv_bfloat16>(x); a.dw = P<float>(dw); a.M = M; a.Cout = Cout; a.ldw = ldw; a.ncols = ncols;
+          a.x = P<const __nv_bfloat16>(x); a.dw = P<float>(dw); a.M = M; a.Cout = Cout; a.dy_ld = dy_ld; a.ldw = ldw; a.ncols = ncols;
           a.H = H; a.W = W; a.C = C; a.P = Pq; a.Q = Q; a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil;
           a.cchunks = cchunks; a.kb_per_split = 0; a.total_kb = 0; a.mode = mode;
           check(ddl::launch_conv_wgrad(a, P<const void>(dy), P<const void>(x), splits, S(stream)), "conv_wgrad");
@@ -280,6 +280,10 @@ PYBIND11_MODULE(_C, m) {
                                 ptr_t stream) {
     check(ddl::launch_nchw_to_nhwc_norm(P<const float>(in), P<__nv_bfloat16>(out), N, C, H, W, cpad,
                                         P<const float>(mean), P<const float>(stdv), S(stream)), "nchw_to_nhwc_norm");
+  });
+  m.def("nhwc_u8_to_nhwc4", [](ptr_t in, ptr_t out, int64_t pixels, ptr_t mean, ptr_t stdv, ptr_t stream) {
+    check(ddl::launch_nhwc_u8_to_nhwc4(P<const uint8_t>(in), P<__nv_bfloat16>(out), pixels, P<const float>(mean),
+                                       P<const float>(stdv), S(stream)), "nhwc_u8_to_nhwc4");
   });
   m.def("cast_f32_bf16", [](ptr_t in, ptr_t out, int64_t n, ptr_t stream) {
     check(ddl::launch_cast_f32_bf16(P<const float>(in), P<__nv_bfloat16>(out), n, S(stream)), "cast_f32_bf16");

@@ -182,7 +182,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-        if (a.bias) { x0 += a.bias[n0 + c0 + 2 * j]; x1 += a.bias[n0 + c0 + 2 * j + 1]; }
+        if (a.bias) {
+          const int cb = n0 + c0 + 2 * j;
+          if (cb < a.n_valid) x0 += a.bias[cb];
+          if (cb + 1 < a.n_valid) x1 += a.bias[cb + 1];
+        }
         if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
         packed[j] = pack_bf16x2(x0, x1);
       }
@@ -568,7 +572,7 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void*
                               cudaStream_t stream) {
   WgradArgs a = a_in;
   CUtensorMap tmDy, tmX;
-  if (!make_map_2d(&tmDy, dy, a.M, a.Cout, a.Cout, 64, 64)) return cudaErrorUnknown;
+  if (!make_map_2d(&tmDy, dy, a.M, a.dy_ld, a.dy_ld, 64, 64)) return cudaErrorUnknown;
   if (a.mode == kConvGemm) {
     if (!make_map_2d(&tmX, x_matrix, a.M, a.ncols, a.ncols, 64, 64)) return cudaErrorUnknown;
   } else {

@@ -30,6 +30,7 @@ struct ConvArgs {
   int R, S, stride, pad, dil;
   int cchunks;                // srcC / 64
   int relu;                   // apply ReLU in the epilogue (after bias)
+  int n_valid;                // output channels that really exist (bias is read only below this)
 };
 
 struct WgradArgs {
@@ -37,6 +38,7 @@ struct WgradArgs {
   float* dw;                  // fp32 accumulator [Cout][ldw]  (split-K: red.add)
   int M;                      // pixels = batch * P * Q  (GEMM reduction dim)
   int Cout;
+  int dy_ld;                  // row stride (elements) of dy; >= Cout (padded FC logits)
   int ldw;                    // row stride of dw = R*S*Cin (or 256 for the stem scratch)
   int ncols;                  // valid columns of dw
   int H, W, C;                // x geometry

@@ -356,6 +356,47 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_norm_kernel(const float* __r
   }
 }
 
+// uint8 NHWC3 (decoded image bytes) -> bf16 NHWC4, (x/255 - mean) / std, 4 pixels per thread
+__global__ void __launch_bounds__(256) nhwc_u8_to_nhwc4_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* out,
+                                                               int64_t pixels, const float* mean, const float* stdv) {
+  float m[3] = {0.f, 0.f, 0.f}, is[3] = {1.f / 255.f, 1.f / 255.f, 1.f / 255.f};
+  if (mean) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { m[c] = mean[c]; is[c] = 1.f / (255.f * stdv[c]); }
+  }
+  const int64_t quads = pixels / 4;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < quads;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    // 4 pixels = 12 bytes in, 32 bytes out
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in + i * 12);
+    const uint32_t w0 = src[0], w1 = src[1], w2 = src[2];
+    const uint8_t b[12] = {uint8_t(w0), uint8_t(w0 >> 8), uint8_t(w0 >> 16), uint8_t(w0 >> 24),
+                           uint8_t(w1), uint8_t(w1 >> 8), uint8_t(w1 >> 16), uint8_t(w1 >> 24),
+                           uint8_t(w2), uint8_t(w2 >> 8), uint8_t(w2 >> 16), uint8_t(w2 >> 24)};
+    uint32_t o[8];
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      const float r = b[3 * px] * is[0] - m[0] * is[0] * 255.f;
+      const float g = b[3 * px + 1] * is[1] - m[1] * is[1] * 255.f;
+      const float bl = b[3 * px + 2] * is[2] - m[2] * is[2] * 255.f;
+      o[2 * px] = pack_bf16x2(r, g);
+      o[2 * px + 1] = pack_bf16x2(bl, 0.f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + i * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+  }
+  // tail (pixels % 4)
+  if (blockIdx.x == 0 && threadIdx.x < (pixels & 3)) {
+    const int64_t px = quads * 4 + threadIdx.x;
+    for (int c = 0; c < 4; ++c) {
+      float v = 0.f;
+      if (c < 3) v = in[px * 3 + c] * is[c] - m[c] * is[c] * 255.f;
+      out[px * 4 + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* out,
                                                             int64_t n) {
   const int64_t n4 = n / 4;
@@ -538,6 +579,11 @@ cudaError_t launch_philox_labels(int64_t* out, int64_t n, int classes, uint64_t 
 cudaError_t launch_nchw_to_nhwc_norm(const float* in, __nv_bfloat16* out, int N, int C, int H, int W, int cpad,
                                      const float* mean, const float* stdv, cudaStream_t stream) {
   nchw_to_nhwc_norm_kernel<<<grid_for(static_cast<int64_t>(N) * H * W), 256, 0, stream>>>(in, out, N, C, H, W, cpad, mean, stdv);
+  return cudaGetLastError();
+}
+cudaError_t launch_nhwc_u8_to_nhwc4(const uint8_t* in, __nv_bfloat16* out, int64_t pixels, const float* mean,
+                                    const float* stdv, cudaStream_t stream) {
+  nhwc_u8_to_nhwc4_kernel<<<grid_for(pixels / 4 + 1), 256, 0, stream>>>(in, out, pixels, mean, stdv);
   return cudaGetLastError();
 }
 cudaError_t launch_cast_f32_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t stream) {

@@ -89,6 +89,9 @@ cudaError_t launch_philox_labels(int64_t* out, int64_t n, int classes, uint64_t 
 // NCHW fp32 -> NHWC(cpad) bf16 with per-channel (x - mean) / std   (real-image input path, K21)
 cudaError_t launch_nchw_to_nhwc_norm(const float* in, __nv_bfloat16* out, int N, int C, int H, int W, int cpad,
                                      const float* mean, const float* stdv, cudaStream_t stream);
+// uint8 NHWC3 -> bf16 NHWC4 with (x/255 - mean)/std  (end-to-end input path: 3 bytes/pixel over PCIe)
+cudaError_t launch_nhwc_u8_to_nhwc4(const uint8_t* in, __nv_bfloat16* out, int64_t pixels, const float* mean,
+                                    const float* stdv, cudaStream_t stream);
 cudaError_t launch_cast_f32_bf16(const float* in, __nv_bfloat16* out, int64_t n, cudaStream_t stream);
 // stem weights: fp32 [Cout][R][S][Cin<=4] (KRSC) <-> packed bf16 [Cout][KBR][SP][4] (zero padded)
 cudaError_t launch_pack_stem_weight(const float* w, __nv_bfloat16* packed, int Cout, int R, int S, int Cin, int RP,

@@ -1,0 +1,418 @@
+"""Checked Python wrappers over the sm_100a kernels in ``_C`` (GPU only).
+
+Activations are ``torch.bfloat16`` tensors with logical shape ``[N, C, H, W]`` and
+``channels_last`` memory (physically NHWC).  Convolution weights are logical
+``[Cout, Cin, R, S]`` ``channels_last`` (physically KRSC), which is exactly the row-major
+``[Cout][R*S*Cin]`` GEMM operand the tcgen05 kernels consume — the bf16 compute copy is a flat
+cast of the fp32 master, and wgrad writes the fp32 gradient in the same layout.
+"""
+from __future__ import annotations
+
+import functools
+from typing import Optional, Tuple
+
+import torch
+
+from .. import _ext
+
+CL = torch.channels_last
+
+
+@functools.lru_cache(maxsize=None)
+def _C():
+    return _ext.load()
+
+
+@functools.lru_cache(maxsize=None)
+def sm_count(device_index: int = 0) -> int:
+    return torch.cuda.get_device_properties(device_index).multi_processor_count
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _check_act(x: torch.Tensor, name: str = "x") -> None:
+    if x.dtype != torch.bfloat16 or not x.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA bfloat16 tensor, got {x.dtype} on {x.device}")
+    if x.dim() == 4 and not x.is_contiguous(memory_format=CL):
+        raise ValueError(f"{name}: expected channels_last memory, strides={x.stride()}")
+    if x.dim() == 2 and not x.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous matrix")
+
+
+def empty_act(n: int, c: int, h: int, w: int, device) -> torch.Tensor:
+    return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=CL)
+
+
+def conv_out_hw(h: int, w: int, k: Tuple[int, int], stride: int, pad: int, dil: int = 1) -> Tuple[int, int]:
+    return ((h + 2 * pad - dil * (k[0] - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k[1] - 1) - 1) // stride + 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# stem geometry helpers (Cin <= 4): k-block = RPK filter rows x SP padded taps x 4 channels
+# ------------------------------------------------------------------------------------------------
+def stem_geometry(R: int, S: int) -> Tuple[int, int, int, int]:
+    """Returns (SP, RPK, KB, RP): padded taps per row, rows per k-block, k-blocks, padded rows."""
+    SP = 4 if S <= 4 else (8 if S <= 8 else 16)
+    if S > 16:
+        raise ValueError("stem kernels support at most 16 taps per filter row")
+    RPK = 16 // SP
+    KB = (R + RPK - 1) // RPK
+    return SP, RPK, KB, KB * RPK
+
+
+def supports_conv(cin: int, cout: int) -> bool:
+    """Shapes the tcgen05 implicit-GEMM kernels handle natively."""
+    return cout % 64 == 0 and (cin % 64 == 0 or cin <= 4)
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution forward / dgrad / wgrad
+# ------------------------------------------------------------------------------------------------
+def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], stride: int, pad: int, dil: int = 1,
+             stats: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False,
+             cout: Optional[int] = None):
+    """y = conv(x, w) [+ bias][ReLU]; optionally per-channel (sum, sumsq) of y for BatchNorm.
+
+    ``w_bf16``: [Cout, R*S*Cin] bf16 (or the packed stem matrix [Cout, KB*64]).
+    """
+    C = _C()
+    _check_act(x)
+    N, Cin, H, W = x.shape
+    R, S = kernel
+    Cout = cout if cout is not None else w_bf16.shape[0]
+    P, Q = conv_out_hw(H, W, kernel, stride, pad, dil)
+    M = N * P * Q
+    y = empty_act(N, Cout, P, Q, x.device)
+    st = torch.zeros((2, Cout), dtype=torch.float32, device=x.device) if stats else None
+    s_ptr, ss_ptr = (st[0].data_ptr(), st[1].data_ptr()) if stats else (0, 0)
+    if Cin <= 4:
+        if Cin != 4:
+            raise ValueError("stem input must be padded to 4 channels (NHWC4)")
+        SP, RPK, KB, RP = stem_geometry(R, S)
+        C.conv_gemm(C.CONV_STEM, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, H, W, 4,
+                    P, Q, R, S, stride, pad, dil, SP, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
+                    w_bf16.shape[1], Cout, 0, 0, _stream())
+    elif R == 1 and S == 1 and stride == 1 and pad == 0:
+        C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, Cin // 64, Cout, H, W, Cin, P, Q,
+                    1, 1, 1, 0, 1, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1],
+                    Cout, x.data_ptr(), Cin, _stream())
+    else:
+        C.conv_gemm(C.CONV_FWD, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64),
+                    Cout, H, W, Cin, P, Q, R, S, stride, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(),
+                    w_bf16.shape[0], w_bf16.shape[1], Cout, 0, 0, _stream())
+    return (y, st) if stats else y
+
+
+def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[int, int], stride: int, pad: int,
+               dil: int = 1, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = conv_transpose(dy, w) (+ add).  ``w_bf16`` is the forward matrix [Cout, R*S*Cin]."""
+    C = _C()
+    _check_act(dy, "dy")
+    N, Cin, H, W = x_shape
+    _, Cout, P, Q = dy.shape
+    R, S = kernel
+    if Cin % 64 != 0 or Cout % 64 != 0:
+        raise ValueError("conv_dgrad needs Cin, Cout multiples of 64")
+    dx = empty_act(N, Cin, H, W, dy.device)
+    if add is not None:
+        _check_act(add, "add")
+    C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin,
+                P, Q, Cout, H, W, R, S, stride, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
+                w_bf16.shape[1], Cin, 0, 0, _stream())
+    return dx
+
+
+def _wgrad_splits(tiles: int, total_kb: int, device_index: int) -> int:
+    target = 2 * sm_count(device_index)
+    return max(1, min(total_kb, (target + tiles - 1) // tiles))
+
+
+def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: Tuple[int, int], stride: int,
+               pad: int, dil: int = 1) -> None:
+    """grad_w[Cout][R*S*Cin] (fp32, KRSC) += dy^T * im2col(x)."""
+    C = _C()
+    _check_act(x)
+    _check_act(dy, "dy")
+    N, Cin, H, W = x.shape
+    _, Cout, P, Q = dy.shape
+    R, S = kernel
+    M = N * P * Q
+    dev = x.device.index or 0
+    if grad_w.dtype != torch.float32:
+        raise TypeError("grad_w must be fp32")
+    if Cin <= 4:
+        SP, RPK, KB, RP = stem_geometry(R, S)
+        ncols = KB * 64
+        scratch = torch.zeros((Cout, ncols), dtype=torch.float32, device=x.device)
+        tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
+        C.conv_wgrad(C.CONV_STEM, x.data_ptr(), dy.data_ptr(), scratch.data_ptr(), M, Cout, Cout, ncols, ncols, H, W,
+                     4, P, Q, R, S, stride, pad, dil, SP, _wgrad_splits(tiles, (M + 63) // 64, dev), _stream())
+        # grad_w is KRSC with the TRUE channel count (3): fold the packed scratch back
+        cin_true = grad_w.shape[1]
+        C.unpack_stem_grad(scratch.data_ptr(), grad_w.data_ptr(), Cout, R, S, cin_true, RP, SP, _stream())
+        return
+    ncols = R * S * Cin
+    tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
+    splits = _wgrad_splits(tiles, (M + 63) // 64, dev)
+    mode = C.CONV_GEMM if (R == 1 and S == 1 and stride == 1 and pad == 0) else C.CONV_FWD
+    C.conv_wgrad(mode, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), M, Cout, Cout, ncols, ncols, H, W, Cin, P, Q,
+                 R, S, stride, pad, dil, Cin // 64, splits, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# linear (FC) = 1x1 conv on [B, K]
+# ------------------------------------------------------------------------------------------------
+def linear_fwd(x: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tensor], relu: bool = False):
+    """x [B, K] bf16, w [Nout, K] bf16 -> y [B, Npad] bf16 (Npad = Nout rounded up to 64; pad cols = 0)."""
+    C = _C()
+    _check_act(x)
+    B, K = x.shape
+    Nout = w_bf16.shape[0]
+    if K % 64 != 0:
+        raise ValueError("linear: in_features must be a multiple of 64")
+    Npad = (Nout + 63) // 64 * 64
+    y = torch.empty((B, Npad), dtype=torch.bfloat16, device=x.device)
+    C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), 0, 0, B, K // 64, Npad, 1, 1, K, 1, 1, 1, 1, 1, 0, 1,
+                K // 64, int(relu), Nout, w_bf16.data_ptr(), Nout, K, Npad, x.data_ptr(), K, _stream())
+    return y
+
+
+def linear_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor) -> torch.Tensor:
+    """dy [B, Npad] bf16, w [Nout, K] -> dx [B, K]."""
+    C = _C()
+    B, Npad = dy.shape
+    Nout, K = w_bf16.shape
+    dx = torch.empty((B, K), dtype=torch.bfloat16, device=dy.device)
+    C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), 0, 0, 0, 0, B, Npad // 64, K, 1, 1, Npad, 1, 1, 1, 1, 1, 0,
+                1, Npad // 64, 0, K, w_bf16.data_ptr(), Nout, K, K, 0, 0, _stream())
+    return dx
+
+
+def linear_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor) -> None:
+    """grad_w [Nout, K] fp32 += dy[:, :Nout]^T x."""
+    C = _C()
+    B, K = x.shape
+    Nout = grad_w.shape[0]
+    Npad = dy.shape[1]
+    tiles = ((K + 127) // 128) * ((Nout + 127) // 128)
+    splits = _wgrad_splits(tiles, (B + 63) // 64, x.device.index or 0)
+    C.conv_wgrad(C.CONV_GEMM, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), B, Nout, Npad, K, K, 1, 1, K, 1, 1, 1,
+                 1, 1, 0, 1, K // 64, splits, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm + activation
+# ------------------------------------------------------------------------------------------------
+def bn_supported(c: int) -> bool:
+    g = c // 8
+    return c % 8 == 0 and g > 0 and 256 % g == 0
+
+
+def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, running_mean, running_var,
+               eps: float, momentum: float, relu: bool, residual: Optional[torch.Tensor], train: bool):
+    C = _C()
+    _check_act(y, "y")
+    N, Ch, H, W = y.shape
+    M = N * H * W
+    z = torch.empty_like(y)
+    if train:
+        if stats is None:
+            stats = torch.zeros((2, Ch), dtype=torch.float32, device=y.device)
+            C.channel_stats(y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), M, Ch, sm_count(y.device.index or 0),
+                            _stream())
+        save = torch.empty((2, Ch), dtype=torch.float32, device=y.device)
+        C.bn_act_fwd(y.data_ptr(), _ptr(residual), z.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                     gamma.data_ptr(), beta.data_ptr(), save[0].data_ptr(), save[1].data_ptr(), _ptr(running_mean),
+                     _ptr(running_var), eps, momentum, M, Ch, int(relu), True, sm_count(y.device.index or 0), _stream())
+        return z, save
+    C.bn_act_fwd(y.data_ptr(), _ptr(residual), z.data_ptr(), 0, 0, gamma.data_ptr(), beta.data_ptr(), 0, 0,
+                 running_mean.data_ptr(), running_var.data_ptr(), eps, momentum, M, Ch, int(relu), False,
+                 sm_count(y.device.index or 0), _stream())
+    return z, None
+
+
+def bn_act_bwd(dz: torch.Tensor, z: torch.Tensor, y: torch.Tensor, save: torch.Tensor, gamma: torch.Tensor,
+               relu: bool, want_dres: bool, gamma_grad: Optional[torch.Tensor], beta_grad: Optional[torch.Tensor]):
+    """Returns (dy, dres|None); accumulates into gamma_grad / beta_grad (fp32) when given."""
+    C = _C()
+    _check_act(dz, "dz")
+    N, Ch, H, W = y.shape
+    M = N * H * W
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if want_dres else None
+    scratch = torch.zeros((2, Ch), dtype=torch.float32, device=y.device)
+    C.bn_act_bwd(dz.data_ptr(), z.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dres), save[0].data_ptr(),
+                 save[1].data_ptr(), gamma.data_ptr(), scratch[0].data_ptr(), scratch[1].data_ptr(), _ptr(gamma_grad),
+                 _ptr(beta_grad), M, Ch, int(relu), sm_count(y.device.index or 0), _stream())
+    return dy, dres, scratch
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling
+# ------------------------------------------------------------------------------------------------
+def maxpool_fwd(x: torch.Tensor, k: int, stride: int, pad: int, ceil_mode: bool = False):
+    C = _C()
+    _check_act(x)
+    N, Ch, H, W = x.shape
+    P, Q = _pool_out(H, k, stride, pad, ceil_mode), _pool_out(W, k, stride, pad, ceil_mode)
+    y = empty_act(N, Ch, P, Q, x.device)
+    arg = torch.empty((N, P, Q, Ch), dtype=torch.uint8, device=x.device)
+    C.maxpool_fwd(x.data_ptr(), y.data_ptr(), arg.data_ptr(), N, H, W, Ch, P, Q, k, stride, pad, _stream())
+    return y, arg
+
+
+def maxpool_bwd(dy: torch.Tensor, arg: torch.Tensor, x_shape, k: int, stride: int, pad: int) -> torch.Tensor:
+    C = _C()
+    N, Ch, H, W = x_shape
+    P, Q = dy.shape[2], dy.shape[3]
+    dx = empty_act(N, Ch, H, W, dy.device)
+    C.maxpool_bwd(dy.data_ptr(), arg.data_ptr(), dx.data_ptr(), N, H, W, Ch, P, Q, k, stride, pad, _stream())
+    return dx
+
+
+def _pool_out(h: int, k: int, stride: int, pad: int, ceil_mode: bool) -> int:
+    if ceil_mode:
+        o = -(-(h + 2 * pad - k) // stride) + 1
+        if (o - 1) * stride >= h + pad:
+            o -= 1
+        return o
+    return (h + 2 * pad - k) // stride + 1
+
+
+def avgpool_fwd(x: torch.Tensor, k: int, stride: int, pad: int, count_include_pad: bool = True) -> torch.Tensor:
+    C = _C()
+    _check_act(x)
+    N, Ch, H, W = x.shape
+    P, Q = _pool_out(H, k, stride, pad, False), _pool_out(W, k, stride, pad, False)
+    y = empty_act(N, Ch, P, Q, x.device)
+    C.avgpool_fwd(x.data_ptr(), y.data_ptr(), N, H, W, Ch, P, Q, k, stride, pad, int(count_include_pad), _stream())
+    return y
+
+
+def avgpool_bwd(dy: torch.Tensor, x_shape, k: int, stride: int, pad: int, count_include_pad: bool = True):
+    C = _C()
+    N, Ch, H, W = x_shape
+    dx = empty_act(N, Ch, H, W, dy.device)
+    C.avgpool_bwd(dy.data_ptr(), dx.data_ptr(), N, H, W, Ch, dy.shape[2], dy.shape[3], k, stride, pad,
+                  int(count_include_pad), _stream())
+    return dx
+
+
+def global_avgpool_fwd(x: torch.Tensor) -> torch.Tensor:
+    C = _C()
+    _check_act(x)
+    N, Ch, H, W = x.shape
+    y = torch.empty((N, Ch), dtype=torch.bfloat16, device=x.device)
+    C.global_avgpool_fwd(x.data_ptr(), y.data_ptr(), N, H * W, Ch, _stream())
+    return y
+
+
+def global_avgpool_bwd(dy: torch.Tensor, x_shape) -> torch.Tensor:
+    C = _C()
+    N, Ch, H, W = x_shape
+    dx = empty_act(N, Ch, H, W, dy.device)
+    C.global_avgpool_bwd(dy.contiguous().data_ptr(), dx.data_ptr(), N, H * W, Ch, _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# loss, data, misc
+# ------------------------------------------------------------------------------------------------
+def softmax_xent(logits: torch.Tensor, labels: torch.Tensor, classes: int, want_grad: bool = True,
+                 grad_scale: Optional[float] = None, count_correct: bool = False):
+    """Returns (mean loss [fp32 scalar tensor], dlogits|None, correct[2] int32|None).
+
+    ``logits`` may be a column slice of a wider (padded) matrix: only ``stride(1) == 1`` is required.
+    ``dlogits`` has the logical shape of ``logits`` and the same row stride (pad columns are zero).
+    """
+    C = _C()
+    if logits.dtype != torch.bfloat16 or logits.stride(1) != 1:
+        raise ValueError("softmax_xent: bf16 logits with unit column stride required")
+    B, ncol = logits.shape
+    ld = logits.stride(0) if B > 1 else max(ncol, logits.stride(0))
+    loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+    dlog_full = torch.empty((B, ld), dtype=torch.bfloat16, device=logits.device) if want_grad else None
+    corr = torch.zeros(2, dtype=torch.int32, device=logits.device) if count_correct else None
+    C.softmax_xent(logits.data_ptr(), labels.data_ptr(), _ptr(dlog_full), loss.data_ptr(), 0, _ptr(corr), 1.0 / B,
+                   (1.0 / B) if grad_scale is None else grad_scale, B, classes, ld, _stream())
+    dlog = dlog_full[:, :ncol] if want_grad else None
+    return loss, dlog, corr
+
+
+def philox_images(n: int, h: int, w: int, seed: int, offset: int = 0, device=None, c_valid: int = 3) -> torch.Tensor:
+    """Synthetic normal(0,1) batch as NHWC4 bf16 (logical [N,4,H,W] channels_last; channel 3 = 0)."""
+    C = _C()
+    x = empty_act(n, 4, h, w, device or torch.device("cuda", torch.cuda.current_device()))
+    C.philox_normal_nhwc(x.data_ptr(), n * h * w, c_valid, 4, seed, offset, _stream())
+    return x
+
+
+def philox_labels(n: int, classes: int, seed: int, offset: int = 0, device=None) -> torch.Tensor:
+    C = _C()
+    t = torch.empty(n, dtype=torch.int64, device=device or torch.device("cuda", torch.cuda.current_device()))
+    C.philox_labels(t.data_ptr(), n, classes, seed, offset, _stream())
+    return t
+
+
+def nchw_to_nhwc4(x: torch.Tensor, mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None):
+    """fp32 NCHW (C<=4) -> bf16 NHWC4 with optional per-channel normalisation."""
+    C = _C()
+    N, Ch, H, W = x.shape
+    x = x.contiguous().float()
+    out = empty_act(N, 4, H, W, x.device)
+    C.nchw_to_nhwc_norm(x.data_ptr(), out.data_ptr(), N, Ch, H, W, 4, _ptr(mean), _ptr(std), _stream())
+    return out
+
+
+def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
+    _C().cast_f32_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+
+
+def pack_stem_weight(w: torch.Tensor, R: int, S: int) -> torch.Tensor:
+    """fp32 KRSC [Cout,Cin,R,S] channels_last -> packed bf16 [Cout, KB*64]."""
+    C = _C()
+    Cout, Cin = w.shape[0], w.shape[1]
+    SP, RPK, KB, RP = stem_geometry(R, S)
+    packed = torch.empty((Cout, KB * 64), dtype=torch.bfloat16, device=w.device)
+    C.pack_stem_weight(w.data_ptr(), packed.data_ptr(), Cout, R, S, Cin, RP, SP, _stream())
+    return packed
+
+
+def bias_relu_bwd(dy: torch.Tensor, z: torch.Tensor, dbias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
+    """Returns masked dy (= dy when relu is False); dbias[c] += column sums."""
+    C = _C()
+    Ch = dy.shape[1]
+    M = dy.numel() // Ch
+    dx = torch.empty_like(dy) if relu else dy
+    C.bias_relu_bwd(dy.data_ptr(), z.data_ptr(), dx.data_ptr(), _ptr(dbias), M, Ch, int(relu),
+                    sm_count(dy.device.index or 0), _stream())
+    return dx
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
+    y = torch.empty_like(x)
+    _C().dropout(x.data_ptr(), y.data_ptr(), x.numel(), p, seed, offset, _stream())
+    return y
+
+
+def add(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    y = torch.empty_like(a)
+    _C().add_bf16(a.data_ptr(), b.data_ptr(), y.data_ptr(), a.numel(), _stream())
+    return y
+
+
+def u8_nhwc_to_nhwc4(x_u8: torch.Tensor, mean: Optional[torch.Tensor] = None, std: Optional[torch.Tensor] = None):
+    """uint8 [N, H, W, 3] (decoded image bytes) -> bf16 NHWC4 activations, normalised on the device."""
+    C = _C()
+    if x_u8.dtype != torch.uint8 or x_u8.dim() != 4 or x_u8.shape[3] != 3 or not x_u8.is_contiguous():
+        raise ValueError("expected a contiguous uint8 [N, H, W, 3] tensor")
+    N, H, W, _ = x_u8.shape
+    out = empty_act(N, 4, H, W, x_u8.device)
+    C.nhwc_u8_to_nhwc4(x_u8.data_ptr(), out.data_ptr(), N * H * W, _ptr(mean), _ptr(std), _stream())
+    return out

@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""GPU kernel diagnostics: every native kernel vs a plain PyTorch fp32 reference of the same op.
+
+Each group runs in its own subprocess with a timeout, so a trap / illegal address / hang in one
+kernel cannot take the others (or the GPU box) down.  Prints one line per check:
+    [ok|FAIL] name  max_abs=..  rel=..
+Usage:  python tools/gpu_diag.py            (all groups)      python tools/gpu_diag.py --group conv_fwd
+"""
+import argparse
+import os
+import subprocess
+import sys
+import time
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+GROUPS = ["elementwise", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
+RESULTS = []
+
+
+def report(name, got, ref, tol=2e-2, atol=None):
+    import torch
+
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    rel = err / scale
+    ok = (rel <= tol) if atol is None else (err <= atol + tol * scale)
+    bad = not torch.isfinite(got).all().item()
+    ok = ok and not bad
+    print(f"[{'ok' if ok else 'FAIL'}] {name:58s} max_abs={err:.4e} rel={rel:.3e}" + (" NONFINITE" if bad else ""), flush=True)
+    RESULTS.append(ok)
+    return ok
+
+
+def cl(t):
+    import torch
+
+    return t.contiguous(memory_format=torch.channels_last)
+
+
+def bf(t):
+    import torch
+
+    return t.to(torch.bfloat16)
+
+
+# ------------------------------------------------------------------------------------------------
+def g_elementwise():
+    import torch
+    import torch.nn.functional as F
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    x = nv.philox_images(8, 64, 64, 7, 0, torch.device(dev))
+    xf = x.float()
+    print(f"philox: mean={xf[:, :3].mean().item():.4f} std={xf[:, :3].std().item():.4f} pad_max={xf[:, 3].abs().max().item()}")
+    RESULTS.append(abs(xf[:, :3].mean().item()) < 0.02 and abs(xf[:, :3].std().item() - 1) < 0.02 and xf[:, 3].abs().max().item() == 0)
+    lab = nv.philox_labels(4096, 1000, 3, 0, torch.device(dev))
+    RESULTS.append(int(lab.min()) >= 0 and int(lab.max()) < 1000 and lab.float().std().item() > 200)
+    print(f"labels: min={int(lab.min())} max={int(lab.max())} std={lab.float().std().item():.1f}")
+    # softmax xent (padded logits)
+    B, Cn, ld = 64, 1000, 1024
+    lg = torch.randn(B, ld, device=dev) * 3
+    lg[:, Cn:] = 0
+    lgb = bf(lg)
+    y = torch.randint(0, Cn, (B,), device=dev)
+    loss, dl, corr = nv.softmax_xent(lgb[:, :Cn], y, Cn, True, None, True)
+    ref = lgb[:, :Cn].float().requires_grad_(True)
+    rl = F.cross_entropy(ref, y)
+    rl.backward()
+    report("softmax_xent loss", loss.reshape(1), rl.detach().reshape(1), 1e-3)
+    report("softmax_xent dlogits", dl, ref.grad, 2e-2)
+    top = ref.detach().topk(5, 1)[1]
+    r1, r5 = (top[:, 0] == y).sum().item(), (top == y[:, None]).sum().item()
+    print(f"topk: got {corr.tolist()} ref {[r1, r5]}")
+    RESULTS.append(corr.tolist() == [r1, r5])
+    # pools
+    x = cl(bf(torch.randn(4, 64, 17, 17, device=dev)))
+    for (k, s, p) in [(3, 2, 1), (2, 2, 0), (3, 2, 0)]:
+        yk, arg = nv.maxpool_fwd(x, k, s, p)
+        xr = x.float().requires_grad_(True)
+        yr = F.max_pool2d(xr, k, s, p)
+        report(f"maxpool fwd k{k}s{s}p{p}", yk, yr.detach(), 1e-6)
+        dy = cl(bf(torch.randn_like(yr)))
+        yr.backward(dy.float())
+        report(f"maxpool bwd k{k}s{s}p{p}", nv.maxpool_bwd(dy, arg, x.shape, k, s, p), xr.grad, 1e-2)
+    for cip in (True, False):
+        ya = nv.avgpool_fwd(x, 3, 1, 1, cip)
+        xr = x.float().requires_grad_(True)
+        yr = F.avg_pool2d(xr, 3, 1, 1, count_include_pad=cip)
+        report(f"avgpool fwd cip={cip}", ya, yr.detach(), 1e-2)
+        dy = cl(bf(torch.randn_like(yr)))
+        yr.backward(dy.float())
+        report(f"avgpool bwd cip={cip}", nv.avgpool_bwd(dy, x.shape, 3, 1, 1, cip), xr.grad, 1e-2)
+    g = nv.global_avgpool_fwd(x)
+    report("global_avgpool fwd", g, x.float().mean((2, 3)), 1e-2)
+    dg = bf(torch.randn(4, 64, device=dev))
+    report("global_avgpool bwd", nv.global_avgpool_bwd(dg, x.shape), (dg.float() / 289)[:, :, None, None].expand(4, 64, 17, 17), 1e-2)
+    # conversions
+    img = torch.rand(3, 3, 20, 24, device=dev)
+    mean, std = torch.tensor([0.485, 0.456, 0.406], device=dev), torch.tensor([0.229, 0.224, 0.225], device=dev)
+    o = nv.nchw_to_nhwc4(img, mean, std)
+    report("nchw_to_nhwc4", o[:, :3], (img - mean.view(1, 3, 1, 1)) / std.view(1, 3, 1, 1), 1e-2)
+    u8 = torch.randint(0, 256, (3, 21, 23, 3), dtype=torch.uint8, device=dev)
+    o = nv.u8_nhwc_to_nhwc4(u8, mean, std)
+    refu = ((u8.float() / 255 - mean) / std).permute(0, 3, 1, 2)
+    report("u8_nhwc_to_nhwc4", o[:, :3], refu, 1e-2)
+    RESULTS.append(o[:, 3].abs().max().item() == 0)
+    a, b = bf(torch.randn(4096, device=dev)), bf(torch.randn(4096, device=dev))
+    report("add", nv.add(a, b), a.float() + b.float(), 1e-2)
+    d = nv.dropout(bf(torch.ones(1 << 16, device=dev)), 0.5, 1, 0)
+    keep = (d != 0).float().mean().item()
+    print(f"dropout keep={keep:.4f} scale={d.max().item()}")
+    RESULTS.append(abs(keep - 0.5) < 0.02 and d.max().item() == 2.0)
+    dz, z = cl(bf(torch.randn(2, 192, 5, 5, device=dev))), cl(bf(torch.randn(2, 192, 5, 5, device=dev)))
+    db = torch.zeros(192, device=dev)
+    dx = nv.bias_relu_bwd(dz, z, db, True)
+    refdx = dz.float() * (z.float() > 0)
+    report("bias_relu_bwd dx", dx, refdx, 1e-6)
+    report("bias_relu_bwd dbias", db, refdx.sum((0, 2, 3)), 1e-3)
+
+
+def _conv_ref(x, w, stride, pad, dil=1):
+    import torch
+    import torch.nn.functional as F
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return F.conv2d(x.float(), w.float(), None, stride, pad, dil)
+
+
+def _w_bf16(w):
+    # logical [Cout,Cin,R,S] -> KRSC matrix [Cout, R*S*Cin] bf16
+    return bf(w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous())
+
+
+def g_gemm():
+    import torch
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    for (M, K, N) in [(128, 64, 64), (256, 128, 128), (300, 256, 192), (1000, 512, 256), (4099, 64, 128)]:
+        hw = 1
+        x = cl(bf(torch.randn(M, K, 1, 1, device=dev)))
+        w = bf(torch.randn(N, K, 1, 1, device=dev) * 0.1)
+        y, st = nv.conv_fwd(x, _w_bf16(w), (1, 1), 1, 0, stats=True)
+        ref = _conv_ref(x, w, 1, 0)
+        report(f"gemm(1x1 TMA-A) M{M} K{K} N{N}", y, ref, 2e-2)
+        yb = y.float()
+        report(f"  stats sum  M{M} K{K} N{N}", st[0], yb.sum((0, 2, 3)), 2e-3, atol=1e-2)
+        report(f"  stats sumsq M{M} K{K} N{N}", st[1], (yb * yb).sum((0, 2, 3)), 2e-3)
+
+
+def g_conv_fwd():
+    import torch
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    cases = [(2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (3, 128, 14, 14, 128, 3, 1, 1),
+             (2, 256, 7, 7, 512, 1, 2, 0), (2, 64, 12, 12, 192, 5, 1, 2), (1, 192, 13, 13, 384, 3, 1, 1),
+             (4, 64, 56, 56, 64, 3, 1, 1)]
+    for (n, ci, h, w_, co, k, s, p) in cases:
+        x = cl(bf(torch.randn(n, ci, h, w_, device=dev)))
+        w = bf(torch.randn(co, ci, k, k, device=dev) * (1.0 / (ci * k * k) ** 0.5))
+        y, st = nv.conv_fwd(x, _w_bf16(w), (k, k), s, p, stats=True)
+        ref = _conv_ref(x, w, s, p)
+        report(f"conv_fwd n{n} c{ci} {h}x{w_} ->{co} k{k}s{s}p{p}", y, ref, 2e-2)
+        report("  stats sum", st[0], y.float().sum((0, 2, 3)), 2e-3, atol=1e-2)
+    # bias + relu epilogue
+    x = cl(bf(torch.randn(2, 64, 10, 10, device=dev)))
+    w = bf(torch.randn(128, 64, 3, 3, device=dev) * 0.05)
+    b = torch.randn(128, device=dev)
+    y = nv.conv_fwd(x, _w_bf16(w), (3, 3), 1, 1, bias=b, relu=True)
+    report("conv_fwd bias+relu", y, torch.relu(_conv_ref(x, w, 1, 1) + b.view(1, -1, 1, 1)), 2e-2)
+    # stems: ResNet 7x7/2, AlexNet 11x11/4, VGG 3x3/1
+    for (k, s, p, hw) in [(7, 2, 3, 32), (11, 4, 2, 63), (3, 1, 1, 16)]:
+        img = torch.randn(2, 3, hw, hw, device=dev)
+        x4 = nv.nchw_to_nhwc4(img)
+        w = torch.randn(64, 3, k, k, device=dev) * 0.1
+        wp = nv.pack_stem_weight(cl(w), k, k)
+        y, st = nv.conv_fwd(x4, wp, (k, k), s, p, stats=True, cout=64)
+        ref = _conv_ref(bf(img), bf(w), s, p)
+        report(f"stem conv k{k}s{s}p{p} {hw}x{hw}", y, ref, 2e-2)
+
+
+def g_conv_dgrad():
+    import torch
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    cases = [(2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (2, 128, 14, 14, 128, 3, 1, 1),
+             (2, 256, 8, 8, 512, 1, 2, 0), (2, 256, 7, 7, 64, 1, 1, 0), (2, 64, 12, 12, 192, 5, 1, 2),
+             (2, 128, 28, 28, 128, 3, 2, 1)]
+    for (n, ci, h, w_, co, k, s, p) in cases:
+        x = torch.randn(n, ci, h, w_, device=dev).float().requires_grad_(True)
+        w = bf(torch.randn(co, ci, k, k, device=dev) * (1.0 / (co * k * k) ** 0.5))
+        yr = _conv_ref(x, w, s, p)
+        dy = cl(bf(torch.randn_like(yr)))
+        yr.backward(dy.float())
+        dx = nv.conv_dgrad(dy, _w_bf16(w), x.shape, (k, k), s, p)
+        report(f"conv_dgrad n{n} c{ci} {h}x{w_} <-{co} k{k}s{s}p{p}", dx, x.grad, 2e-2)
+    # epilogue add
+    add = cl(bf(torch.randn(2, 64, 8, 8, device=dev)))
+    x = torch.randn(2, 64, 8, 8, device=dev).requires_grad_(True)
+    w = bf(torch.randn(64, 64, 3, 3, device=dev) * 0.05)
+    yr = _conv_ref(x, w, 1, 1)
+    dy = cl(bf(torch.randn_like(yr)))
+    yr.backward(dy.float())
+    dx = nv.conv_dgrad(dy, _w_bf16(w), x.shape, (3, 3), 1, 1, add=add)
+    report("conv_dgrad + add", dx, x.grad + add.float(), 2e-2)
+
+
+def g_conv_wgrad():
+    import torch
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    cases = [(2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (3, 128, 14, 14, 128, 3, 1, 1),
+             (2, 256, 8, 8, 512, 1, 2, 0), (4, 256, 7, 7, 64, 1, 1, 0), (2, 64, 12, 12, 192, 5, 1, 2),
+             (8, 64, 56, 56, 64, 3, 1, 1), (8, 512, 7, 7, 2048, 1, 1, 0)]
+    for (n, ci, h, w_, co, k, s, p) in cases:
+        x = cl(bf(torch.randn(n, ci, h, w_, device=dev)))
+        w = torch.randn(co, ci, k, k, device=dev).requires_grad_(True)
+        yr = _conv_ref(x, w, s, p)
+        dy = cl(bf(torch.randn_like(yr)))
+        yr.backward(dy.float())
+        gw = cl(torch.zeros(co, ci, k, k, device=dev))
+        nv.conv_wgrad(x, dy, gw, (k, k), s, p)
+        report(f"conv_wgrad n{n} c{ci} {h}x{w_} ->{co} k{k}s{s}p{p}", gw, w.grad, 2e-2)
+    for (k, s, p, hw) in [(7, 2, 3, 32), (11, 4, 2, 63), (3, 1, 1, 16)]:
+        img = torch.randn(2, 3, hw, hw, device=dev)
+        x4 = nv.nchw_to_nhwc4(img)
+        w = torch.randn(64, 3, k, k, device=dev).requires_grad_(True)
+        yr = _conv_ref(bf(img), w, s, p)
+        dy = cl(bf(torch.randn_like(yr)))
+        yr.backward(dy.float())
+        gw = cl(torch.zeros(64, 3, k, k, device=dev))
+        nv.conv_wgrad(x4, dy, gw, (k, k), s, p)
+        report(f"stem wgrad k{k}s{s}p{p}", gw, w.grad, 2e-2)
+
+
+def g_linear():
+    import torch
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    for (B, K, N) in [(256, 2048, 1000), (64, 512, 1000), (32, 9216, 4096)]:
+        x = bf(torch.randn(B, K, device=dev))
+        w = torch.randn(N, K, device=dev) * 0.02
+        b = torch.randn(N, device=dev)
+        y = nv.linear_fwd(x, bf(w), b)
+        ref = x.float() @ bf(w).float().t() + b
+        report(f"linear fwd B{B} K{K} N{N}", y[:, :N], ref, 2e-2)
+        RESULTS.append(y[:, N:].abs().max().item() == 0 if y.shape[1] > N else True)
+        dy = torch.zeros_like(y)
+        dy[:, :N] = bf(torch.randn(B, N, device=dev))
+        dx = nv.linear_dgrad(dy, bf(w))
+        report(f"linear dgrad B{B} K{K} N{N}", dx, dy[:, :N].float() @ bf(w).float(), 2e-2)
+        gw = torch.zeros(N, K, device=dev)
+        nv.linear_wgrad(x, dy, gw)
+        report(f"linear wgrad B{B} K{K} N{N}", gw, dy[:, :N].float().t() @ x.float(), 2e-2)
+
+
+def g_bn():
+    import torch
+    import torch.nn.functional as F
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    for (n, c, h, relu, res) in [(4, 64, 14, True, False), (2, 256, 7, True, True), (3, 2048, 4, False, False), (2, 128, 9, True, True)]:
+        y = cl(bf(torch.randn(n, c, h, h, device=dev) * 2 + 0.5))
+        r = cl(bf(torch.randn(n, c, h, h, device=dev))) if res else None
+        gamma, beta = torch.rand(c, device=dev) + 0.5, torch.randn(c, device=dev)
+        rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        z, save = nv.bn_act_fwd(y, None, gamma, beta, rm, rv, 1e-5, 0.1, relu, r, True)
+        yr = y.float().requires_grad_(True)
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        rm2, rv2 = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        zr = F.batch_norm(yr, rm2, rv2, gr, br, True, 0.1, 1e-5)
+        rr = r.float().requires_grad_(True) if res else None
+        if res:
+            zr = zr + rr
+        if relu:
+            zr = torch.relu(zr)
+        report(f"bn_act fwd c{c} relu={relu} res={res}", z, zr.detach(), 2e-2)
+        report("  running_mean", rm, rm2, 1e-3, atol=1e-3)
+        report("  running_var", rv, rv2, 1e-2)
+        dz = cl(bf(torch.randn_like(zr)))
+        zr.backward(dz.float())
+        gg, bg = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+        dy, dres, _ = nv.bn_act_bwd(dz, z, y, save, gamma, relu, res, gg, bg)
+        report("  bwd dy", dy, yr.grad, 3e-2)
+        report("  bwd dgamma", gg, gr.grad, 2e-2)
+        report("  bwd dbeta", bg, br.grad, 2e-2)
+        if res:
+            report("  bwd dres", dres, rr.grad, 2e-2)
+
+
+def g_sgd():
+    import torch
+
+    from distributeddeeplearning_b200.parallel import dist
+    from distributeddeeplearning_b200.parallel.engine import FusedSGD
+
+    dist.init()
+    for (mom, wd, nest) in [(0.0, 0.0, False), (0.9, 5e-5, False), (0.9, 1e-4, True)]:
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in [(64, 3, 7, 7), (1000, 512), (77,), (256, 64, 3, 3)]]
+        ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+        opt = FusedSGD(ps, lr=0.1, momentum=mom, weight_decay=wd, nesterov=nest)
+        ropt = torch.optim.SGD(ref, lr=0.1, momentum=mom, weight_decay=wd, nesterov=nest)
+        for it in range(3):
+            for p, r in zip(ps, ref):
+                g = torch.randn_like(r)
+                r.grad = g.clone()
+                p.grad.add_(g.view_as(p.grad))
+                p._ddl_ready()
+            opt.step()
+            ropt.step()
+        torch.cuda.synchronize()
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            report(f"fused_sgd mom={mom} wd={wd} nest={nest} p{i}", p.detach(), r.detach(), 1e-5)
+            report("   bf16 copy", p._ddl_bf16.float().reshape(-1), r.detach().to(torch.bfloat16).float().reshape(-1), 1e-2)
+        RESULTS.append(all(float(p.grad.abs().max()) == 0 for p in ps))
+        print("grads cleared:", RESULTS[-1])
+
+
+def g_model():
+    import torch
+
+    import torchvision
+
+    from distributeddeeplearning_b200 import models, ops
+
+    torch.manual_seed(0)
+    for name, bs in [("resnet18", 8), ("resnet50", 8)]:
+        m = models.get_model(name).cuda().train()
+        tv = getattr(torchvision.models, name)().cuda().train()
+        tv.load_state_dict(m.state_dict())
+        x = torch.randn(bs, 3, 224, 224, device="cuda")
+        y = torch.randint(0, 1000, (bs,), device="cuda")
+        out = m(x)
+        loss = ops.softmax_cross_entropy(out, y, 1000)
+        loss.backward()
+        torch.backends.cudnn.allow_tf32 = False
+        ro = tv(x.to(torch.bfloat16).float())
+        rl = torch.nn.functional.cross_entropy(ro, y)
+        rl.backward()
+        report(f"{name} logits", out, ro.detach(), 8e-2)
+        report(f"{name} loss", loss.reshape(1), rl.detach().reshape(1), 2e-2)
+        gn = dict(m.named_parameters())
+        for k, p in list(tv.named_parameters())[:3] + list(tv.named_parameters())[-4:]:
+            report(f"{name} grad {k}", gn[k].grad, p.grad, 1.5e-1)
+
+
+def run_group(name):
+    fn = globals()["g_" + name]
+    fn()
+    import torch
+
+    torch.cuda.synchronize()
+    ok = all(RESULTS)
+    print(f"== group {name}: {sum(RESULTS)}/{len(RESULTS)} checks passed ==", flush=True)
+    return 0 if ok else 1
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--group", default=None)
+    ap.add_argument("--timeout", type=int, default=240)
+    ap.add_argument("--groups", default=",".join(GROUPS))
+    a = ap.parse_args()
+    if a.group:
+        return run_group(a.group)
+    bad = []
+    for g in a.groups.split(","):
+        t0 = time.time()
+        print(f"######## {g}", flush=True)
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--group", g], timeout=a.timeout)
+            rc = r.returncode
+        except subprocess.TimeoutExpired:
+            rc = 124
+            print(f"== group {g}: TIMEOUT after {a.timeout}s ==", flush=True)
+        print(f"######## {g} rc={rc} {time.time() - t0:.1f}s", flush=True)
+        if rc != 0:
+            bad.append(g)
+    print("FAILED GROUPS:", bad if bad else "none", flush=True)
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
