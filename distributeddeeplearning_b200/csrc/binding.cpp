@@ -298,10 +298,10 @@ PYBIND11_MODULE(_C, m) {
     check(ddl::launch_unpack_stem_grad(P<const float>(packed), P<float>(gw), Cout, R, Sx, Cin, RP, SP, S(stream)),
           "unpack_stem_grad");
   });
-  m.def("bias_relu_bwd", [](ptr_t dy, ptr_t z, ptr_t dx, ptr_t dbias, int M, int C, int relu, int sms,
+  m.def("bias_relu_bwd", [](ptr_t dy, ptr_t z, ptr_t dx, ptr_t dbias, int M, int C, int c_valid, int relu, int sms,
                             ptr_t stream) {
     check(ddl::launch_bias_relu_bwd(P<const __nv_bfloat16>(dy), P<const __nv_bfloat16>(z), P<__nv_bfloat16>(dx),
-                                    P<float>(dbias), M, C, relu, sms, S(stream)), "bias_relu_bwd");
+                                    P<float>(dbias), M, C, c_valid, relu, sms, S(stream)), "bias_relu_bwd");
   });
   m.def("dropout", [](ptr_t x, ptr_t y, int64_t n, float p, uint64_t seed, uint64_t offset, ptr_t stream) {
     check(ddl::launch_dropout(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), n, p, seed, offset, S(stream)),

@@ -441,7 +441,7 @@ __global__ void unpack_stem_grad_kernel(const float* __restrict__ packed, float*
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bias_relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy,
                                                             const __nv_bfloat16* __restrict__ z, __nv_bfloat16* dx,
-                                                            float* dbias, int M, int C, int relu) {
+                                                            float* dbias, int M, int C, int c_valid, int relu) {
   const int groups = C / 8;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = tid % groups, row0 = tid / groups;
@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(256) bias_relu_bwd_kernel(const __nv_bfloat16*
   }
   if (dbias) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) atomicAdd(dbias + g * 8 + i, s[i]);
+    for (int i = 0; i < 8; ++i)
+      if (g * 8 + i < c_valid) atomicAdd(dbias + g * 8 + i, s[i]);
   }
 }
 
@@ -602,7 +603,7 @@ cudaError_t launch_unpack_stem_grad(const float* packed, float* gw, int Cout, in
 }
 
 cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z, __nv_bfloat16* dx, float* dbias,
-                                 int M, int C, int relu, int sms, cudaStream_t stream) {
+                                 int M, int C, int c_valid, int relu, int sms, cudaStream_t stream) {
   const int groups = C / 8;
   if (C % 8 != 0) return cudaErrorInvalidValue;
   // total threads must be a multiple of `groups`
@@ -615,7 +616,7 @@ cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z
   unit = l / 256;
   int64_t blocks = (threads + 255) / 256;
   blocks = (blocks + unit - 1) / unit * unit;
-  bias_relu_bwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dy, z, dx, dbias, M, C, relu);
+  bias_relu_bwd_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(dy, z, dx, dbias, M, C, c_valid, relu);
   return cudaGetLastError();
 }
 cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,

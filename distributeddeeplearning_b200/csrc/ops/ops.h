@@ -102,7 +102,7 @@ cudaError_t launch_unpack_stem_grad(const float* packed, float* gw, int Cout, in
 // ---- bias / activation / dropout (VGG / AlexNet classifier paths) ---------------------------------
 // dy_masked = dy * (z > 0) ; dbias[c] += sum_m dy_masked    (z = relu(conv + bias) saved output)
 cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z, __nv_bfloat16* dx, float* dbias,
-                                 int M, int C, int relu, int sms, cudaStream_t stream);
+                                 int M, int C, int c_valid, int relu, int sms, cudaStream_t stream);
 cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,
                            uint64_t offset, cudaStream_t stream);
 // y = a + b (bf16)

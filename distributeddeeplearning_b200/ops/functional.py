@@ -100,28 +100,36 @@ class _ConvBnAct(torch.autograd.Function):
         ctx.cfg = (stride, pad, dil, relu, residual is not None, (R, S))
         ctx.params = (weight, gamma, beta)
         if train:
-            ctx.save_for_backward(x, y, z, save, wb)
+            # wb is a view of the engine's bf16 weight arena: kept as a plain attribute (no autograd
+            # version check) — the arena is only rewritten by the bucket kernel, which is ordered after
+            # this layer's backward (see notify_ready at the end of backward)
+            ctx.wb = wb
+            ctx.save_for_backward(x, y, z, save)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         stride, pad, dil, relu, has_res, kernel = ctx.cfg
         weight, gamma, beta = ctx.params
-        x, y, z, save, wb = ctx.saved_tensors
+        x, y, z, save = ctx.saved_tensors
+        wb = ctx.wb
         if not dz.is_contiguous(memory_format=CL):
             dz = dz.contiguous(memory_format=CL)
         gg = grad_buffer(gamma) if gamma.requires_grad else None
         bg = grad_buffer(beta) if beta.requires_grad else None
         dy, dres, _ = native.bn_act_bwd(dz, z, y, save, gamma, relu, has_res and ctx.needs_input_grad[1], gg, bg)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil)
+        if weight.requires_grad:
+            native.conv_wgrad(x, dy, grad_buffer(weight), kernel, stride, pad, dil)
+        # LAST: a ready bucket may launch its allreduce+update kernel on the side stream now; everything
+        # this layer still needed from the weight arenas (gamma, wb) has been enqueued before the event
         if gamma.requires_grad:
             notify_ready(gamma)
             notify_ready(beta)
         if weight.requires_grad:
-            native.conv_wgrad(x, dy, grad_buffer(weight), kernel, stride, pad, dil)
             notify_ready(weight)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil)
         return (dx, dres) + (None,) * 12
 
 
@@ -152,24 +160,27 @@ class _ConvBiasAct(torch.autograd.Function):
         z = native.conv_fwd(x, wb, (R, S), stride, pad, dil, bias=bias, relu=relu, cout=weight.shape[0])
         ctx.cfg = (stride, pad, dil, relu, (R, S))
         ctx.params = (weight, bias)
-        ctx.save_for_backward(x, z, wb)
+        ctx.wb = wb
+        ctx.save_for_backward(x, z)
         return z
 
     @staticmethod
     def backward(ctx, dz):
         stride, pad, dil, relu, kernel = ctx.cfg
         weight, bias = ctx.params
-        x, z, wb = ctx.saved_tensors
+        x, z = ctx.saved_tensors
+        wb = ctx.wb
         if not dz.is_contiguous(memory_format=CL):
             dz = dz.contiguous(memory_format=CL)
         db = grad_buffer(bias) if (bias is not None and bias.requires_grad) else None
         dy = native.bias_relu_bwd(dz, z, db, relu) if (relu or db is not None) else dz
+        dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil) if ctx.needs_input_grad[0] else None
+        if weight.requires_grad:
+            native.conv_wgrad(x, dy, grad_buffer(weight), kernel, stride, pad, dil)
         if db is not None:
             notify_ready(bias)
         if weight.requires_grad:
-            native.conv_wgrad(x, dy, grad_buffer(weight), kernel, stride, pad, dil)
             notify_ready(weight)
-        dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil) if ctx.needs_input_grad[0] else None
         return dx, None, None, None, None, None, None
 
 
@@ -193,30 +204,27 @@ class _Linear(torch.autograd.Function):
         y = native.linear_fwd(x, wb, bias, relu)
         ctx.relu = relu
         ctx.params = (weight, bias)
-        ctx.save_for_backward(x, y, wb)
+        ctx.wb = wb
+        ctx.save_for_backward(x, y)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         weight, bias = ctx.params
-        x, y, wb = ctx.saved_tensors
+        x, y = ctx.saved_tensors
+        wb = ctx.wb
         dy = dy.contiguous()
         db = grad_buffer(bias) if (bias is not None and bias.requires_grad) else None
         if ctx.relu or db is not None:
-            # padded logits columns carry zero gradient, so summing all Npad columns is safe
-            if db is not None and db.numel() != dy.shape[1]:
-                tmp = torch.zeros(dy.shape[1], dtype=torch.float32, device=dy.device)
-                dyc = native.bias_relu_bwd(dy, y, tmp, ctx.relu)
-                db += tmp[: db.numel()]
-            else:
-                dyc = native.bias_relu_bwd(dy, y, db, ctx.relu)
-            dy = dyc
+            # dy may be wider than the bias (padded logits): the kernel only reduces the valid columns
+            dy = native.bias_relu_bwd(dy, y, db, ctx.relu, c_valid=db.numel() if db is not None else None)
+        dx = native.linear_dgrad(dy, wb) if ctx.needs_input_grad[0] else None
+        if weight.requires_grad:
+            native.linear_wgrad(x, dy, grad_buffer(weight))
         if db is not None:
             notify_ready(bias)
         if weight.requires_grad:
-            native.linear_wgrad(x, dy, grad_buffer(weight))
             notify_ready(weight)
-        dx = native.linear_dgrad(dy, wb) if ctx.needs_input_grad[0] else None
         return dx, None, None, None
 
 

@@ -384,14 +384,15 @@ def pack_stem_weight(w: torch.Tensor, R: int, S: int) -> torch.Tensor:
     return packed
 
 
-def bias_relu_bwd(dy: torch.Tensor, z: torch.Tensor, dbias: Optional[torch.Tensor], relu: bool) -> torch.Tensor:
-    """Returns masked dy (= dy when relu is False); dbias[c] += column sums."""
+def bias_relu_bwd(dy: torch.Tensor, z: torch.Tensor, dbias: Optional[torch.Tensor], relu: bool,
+                  c_valid: Optional[int] = None) -> torch.Tensor:
+    """Returns masked dy (= dy when relu is False); dbias[c] += column sums for c < c_valid."""
     C = _C()
     Ch = dy.shape[1]
     M = dy.numel() // Ch
     dx = torch.empty_like(dy) if relu else dy
-    C.bias_relu_bwd(dy.data_ptr(), z.data_ptr(), dx.data_ptr(), _ptr(dbias), M, Ch, int(relu),
-                    sm_count(dy.device.index or 0), _stream())
+    C.bias_relu_bwd(dy.data_ptr(), z.data_ptr(), dx.data_ptr(), _ptr(dbias), M, Ch, Ch if c_valid is None else c_valid,
+                    int(relu), sm_count(dy.device.index or 0), _stream())
     return dx
 
 

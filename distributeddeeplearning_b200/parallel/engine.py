@@ -62,9 +62,13 @@ class SymmetricArena:
         self.nbytes = cur
         self.native = None
         self.mc_ptr = 0
+        self._regions: Dict[str, torch.Tensor] = {}
         if self.world == 1:
-            self._buf = torch.zeros(self.nbytes, dtype=torch.uint8, device=device)
-            self.peer_ptrs = [self._buf.data_ptr()]
+            # no peers: every region is its own torch allocation (own autograd version counter)
+            self._buf = None
+            for name, nbytes in regions:
+                self._regions[name] = torch.zeros(_round_up(max(nbytes, 16), _ALIGN), dtype=torch.uint8, device=device)
+            self.peer_ptrs = [0]
         else:
             torch.cuda.synchronize(device)
             dev_index = device.index if device.index is not None else torch.cuda.current_device()
@@ -88,20 +92,21 @@ class SymmetricArena:
                     if bound > 0:
                         self.mc_ptr = int(self.native.mc_ptr)
             dist.barrier()
-            self._buf = torch.as_tensor(_DevMem(self.peer_ptrs[self.rank], int(self.native.bytes), self.native),
-                                        device=device)
+            # one torch base tensor PER REGION (separate autograd version counters: in-place gradient
+            # accumulation into the grad region must not invalidate saved views of the weight regions)
+            base = self.peer_ptrs[self.rank]
+            ends = sorted(self.offsets.values()) + [self.nbytes]
+            for name, off in self.offsets.items():
+                nb = ends[ends.index(off) + 1] - off
+                self._regions[name] = torch.as_tensor(_DevMem(base + off, nb, self.native), device=device)
 
     @property
     def has_multicast(self) -> bool:
         return self.mc_ptr != 0
 
     def region(self, name: str, dtype: torch.dtype, numel: int) -> torch.Tensor:
-        off = self.offsets[name]
         nbytes = numel * torch.empty((), dtype=dtype).element_size()
-        return self._buf[off: off + nbytes].view(dtype)
-
-    def local_ptr(self) -> int:
-        return self.peer_ptrs[self.rank]
+        return self._regions[name][:nbytes].view(dtype)
 
 
 def _param_view(flat: torch.Tensor, p: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,252 @@
+"""ImageNet trainer with synthetic or real data — parity with the reference's
+``PyTorch_imagenet/src/imagenet_pytorch_horovod.py`` (call stack SURVEY.md 3.3).
+
+Same CLI (python-fire style ``main`` kwargs, ``:292-303``), env (``DISTRIBUTED``, ``EPOCHS``,
+``FAKE_DATA_LENGTH``, ``LOG_CONFIG``), log lines (per-100-step ``" duration({})  loss:{}
+total-samples: {}"`` ``:173,197``; ``"setting lr to ..."`` ``:289``; ``"Training epoch N took X
+seconds"`` ``:416``; summary block ``:233-245``), TensorBoard scalars (``Train/Loss``, ``Train/Acc``,
+``Train/BatchTime``, ``Validation/*`` ``:426-436``) and run-history rows (``:425,434``).
+
+Deliberate fixes of reference bugs: the summary divides ALL epochs' images by ALL
+epochs' time (Q3); checkpoints work on every rank and per epoch when the path has ``{epoch}`` (Q4);
+validation runs under ``no_grad`` (Q5); metrics are accumulated on the device and read back every
+``log_interval`` steps instead of three ``.item()`` syncs per step (K18).
+"""
+from __future__ import annotations
+
+import logging
+import os
+import shutil
+import sys
+from typing import Optional
+
+import torch
+
+from .. import models, ops
+from ..data import DeviceSyntheticLoader, FakeData, get_sampler
+from ..parallel import Compression, DistributedOptimizer, dist
+from ..utils import Timer, logconf
+from ..utils.checkpoint import save_checkpoint
+from ..utils.firelite import Fire
+from ..utils.lr_schedule import adjust_learning_rate
+from ..utils.meters import AverageMeter
+from ..utils.runs import Run, summary_writer
+
+_WIDTH = _HEIGHT = 224
+_LR = 0.001
+_EPOCHS = os.getenv("EPOCHS", 5)
+_BATCHSIZE = 64
+_SEED = 42
+_LOG_INTERVAL = 100
+
+
+def _str_to_bool(s) -> bool:
+    return "t" in str(s).lower()
+
+
+def _data_length() -> int:
+    return int(os.getenv("FAKE_DATA_LENGTH", 1281167))
+
+
+def _log_summary(data_length, duration, batch_size, world):
+    logger = logging.getLogger(__name__)
+    logger.info("Data length:      {}".format(data_length))
+    logger.info("Total duration:   {:.3f}".format(duration))
+    logger.info("Total images/sec: {:.3f}".format(data_length / max(duration, 1e-9)))
+    logger.info("Batch size:       (Per GPU {}: Total {})".format(batch_size, world * batch_size))
+    logger.info("Distributed:      {}".format("True" if world > 1 else "False"))
+    logger.info("Num GPUs:         {:.3f}".format(world))
+
+
+class _DeviceMetrics:
+    """loss / top-1 / top-5 accumulated on the device; one readback per log interval."""
+
+    def __init__(self, device):
+        self.loss_sum = torch.zeros((), dtype=torch.float32, device=device)
+        self.correct = torch.zeros(2, dtype=torch.int64, device=device)
+        self.samples = 0
+        self.steps = 0
+
+    def update(self, loss, output, target, classes):
+        self.loss_sum += loss.detach().float()
+        self.correct += ops.topk_correct(output.detach() if not isinstance(output, tuple) else output[0].detach(),
+                                         target, classes).to(torch.int64)
+        self.samples += int(target.shape[0])
+        self.steps += 1
+
+    def read(self):
+        n = max(self.samples, 1)
+        c = self.correct.tolist()
+        return {"loss": float(self.loss_sum) / max(self.steps, 1), "acc": 100.0 * c[0] / n, "acc5": 100.0 * c[1] / n}
+
+
+def train(train_loader, model, criterion, optimizer, base_lr, warmup_epochs, epoch, device, classes, world,
+          prepare=None):
+    logger = logging.getLogger(__name__)
+    batch_time = AverageMeter()
+    metrics = _DeviceMetrics(device)
+    msg = " duration({})  loss:{} total-samples: {}"
+    t = Timer().start()
+    nb = len(train_loader)
+    last_loss = None
+    for i, (data, target) in enumerate(train_loader):
+        adjust_learning_rate(optimizer, base_lr, warmup_epochs, nb, epoch, i, world, log=dist.rank() == 0)
+        data, target = data.to(device, non_blocking=True), target.to(device, non_blocking=True)
+        if prepare is not None:
+            data = prepare(data)
+        optimizer.zero_grad()
+        output = model(data)
+        loss = criterion(output, target)
+        loss.backward()
+        optimizer.step()
+        metrics.update(loss, output, target, classes)
+        last_loss = loss
+        if i % _LOG_INTERVAL == 0:
+            t.stop()
+            batch_time.update(t.elapsed, n=_LOG_INTERVAL)
+            logger.info(msg.format(t.elapsed, float(last_loss), i * int(target.shape[0])))
+            t.start()
+    out = metrics.read()
+    out["batch_time"] = batch_time.avg
+    return out
+
+
+@torch.no_grad()
+def validate(val_loader, model, criterion, device, classes, prepare=None):
+    logger = logging.getLogger(__name__)
+    metrics = _DeviceMetrics(device)
+    msg = " duration({})  loss:{} total-samples: {}"
+    t = Timer().start()
+    for i, (data, target) in enumerate(val_loader):
+        data, target = data.to(device, non_blocking=True), target.to(device, non_blocking=True)
+        if prepare is not None:
+            data = prepare(data)
+        output = model(data)
+        loss = criterion(output, target)
+        metrics.update(loss, output, target, classes)
+        if i % _LOG_INTERVAL == 0:
+            logger.info(msg.format(t.elapsed, float(loss), i * int(target.shape[0])))
+            t.start()
+    return metrics.read()
+
+
+def main(training_data_path=None, validation_data_path=None, use_gpu=False, save_filepath=None, model="resnet50",
+         epochs=_EPOCHS, batch_size=_BATCHSIZE, fp16_allreduce=False, base_lr=0.0125, warmup_epochs=5,
+         num_workers=5, host_data=False):
+    logger = logging.getLogger(__name__)
+    epochs = int(epochs)
+    use_gpu = _str_to_bool(use_gpu) if isinstance(use_gpu, str) else bool(use_gpu)
+    use_gpu = use_gpu and torch.cuda.is_available()
+    if not use_gpu:
+        os.environ["DDL_NO_CUDA"] = "1"
+    dist.init()
+    world, rank = dist.size(), dist.rank()
+    device = torch.device("cuda", torch.cuda.current_device()) if use_gpu else torch.device("cpu")
+    logger.info(f"Running on {device}")
+    if world > 1:
+        logger.info("Running Distributed")
+    torch.manual_seed(_SEED)
+    if use_gpu:
+        torch.cuda.manual_seed(_SEED)
+    logger.info("PyTorch version {}".format(torch.__version__))
+
+    run = writer = None
+    if rank == 0:
+        run = Run.get_context("pytorch_imagenet")
+        run.tag("model", value=model)
+        logs_dir = os.path.join(os.curdir, "logs")
+        if os.path.exists(logs_dir):
+            shutil.rmtree(logs_dir, ignore_errors=True)
+        writer = summary_writer(logs_dir)
+
+    net = models.get_model(model)
+    size = models.input_size(net)
+    classes = getattr(net, "num_classes", 1000)
+    prepare = None
+    val_loader = None
+    if training_data_path is None:
+        logger.info("Setting up fake loaders")
+        if use_gpu and not host_data:
+            train_loader = DeviceSyntheticLoader(_data_length(), batch_size, size, classes, device, rank, world, _SEED)
+            train_sampler = train_loader
+        else:
+            ds = FakeData(n_classes=classes, dim=(size, size), length=_data_length(), data_transform=torch.FloatTensor)
+            train_sampler = get_sampler(ds)
+            train_loader = torch.utils.data.DataLoader(ds, batch_size=batch_size, sampler=train_sampler,
+                                                       num_workers=num_workers if use_gpu else 0, pin_memory=use_gpu)
+    else:
+        from ..data.images import DeviceNormalizer, image_folder_loader
+
+        logger.info("Setting up loaders")
+        logger.info(f"Loading training from {training_data_path}")
+        train_loader, train_sampler = image_folder_loader(training_data_path, batch_size, True, size, num_workers,
+                                                          device_normalize=use_gpu)
+        prepare = DeviceNormalizer(device) if use_gpu else None
+        if validation_data_path is not None:
+            logger.info(f"Loading validation from {validation_data_path}")
+            val_loader, _ = image_folder_loader(validation_data_path, batch_size, False, size, num_workers,
+                                                device_normalize=use_gpu)
+
+    logger.info("Loading model")
+    if use_gpu:
+        net.cuda()
+    optimizer = torch.optim.SGD(net.parameters(), lr=_LR * world, momentum=0.9)
+    compression = Compression.fp16 if _str_to_bool(fp16_allreduce) else Compression.none
+    optimizer = DistributedOptimizer(optimizer, named_parameters=net.named_parameters(), compression=compression)
+    if hasattr(optimizer, "broadcast_parameters"):
+        dist.broadcast_parameters({k: v for k, v in net.named_buffers()}, root_rank=0)
+    else:
+        dist.broadcast_parameters(net.state_dict(), root_rank=0)
+    dist.broadcast_optimizer_state(optimizer, root_rank=0)
+
+    def criterion(output, target):
+        if isinstance(output, tuple):
+            return ops.softmax_cross_entropy(output[0], target, classes) + 0.4 * ops.softmax_cross_entropy(
+                output[1], target, classes)
+        return ops.softmax_cross_entropy(output, target, classes)
+
+    logger.info("Training ...")
+    total_time = 0.0
+    for epoch in range(epochs):
+        with Timer(output=logger.info, prefix=f"Training epoch {epoch} ") as t:
+            net.train()
+            if hasattr(train_sampler, "set_epoch"):
+                train_sampler.set_epoch(epoch)
+            metrics = train(train_loader, net, criterion, optimizer, base_lr, warmup_epochs, epoch, device, classes,
+                            world, prepare)
+            if use_gpu:
+                torch.cuda.synchronize()
+        total_time += t.elapsed
+        if rank == 0:
+            run.log_row("Training metrics", epoch=epoch, **metrics)
+            writer.add_scalar("Train/Loss", metrics["loss"], epoch)
+            writer.add_scalar("Train/Acc", metrics["acc"], epoch)
+            writer.add_scalar("Train/BatchTime", metrics["batch_time"], epoch)
+        if val_loader is not None:
+            net.eval()
+            vm = validate(val_loader, net, criterion, device, classes, prepare)
+            if rank == 0:
+                run.log_row("Validation metrics", epoch=epoch, **vm)
+                writer.add_scalar("Validation/Loss", vm["loss"], epoch)
+                writer.add_scalar("Validation/Acc", vm["acc"], epoch)
+        if save_filepath is not None:
+            save_checkpoint(str(save_filepath).format(epoch=epoch + 1), net, optimizer, epoch=epoch + 1)
+    if hasattr(optimizer, "check_errors"):
+        optimizer.check_errors()
+    per_rank = getattr(train_loader, "per_rank", None)
+    seen = epochs * (per_rank * world if per_rank is not None else len(train_loader.dataset))
+    if rank == 0:
+        _log_summary(seen, total_time, batch_size, world)
+        writer.flush()
+        run.complete()
+    dist.shutdown()
+    return {"images": seen, "seconds": total_time}
+
+
+def cli(argv=None):
+    logconf.configure("imagenet")
+    return Fire(main, argv)
+
+
+if __name__ == "__main__":
+    cli()

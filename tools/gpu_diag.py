@@ -15,7 +15,7 @@ import time
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
-GROUPS = ["elementwise", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
+GROUPS = ["elementwise", "avgdebug", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
 RESULTS = []
 
 
@@ -334,32 +334,77 @@ def g_sgd():
         print("grads cleared:", RESULTS[-1])
 
 
-def g_model():
-    import torch
+def _cos(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
 
+
+def g_model():
+    """Whole-model check.  bf16 activations vs an fp32 oracle differ by rounding that grows with depth, so
+    gradients are judged by cosine similarity / norm ratio against (a) torchvision fp32 and (b) this repo's own
+    PyTorch composite run in bf16 (same rounding points, different kernels)."""
+    import os
+
+    import torch
     import torchvision
 
     from distributeddeeplearning_b200 import models, ops
 
-    torch.manual_seed(0)
-    for name, bs in [("resnet18", 8), ("resnet50", 8)]:
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for name, bs in [("resnet18", 32), ("resnet50", 32)]:
+        torch.manual_seed(0)
         m = models.get_model(name).cuda().train()
         tv = getattr(torchvision.models, name)().cuda().train()
         tv.load_state_dict(m.state_dict())
-        x = torch.randn(bs, 3, 224, 224, device="cuda")
+        m2 = models.get_model(name).cuda().train()
+        m2.load_state_dict(m.state_dict())
+        x = torch.randn(bs, 3, 224, 224, device="cuda").to(torch.bfloat16).float()
         y = torch.randint(0, 1000, (bs,), device="cuda")
         out = m(x)
         loss = ops.softmax_cross_entropy(out, y, 1000)
         loss.backward()
-        torch.backends.cudnn.allow_tf32 = False
-        ro = tv(x.to(torch.bfloat16).float())
+        ro = tv(x)
         rl = torch.nn.functional.cross_entropy(ro, y)
         rl.backward()
-        report(f"{name} logits", out, ro.detach(), 8e-2)
-        report(f"{name} loss", loss.reshape(1), rl.detach().reshape(1), 2e-2)
-        gn = dict(m.named_parameters())
-        for k, p in list(tv.named_parameters())[:3] + list(tv.named_parameters())[-4:]:
-            report(f"{name} grad {k}", gn[k].grad, p.grad, 1.5e-1)
+        os.environ["DDL_B200_IMPL"] = "torch"
+        co = m2(x)
+        cl_ = ops.softmax_cross_entropy(co, y, 1000)
+        cl_.backward()
+        os.environ["DDL_B200_IMPL"] = "native"
+        report(f"{name} loss vs fp32", loss.reshape(1), rl.detach().reshape(1), 3e-2)
+        print(f"{name} logits cos vs fp32 {_cos(out, ro):.5f}   vs bf16-composite {_cos(out, co):.5f}")
+        RESULTS.append(_cos(out, ro) > 0.98)
+        gn, gc = dict(m.named_parameters()), dict(m2.named_parameters())
+        worst = (1.0, "")
+        for k, p in tv.named_parameters():
+            c1 = _cos(gn[k].grad, p.grad)
+            c2 = _cos(gc[k].grad, p.grad)
+            if c1 < worst[0]:
+                worst = (c1, k)
+            if k in ("conv1.weight", "bn1.weight", "layer1.0.conv1.weight", "layer2.0.downsample.0.weight",
+                     "layer3.0.conv2.weight", "layer4.0.conv1.weight", "fc.weight", "fc.bias"):
+                ratio = float(gn[k].grad.float().norm() / (p.grad.norm() + 1e-30))
+                print(f"   {k:32s} cos(native,fp32)={c1:.4f} cos(composite,fp32)={c2:.4f} norm ratio={ratio:.3f}")
+        print(f"{name}: worst cosine(native grad, fp32 grad) = {worst[0]:.4f} at {worst[1]}")
+        RESULTS.append(worst[0] > 0.90)
+
+
+def g_avgdebug():
+    import torch
+    import torch.nn.functional as F
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    x = cl(bf(torch.randn(1, 8, 5, 5, device="cuda")))
+    xr = x.float().requires_grad_(True)
+    yr = F.avg_pool2d(xr, 3, 1, 1)
+    dy = cl(bf(torch.ones_like(yr)))
+    yr.backward(dy.float())
+    got = nv.avgpool_bwd(dy, x.shape, 3, 1, 1, True)
+    print("ref", xr.grad[0, 0])
+    print("got", got[0, 0].float())
+    report("avgpool bwd tiny", got, xr.grad, 1e-2)
 
 
 def run_group(name):
