@@ -1,0 +1,138 @@
+import io
+import os
+import tarfile
+
+import pytest
+import torch
+
+from distributeddeeplearning_b200.control import template
+from distributeddeeplearning_b200.data import DeviceSyntheticLoader, DistributedSampler, FakeData, fixed_synthetic_batch
+from distributeddeeplearning_b200.data import prepare_imagenet, records
+from distributeddeeplearning_b200.parallel.compression import Compression
+
+
+def test_task_tree_matches_reference_surface():
+    from distributeddeeplearning_b200.cli.tasks import namespace
+
+    names = set(namespace.task_names)
+    for t in ("setup", "login", "select-subscription", "delete", "interactive", "tensorboard", "runs", "experiments",
+              "pytorch-benchmark.submit.local.synthetic", "pytorch-benchmark.submit.remote.synthetic",
+              "pytorch-imagenet.submit.local.synthetic", "pytorch-imagenet.submit.remote.synthetic",
+              "pytorch-imagenet.submit.local.images", "pytorch-imagenet.submit.remote.images",
+              "pytorch-experiment.submit.local.synthetic", "tf-benchmark.submit.remote.synthetic",
+              "tf-imagenet.submit.remote.tfrecords", "storage.create-container", "storage.image.upload-data",
+              "storage.image.prepare-imagenet", "storage.tfrecords.generate-tf-records"):
+        assert t in names, t
+
+
+def test_experiment_template_tasks_raise():
+    from invoke import Context
+
+    from distributeddeeplearning_b200.cli.tasks import namespace
+
+    t = namespace["pytorch-experiment.submit.local.synthetic"]
+    with pytest.raises(NotImplementedError):
+        t(Context())
+
+
+def test_render_project(tmp_path):
+    p = template.render_project(str(tmp_path / "proj"), project_name="proj", experiment_name="myexp",
+                                maximum_number_nodes=4)
+    for f in (".env", "Makefile", "tasks.py", "README.md", "control/Docker/dockerfile", "myexp/src/train_model.py",
+              "environment_gpu.yml", "environment_cpu.yml"):
+        assert os.path.isfile(os.path.join(p, f)), f
+    env = open(os.path.join(p, ".env")).read()
+    assert 'CLUSTER_MAX_NODES="4"' in env and 'PROJECT_NAME="proj"' in env
+    with pytest.raises(FileExistsError):
+        template.render_project(p)
+    with pytest.raises(ValueError):
+        template.render_project(str(tmp_path / "x"), nonsense=1)
+
+
+def test_fake_data_matches_reference_shape():
+    ds = FakeData(batch_size=4, num_batches=3, dim=(8, 8), n_classes=10, length=50, data_transform=torch.FloatTensor)
+    assert len(ds) == 50 and len(ds._data) == 12
+    x, y = ds[7]
+    assert x.shape == (3, 8, 8) and 0 <= y < 10
+    assert torch.equal(ds[7][0], ds[7][0])
+
+
+def test_sampler_shards_cover_dataset():
+    ds = list(range(10))
+    seen = []
+    for r in range(3):
+        s = DistributedSampler(ds, num_replicas=3, rank=r, shuffle=True, seed=1)
+        s.set_epoch(2)
+        idx = list(s)
+        assert len(idx) == len(s) == 4
+        seen += idx
+    assert set(seen) == set(range(10)) and len(seen) == 12
+    a = list(DistributedSampler(ds, num_replicas=2, rank=0, shuffle=True))
+    s2 = DistributedSampler(ds, num_replicas=2, rank=0, shuffle=True)
+    s2.set_epoch(1)
+    assert a != list(s2)
+
+
+def test_device_synthetic_loader_cpu_lengths():
+    l = DeviceSyntheticLoader(length=21, batch_size=4, size=8, classes=10, device="cpu", rank=1, world=2)
+    assert l.per_rank == 11 and len(l) == 3
+    sizes = [x.shape[0] for x, _ in l]
+    assert sizes == [4, 4, 3]
+    x, y = fixed_synthetic_batch(2, 16, 10, "cpu")
+    assert x.shape == (2, 3, 16, 16) and y.shape == (2,)
+
+
+def test_compression_registry():
+    t = torch.randn(8)
+    w, ctx = Compression.fp16.compress(t)
+    assert w.dtype == torch.float16 and Compression.fp16.decompress(w, ctx).dtype == torch.float32
+    w, ctx = Compression.none.compress(t)
+    assert w is t
+    assert Compression.by_name("bf16").wire_dtype == torch.bfloat16
+    with pytest.raises(ValueError):
+        Compression.by_name("int3")
+
+
+def _tiny_jpeg():
+    from PIL import Image
+
+    buf = io.BytesIO()
+    Image.new("RGB", (8, 8), (255, 0, 0)).save(buf, format="JPEG")
+    return buf.getvalue()
+
+
+def test_prepare_imagenet_and_records(tmp_path):
+    jpg = _tiny_jpeg()
+    dl = tmp_path / "dl"
+    dl.mkdir()
+    # train: tar of per-class tars
+    with tarfile.open(dl / prepare_imagenet.TRAIN_TAR, "w") as outer:
+        for wnid in ("n01440764", "n01443537"):
+            inner_buf = io.BytesIO()
+            with tarfile.open(fileobj=inner_buf, mode="w") as inner:
+                for i in range(2):
+                    ti = tarfile.TarInfo(f"{wnid}_{i}.JPEG")
+                    ti.size = len(jpg)
+                    inner.addfile(ti, io.BytesIO(jpg))
+            data = inner_buf.getvalue()
+            ti = tarfile.TarInfo(f"{wnid}.tar")
+            ti.size = len(data)
+            outer.addfile(ti, io.BytesIO(data))
+    with tarfile.open(dl / prepare_imagenet.VAL_TAR, "w") as tf:
+        for i in range(3):
+            ti = tarfile.TarInfo(f"ILSVRC2012_val_{i:08d}.JPEG")
+            ti.size = len(jpg)
+            tf.addfile(ti, io.BytesIO(jpg))
+    (dl / "imagenet_val_maps.csv").write_text("filename,wnid\n" + "\n".join(
+        f"ILSVRC2012_val_{i:08d}.JPEG,{'n01440764' if i % 2 == 0 else 'n01443537'}" for i in range(3)))
+    out = tmp_path / "data"
+    counts = prepare_imagenet.main(str(dl), str(out), check=False)
+    assert counts == {"train": 4, "validation": 3}
+    assert len(os.listdir(out / "train" / "n01440764")) == 2
+    with pytest.raises(ValueError):
+        prepare_imagenet.check_sha1(str(dl / prepare_imagenet.VAL_TAR), "00" * 20)
+    n = records.convert(str(out), str(tmp_path / "rec"), shards_train=2, shards_val=1)
+    assert n == {"train": 4, "validation": 3}
+    ds0 = list(records.RecordDataset(str(tmp_path / "rec" / "train"), "train", rank=0, world=2))
+    ds1 = list(records.RecordDataset(str(tmp_path / "rec" / "train"), "train", rank=1, world=2))
+    assert len(ds0) + len(ds1) == 4 and {y for _, y in ds0 + ds1} == {0, 1}

@@ -1,0 +1,94 @@
+"""C++ host runtime: bucket planner, fd channel (determinism of the bucket plan)."""
+import multiprocessing as mp
+import os
+
+import pytest
+
+from distributeddeeplearning_b200 import _ext
+
+
+@pytest.fixture(scope="module")
+def C():
+    return _ext.load()
+
+
+def test_plan_is_deterministic_and_aligned(C):
+    numels = [1000, 64, 64, 2048 * 1000, 10, 513, 4096]
+    a = C.plan_buckets(numels, 256, 4096, 64, 2048)
+    b = C.plan_buckets(numels, 256, 4096, 64, 2048)
+    assert a == b and a["hash"] == b["hash"]
+    for off in a["param_offset"]:
+        assert off % 64 == 0
+    for start, n in zip(a["bucket_start"], a["bucket_numel"]):
+        assert n % 2048 == 0 and start % 2048 == 0
+    # buckets tile the arena without gaps
+    pos = 0
+    for start, n in zip(a["bucket_start"], a["bucket_numel"]):
+        assert start == pos
+        pos += n
+    assert pos == a["total_elems"]
+    # every parameter lies inside its bucket, in order
+    for i, (bk, off) in enumerate(zip(a["param_bucket"], a["param_offset"])):
+        assert a["bucket_start"][bk] <= off
+        assert off + numels[i] <= a["bucket_start"][bk] + a["bucket_numel"][bk]
+    assert sum(a["bucket_param_count"]) == len(numels)
+
+
+def test_plan_hash_changes_with_sizes(C):
+    a = C.plan_buckets([100, 200, 300], 256, 4096, 64, 2048)
+    b = C.plan_buckets([100, 201, 300], 256, 4096, 64, 2048)
+    assert a["hash"] != b["hash"]
+
+
+def test_first_bucket_is_small(C):
+    a = C.plan_buckets([1 << 16] * 20, 1 << 16, 1 << 20, 64, 2048)
+    assert a["bucket_param_count"][0] == 1 and a["bucket_param_count"][1] > 1
+
+
+def test_plan_rejects_bad_args(C):
+    with pytest.raises(Exception):
+        C.plan_buckets([10], 0, 10, 64, 2048)
+    with pytest.raises(Exception):
+        C.plan_buckets([10], 256, 4096, 64, 100)
+
+
+def _fd_worker(rank, world, session, q):
+    from distributeddeeplearning_b200 import _ext
+
+    C = _ext.load()
+    # memfd + pread: several peers read the same descriptor without consuming it (like a VMM handle)
+    fd = os.memfd_create(f"r{rank}")
+    os.write(fd, f"hello from {rank}".encode())
+    fds = C.exchange_fds(rank, world, fd, session, 20000)
+    got = {}
+    for src, pfd in enumerate(fds):
+        if src == rank:
+            assert pfd == -1
+            continue
+        got[src] = os.pread(pfd, 64, 0).decode()
+    fd2 = os.memfd_create("root")
+    os.write(fd2, b"root-payload")
+    bfd = C.broadcast_fd(rank, world, 0, fd2, session + "b", 20000)
+    got["bcast"] = os.pread(bfd, 64, 0).decode() if rank != 0 else "root"
+    q.put((rank, got))
+
+
+def test_fd_exchange_between_processes():
+    ctx = mp.get_context("spawn")
+    world, session = 3, f"ddltest{os.getpid()}"
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_fd_worker, args=(r, world, session, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=60) for _ in range(world))
+    for p in ps:
+        p.join(30)
+    for r in range(world):
+        for src in range(world):
+            if src != r:
+                assert res[r][src] == f"hello from {src}"
+        assert res[r]["bcast"] == ("root" if r == 0 else "root-payload")
+
+
+def test_driver_probe_does_not_raise(C):
+    assert C.driver_available() in (True, False)

@@ -1,0 +1,94 @@
+"""Model zoo + op composites on CPU: torchvision parity (state_dict keys, forward, gradients)."""
+import pytest
+import torch
+import torchvision
+
+from distributeddeeplearning_b200 import models, ops
+from distributeddeeplearning_b200.ops import native
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet50", "resnet101", "resnet152", "vgg16", "vgg11_bn", "alexnet",
+                                  "inception_v3"])
+def test_state_dict_matches_torchvision(name):
+    m = models.get_model(name)
+    kw = {"init_weights": False} if "inception" in name else {}
+    tv = getattr(torchvision.models, name)(**kw)
+    a = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    b = {k: tuple(v.shape) for k, v in tv.state_dict().items()}
+    assert a == b
+
+
+def test_param_counts_match_survey():
+    # SURVEY.md 2.7 [measured-here]
+    assert sum(p.numel() for p in models.get_model("resnet50").parameters()) == 25_557_032
+    assert sum(p.numel() for p in models.get_model("vgg16").parameters()) == 138_357_544
+    assert sum(p.numel() for p in models.get_model("alexnet").parameters()) == 61_100_840
+    assert sum(p.numel() for p in models.get_model("inception_v3").parameters()) == 27_161_264
+    assert len(list(models.get_model("resnet50").parameters())) == 161
+
+
+def test_resnet18_forward_backward_equals_torchvision():
+    torch.manual_seed(0)
+    m, tv = models.get_model("resnet18"), torchvision.models.resnet18()
+    m.load_state_dict(tv.state_dict())
+    m.train(), tv.train()
+    x = torch.randn(2, 3, 64, 64)
+    y = torch.tensor([1, 7])
+    o1, o2 = m(x), tv(x)
+    assert torch.allclose(o1, o2, atol=1e-4, rtol=1e-4)
+    ops.softmax_cross_entropy(o1, y).backward()
+    torch.nn.functional.cross_entropy(o2, y).backward()
+    g1, g2 = dict(m.named_parameters()), dict(tv.named_parameters())
+    for k in ("conv1.weight", "layer2.0.downsample.0.weight", "fc.bias", "layer4.1.bn2.weight"):
+        assert torch.allclose(g1[k].grad, g2[k].grad, atol=1e-4, rtol=1e-3), k
+    # running statistics were updated identically
+    assert torch.allclose(m.bn1.running_mean, tv.bn1.running_mean, atol=1e-5)
+
+
+def test_vgg_alexnet_forward_equal_torchvision_eval():
+    torch.manual_seed(0)
+    for name in ("alexnet", "vgg11"):
+        m, tv = models.get_model(name), getattr(torchvision.models, name)()
+        m.load_state_dict(tv.state_dict())
+        m.eval(), tv.eval()
+        x = torch.randn(1, 3, 224, 224)
+        with torch.no_grad():
+            assert torch.allclose(m(x), tv(x), atol=1e-3, rtol=1e-3), name
+
+
+def test_inception_returns_aux_in_train_mode():
+    m = models.get_model("inception_v3")
+    assert models.input_size(m) == 299 and models.input_size("inception_v3") == 299
+    m.train()
+    out = m(torch.randn(2, 3, 299, 299))
+    assert isinstance(out, tuple) and out[0].shape == (2, 1000) and out[1].shape == (2, 1000)
+    m.eval()
+    with torch.no_grad():
+        assert m(torch.randn(1, 3, 299, 299)).shape == (1, 1000)
+
+
+def test_registry():
+    assert "resnet50" in models.available_models() and "vgg16" in models.available_models()
+    with pytest.raises(ValueError):
+        models.get_model("nope")
+    with pytest.raises(ValueError):
+        models.get_model("resnet50", pretrained=True)
+
+
+def test_topk_and_xent_composites():
+    logits = torch.tensor([[5.0, 1.0, 0.0, 0.0, 0.0, 0.0, 9.0], [0.0, 3.0, 2.0, 1.0, 0.5, 0.4, 9.0]])
+    labels = torch.tensor([0, 5])
+    # last column is padding: classes=6 must ignore it
+    corr = ops.topk_correct(logits, labels, classes=6)
+    assert corr.tolist() == [1, 2]
+    loss = ops.softmax_cross_entropy(logits, labels, classes=6)
+    assert loss.item() == pytest.approx(torch.nn.functional.cross_entropy(logits[:, :6], labels).item())
+
+
+def test_stem_geometry_and_support_matrix():
+    assert native.stem_geometry(7, 7) == (8, 2, 4, 8)       # ResNet stem: 4 k-blocks of 2 rows x 8 taps x 4 ch
+    assert native.stem_geometry(11, 11) == (16, 1, 11, 11)  # AlexNet
+    assert native.stem_geometry(3, 3) == (4, 4, 1, 4)       # VGG
+    assert native.supports_conv(64, 256) and native.supports_conv(3, 64) and not native.supports_conv(80, 192)
+    assert native.bn_supported(2048) and native.bn_supported(64) and not native.bn_supported(80)
+    assert native.conv_out_hw(224, 224, (7, 7), 2, 3) == (112, 112)

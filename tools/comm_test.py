@@ -1,0 +1,207 @@
+#!/usr/bin/env python
+"""Multi-GPU validation + bandwidth sweep of the hand-written NVLink kernels (run under torchrun).
+
+1. correctness: FusedSGD (allreduce + average + SGD + bf16 refresh + grad clear in one kernel per bucket)
+   vs the same maths done with torch ops on the gathered per-rank gradients — fp32 wire and bf16 wire,
+   multicast (NVLS) and peer-to-peer transports; replicas must stay bit-identical; broadcast kernel.
+2. sweep: in-place allreduce 64 KiB .. 1 GiB (fp32 / bf16; one-shot / two-shot; NVLS / P2P), device-timed
+   with CUDA events, max over ranks, busbw = algbw * 2(N-1)/N, next to NCCL's all_reduce on the same sizes.
+Writes gpurun_out/comm_sweep_N{world}.json.
+"""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as td
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from distributeddeeplearning_b200 import _ext  # noqa: E402
+from distributeddeeplearning_b200.parallel import Compression, dist  # noqa: E402
+from distributeddeeplearning_b200.parallel.engine import FusedSGD, SymmetricArena  # noqa: E402
+
+
+def log(*a):
+    if dist.rank() == 0:
+        print(*a, flush=True)
+
+
+def check_engine(use_mc, wire):
+    torch.manual_seed(1234)               # same init everywhere
+    shapes = [(64, 3, 7, 7), (1000, 512), (77,), (256, 64, 3, 3), (512, 512, 3, 3), (2048,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref_w = [p.detach().clone() for p in ps]
+    ref_m = [torch.zeros_like(p) for p in ps]
+    lr, mom, wd = 0.05, 0.9, 1e-4
+    opt = FusedSGD(ps, lr=lr, momentum=mom, weight_decay=wd, compression=wire, use_multicast=use_mc,
+                   first_bucket_mb=0.25, bucket_mb=2.0)
+    world, rank = dist.size(), dist.rank()
+    ok = True
+    for it in range(3):
+        gs = []
+        for i, p in enumerate(ps):
+            g_all = [torch.randn(p.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(100 * it + 10 * r + i))
+                     for r in range(world)]
+            if wire is not Compression.none:
+                g_avg = sum((g / world).to(torch.bfloat16).float() for g in g_all)
+            else:
+                g_avg = sum(g_all) / world
+            gs.append(g_avg)
+            p.grad.add_(g_all[rank].view_as(p.grad))
+            p._ddl_ready()
+        opt.step()
+        for i in range(len(ps)):
+            g = gs[i] + wd * ref_w[i]
+            ref_m[i] = g.clone() if it == 0 else mom * ref_m[i] + g
+            ref_w[i] = ref_w[i] - lr * ref_m[i]
+    torch.cuda.synchronize()
+    opt.check_errors()
+    tol = 2e-2 if wire is not Compression.none else 1e-5
+    for i, p in enumerate(ps):
+        err = (p.detach() - ref_w[i]).abs().max().item() / (ref_w[i].abs().max().item() + 1e-9)
+        # replicas identical?
+        mx = p.detach().clone()
+        td.all_reduce(mx, op=td.ReduceOp.MAX)
+        same = bool((mx == p.detach()).all())
+        cleared = float(p.grad.abs().max()) == 0.0
+        bf_ok = bool((p._ddl_bf16.float().reshape(-1) == p.detach().to(torch.bfloat16).float().reshape(-1)).all())
+        if err > tol or not same or not cleared or not bf_ok:
+            ok = False
+            log(f"  FAIL param {i}: rel_err={err:.3e} replicas_identical={same} grads_cleared={cleared} bf16_copy={bf_ok}")
+    # momentum gather + broadcast kernel
+    full = opt.full_momentum()
+    for i, p in enumerate(ps):
+        o = int(opt.plan["param_offset"][i])
+    with torch.no_grad():
+        if rank == 1:
+            for p in ps:
+                p.add_(1.0)
+    opt.broadcast_parameters(0)
+    torch.cuda.synchronize()
+    for i, p in enumerate(ps):
+        mx = p.detach().clone()
+        td.all_reduce(mx, op=td.ReduceOp.MAX)
+        if not bool((mx == p.detach()).all()):
+            ok = False
+            log(f"  FAIL broadcast param {i}")
+    name = f"fused engine transport={'nvls' if opt.use_mc else 'p2p'} wire={'bf16' if wire is not Compression.none else 'fp32'}"
+    log(f"[{'ok' if ok else 'FAIL'}] {name}  ({opt.describe()})")
+    return ok, opt.use_mc
+
+
+def sweep(max_bytes):
+    C = _ext.load()
+    world, rank = dist.size(), dist.rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    arena = SymmetricArena([("flags", int(C.SIGNAL_PAD_BYTES)), ("data", 2 * max_bytes)], dev, None)
+    epochs = torch.zeros(int(C.COMM_CHANNELS) * int(C.MAX_COMM_BLOCKS), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    off = arena.offsets
+    ctx = C.CommCtx(arena.peer_ptrs, arena.mc_ptr, rank, world, off["flags"], 0, 0, 0, 0, epochs.data_ptr(),
+                    err.data_ptr(), int(30e9))
+    st = torch.cuda.current_stream().cuda_stream
+    results = []
+    sizes = [1 << k for k in range(16, 31) if (1 << k) <= max_bytes]
+    # correctness of the plain allreduce first
+    n = 1 << 20
+    for bf16 in (False, True):
+        for use_mc in ([True, False] if arena.has_multicast else [False]):
+            for oneshot in (False, True):
+                dt = torch.bfloat16 if bf16 else torch.float32
+                buf = arena.region("data", dt, 2 * n)
+                buf[:n] = (torch.arange(n, device=dev) % 13).to(dt) * (rank + 1)
+                torch.cuda.synchronize()
+                td.barrier()
+                C.allreduce(ctx, 4, off["data"], n, bf16, 1.0, use_mc, oneshot, 32, st)
+                torch.cuda.synchronize()
+                out = buf[n:2 * n] if oneshot else buf[:n]
+                exp = (torch.arange(n, device=dev) % 13).float() * (world * (world + 1) / 2)
+                good = bool(torch.allclose(out.float(), exp, rtol=1e-2 if bf16 else 1e-6))
+                log(f"[{'ok' if good else 'FAIL'}] allreduce {'bf16' if bf16 else 'fp32'} {'nvls' if use_mc else 'p2p'} "
+                    f"{'one-shot' if oneshot else 'two-shot'}")
+                td.barrier()
+    for nbytes in sizes:
+        for bf16 in (False, True):
+            es = 2 if bf16 else 4
+            numel = nbytes // es
+            variants = []
+            if arena.has_multicast:
+                variants += [("nvls-2shot", True, False)]
+                if nbytes <= (8 << 20):
+                    variants += [("nvls-1shot", True, True)]
+            variants += [("p2p-2shot", False, False)]
+            if nbytes <= (8 << 20):
+                variants += [("p2p-1shot", False, True)]
+            for blocks in (16, 32, 64):
+                for name, use_mc, oneshot in variants:
+                    def run():
+                        C.allreduce(ctx, 4, off["data"], numel, bf16, 1.0, use_mc, oneshot, blocks, st)
+                    for _ in range(3):
+                        run()
+                    torch.cuda.synchronize()
+                    td.barrier()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 20 if nbytes <= (16 << 20) else 5
+                    a.record()
+                    for _ in range(reps):
+                        run()
+                    b.record()
+                    b.synchronize()
+                    ms = dist.allreduce_scalar(a.elapsed_time(b) / reps, op="max")
+                    algbw = nbytes / ms / 1e6
+                    results.append({"bytes": nbytes, "dtype": "bf16" if bf16 else "fp32", "impl": name, "blocks": blocks,
+                                    "ms": ms, "algbw_gbs": algbw, "busbw_gbs": algbw * 2 * (world - 1) / world})
+            # NCCL reference on the same size
+            t = torch.zeros(numel, dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
+            for _ in range(3):
+                td.all_reduce(t)
+            torch.cuda.synchronize()
+            td.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20 if nbytes <= (16 << 20) else 5
+            a.record()
+            for _ in range(reps):
+                td.all_reduce(t)
+            b.record()
+            b.synchronize()
+            ms = dist.allreduce_scalar(a.elapsed_time(b) / reps, op="max")
+            algbw = nbytes / ms / 1e6
+            results.append({"bytes": nbytes, "dtype": "bf16" if bf16 else "fp32", "impl": "nccl", "blocks": 0, "ms": ms,
+                            "algbw_gbs": algbw, "busbw_gbs": algbw * 2 * (world - 1) / world})
+        best = {}
+        for r in results:
+            if r["bytes"] == nbytes and r["dtype"] == "fp32":
+                k = r["impl"]
+                if k not in best or r["ms"] < best[k]["ms"]:
+                    best[k] = r
+        log(f"{nbytes >> 10:>8d} KiB fp32: " + "  ".join(f"{k} {v['ms'] * 1e3:8.1f}us {v['busbw_gbs']:6.1f}GB/s(b{v['blocks']})"
+                                                        for k, v in sorted(best.items())))
+    if int(err.item()):
+        log("barrier timeout flag set:", int(err.item()))
+    return results
+
+
+def main():
+    dist.init()
+    world = dist.size()
+    log(f"world={world} device={torch.cuda.get_device_name()}")
+    oks = []
+    ok, had_mc = check_engine(None, Compression.none)
+    oks.append(ok)
+    oks.append(check_engine(None, Compression.bf16)[0])
+    if had_mc:
+        oks.append(check_engine(False, Compression.none)[0])
+        oks.append(check_engine(False, Compression.bf16)[0])
+    max_bytes = int(os.environ.get("SWEEP_MAX", 1 << 30))
+    res = sweep(max_bytes)
+    if dist.rank() == 0:
+        os.makedirs("gpurun_out", exist_ok=True)
+        json.dump({"world": world, "multicast": had_mc, "results": res, "engine_checks_ok": all(oks)},
+                  open(f"gpurun_out/comm_sweep_N{world}.json", "w"), indent=1)
+    log("ENGINE CHECKS:", "all ok" if all(oks) else "FAILURES")
+    dist.shutdown()
+    return 0 if all(oks) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

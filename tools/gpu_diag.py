@@ -89,11 +89,11 @@ def g_elementwise():
         report(f"maxpool bwd k{k}s{s}p{p}", nv.maxpool_bwd(dy, arg, x.shape, k, s, p), xr.grad, 1e-2)
     for cip in (True, False):
         ya = nv.avgpool_fwd(x, 3, 1, 1, cip)
-        xr = x.float().requires_grad_(True)
-        yr = F.avg_pool2d(xr, 3, 1, 1, count_include_pad=cip)
+        xr = x.float().contiguous().requires_grad_(True)      # NCHW-contiguous oracle (torch's channels_last
+        yr = F.avg_pool2d(xr, 3, 1, 1, count_include_pad=cip)  # avg_pool2d backward mis-handles strided grads)
         report(f"avgpool fwd cip={cip}", ya, yr.detach(), 1e-2)
         dy = cl(bf(torch.randn_like(yr)))
-        yr.backward(dy.float())
+        yr.backward(dy.float().contiguous())
         report(f"avgpool bwd cip={cip}", nv.avgpool_bwd(dy, x.shape, 3, 1, 1, cip), xr.grad, 1e-2)
     g = nv.global_avgpool_fwd(x)
     report("global_avgpool fwd", g, x.float().mean((2, 3)), 1e-2)
@@ -397,10 +397,10 @@ def g_avgdebug():
     from distributeddeeplearning_b200.ops import native as nv
 
     x = cl(bf(torch.randn(1, 8, 5, 5, device="cuda")))
-    xr = x.float().requires_grad_(True)
+    xr = x.float().contiguous().requires_grad_(True)
     yr = F.avg_pool2d(xr, 3, 1, 1)
     dy = cl(bf(torch.ones_like(yr)))
-    yr.backward(dy.float())
+    yr.backward(dy.float().contiguous())
     got = nv.avgpool_bwd(dy, x.shape, 3, 1, 1, True)
     print("ref", xr.grad[0, 0])
     print("got", got[0, 0].float())
@@ -421,7 +421,7 @@ def run_group(name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--group", default=None)
-    ap.add_argument("--timeout", type=int, default=240)
+    ap.add_argument("--timeout", type=int, default=600)
     ap.add_argument("--groups", default=",".join(GROUPS))
     a = ap.parse_args()
     if a.group:
