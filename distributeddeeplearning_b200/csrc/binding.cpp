@@ -69,6 +69,9 @@ PYBIND11_MODULE(_C, m) {
   m.attr("CONV_DGRAD") = static_cast<int>(ddl::kConvDgrad);
   m.attr("CONV_GEMM") = static_cast<int>(ddl::kConvGemm);
   m.attr("CONV_STEM") = static_cast<int>(ddl::kConvStem);
+  m.attr("CONV_TILE_FWD") = static_cast<int>(ddl::kConvTileFwd);
+  m.attr("CONV_TILE_DGRAD") = static_cast<int>(ddl::kConvTileDgrad);
+  m.attr("CONV_GEMM_DGRAD") = static_cast<int>(ddl::kConvGemmDgrad);
 
   // ------------------------------------------------------------------ host runtime
   m.def("driver_available", &ddl::driver_available);
@@ -178,19 +181,22 @@ PYBIND11_MODULE(_C, m) {
         [](int mode, ptr_t src, ptr_t out, ptr_t add, ptr_t bias, ptr_t sum, ptr_t sumsq, int M, int KB, int ldc,
            int srcH, int srcW, int srcC, int dstH, int dstW, int R, int Sx, int stride, int pad, int dil,
            int cchunks, int relu, int n_valid, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
-           ptr_t stream) {
+           int batch, int tw, int th, int tn, ptr_t stream) {
           ConvArgs a;
           a.src = P<const __nv_bfloat16>(src); a.out = P<__nv_bfloat16>(out); a.add = P<const __nv_bfloat16>(add);
           a.bias = P<const float>(bias); a.sum = P<float>(sum); a.sumsq = P<float>(sumsq);
           a.M = M; a.KB = KB; a.ldc = ldc; a.srcH = srcH; a.srcW = srcW; a.srcC = srcC; a.dstH = dstH; a.dstW = dstW;
           a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil; a.cchunks = cchunks; a.relu = relu; a.n_valid = n_valid;
+          a.stages = 0; a.batch = batch; a.tw = tw; a.th = th; a.tn = tn; a.tiles_w = 0; a.tiles_h = 0;
           check(ddl::launch_conv_gemm(mode, a, P<const void>(w), w_rows, w_cols, n_total, P<const void>(a_matrix),
                                       a_cols, S(stream)), "conv_gemm");
         });
   m.def("conv_wgrad",
         [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int dy_ld, int ldw, int ncols, int H, int W, int C, int Pq,
-           int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, ptr_t stream) {
+           int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, int batch, int tw, int th, int tn,
+           ptr_t stream) {
           WgradArgs a;
+          a.stages = 0; a.batch = batch; a.tw = tw; a.th = th; a.tn = tn; a.tiles_w = 0; a.tiles_h = 0;
           a.x = P<const __nv_bfloat16>(x); a.dw = P<float>(dw); a.M = M; a.Cout = Cout; a.dy_ld = dy_ld; a.ldw = ldw; a.ncols = ncols;
           a.H = H; a.W = W; a.C = C; a.P = Pq; a.Q = Q; a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil;
           a.cchunks = cchunks; a.kb_per_split = 0; a.total_kb = 0; a.mode = mode;
@@ -210,14 +216,14 @@ PYBIND11_MODULE(_C, m) {
     check(ddl::launch_bn_act_fwd(a, train, sms, S(stream)), "bn_act_fwd");
   });
   m.def("bn_act_bwd", [](ptr_t dz, ptr_t z, ptr_t x, ptr_t dx, ptr_t dres, ptr_t mean, ptr_t invstd, ptr_t gamma,
-                         ptr_t dgamma, ptr_t dbeta, ptr_t gamma_grad, ptr_t beta_grad, int M, int C, int relu,
-                         int sms, ptr_t stream) {
+                         ptr_t beta, ptr_t dgamma, ptr_t dbeta, ptr_t gamma_grad, ptr_t beta_grad, int M, int C,
+                         int relu, int mask_from_x, int sms, ptr_t stream) {
     BnBwdArgs a;
     a.dz = P<const __nv_bfloat16>(dz); a.z = P<const __nv_bfloat16>(z); a.x = P<const __nv_bfloat16>(x);
     a.dx = P<__nv_bfloat16>(dx); a.dres = P<__nv_bfloat16>(dres); a.mean = P<const float>(mean);
     a.invstd = P<const float>(invstd); a.gamma = P<const float>(gamma); a.dgamma = P<float>(dgamma);
     a.dbeta = P<float>(dbeta); a.gamma_grad = P<float>(gamma_grad); a.beta_grad = P<float>(beta_grad);
-    a.M = M; a.C = C; a.relu = relu;
+    a.M = M; a.C = C; a.relu = relu; a.beta = P<const float>(beta); a.mask_from_x = mask_from_x;
     check(ddl::launch_bn_act_bwd(a, sms, S(stream)), "bn_act_bwd");
   });
   m.def("channel_stats", [](ptr_t x, ptr_t sum, ptr_t sumsq, int M, int C, int sms, ptr_t stream) {

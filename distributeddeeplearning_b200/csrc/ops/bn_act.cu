@@ -112,17 +112,27 @@ __global__ void __launch_bounds__(kBnThreads) bn_act_bwd_reduce_kernel(BnBwdArgs
   const int row_stride = (gridDim.x * blockDim.x) / groups;
   const int c0 = g * 8;
   Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0);
-  float sdy[8], sdyx[8];
+  float sdy[8], sdyx[8], msc[8], msh[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sdy[i] = 0.f; sdyx[i] = 0.f; }
+  for (int i = 0; i < 8; ++i) { sdy[i] = 0.f; sdyx[i] = 0.f; msc[i] = 0.f; msh[i] = 0.f; }
+  if (a.relu && a.mask_from_x) {
+    Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { msc[i] = gam.v[i] * invstd.v[i]; msh[i] = bet.v[i] - mean.v[i] * msc[i]; }
+  }
   for (int r = row0; r < a.M; r += row_stride) {
     const size_t off = static_cast<size_t>(r) * a.C + c0;
     Vec8 dz = load8_bf16(a.dz + off);
     Vec8 x = load8_bf16(a.x + off);
     if (a.relu) {
-      Vec8 z = load8_bf16(a.z + off);
+      if (a.mask_from_x) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
+        for (int i = 0; i < 8; ++i) dz.v[i] = fmaf(x.v[i], msc[i], msh[i]) > 0.f ? dz.v[i] : 0.f;
+      } else {
+        Vec8 z = load8_bf16(a.z + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
+      }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -176,21 +186,32 @@ __global__ void __launch_bounds__(kBnThreads) bn_act_bwd_apply_kernel(BnBwdArgs 
       a.beta_grad[c0 + i] += db.v[i];
     }
   }
-  float k1[8], k2[8], k3[8];
+  float k1[8], k2[8], k3[8], msh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     k1[i] = gam.v[i] * invstd.v[i];
     k2[i] = db.v[i] * inv_n;
     k3[i] = dg.v[i] * inv_n;
+    msh[i] = 0.f;
+  }
+  if (a.relu && a.mask_from_x) {
+    Vec8 bet = load8_f32(a.beta + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) msh[i] = bet.v[i] - mean.v[i] * k1[i];
   }
   for (int r = row0; r < a.M; r += row_stride) {
     const size_t off = static_cast<size_t>(r) * a.C + c0;
     Vec8 dz = load8_bf16(a.dz + off);
     Vec8 x = load8_bf16(a.x + off);
     if (a.relu) {
-      Vec8 z = load8_bf16(a.z + off);
+      if (a.mask_from_x) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
+        for (int i = 0; i < 8; ++i) dz.v[i] = fmaf(x.v[i], k1[i], msh[i]) > 0.f ? dz.v[i] : 0.f;
+      } else {
+        Vec8 z = load8_bf16(a.z + off);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
+      }
     }
     if (a.dres) store8_bf16(a.dres + off, dz);
     Vec8 dx;

@@ -8,15 +8,17 @@
 //   wgrad  dW[co][k] = sum_m  dY[m][co]        * im2col(X)[m][k]    (A and B are MN-major, split-K)
 //
 // One CTA = 6 warps:
-//   warps 0-3  gather producers: each thread owns one 128-byte row of the operand tile and fills it
-//              with 16-byte cp.async (zero-fill = padding / tails) straight into the 128B-swizzled
-//              image tcgen05 expects; afterwards the same warps run the epilogue (TMEM -> registers
-//              -> smem -> coalesced global stores, fused BN statistics / bias / ReLU / residual add)
-//   warp 4     TMA producer (weights, and the activation operand when it is a plain matrix)
+//   warps 0-3  epilogue (TMEM -> registers -> smem -> coalesced global stores; fused BN statistics /
+//              bias / ReLU / residual add).  In the gather modes (strided convs, stem) the same warps
+//              first act as im2col producers: each thread owns one 128-byte row of the operand tile and
+//              fills it with cp.async (zero-fill = padding / tails) in the 128B-swizzled image tcgen05 reads.
+//   warp 4     TMA producer: weights always; the activation operand too whenever it is a plain matrix
+//              (2-D map) or a stride-1 convolution window (ONE 4-D box per filter tap — the hardware does
+//              the im2col, out-of-bounds coordinates supply the zero padding)
 //   warp 5     TMEM allocator + the single thread that issues tcgen05.mma and tcgen05.commit
-// Stages are handed over with mbarriers (full/empty ring + one accumulator-ready barrier).
-// Two CTAs fit per SM (<= 100 KB smem, <= 256 TMEM columns), so one CTA's epilogue overlaps the
-// other's main loop without a persistent scheduler.
+// Stages are handed over with mbarriers (full/empty ring + one accumulator-ready barrier).  The pipeline
+// depth is chosen per launch (short-K layers take less shared memory, so more CTAs are resident per SM
+// and one CTA's epilogue overlaps the others' loads).
 #include "conv_gemm.cuh"
 #include "tc_utils.cuh"
 
@@ -33,46 +35,75 @@ constexpr int kATileBytes = kBlockM * 128;        // 16 KB
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 192;
 constexpr int kLag = 2;                           // cp.async groups kept in flight per producer
+constexpr int kMaxStages = 4;
 
 template <int BLOCK_N>
 struct FwdCfg {
   static constexpr int kBTileBytes = BLOCK_N * 128;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (BLOCK_N <= 64) ? 4 : (BLOCK_N <= 128 ? 3 : 4);
   static constexpr int kPitch = BLOCK_N * 2 + 16;                 // epilogue staging row pitch (bytes)
-  static constexpr int kStageTotal = kStages * kStageBytes;
   static constexpr int kEpiBytes = kBlockM * kPitch;
-  static_assert(kEpiBytes <= kStageTotal, "epilogue staging must fit in the pipeline buffers");
-  static constexpr int kSmemBytes = kStageTotal + 256 /*barriers*/ + 1024 /*alignment slack*/;
+  static constexpr int kMaxStagesN = (BLOCK_N <= 64) ? 4 : 3;
+  static constexpr int smem_bytes(int stages) {
+    const int pipe = stages * kStageBytes;
+    return (pipe > kEpiBytes ? pipe : kEpiBytes) + 256 /*barriers*/ + 4096 /*stats scratch*/ + 1024 /*alignment*/;
+  }
 };
 
 DDL_DEVICE void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
 
+DDL_DEVICE void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+constexpr bool mode_a_tma(int mode) {
+  return mode == kConvGemm || mode == kConvTileFwd || mode == kConvTileDgrad || mode == kConvGemmDgrad;
+}
+constexpr bool mode_b_mn(int mode) { return mode == kConvDgrad || mode == kConvTileDgrad || mode == kConvGemmDgrad; }
+constexpr bool mode_tile(int mode) { return mode == kConvTileFwd || mode == kConvTileDgrad; }
+
 // ---------------------------------------------------------------------------------------------
 // fwd / dgrad / plain-GEMM / stem kernel
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int MODE, bool STATS>
-__global__ void __launch_bounds__(kThreads, (BLOCK_N <= 128) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, 2)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA, ConvArgs a) {
   using Cfg = FwdCfg<BLOCK_N>;
-  constexpr bool kATma = (MODE == kConvGemm);
-  constexpr bool kBMn = (MODE == kConvDgrad);
+  constexpr bool kATma = mode_a_tma(MODE);
+  constexpr bool kBMn = mode_b_mn(MODE);
+  constexpr bool kTile = mode_tile(MODE);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + Cfg::kStageTotal);
-  uint64_t* empty = full + Cfg::kStages;
-  uint64_t* acc_full = empty + Cfg::kStages;
+  const int nstages = a.stages;
+  const int pipe_bytes = nstages * Cfg::kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (pipe_bytes > Cfg::kEpiBytes ? pipe_bytes : Cfg::kEpiBytes));
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* acc_full = empty + kMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int n0 = blockIdx.x * BLOCK_N;
-  const int m0 = blockIdx.y * kBlockM;
   const int KB = a.KB;
 
+  // ---- tile -> output rows ------------------------------------------------------------------------
+  int m0 = blockIdx.y * kBlockM;          // linear modes: rows [m0, m0+128)
+  int tq0 = 0, tp0 = 0, tn0 = 0;          // tile modes: box origin in the output's (w, h, n) space
+  if (kTile) {
+    int t = blockIdx.y;
+    const int wb = t % a.tiles_w; t /= a.tiles_w;
+    const int hb = t % a.tiles_h;
+    const int nb = t / a.tiles_h;
+    tq0 = wb * a.tw; tp0 = hb * a.th; tn0 = nb * a.tn;
+    m0 = 0;
+  }
+
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&full[s], kATma ? 1u : (kProducerThreads + 1u));
       mbar_init(&empty[s], 1u);
     }
@@ -103,7 +134,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
         dh = rem / a.dstW;
         dw = rem - dh * a.dstW;
       }
-      // base coordinates in the gather source
       int hb, wb;
       if (MODE == kConvDgrad) { hb = dh + a.pad; wb = dw + a.pad; }
       else { hb = dh * a.stride - a.pad; wb = dw * a.stride - a.pad; }
@@ -111,9 +141,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
       const uint32_t row_off = row * 128u;
       const uint32_t sw = row & 7u;
       int tap_r = 0, tap_s = 0, cc = 0;   // incremental decode of kb -> (r, s, channel chunk)
+      int stage = 0;
+      uint32_t phase = 0;
       for (int kb = 0; kb < KB; ++kb) {
-        const int stage = kb % Cfg::kStages;
-        const uint32_t phase = (kb / Cfg::kStages) & 1u;
         mbar_wait(&empty[stage], phase ^ 1u);
         const uint32_t dst = smem_u32(smem + stage * Cfg::kStageBytes) + row_off;
         if (MODE == kConvStem) {
@@ -160,19 +190,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
         if (kb >= kLag) {
           cp_async_wait<kLag>();
           fence_proxy_async_smem();
-          mbar_arrive(&full[(kb - kLag) % Cfg::kStages]);
+          mbar_arrive(&full[(kb - kLag) % nstages]);
         }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
       cp_async_wait<0>();
       fence_proxy_async_smem();
-      for (int kb = (KB > kLag ? KB - kLag : 0); kb < KB; ++kb) mbar_arrive(&full[kb % Cfg::kStages]);
+      for (int kb = (KB > kLag ? KB - kLag : 0); kb < KB; ++kb) mbar_arrive(&full[kb % nstages]);
     }
 
     // =================================== epilogue ========================================
+    // my accumulator row -> output row
+    const int row = threadIdx.x;
+    int my_m;                     // linear output row index of this thread's accumulator row, or -1
+    if (kTile) {
+      const int wl = row % a.tw;
+      const int t2 = row / a.tw;
+      const int hl = t2 % a.th;
+      const int nl = t2 / a.th;
+      const bool ok = nl < a.tn && (tn0 + nl) < a.batch && (tp0 + hl) < a.dstH && (tq0 + wl) < a.dstW;
+      my_m = ok ? ((tn0 + nl) * a.dstH + (tp0 + hl)) * a.dstW + (tq0 + wl) : -1;
+    } else {
+      my_m = (m0 + row) < a.M ? (m0 + row) : -1;
+    }
     mbar_wait(acc_full, 0);
     tc_fence_after();
     uint8_t* stg = smem;  // pipeline buffers are free: every MMA that read them has completed
-    const int row = threadIdx.x;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t v[32];
@@ -188,41 +231,69 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
           if (cb + 1 < a.n_valid) x1 += a.bias[cb + 1];
         }
         if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-        packed[j] = pack_bf16x2(x0, x1);
+        packed[j] = (kTile && my_m < 0) ? 0u : pack_bf16x2(x0, x1);   // rows outside the image: exact zeros
       }
       uint4* dstp = reinterpret_cast<uint4*>(stg + row * Cfg::kPitch + c0 * 2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) dstp[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     }
+    // the row's destination index rides in the pad bytes of its staging row (pitch = 2*BLOCK_N + 16)
+    *reinterpret_cast<int*>(stg + row * Cfg::kPitch + BLOCK_N * 2) = my_m;
     tc_fence_before();
     named_bar_sync(1, kProducerThreads);
     if (STATS) {
-      // per-channel sum / sum of squares of the bf16-rounded outputs of this tile (rows >= M are 0)
-      constexpr int kGroups = (BLOCK_N >= 128) ? 1 : 128 / BLOCK_N;   // row groups sharing a column
-      constexpr int kColsPerThread = (BLOCK_N > 128) ? BLOCK_N / 128 : 1;
+      // per-channel sum / sum of squares of the bf16-rounded outputs of this tile (invalid rows hold zeros).
+      // thread = (column group of 8, row slice): 16-byte shared loads, fp32 accumulation.
+      constexpr int kColGroups = BLOCK_N / 8;                 // 16 (N=128) or 8 (N=64)
+      constexpr int kSlices = kProducerThreads / kColGroups;  // 8 or 16 row slices
+      constexpr int kRowsPer = kBlockM / kSlices;             // 16 or 8 rows per thread
+      const int cg = threadIdx.x % kColGroups;
+      const int sl = threadIdx.x / kColGroups;
+      float s[8], ss[8];
 #pragma unroll
-      for (int cidx = 0; cidx < kColsPerThread; ++cidx) {
-        const int col = (threadIdx.x % (BLOCK_N >= 128 ? 128 : BLOCK_N)) + cidx * 128;
-        const int grp = (BLOCK_N >= 128) ? 0 : threadIdx.x / BLOCK_N;
-        const int rows_per = kBlockM / kGroups;
-        float s = 0.f, ss = 0.f;
-        const uint8_t* colp = stg + col * 2 + grp * rows_per * Cfg::kPitch;
-#pragma unroll 8
-        for (int r = 0; r < rows_per; ++r) {
-          const float x = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(colp + r * Cfg::kPitch));
-          s += x;
-          ss = fmaf(x, x, ss);
+      for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+      const uint8_t* p0 = stg + (sl * kRowsPer) * Cfg::kPitch + cg * 16;
+#pragma unroll 4
+      for (int r = 0; r < kRowsPer; ++r) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p0 + r * Cfg::kPitch);
+        float2 f;
+        f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
+        f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
+        f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
+        f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
+      }
+      // threads with the same column group inside a warp: lanes cg, cg+kColGroups, ... -> xor shuffles
+#pragma unroll
+      for (int off = kColGroups; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+          ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
         }
-        atomicAdd(a.sum + n0 + col, s);
-        atomicAdd(a.sumsq + n0 + col, ss);
+      }
+      // cross-warp fold in shared memory, then ONE atomic per channel and statistic per tile
+      float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][2][BLOCK_N]
+      if ((threadIdx.x & 31) < kColGroups) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          red[(warp * 2 + 0) * BLOCK_N + cg * 8 + i] = s[i];
+          red[(warp * 2 + 1) * BLOCK_N + cg * 8 + i] = ss[i];
+        }
+      }
+      named_bar_sync(1, kProducerThreads);
+      for (int c = threadIdx.x; c < 2 * BLOCK_N; c += kProducerThreads) {
+        const int which = c / BLOCK_N, col = c - which * BLOCK_N;
+        const float v = red[(0 * 2 + which) * BLOCK_N + col] + red[(1 * 2 + which) * BLOCK_N + col] +
+                        red[(2 * 2 + which) * BLOCK_N + col] + red[(3 * 2 + which) * BLOCK_N + col];
+        atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
       }
     }
     // coalesced stores: 16 bytes per thread, a row of the tile is BLOCK_N*2 contiguous bytes
     constexpr int kVecPerRow = BLOCK_N / 8;
     for (int idx = threadIdx.x; idx < kBlockM * kVecPerRow; idx += kProducerThreads) {
       const int r = idx / kVecPerRow, ch = idx - r * kVecPerRow;
-      const int m = m0 + r;
-      if (m < a.M) {
+      const int m = *reinterpret_cast<const int*>(stg + r * Cfg::kPitch + BLOCK_N * 2);
+      if (m >= 0) {
         uint4 val = *reinterpret_cast<const uint4*>(stg + r * Cfg::kPitch + ch * 16);
         const size_t off = static_cast<size_t>(m) * a.ldc + n0 + ch * 8;
         if (a.add) {
@@ -239,32 +310,42 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
   } else if (warp == 4) {
     // ================================== TMA producer =====================================
     if (elect_one()) {
-      int tap = 0, cc = 0;
+      int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : kATileBytes;
       for (int kb = 0; kb < KB; ++kb) {
-        const int stage = kb % Cfg::kStages;
-        const uint32_t phase = (kb / Cfg::kStages) & 1u;
         mbar_wait(&empty[stage], phase ^ 1u);
         uint8_t* sA = smem + stage * Cfg::kStageBytes;
         const uint32_t sB = smem_u32(sA + kATileBytes);
-        mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + (kATma ? kATileBytes : 0));
+        mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + (kATma ? a_bytes : 0u));
         if (kBMn) {
           // weights W[co][(r,s,ci)]: K rows = 64 output channels, N = input channels (contiguous)
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_2d(sB + j * 8192, &tmB, tap * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
-          if (++cc == a.cchunks) { cc = 0; ++tap; }
         } else {
           tma_load_2d(sB, &tmB, kb * kBlockK, n0, &full[stage]);
         }
-        if (kATma) tma_load_2d(smem_u32(sA), &tmA, kb * kBlockK, m0, &full[stage]);
+        if (MODE == kConvGemm || MODE == kConvGemmDgrad) {
+          tma_load_2d(smem_u32(sA), &tmA, kb * kBlockK, m0, &full[stage]);
+        } else if (MODE == kConvTileFwd) {
+          tma_load_4d(smem_u32(sA), &tmA, cc * 64, tq0 - a.pad + tap_s * a.dil, tp0 - a.pad + tap_r * a.dil, tn0,
+                      &full[stage]);
+        } else if (MODE == kConvTileDgrad) {
+          tma_load_4d(smem_u32(sA), &tmA, cc * 64, tq0 + a.pad - tap_s * a.dil, tp0 + a.pad - tap_r * a.dil, tn0,
+                      &full[stage]);
+        }
+        if (++cc == a.cchunks) { cc = 0; ++tap; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     // =================================== MMA issuer =======================================
     constexpr uint32_t idesc = idesc_bf16(kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
     for (int kb = 0; kb < KB; ++kb) {
-      const int stage = kb % Cfg::kStages;
-      const uint32_t phase = (kb / Cfg::kStages) & 1u;
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
@@ -280,6 +361,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
         if (kb == KB - 1) umma_commit(acc_full);
       }
       __syncwarp();
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
     }
   }
 
@@ -294,21 +376,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
 // ---------------------------------------------------------------------------------------------
 // wgrad kernel: dW[co][k] += sum over a pixel range of dY[m][co] * im2col(X)[m][k]
 // ---------------------------------------------------------------------------------------------
-constexpr int kWgStages = 3;
+constexpr int kWgMaxStages = 3;
 constexpr int kWgStageBytes = 32768;           // A: 2 x [64 pix][64 co], B: 2 x [64 pix][64 k]
 constexpr int kWgPitch = 132;                  // fp32 staging pitch (floats)
-constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 256 + 1024;
-static_assert(kBlockM * kWgPitch * 4 <= kWgStages * kWgStageBytes, "wgrad staging must fit");
+constexpr int kWgEpiBytes = kBlockM * kWgPitch * 4;
+constexpr int wg_smem_bytes(int stages) {
+  return (stages * kWgStageBytes > kWgEpiBytes ? stages * kWgStageBytes : kWgEpiBytes) + 256 + 1024;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, WgradArgs a) {
-  constexpr bool kXTma = (MODE == kConvGemm);
+  constexpr bool kXTma = (MODE == kConvGemm || MODE == kConvTileFwd);
+  constexpr bool kTile = (MODE == kConvTileFwd);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
-  uint64_t* empty = full + kWgStages;
-  uint64_t* acc_full = empty + kWgStages;
+  const int nstages = a.stages;
+  const int pipe_bytes = nstages * kWgStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (pipe_bytes > kWgEpiBytes ? pipe_bytes : kWgEpiBytes));
+  uint64_t* empty = full + kWgMaxStages;
+  uint64_t* acc_full = empty + kWgMaxStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -320,7 +407,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   if (KB <= 0) return;                         // uniform per CTA
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kWgStages; ++s) {
+    for (int s = 0; s < nstages; ++s) {
       mbar_init(&full[s], kXTma ? 1u : (kProducerThreads + 1u));
       mbar_init(&empty[s], 1u);
     }
@@ -332,6 +419,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     if (kXTma) tma_prefetch_desc(&tmX);
   }
   if (warp == 5) tmem_alloc<128>(tmem_slot);
+  if (kTile) {
+    // pixel boxes may hold fewer than 64 rows: the unused K rows of EVERY operand chunk must read as zero
+    const int rows = a.tw * a.th * a.tn;
+    const int tail16 = (64 - rows) * 8;        // 16-byte units per 8 KB chunk
+    for (int st = 0; st < nstages; ++st)
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        uint4* base = reinterpret_cast<uint4*>(smem + st * kWgStageBytes + chunk * 8192 + rows * 128);
+        for (int i = threadIdx.x; i < tail16; i += kThreads) base[i] = make_uint4(0, 0, 0, 0);
+      }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -353,9 +451,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       const uint32_t row_off = 16384u + chunk * 8192u + row * 128u;
       const uint32_t sw = row & 7u;
       const int pq = a.P * a.Q;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int i = 0; i < KB; ++i) {
-        const int stage = i % kWgStages;
-        const uint32_t phase = (i / kWgStages) & 1u;
         mbar_wait(&empty[stage], phase ^ 1u);
         const uint32_t dst = smem_u32(smem + stage * kWgStageBytes) + row_off;
         const int m = (kb_begin + i) * 64 + row;
@@ -395,12 +493,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         if (i >= kLag) {
           cp_async_wait<kLag>();
           fence_proxy_async_smem();
-          mbar_arrive(&full[(i - kLag) % kWgStages]);
+          mbar_arrive(&full[(i - kLag) % nstages]);
         }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
       cp_async_wait<0>();
       fence_proxy_async_smem();
-      for (int i = (KB > kLag ? KB - kLag : 0); i < KB; ++i) mbar_arrive(&full[i % kWgStages]);
+      for (int i = (KB > kLag ? KB - kLag : 0); i < KB; ++i) mbar_arrive(&full[i % nstages]);
     }
 
     // epilogue: TMEM -> fp32 staging -> coalesced vector reductions into the gradient arena
@@ -434,26 +533,55 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     }
   } else if (warp == 4) {
     if (elect_one()) {
+      // taps / channel offsets of the two 64-column chunks of the B tile (tile mode)
+      int tr[2] = {0, 0}, ts[2] = {0, 0}, tc0[2] = {0, 0};
+      if (kTile) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int colc = col0 + j * 64;
+          const int tap = colc / a.C;
+          tc0[j] = colc - tap * a.C;
+          tr[j] = tap / a.S;
+          ts[j] = tap - tr[j] * a.S;
+        }
+      }
+      const uint32_t box_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : 8192u;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int i = 0; i < KB; ++i) {
-        const int stage = i % kWgStages;
-        const uint32_t phase = (i / kWgStages) & 1u;
         mbar_wait(&empty[stage], phase ^ 1u);
         const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
-        const int m = (kb_begin + i) * 64;
-        mbar_arrive_expect_tx(&full[stage], 16384u + (kXTma ? 16384u : 0u));
-        tma_load_2d(sA, &tmDy, co0, m, &full[stage]);
-        tma_load_2d(sA + 8192, &tmDy, co0 + 64, m, &full[stage]);
-        if (kXTma) {
-          tma_load_2d(sA + 16384, &tmX, col0, m, &full[stage]);
-          tma_load_2d(sA + 24576, &tmX, col0 + 64, m, &full[stage]);
+        if (kTile) {
+          int t = kb_begin + i;
+          const int wb = t % a.tiles_w; t /= a.tiles_w;
+          const int hb = t % a.tiles_h;
+          const int nb = t / a.tiles_h;
+          const int q0 = wb * a.tw, p0 = hb * a.th, n0 = nb * a.tn;
+          const bool second = (col0 + 64) < a.ncols;
+          mbar_arrive_expect_tx(&full[stage], box_bytes * (second ? 4u : 3u));
+          tma_load_4d(sA, &tmDy, co0, q0, p0, n0, &full[stage]);
+          tma_load_4d(sA + 8192, &tmDy, co0 + 64, q0, p0, n0, &full[stage]);
+          tma_load_4d(sA + 16384, &tmX, tc0[0], q0 - a.pad + ts[0] * a.dil, p0 - a.pad + tr[0] * a.dil, n0, &full[stage]);
+          if (second)
+            tma_load_4d(sA + 24576, &tmX, tc0[1], q0 - a.pad + ts[1] * a.dil, p0 - a.pad + tr[1] * a.dil, n0, &full[stage]);
+        } else {
+          const int m = (kb_begin + i) * 64;
+          mbar_arrive_expect_tx(&full[stage], 16384u + (kXTma ? 16384u : 0u));
+          tma_load_2d(sA, &tmDy, co0, m, &full[stage]);
+          tma_load_2d(sA + 8192, &tmDy, co0 + 64, m, &full[stage]);
+          if (kXTma) {
+            tma_load_2d(sA + 16384, &tmX, col0, m, &full[stage]);
+            tma_load_2d(sA + 24576, &tmX, col0 + 64, m, &full[stage]);
+          }
         }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
     for (int i = 0; i < KB; ++i) {
-      const int stage = i % kWgStages;
-      const uint32_t phase = (i / kWgStages) & 1u;
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
@@ -469,6 +597,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         if (i == KB - 1) umma_commit(acc_full);
       }
       __syncwarp();
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
     }
   }
   tc_fence_before();
@@ -510,60 +639,93 @@ bool make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t col
   return r == CUDA_SUCCESS;
 }
 
+// 4-D NHWC bf16 activation [N][H][W][C]; box = {64 channels, tw, th, tn}; out-of-bounds -> zeros.
+bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int tw, int th, int tn) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tn)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 template <int BLOCK_N, int MODE, bool STATS>
-cudaError_t launch_fwd_t(const CUtensorMap& tmB, const CUtensorMap& tmA, const ConvArgs& a, int n_total,
+cudaError_t launch_fwd_t(const CUtensorMap& tmB, const CUtensorMap& tmA, const ConvArgs& a, int n_total, int m_tiles,
                          cudaStream_t stream) {
   using Cfg = FwdCfg<BLOCK_N>;
   auto kern = conv_gemm_kernel<BLOCK_N, MODE, STATS>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  static int configured = 0;
+  const int smem = Cfg::smem_bytes(a.stages);
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::smem_bytes(Cfg::kMaxStagesN));
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured = Cfg::smem_bytes(Cfg::kMaxStagesN);
   }
-  dim3 grid(n_total / BLOCK_N, (a.M + kBlockM - 1) / kBlockM);
-  kern<<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmB, tmA, a);
+  dim3 grid(n_total / BLOCK_N, m_tiles);
+  kern<<<grid, kThreads, smem, stream>>>(tmB, tmA, a);
   return cudaGetLastError();
 }
 
 template <int MODE>
-cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmA, const ConvArgs& a, int n_total,
+cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmA, ConvArgs a, int n_total, int m_tiles,
                             bool stats, cudaStream_t stream) {
   if (n_total % 128 == 0) {
-    return stats ? launch_fwd_t<128, MODE, true>(tmB, tmA, a, n_total, stream)
-                 : launch_fwd_t<128, MODE, false>(tmB, tmA, a, n_total, stream);
+    a.stages = a.KB < FwdCfg<128>::kMaxStagesN ? a.KB : FwdCfg<128>::kMaxStagesN;
+    if (!mode_a_tma(MODE) && a.stages < 3 && a.KB >= 3) a.stages = 3;
+    return stats ? launch_fwd_t<128, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
+                 : launch_fwd_t<128, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
   }
   if (n_total % 64 == 0) {
-    return stats ? launch_fwd_t<64, MODE, true>(tmB, tmA, a, n_total, stream)
-                 : launch_fwd_t<64, MODE, false>(tmB, tmA, a, n_total, stream);
+    a.stages = a.KB < FwdCfg<64>::kMaxStagesN ? a.KB : FwdCfg<64>::kMaxStagesN;
+    return stats ? launch_fwd_t<64, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
+                 : launch_fwd_t<64, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
   }
   return cudaErrorInvalidValue;
 }
 
 }  // namespace
 
-// `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad).
-cudaError_t launch_conv_gemm(int mode, const ConvArgs& a, const void* w, int w_rows, int w_cols, int n_total,
+// `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
+// `a_matrix`: the A operand for the TMA-A modes (2-D matrix [M][a_cols], or the NHWC tensor in tile modes).
+cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int w_rows, int w_cols, int n_total,
                              const void* a_matrix, int a_cols, cudaStream_t stream) {
+  ConvArgs a = a_in;
   CUtensorMap tmB, tmA;
   const int bn = (n_total % 128 == 0) ? 128 : 64;
   if (n_total % 64 != 0) return cudaErrorInvalidValue;
-  if (mode == kConvDgrad) {
+  if (mode_b_mn(mode)) {
     if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, 64)) return cudaErrorUnknown;
   } else {
     if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, bn)) return cudaErrorUnknown;
   }
-  if (mode == kConvGemm) {
+  int m_tiles = (a.M + kBlockM - 1) / kBlockM;
+  if (mode == kConvGemm || mode == kConvGemmDgrad) {
     if (!make_map_2d(&tmA, a_matrix, a.M, a_cols, a_cols, 64, 128)) return cudaErrorUnknown;
+  } else if (mode_tile(mode)) {
+    if (a.tw * a.th * a.tn > 128 || a.tw < 1 || a.th < 1 || a.tn < 1) return cudaErrorInvalidValue;
+    if (!make_map_nhwc(&tmA, a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+    a.tiles_w = (a.dstW + a.tw - 1) / a.tw;
+    a.tiles_h = (a.dstH + a.th - 1) / a.th;
+    m_tiles = a.tiles_w * a.tiles_h * ((a.batch + a.tn - 1) / a.tn);
   } else {
     tmA = tmB;
   }
   const bool stats = a.sum != nullptr;
   switch (mode) {
-    case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmA, a, n_total, stats, stream);
-    case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmA, a, n_total, stats, stream);
-    case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmA, a, n_total, stats, stream);
-    case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmA, a, n_total, stats, stream);
+    case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmA, a, n_total, m_tiles, stats, stream);
+    case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmA, a, n_total, m_tiles, stats, stream);
+    case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmA, a, n_total, m_tiles, stats, stream);
+    case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmA, a, n_total, m_tiles, stats, stream);
+    case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(tmB, tmA, a, n_total, m_tiles, stats, stream);
+    case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(tmB, tmA, a, n_total, m_tiles, stats, stream);
+    case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(tmB, tmA, a, n_total, m_tiles, stats, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -572,33 +734,47 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void*
                               cudaStream_t stream) {
   WgradArgs a = a_in;
   CUtensorMap tmDy, tmX;
-  if (!make_map_2d(&tmDy, dy, a.M, a.dy_ld, a.dy_ld, 64, 64)) return cudaErrorUnknown;
-  if (a.mode == kConvGemm) {
-    if (!make_map_2d(&tmX, x_matrix, a.M, a.ncols, a.ncols, 64, 64)) return cudaErrorUnknown;
+  if (a.mode == kConvTileFwd) {
+    if (a.tw * a.th * a.tn > 64 || a.tw < 1 || a.th < 1 || a.tn < 1) return cudaErrorInvalidValue;
+    if (!make_map_nhwc(&tmDy, dy, a.batch, a.P, a.Q, a.dy_ld, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+    if (!make_map_nhwc(&tmX, x_matrix, a.batch, a.H, a.W, a.C, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+    a.tiles_w = (a.Q + a.tw - 1) / a.tw;
+    a.tiles_h = (a.P + a.th - 1) / a.th;
+    a.total_kb = a.tiles_w * a.tiles_h * ((a.batch + a.tn - 1) / a.tn);
   } else {
-    tmX = tmDy;
+    if (!make_map_2d(&tmDy, dy, a.M, a.dy_ld, a.dy_ld, 64, 64)) return cudaErrorUnknown;
+    if (a.mode == kConvGemm) {
+      if (!make_map_2d(&tmX, x_matrix, a.M, a.ncols, a.ncols, 64, 64)) return cudaErrorUnknown;
+    } else {
+      tmX = tmDy;
+    }
+    a.total_kb = (a.M + 63) / 64;
   }
-  a.total_kb = (a.M + 63) / 64;
   if (splits < 1) splits = 1;
   if (splits > a.total_kb) splits = a.total_kb;
   a.kb_per_split = (a.total_kb + splits - 1) / splits;
   splits = (a.total_kb + a.kb_per_split - 1) / a.kb_per_split;
+  a.stages = a.kb_per_split < kWgMaxStages ? a.kb_per_split : kWgMaxStages;
+  if (a.stages < 1) a.stages = 1;
+  const int smem = wg_smem_bytes(a.stages);
   dim3 grid((a.ncols + 127) / 128, (a.Cout + 127) / 128, splits);
-  static bool configured[4] = {false, false, false, false};
+  static bool configured[8] = {false, false, false, false, false, false, false, false};
 #define DDL_WG(MODE)                                                                                          \
   do {                                                                                                        \
     auto kern = conv_wgrad_kernel<MODE>;                                                                      \
     if (!configured[MODE]) {                                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);  \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
+                                           wg_smem_bytes(kWgMaxStages));                                      \
       if (e != cudaSuccess) return e;                                                                         \
       configured[MODE] = true;                                                                                \
     }                                                                                                         \
-    kern<<<grid, kThreads, kWgSmemBytes, stream>>>(tmDy, tmX, a);                                             \
+    kern<<<grid, kThreads, smem, stream>>>(tmDy, tmX, a);                                                     \
   } while (0)
   switch (a.mode) {
     case kConvFwd: DDL_WG(kConvFwd); break;
     case kConvGemm: DDL_WG(kConvGemm); break;
     case kConvStem: DDL_WG(kConvStem); break;
+    case kConvTileFwd: DDL_WG(kConvTileFwd); break;
     default: return cudaErrorInvalidValue;
   }
 #undef DDL_WG

@@ -9,28 +9,35 @@
 namespace ddl {
 
 enum ConvMode : int {
-  kConvFwd = 0,     // A = im2col(x) gathered, rows = output pixels
-  kConvDgrad = 1,   // A = transposed-conv gather of dy, rows = input pixels, B is MN-major
-  kConvGemm = 2,    // A is a plain [M][K] matrix fetched by TMA (1x1 stride-1 convs, FC)
-  kConvStem = 3,    // 7x7 s2 conv on a 4-channel (3+pad) image: k-block = 2 filter rows x 8 taps x 4 ch
+  kConvFwd = 0,        // A = im2col(x) gathered with cp.async, rows = output pixels (any stride / dilation)
+  kConvDgrad = 1,      // A = transposed-conv gather of dy, rows = input pixels, B is MN-major (any stride)
+  kConvGemm = 2,       // A is a plain [M][K] matrix fetched by 2-D TMA (1x1 stride-1 convs, FC)
+  kConvStem = 3,       // small-Cin first conv on a 4-channel image: k-block = RPK filter rows x SP taps x 4 ch
+  kConvTileFwd = 4,    // stride-1 conv: A tile = rectangle of output pixels fetched by ONE 4-D TMA box per tap
+                       //   (padding = TMA out-of-bounds zero fill), rows = (n, h, w) of the rectangle
+  kConvTileDgrad = 5,  // same for the data gradient of a stride-1 conv (source = dy, B MN-major)
+  kConvGemmDgrad = 6,  // 1x1 stride-1 data gradient: A = dy matrix via 2-D TMA, B MN-major
 };
 
 struct ConvArgs {
-  const __nv_bfloat16* src;   // gather source (x for fwd / stem, dy for dgrad); unused for kConvGemm
+  const __nv_bfloat16* src;   // gather source (x for fwd / stem, dy for dgrad); unused for TMA-A modes
   __nv_bfloat16* out;         // [M][ldc] (NHWC activations / gradients)
   const __nv_bfloat16* add;   // optional: out = acc + add   (same layout as out)
   const float* bias;          // optional: per output channel
   float* sum;                 // optional BN statistics: sum[c]   += sum_m out[m][c]   (of the bf16-rounded value)
   float* sumsq;               //                         sumsq[c] += sum_m out[m][c]^2
-  int M;                      // GEMM rows
+  int M;                      // GEMM rows (= batch * dstH * dstW)
   int KB;                     // number of 64-element k-blocks
   int ldc;                    // channels of `out` (row stride in elements)
   int srcH, srcW, srcC;       // gather-source geometry
-  int dstH, dstW;             // GEMM-row geometry (M = batch * dstH * dstW)
+  int dstH, dstW;             // GEMM-row geometry
   int R, S, stride, pad, dil;
-  int cchunks;                // srcC / 64
+  int cchunks;                // srcC / 64   (stem: padded taps per filter row)
   int relu;                   // apply ReLU in the epilogue (after bias)
   int n_valid;                // output channels that really exist (bias is read only below this)
+  int stages;                 // pipeline depth actually used (<= compile-time maximum)
+  // tile modes: the M tile is a tw x th x tn box of output pixels (w fastest); tw*th*tn <= 128
+  int batch, tw, th, tn, tiles_w, tiles_h;
 };
 
 struct WgradArgs {
@@ -45,9 +52,11 @@ struct WgradArgs {
   int P, Q;                   // dy geometry
   int R, S, stride, pad, dil;
   int cchunks;                // C / 64
-  int kb_per_split;           // 64-pixel blocks handled by one CTA
-  int total_kb;               // ceil(M / 64)
-  int mode;                   // kConvFwd (gather), kConvGemm (x via TMA), kConvStem
+  int kb_per_split;           // pixel blocks handled by one CTA
+  int total_kb;               // number of pixel blocks
+  int mode;                   // kConvFwd (gather), kConvGemm (x via 2-D TMA), kConvStem, kConvTileFwd (4-D TMA)
+  int stages;
+  int batch, tw, th, tn, tiles_w, tiles_h;   // tile mode: a pixel block is a tw x th x tn box (<= 64 pixels)
 };
 
 }  // namespace ddl

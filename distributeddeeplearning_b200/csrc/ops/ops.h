@@ -36,7 +36,9 @@ struct BnBwdArgs {
   float* dbeta;                   // [C] scratch
   float* gamma_grad;              // optional accumulate targets (parameter gradients)
   float* beta_grad;
+  const float* beta;              // needed when the ReLU mask is recomputed from x (mask_from_x)
   int M, C, relu;
+  int mask_from_x;                // no residual: z > 0  <=>  x*scale + shift > 0, so z is never read
 };
 
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream);

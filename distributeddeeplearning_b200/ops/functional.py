@@ -117,7 +117,8 @@ class _ConvBnAct(torch.autograd.Function):
             dz = dz.contiguous(memory_format=CL)
         gg = grad_buffer(gamma) if gamma.requires_grad else None
         bg = grad_buffer(beta) if beta.requires_grad else None
-        dy, dres, _ = native.bn_act_bwd(dz, z, y, save, gamma, relu, has_res and ctx.needs_input_grad[1], gg, bg)
+        dy, dres, _ = native.bn_act_bwd(dz, z, y, save, gamma, relu, has_res and ctx.needs_input_grad[1], gg, bg,
+                                        beta=beta, had_residual=has_res)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil)

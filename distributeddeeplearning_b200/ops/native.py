@@ -9,6 +9,7 @@ cast of the fp32 master, and wgrad writes the fp32 gradient in the same layout.
 from __future__ import annotations
 
 import functools
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -66,6 +67,22 @@ def stem_geometry(R: int, S: int) -> Tuple[int, int, int, int]:
     return SP, RPK, KB, KB * RPK
 
 
+USE_TILE_TMA = os.environ.get("DDL_DISABLE_TILE_TMA", "0") != "1"
+
+
+def tile_geometry(P: int, Q: int, N: int, max_rows: int) -> Tuple[int, int, int]:
+    """(tw, th, tn): the box of output pixels one TMA request covers (w fastest), tw*th*tn <= max_rows."""
+    if Q > max_rows:
+        nw = -(-Q // max_rows)
+        return -(-Q // nw), 1, 1
+    tw = Q
+    th = max(1, min(P, max_rows // tw))
+    tn = 1
+    if th == P:
+        tn = max(1, min(N, max_rows // (tw * th)))
+    return tw, th, tn
+
+
 def supports_conv(cin: int, cout: int) -> bool:
     """Shapes the tcgen05 implicit-GEMM kernels handle natively."""
     return cout % 64 == 0 and (cin % 64 == 0 or cin <= 4)
@@ -97,15 +114,21 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
         SP, RPK, KB, RP = stem_geometry(R, S)
         C.conv_gemm(C.CONV_STEM, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, H, W, 4,
                     P, Q, R, S, stride, pad, dil, SP, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cout, 0, 0, _stream())
+                    w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, _stream())
     elif R == 1 and S == 1 and stride == 1 and pad == 0:
         C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, Cin // 64, Cout, H, W, Cin, P, Q,
                     1, 1, 1, 0, 1, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1],
-                    Cout, x.data_ptr(), Cin, _stream())
+                    Cout, x.data_ptr(), Cin, N, 0, 0, 0, _stream())
+    elif stride == 1 and USE_TILE_TMA:
+        # stride-1 window conv: the activation operand comes through ONE 4-D TMA box per filter tap
+        tw, th, tn = tile_geometry(P, Q, N, 128)
+        C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64), Cout, H, W,
+                    Cin, P, Q, R, S, 1, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
+                    w_bf16.shape[1], Cout, x.data_ptr(), Cin, N, tw, th, tn, _stream())
     else:
         C.conv_gemm(C.CONV_FWD, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64),
                     Cout, H, W, Cin, P, Q, R, S, stride, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(),
-                    w_bf16.shape[0], w_bf16.shape[1], Cout, 0, 0, _stream())
+                    w_bf16.shape[0], w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, _stream())
     return (y, st) if stats else y
 
 
@@ -122,9 +145,19 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
     dx = empty_act(N, Cin, H, W, dy.device)
     if add is not None:
         _check_act(add, "add")
-    C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin,
-                P, Q, Cout, H, W, R, S, stride, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
-                w_bf16.shape[1], Cin, 0, 0, _stream())
+    if R == 1 and S == 1 and stride == 1 and pad == 0:
+        C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, Cout // 64, Cin, P, Q, Cout, H,
+                    W, 1, 1, 1, 0, 1, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1], Cin,
+                    dy.data_ptr(), Cout, N, 0, 0, 0, _stream())
+    elif stride == 1 and USE_TILE_TMA:
+        tw, th, tn = tile_geometry(H, W, N, 128)
+        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin, P, Q,
+                    Cout, H, W, R, S, 1, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
+                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, _stream())
+    else:
+        C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64),
+                    Cin, P, Q, Cout, H, W, R, S, stride, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(),
+                    w_bf16.shape[0], w_bf16.shape[1], Cin, 0, 0, N, 0, 0, 0, _stream())
     return dx
 
 
@@ -152,17 +185,24 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: 
         scratch = torch.zeros((Cout, ncols), dtype=torch.float32, device=x.device)
         tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
         C.conv_wgrad(C.CONV_STEM, x.data_ptr(), dy.data_ptr(), scratch.data_ptr(), M, Cout, Cout, ncols, ncols, H, W,
-                     4, P, Q, R, S, stride, pad, dil, SP, _wgrad_splits(tiles, (M + 63) // 64, dev), _stream())
+                     4, P, Q, R, S, stride, pad, dil, SP, _wgrad_splits(tiles, (M + 63) // 64, dev), N, 0, 0, 0,
+                     _stream())
         # grad_w is KRSC with the TRUE channel count (3): fold the packed scratch back
         cin_true = grad_w.shape[1]
         C.unpack_stem_grad(scratch.data_ptr(), grad_w.data_ptr(), Cout, R, S, cin_true, RP, SP, _stream())
         return
     ncols = R * S * Cin
     tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
-    splits = _wgrad_splits(tiles, (M + 63) // 64, dev)
-    mode = C.CONV_GEMM if (R == 1 and S == 1 and stride == 1 and pad == 0) else C.CONV_FWD
+    if R == 1 and S == 1 and stride == 1 and pad == 0:
+        mode, (tw, th, tn), total_kb = C.CONV_GEMM, (0, 0, 0), (M + 63) // 64
+    elif stride == 1 and USE_TILE_TMA:
+        mode, (tw, th, tn) = C.CONV_TILE_FWD, tile_geometry(P, Q, N, 64)
+        total_kb = -(-Q // tw) * -(-P // th) * -(-N // tn)
+    else:
+        mode, (tw, th, tn), total_kb = C.CONV_FWD, (0, 0, 0), (M + 63) // 64
+    splits = _wgrad_splits(tiles, total_kb, dev)
     C.conv_wgrad(mode, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), M, Cout, Cout, ncols, ncols, H, W, Cin, P, Q,
-                 R, S, stride, pad, dil, Cin // 64, splits, _stream())
+                 R, S, stride, pad, dil, Cin // 64, splits, N, tw, th, tn, _stream())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -179,7 +219,7 @@ def linear_fwd(x: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tenso
     Npad = (Nout + 63) // 64 * 64
     y = torch.empty((B, Npad), dtype=torch.bfloat16, device=x.device)
     C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), 0, 0, B, K // 64, Npad, 1, 1, K, 1, 1, 1, 1, 1, 0, 1,
-                K // 64, int(relu), Nout, w_bf16.data_ptr(), Nout, K, Npad, x.data_ptr(), K, _stream())
+                K // 64, int(relu), Nout, w_bf16.data_ptr(), Nout, K, Npad, x.data_ptr(), K, B, 0, 0, 0, _stream())
     return y
 
 
@@ -189,8 +229,8 @@ def linear_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor) -> torch.Tensor:
     B, Npad = dy.shape
     Nout, K = w_bf16.shape
     dx = torch.empty((B, K), dtype=torch.bfloat16, device=dy.device)
-    C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), 0, 0, 0, 0, B, Npad // 64, K, 1, 1, Npad, 1, 1, 1, 1, 1, 0,
-                1, Npad // 64, 0, K, w_bf16.data_ptr(), Nout, K, K, 0, 0, _stream())
+    C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, B, Npad // 64, K, 1, 1, Npad, 1, 1, 1, 1, 1, 0,
+                1, Npad // 64, 0, K, w_bf16.data_ptr(), Nout, K, K, dy.data_ptr(), Npad, B, 0, 0, 0, _stream())
     return dx
 
 
@@ -203,7 +243,7 @@ def linear_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor) -> Non
     tiles = ((K + 127) // 128) * ((Nout + 127) // 128)
     splits = _wgrad_splits(tiles, (B + 63) // 64, x.device.index or 0)
     C.conv_wgrad(C.CONV_GEMM, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), B, Nout, Npad, K, K, 1, 1, K, 1, 1, 1,
-                 1, 1, 0, 1, K // 64, splits, _stream())
+                 1, 1, 0, 1, K // 64, splits, B, 0, 0, 0, _stream())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -238,7 +278,8 @@ def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, runn
 
 
 def bn_act_bwd(dz: torch.Tensor, z: torch.Tensor, y: torch.Tensor, save: torch.Tensor, gamma: torch.Tensor,
-               relu: bool, want_dres: bool, gamma_grad: Optional[torch.Tensor], beta_grad: Optional[torch.Tensor]):
+               relu: bool, want_dres: bool, gamma_grad: Optional[torch.Tensor], beta_grad: Optional[torch.Tensor],
+               beta: Optional[torch.Tensor] = None, had_residual: bool = True):
     """Returns (dy, dres|None); accumulates into gamma_grad / beta_grad (fp32) when given."""
     C = _C()
     _check_act(dz, "dz")
@@ -247,9 +288,11 @@ def bn_act_bwd(dz: torch.Tensor, z: torch.Tensor, y: torch.Tensor, save: torch.T
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
     scratch = torch.zeros((2, Ch), dtype=torch.float32, device=y.device)
+    mask_from_x = bool(relu and beta is not None and not had_residual)     # z is not read at all in that case
     C.bn_act_bwd(dz.data_ptr(), z.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dres), save[0].data_ptr(),
-                 save[1].data_ptr(), gamma.data_ptr(), scratch[0].data_ptr(), scratch[1].data_ptr(), _ptr(gamma_grad),
-                 _ptr(beta_grad), M, Ch, int(relu), sm_count(y.device.index or 0), _stream())
+                 save[1].data_ptr(), gamma.data_ptr(), _ptr(beta), scratch[0].data_ptr(), scratch[1].data_ptr(),
+                 _ptr(gamma_grad), _ptr(beta_grad), M, Ch, int(relu), int(mask_from_x), sm_count(y.device.index or 0),
+                 _stream())
     return dy, dres, scratch
 
 
