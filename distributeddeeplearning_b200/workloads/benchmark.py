@@ -28,6 +28,7 @@ import torch
 from .. import models, ops
 from ..data import fixed_synthetic_batch
 from ..parallel import Compression, DistributedOptimizer, dist
+from ..utils.faults import maybe_inject
 
 
 def build_parser() -> argparse.ArgumentParser:
@@ -83,6 +84,7 @@ class BenchmarkSession:
         self.data, self.target = fixed_synthetic_batch(batch_size, size, self.num_classes, self.device, seed=seed + 17)
         self.batch_size = batch_size
         self.last_loss: Optional[torch.Tensor] = None
+        self.steps_done = 0
 
     def loss_fn(self, output, target):
         if isinstance(output, tuple):           # Inception-v3 in train mode: (logits, aux)
@@ -94,6 +96,8 @@ class BenchmarkSession:
     def step(self, data=None, target=None):
         data = self.data if data is None else data
         target = self.target if target is None else target
+        maybe_inject(self.steps_done, dist.rank())
+        self.steps_done += 1
         self.optimizer.zero_grad()
         output = self.model(data)
         loss = self.loss_fn(output, target)
