@@ -5,11 +5,15 @@
 // (conv_gemm.cu, STATS) — the activation tensor is never re-read just to reduce it.
 //
 //   forward   z = relu( (x - mean) * invstd * gamma + beta  (+ residual) )          1 read (+1), 1 write
-//   backward  pass 1: dbeta = sum dy, dgamma = sum dy * xhat   with dy = dz * (z > 0)
+//   backward  pass 1: dbeta = sum dy, dgamma = sum dy * xhat   with dy = dz * mask
 //             pass 2: dx = gamma*invstd * (dy - dbeta/M - xhat*dgamma/M),  dres = dy
+//   mask: none (no ReLU) | z > 0 (residual layers; z is read) | x*scale + shift > 0 (no residual: the
+//   mask is recomputed from x, so z is never read: 2 reads in pass 1, 2 reads + 1 write in pass 2)
 //
 // Thread mapping: a thread owns 8 consecutive channels (one 16-byte vector) of a FIXED channel
-// group and walks rows with a grid stride, so per-channel constants live in registers.
+// group and walks rows with a grid stride, so per-channel constants live in registers.  The loops
+// work on raw x (sum dy*x, then a closed-form fix-up) to keep the live register set under 64 so that
+// 4 CTAs x 256 threads stay resident per SM (these kernels are pure HBM streams).
 #include "../common.cuh"
 #include "ops.h"
 
@@ -18,20 +22,18 @@ namespace ddl {
 namespace {
 
 constexpr int kBnThreads = 256;
+enum { kMaskNone = 0, kMaskZ = 1, kMaskX = 2 };
 
 struct Vec8 {
   float v[8];
 };
-DDL_DEVICE Vec8 load8_bf16(const __nv_bfloat16* p) {
-  const uint4 u = *reinterpret_cast<const uint4*>(p);
-  Vec8 r;
+DDL_DEVICE void unpack8(const uint4& u, float (&v)[8]) {
   float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
-  return r;
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
 }
-DDL_DEVICE void store8_bf16(__nv_bfloat16* p, const Vec8& r) {
-  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(r.v[0], r.v[1]), pack_bf16x2(r.v[2], r.v[3]),
-                                            pack_bf16x2(r.v[4], r.v[5]), pack_bf16x2(r.v[6], r.v[7]));
+DDL_DEVICE void store8_bf16(__nv_bfloat16* p, const float (&v)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                            pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
 }
 DDL_DEVICE Vec8 load8_f32(const float* p) {
   const float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
@@ -44,7 +46,7 @@ DDL_DEVICE Vec8 load8_f32(const float* p) {
 // TRAIN: scale/shift derived from (sum, sumsq); also emits mean/invstd (saved for backward) and
 // updates running stats.  EVAL: scale/shift from running stats.
 template <bool TRAIN>
-__global__ void __launch_bounds__(kBnThreads) bn_act_fwd_kernel(BnFwdArgs a) {
+__global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) {
   const int groups = a.C / 8;                       // channel groups per row
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = tid % groups;
@@ -85,142 +87,142 @@ __global__ void __launch_bounds__(kBnThreads) bn_act_fwd_kernel(BnFwdArgs a) {
   }
   for (int r = row0; r < a.M; r += row_stride) {
     const size_t off = static_cast<size_t>(r) * a.C + c0;
-    Vec8 x = load8_bf16(a.x + off);
-    Vec8 z;
+    float x[8], z[8];
+    unpack8(ld_stream_u4(a.x + off), x);
     if (a.residual) {
-      Vec8 res = load8_bf16(a.residual + off);
+      float res[8];
+      unpack8(ld_stream_u4(a.residual + off), res);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) z.v[i] = fmaf(x.v[i], scale[i], shift[i]) + res.v[i];
+      for (int i = 0; i < 8; ++i) z[i] = fmaf(x[i], scale[i], shift[i]) + res[i];
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) z.v[i] = fmaf(x.v[i], scale[i], shift[i]);
+      for (int i = 0; i < 8; ++i) z[i] = fmaf(x[i], scale[i], shift[i]);
     }
     if (a.relu) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) z.v[i] = fmaxf(z.v[i], 0.f);
+      for (int i = 0; i < 8; ++i) z[i] = fmaxf(z[i], 0.f);
     }
     store8_bf16(a.z + off, z);
   }
 }
 
 // ---- backward pass 1: per-channel reductions ----------------------------------------------------
-__global__ void __launch_bounds__(kBnThreads) bn_act_bwd_reduce_kernel(BnBwdArgs a) {
+// accumulates S1 = sum dy and S2 = sum dy * x (raw x); dbeta = S1, dgamma = invstd * (S2 - mean * S1)
+template <int MASK>
+__global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdArgs a) {
   const int groups = a.C / 8;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = tid % groups;
   const int row0 = tid / groups;
   const int row_stride = (gridDim.x * blockDim.x) / groups;
   const int c0 = g * 8;
-  Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0);
-  float sdy[8], sdyx[8], msc[8], msh[8];
+  float s1[8], s2[8], msc[8], msh[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { sdy[i] = 0.f; sdyx[i] = 0.f; msc[i] = 0.f; msh[i] = 0.f; }
-  if (a.relu && a.mask_from_x) {
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; msc[i] = 0.f; msh[i] = 0.f; }
+  if (MASK == kMaskX) {
+    Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0);
     Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { msc[i] = gam.v[i] * invstd.v[i]; msh[i] = bet.v[i] - mean.v[i] * msc[i]; }
   }
   for (int r = row0; r < a.M; r += row_stride) {
     const size_t off = static_cast<size_t>(r) * a.C + c0;
-    Vec8 dz = load8_bf16(a.dz + off);
-    Vec8 x = load8_bf16(a.x + off);
-    if (a.relu) {
-      if (a.mask_from_x) {
+    float dz[8], x[8];
+    unpack8(ld_stream_u4(a.dz + off), dz);
+    unpack8(ld_stream_u4(a.x + off), x);
+    if (MASK == kMaskZ) {
+      float z[8];
+      unpack8(ld_stream_u4(a.z + off), z);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dz.v[i] = fmaf(x.v[i], msc[i], msh[i]) > 0.f ? dz.v[i] : 0.f;
-      } else {
-        Vec8 z = load8_bf16(a.z + off);
+      for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? dz[i] : 0.f;
+    } else if (MASK == kMaskX) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
-      }
+      for (int i = 0; i < 8; ++i) dz[i] = fmaf(x[i], msc[i], msh[i]) > 0.f ? dz[i] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      sdy[i] += dz.v[i];
-      sdyx[i] = fmaf(dz.v[i], (x.v[i] - mean.v[i]) * invstd.v[i], sdyx[i]);
+      s1[i] += dz[i];
+      s2[i] = fmaf(dz[i], x[i], s2[i]);
     }
   }
-  // threads of a block that share a channel group: blockDim / groups (>= 1 when groups <= 256)
+  // fold the threads of this block that share a channel group, then 16 atomics per group per block
   __shared__ float red[2][kBnThreads][8 + 1];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = sdy[i]; red[1][threadIdx.x][i] = sdyx[i]; }
+  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s1[i]; red[1][threadIdx.x][i] = s2[i]; }
   __syncthreads();
-  const int per_block = blockDim.x >= groups ? blockDim.x / groups : 1;
-  const int lg = threadIdx.x % groups;
-  if (threadIdx.x < groups && threadIdx.x < blockDim.x) {
-    // first thread of each channel group in this block folds its siblings, then 16 atomics
+  if (threadIdx.x < groups) {
+    const int per_block = blockDim.x / groups;
     float t0[8], t1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { t0[i] = 0.f; t1[i] = 0.f; }
     for (int k = 0; k < per_block; ++k) {
-      const int t = lg + k * groups;
-      if (t < blockDim.x) {
+      const int t = threadIdx.x + k * groups;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { t0[i] += red[0][t][i]; t1[i] += red[1][t][i]; }
-      }
+      for (int i = 0; i < 8; ++i) { t0[i] += red[0][t][i]; t1[i] += red[1][t][i]; }
     }
     const int gc = ((blockIdx.x * blockDim.x + threadIdx.x) % groups) * 8;
+    Vec8 mean = load8_f32(a.mean + gc), invstd = load8_f32(a.invstd + gc);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       atomicAdd(a.dbeta + gc + i, t0[i]);
-      atomicAdd(a.dgamma + gc + i, t1[i]);
+      atomicAdd(a.dgamma + gc + i, invstd.v[i] * (t1[i] - mean.v[i] * t0[i]));
     }
   }
 }
 
 // ---- backward pass 2: elementwise ----------------------------------------------------------------
-__global__ void __launch_bounds__(kBnThreads) bn_act_bwd_apply_kernel(BnBwdArgs a) {
+// dx = k1*dy + x*B + A   with k1 = gamma*invstd, B = -k1*invstd*dgamma/M, A = -k1*dbeta/M - mean*B
+template <int MASK>
+__global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdArgs a) {
   const int groups = a.C / 8;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = tid % groups;
   const int row0 = tid / groups;
   const int row_stride = (gridDim.x * blockDim.x) / groups;
   const int c0 = g * 8;
-  Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0), gam = load8_f32(a.gamma + c0);
-  Vec8 db = load8_f32(a.dbeta + c0), dg = load8_f32(a.dgamma + c0);
-  const float inv_n = 1.f / static_cast<float>(a.M);
-  if (row0 == 0 && a.gamma_grad) {   // exactly one thread per channel group: accumulate parameter grads
+  float k1[8], cA[8], cB[8], msh[8];
+  {
+    Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0), gam = load8_f32(a.gamma + c0);
+    Vec8 db = load8_f32(a.dbeta + c0), dg = load8_f32(a.dgamma + c0);
+    const float inv_n = 1.f / static_cast<float>(a.M);
+    if (row0 == 0 && a.gamma_grad) {   // exactly one thread per channel group: accumulate parameter grads
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a.gamma_grad[c0 + i] += dg.v[i];
+        a.beta_grad[c0 + i] += db.v[i];
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      a.gamma_grad[c0 + i] += dg.v[i];
-      a.beta_grad[c0 + i] += db.v[i];
+      k1[i] = gam.v[i] * invstd.v[i];
+      cB[i] = -k1[i] * invstd.v[i] * dg.v[i] * inv_n;
+      cA[i] = -k1[i] * db.v[i] * inv_n - mean.v[i] * cB[i];
+      msh[i] = 0.f;
     }
-  }
-  float k1[8], k2[8], k3[8], msh[8];
+    if (MASK == kMaskX) {
+      Vec8 bet = load8_f32(a.beta + c0);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    k1[i] = gam.v[i] * invstd.v[i];
-    k2[i] = db.v[i] * inv_n;
-    k3[i] = dg.v[i] * inv_n;
-    msh[i] = 0.f;
-  }
-  if (a.relu && a.mask_from_x) {
-    Vec8 bet = load8_f32(a.beta + c0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) msh[i] = bet.v[i] - mean.v[i] * k1[i];
+      for (int i = 0; i < 8; ++i) msh[i] = bet.v[i] - mean.v[i] * k1[i];
+    }
   }
   for (int r = row0; r < a.M; r += row_stride) {
     const size_t off = static_cast<size_t>(r) * a.C + c0;
-    Vec8 dz = load8_bf16(a.dz + off);
-    Vec8 x = load8_bf16(a.x + off);
-    if (a.relu) {
-      if (a.mask_from_x) {
+    float dz[8], x[8];
+    unpack8(ld_stream_u4(a.dz + off), dz);
+    unpack8(ld_stream_u4(a.x + off), x);
+    if (MASK == kMaskZ) {
+      float z[8];
+      unpack8(ld_stream_u4(a.z + off), z);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dz.v[i] = fmaf(x.v[i], k1[i], msh[i]) > 0.f ? dz.v[i] : 0.f;
-      } else {
-        Vec8 z = load8_bf16(a.z + off);
+      for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? dz[i] : 0.f;
+    } else if (MASK == kMaskX) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dz.v[i] = z.v[i] > 0.f ? dz.v[i] : 0.f;
-      }
+      for (int i = 0; i < 8; ++i) dz[i] = fmaf(x[i], k1[i], msh[i]) > 0.f ? dz[i] : 0.f;
     }
     if (a.dres) store8_bf16(a.dres + off, dz);
-    Vec8 dx;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xhat = (x.v[i] - mean.v[i]) * invstd.v[i];
-      dx.v[i] = k1[i] * (dz.v[i] - k2[i] - xhat * k3[i]);
-    }
-    store8_bf16(a.dx + off, dx);
+    for (int i = 0; i < 8; ++i) x[i] = fmaf(dz[i], k1[i], fmaf(x[i], cB[i], cA[i]));
+    store8_bf16(a.dx + off, x);
   }
 }
 
@@ -233,7 +235,6 @@ inline int bn_grid(int M, int C, int sms) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (groups > kBnThreads) {
-    // total threads must be a multiple of groups
     const int need = groups / kBnThreads;
     blocks = (blocks + need - 1) / need * need;
   }
@@ -257,10 +258,19 @@ cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) 
   const int groups = a.C / 8;
   if (kBnThreads % groups != 0) return cudaErrorInvalidValue;   // groups <= 256 (C <= 2048), power of two
   const int grid = bn_grid(a.M, a.C, sms);
-  bn_act_bwd_reduce_kernel<<<grid, kBnThreads, 0, stream>>>(a);
+  const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : kMaskZ);
+  switch (mask) {
+    case kMaskNone: bn_act_bwd_reduce_kernel<kMaskNone><<<grid, kBnThreads, 0, stream>>>(a); break;
+    case kMaskZ: bn_act_bwd_reduce_kernel<kMaskZ><<<grid, kBnThreads, 0, stream>>>(a); break;
+    default: bn_act_bwd_reduce_kernel<kMaskX><<<grid, kBnThreads, 0, stream>>>(a); break;
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  bn_act_bwd_apply_kernel<<<grid, kBnThreads, 0, stream>>>(a);
+  switch (mask) {
+    case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone><<<grid, kBnThreads, 0, stream>>>(a); break;
+    case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ><<<grid, kBnThreads, 0, stream>>>(a); break;
+    default: bn_act_bwd_apply_kernel<kMaskX><<<grid, kBnThreads, 0, stream>>>(a); break;
+  }
   return cudaGetLastError();
 }
 

@@ -673,17 +673,34 @@ cudaError_t launch_fwd_t(const CUtensorMap& tmB, const CUtensorMap& tmA, const C
   return cudaGetLastError();
 }
 
+// Pipeline-depth policy.  Short-K tiles are dominated by per-CTA fixed latency (TMEM alloc, first TMA
+// round trip, epilogue), so they get a shallow ring -> small shared-memory footprint -> 3-4 CTAs per SM whose
+// prologues/epilogues overlap.  Long-K tiles get the deep ring.  g_force_stages (tuning hook) overrides.
+int g_force_stages = 0;
+
+template <int BLOCK_N, int MODE>
+int pick_stages(int KB) {
+  const int max_s = FwdCfg<BLOCK_N>::kMaxStagesN;
+  int s;
+  if (g_force_stages > 0) s = g_force_stages;
+  else if (!mode_a_tma(MODE)) s = max_s;          // cp.async gather: needs depth > kLag whenever it wraps
+  else s = (KB <= 18) ? 2 : max_s;
+  if (s > max_s) s = max_s;
+  if (s > KB) s = KB;
+  if (!mode_a_tma(MODE) && KB > s && s <= kLag) s = kLag + 1;
+  return s < 1 ? 1 : s;
+}
+
 template <int MODE>
 cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmA, ConvArgs a, int n_total, int m_tiles,
                             bool stats, cudaStream_t stream) {
   if (n_total % 128 == 0) {
-    a.stages = a.KB < FwdCfg<128>::kMaxStagesN ? a.KB : FwdCfg<128>::kMaxStagesN;
-    if (!mode_a_tma(MODE) && a.stages < 3 && a.KB >= 3) a.stages = 3;
+    a.stages = pick_stages<128, MODE>(a.KB);
     return stats ? launch_fwd_t<128, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
                  : launch_fwd_t<128, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
   }
   if (n_total % 64 == 0) {
-    a.stages = a.KB < FwdCfg<64>::kMaxStagesN ? a.KB : FwdCfg<64>::kMaxStagesN;
+    a.stages = pick_stages<64, MODE>(a.KB);
     return stats ? launch_fwd_t<64, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
                  : launch_fwd_t<64, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
   }
@@ -691,6 +708,8 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmA, Conv
 }
 
 }  // namespace
+
+void set_conv_force_stages(int s) { g_force_stages = s; }
 
 // `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
 // `a_matrix`: the A operand for the TMA-A modes (2-D matrix [M][a_cols], or the NHWC tensor in tile modes).
@@ -754,7 +773,10 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void*
   if (splits > a.total_kb) splits = a.total_kb;
   a.kb_per_split = (a.total_kb + splits - 1) / splits;
   splits = (a.total_kb + a.kb_per_split - 1) / a.kb_per_split;
-  a.stages = a.kb_per_split < kWgMaxStages ? a.kb_per_split : kWgMaxStages;
+  a.stages = kWgMaxStages;
+  if (g_force_stages > 0 && g_force_stages < a.stages && (a.mode == kConvGemm || a.mode == kConvTileFwd))
+    a.stages = g_force_stages;
+  if (a.stages > a.kb_per_split) a.stages = a.kb_per_split;
   if (a.stages < 1) a.stages = 1;
   const int smem = wg_smem_bytes(a.stages);
   dim3 grid((a.ncols + 127) / 128, (a.Cout + 127) / 128, splits);

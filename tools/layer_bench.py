@@ -53,7 +53,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rows = []
     cl = torch.channels_last
-    tot = {k: 0.0 for k in ("fwd", "bn", "dgrad", "wgrad", "bnb", "cudnn_fwd", "cudnn_bwd")}
+    tot = {k: 0.0 for k in ("fwd", "bn", "dgrad", "wgrad", "bnb", "bnbx", "cudnn_fwd", "cudnn_bwd")}
     for (ci, hw, co, k, s, p, occ) in SHAPES:
         P = (hw + 2 * p - k) // s + 1
         if ci == 3:
@@ -74,11 +74,23 @@ def main():
         gw = torch.zeros(co, ci, k, k, device=dev).contiguous(memory_format=cl)
         z, save = nv.bn_act_fwd(y, st, gamma, beta, rm, rv, 1e-5, 0.1, True, None, True)
         gg, bg = torch.zeros(co, device=dev), torch.zeros(co, device=dev)
+        C = nv._C()
+        sweep = {}
+        if os.environ.get("LB_SWEEP", "1") == "1":
+            for st_ in (1, 2, 3, 4):
+                C.set_conv_force_stages(st_)
+                f_ = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), reps=3, flush=flush)
+                d_ = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), reps=3, flush=flush) if ci != 3 else 0.0
+                w_ = timeit(lambda: nv.conv_wgrad(x, dy, gw, (k, k), s, p), reps=3, flush=flush)
+                sweep[st_] = (round(f_, 4), round(d_, 4), round(w_, 4))
+            C.set_conv_force_stages(0)
         t_fwd = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), flush=flush)
         t_bn = timeit(lambda: nv.bn_act_fwd(y, st, gamma, beta, rm, rv, 1e-5, 0.1, True, None, True), flush=flush)
         t_dg = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), flush=flush) if ci != 3 else 0.0
         t_wg = timeit(lambda: nv.conv_wgrad(x, dy, gw, (k, k), s, p), flush=flush)
         t_bnb = timeit(lambda: nv.bn_act_bwd(dy, z, y, save, gamma, True, False, gg, bg), flush=flush)
+        t_bnbx = timeit(lambda: nv.bn_act_bwd(dy, z, y, save, gamma, True, False, gg, bg, beta=beta, had_residual=False),
+                        flush=flush)
         xr = xt.detach().requires_grad_(ci != 3)
         wr = wt.detach().requires_grad_(True)
         t_cf = timeit(lambda: F.conv2d(xr, wr, None, s, p), flush=flush)
@@ -91,14 +103,15 @@ def main():
         row = {"shape": f"{ci}x{hw}->{co} k{k}s{s}", "occ": occ, "M": M, "gflop": flops / 1e9,
                "fwd_ms": t_fwd, "fwd_tflops": flops / t_fwd / 1e9, "fwd_gbs": act_bytes / t_fwd / 1e6,
                "bn_ms": t_bn, "bn_gbs": 2 * M * co * 2 / t_bn / 1e6,
-               "dgrad_ms": t_dg, "wgrad_ms": t_wg, "bnb_ms": t_bnb, "bnb_gbs": 4 * M * co * 2 / t_bnb / 1e6,
+               "dgrad_ms": t_dg, "wgrad_ms": t_wg, "bnb_ms": t_bnb, "bnb_maskx_ms": t_bnbx, "stage_sweep": sweep, "bnb_gbs": 4 * M * co * 2 / t_bnb / 1e6,
                "cudnn_fwd_ms": t_cf, "cudnn_bwd_ms": t_cb}
         rows.append(row)
-        for key, v in (("fwd", t_fwd), ("bn", t_bn), ("dgrad", t_dg), ("wgrad", t_wg), ("bnb", t_bnb),
+        for key, v in (("fwd", t_fwd), ("bn", t_bn), ("dgrad", t_dg), ("wgrad", t_wg), ("bnb", t_bnb), ("bnbx", t_bnbx),
                        ("cudnn_fwd", t_cf), ("cudnn_bwd", t_cb)):
             tot[key] += v * occ
         print(f"{row['shape']:22s} x{occ} fwd {t_fwd:7.3f}ms {row['fwd_tflops']:7.1f}TF {row['fwd_gbs']:6.0f}GB/s | bn {t_bn:6.3f} "
-              f"| dgrad {t_dg:7.3f} | wgrad {t_wg:7.3f} | bnb {t_bnb:6.3f} || cudnn fwd {t_cf:7.3f} bwd {t_cb:7.3f}", flush=True)
+              f"| dgrad {t_dg:7.3f} | wgrad {t_wg:7.3f} | bnb {t_bnb:6.3f}/{t_bnbx:6.3f} || cudnn fwd {t_cf:7.3f} bwd {t_cb:7.3f}"
+              f" || sweep {sweep}", flush=True)
     print("TOTALS (ms, weighted by occurrences):", {k: round(v, 3) for k, v in tot.items()})
     print("ours conv fwd+dgrad+wgrad = %.2f ms, BN fwd+bwd = %.2f ms ; cuDNN conv fwd+bwd = %.2f ms"
           % (tot["fwd"] + tot["dgrad"] + tot["wgrad"], tot["bn"] + tot["bnb"], tot["cudnn_fwd"] + tot["cudnn_bwd"]))
