@@ -72,7 +72,8 @@ constexpr bool mode_tile(int mode) { return mode == kConvTileFwd || mode == kCon
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int MODE, bool STATS>
 __global__ void __launch_bounds__(kThreads, 2)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA, ConvArgs a) {
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmaSet tmAs, ConvArgs a) {
+  const CUtensorMap& tmA = tmAs.m[0];
   using Cfg = FwdCfg<BLOCK_N>;
   constexpr bool kATma = mode_a_tma(MODE);
   constexpr bool kBMn = mode_b_mn(MODE);
@@ -209,7 +210,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
       const int hl = t2 % a.th;
       const int nl = t2 / a.th;
       const bool ok = nl < a.tn && (tn0 + nl) < a.batch && (tp0 + hl) < a.dstH && (tq0 + wl) < a.dstW;
-      my_m = ok ? ((tn0 + nl) * a.dstH + (tp0 + hl)) * a.dstW + (tq0 + wl) : -1;
+      my_m = ok ? ((tn0 + nl) * a.outH + (tp0 + hl) * a.out_stride + a.out_pa) * a.outW +
+                      (tq0 + wl) * a.out_stride + a.out_pb
+                : -1;
     } else {
       my_m = (m0 + row) < a.M ? (m0 + row) : -1;
     }
@@ -319,22 +322,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
         uint8_t* sA = smem + stage * Cfg::kStageBytes;
         const uint32_t sB = smem_u32(sA + kATileBytes);
         mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + (kATma ? a_bytes : 0u));
+        // tap of this k-block: weight tap index + (tile modes) source box offset / source map
+        int widx = tap, dh = 0, dw = 0, mapi = 0;
+        if (kTile) {
+          if (a.ntaps > 0) {
+            widx = a.tap_widx[tap]; dh = a.tap_dh[tap]; dw = a.tap_dw[tap]; mapi = a.tap_map[tap];
+          } else if (MODE == kConvTileFwd) {
+            dh = tap_r * a.dil - a.pad; dw = tap_s * a.dil - a.pad;
+          } else {
+            dh = a.pad - tap_r * a.dil; dw = a.pad - tap_s * a.dil;
+          }
+        }
         if (kBMn) {
           // weights W[co][(r,s,ci)]: K rows = 64 output channels, N = input channels (contiguous)
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_2d(sB + j * 8192, &tmB, tap * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
+            tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
         } else {
-          tma_load_2d(sB, &tmB, kb * kBlockK, n0, &full[stage]);
+          tma_load_2d(sB, &tmB, (widx * a.cchunks + cc) * kBlockK, n0, &full[stage]);
         }
         if (MODE == kConvGemm || MODE == kConvGemmDgrad) {
           tma_load_2d(smem_u32(sA), &tmA, kb * kBlockK, m0, &full[stage]);
-        } else if (MODE == kConvTileFwd) {
-          tma_load_4d(smem_u32(sA), &tmA, cc * 64, tq0 - a.pad + tap_s * a.dil, tp0 - a.pad + tap_r * a.dil, tn0,
-                      &full[stage]);
-        } else if (MODE == kConvTileDgrad) {
-          tma_load_4d(smem_u32(sA), &tmA, cc * 64, tq0 + a.pad - tap_s * a.dil, tp0 + a.pad - tap_r * a.dil, tn0,
-                      &full[stage]);
+        } else if (kTile) {
+          tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
         }
         if (++cc == a.cchunks) { cc = 0; ++tap; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
@@ -386,7 +396,8 @@ constexpr int wg_smem_bytes(int stages) {
 
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
-conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX, WgradArgs a) {
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ TmaSet tmXs, WgradArgs a) {
+  const CUtensorMap& tmX = tmXs.m[0];
   constexpr bool kXTma = (MODE == kConvGemm || MODE == kConvTileFwd);
   constexpr bool kTile = (MODE == kConvTileFwd);
   extern __shared__ uint8_t smem_raw[];
@@ -534,15 +545,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   } else if (warp == 4) {
     if (elect_one()) {
       // taps / channel offsets of the two 64-column chunks of the B tile (tile mode)
-      int tr[2] = {0, 0}, ts[2] = {0, 0}, tc0[2] = {0, 0};
+      int tdh[2] = {0, 0}, tdw[2] = {0, 0}, tmap[2] = {0, 0}, tc0[2] = {0, 0};
       if (kTile) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int colc = col0 + j * 64;
           const int tap = colc / a.C;
           tc0[j] = colc - tap * a.C;
-          tr[j] = tap / a.S;
-          ts[j] = tap - tr[j] * a.S;
+          const int r = tap / a.S, sx = tap - r * a.S;
+          const int oh = r * a.dil - a.pad, ow = sx * a.dil - a.pad;
+          if (a.stride == 1) {
+            tdh[j] = oh; tdw[j] = ow;
+          } else {               // stride-2 source: box comes from the (pa, pb) phase sub-image
+            const int st = a.stride;
+            const int pa = ((oh % st) + st) % st, pb = ((ow % st) + st) % st;
+            tdh[j] = (oh - pa) / st; tdw[j] = (ow - pb) / st;
+            tmap[j] = pa * st + pb;
+          }
         }
       }
       const uint32_t box_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : 8192u;
@@ -561,9 +580,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           mbar_arrive_expect_tx(&full[stage], box_bytes * (second ? 4u : 3u));
           tma_load_4d(sA, &tmDy, co0, q0, p0, n0, &full[stage]);
           tma_load_4d(sA + 8192, &tmDy, co0 + 64, q0, p0, n0, &full[stage]);
-          tma_load_4d(sA + 16384, &tmX, tc0[0], q0 - a.pad + ts[0] * a.dil, p0 - a.pad + tr[0] * a.dil, n0, &full[stage]);
-          if (second)
-            tma_load_4d(sA + 24576, &tmX, tc0[1], q0 - a.pad + ts[1] * a.dil, p0 - a.pad + tr[1] * a.dil, n0, &full[stage]);
+          tma_load_4d(sA + 16384, &tmXs.m[tmap[0]], tc0[0], q0 + tdw[0], p0 + tdh[0], n0, &full[stage]);
+          if (second) tma_load_4d(sA + 24576, &tmXs.m[tmap[1]], tc0[1], q0 + tdw[1], p0 + tdh[1], n0, &full[stage]);
         } else {
           const int m = (kb_begin + i) * 64;
           mbar_arrive_expect_tx(&full[stage], 16384u + (kXTma ? 16384u : 0u));
@@ -655,8 +673,30 @@ bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int 
   return r == CUDA_SUCCESS;
 }
 
+// Phase (pa, pb) sub-image of a stride-`st` NHWC source: X[n][st*i + pa][st*j + pb][c] as a dense 4-D map.
+bool make_map_nhwc_phase(CUtensorMap* map, const void* base, int N, int H, int W, int C, int st, int pa, int pb,
+                         int tw, int th, int tn) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const int Hp = (H - pa + st - 1) / st, Wp = (W - pb + st - 1) / st;
+  if (Hp <= 0 || Wp <= 0) return make_map_nhwc(map, base, N, H, W, C, tw, th, tn);   // never referenced
+  const char* b = static_cast<const char*>(base) + (static_cast<size_t>(pa) * W + pb) * C * 2;
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(Wp), static_cast<cuuint64_t>(Hp),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(st) * C * 2, static_cast<cuuint64_t>(st) * W * C * 2,
+                           static_cast<cuuint64_t>(H) * W * C * 2};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tn)};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+
 template <int BLOCK_N, int MODE, bool STATS>
-cudaError_t launch_fwd_t(const CUtensorMap& tmB, const CUtensorMap& tmA, const ConvArgs& a, int n_total, int m_tiles,
+cudaError_t launch_fwd_t(const CUtensorMap& tmB, const TmaSet& tmA, const ConvArgs& a, int n_total, int m_tiles,
                          cudaStream_t stream) {
   using Cfg = FwdCfg<BLOCK_N>;
   auto kern = conv_gemm_kernel<BLOCK_N, MODE, STATS>;
@@ -692,7 +732,7 @@ int pick_stages(int KB) {
 }
 
 template <int MODE>
-cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmA, ConvArgs a, int n_total, int m_tiles,
+cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs a, int n_total, int m_tiles,
                             bool stats, cudaStream_t stream) {
   if (n_total % 128 == 0) {
     a.stages = pick_stages<128, MODE>(a.KB);
@@ -716,7 +756,8 @@ void set_conv_force_stages(int s) { g_force_stages = s; }
 cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int w_rows, int w_cols, int n_total,
                              const void* a_matrix, int a_cols, cudaStream_t stream) {
   ConvArgs a = a_in;
-  CUtensorMap tmB, tmA;
+  CUtensorMap tmB;
+  TmaSet tmA;
   const int bn = (n_total % 128 == 0) ? 128 : 64;
   if (n_total % 64 != 0) return cudaErrorInvalidValue;
   if (mode_b_mn(mode)) {
@@ -724,58 +765,142 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
   } else {
     if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, bn)) return cudaErrorUnknown;
   }
+  a.ntaps = 0;
+  a.outH = a.dstH; a.outW = a.dstW; a.out_stride = 1; a.out_pa = 0; a.out_pb = 0;
   int m_tiles = (a.M + kBlockM - 1) / kBlockM;
-  if (mode == kConvGemm || mode == kConvGemmDgrad) {
-    if (!make_map_2d(&tmA, a_matrix, a.M, a_cols, a_cols, 64, 128)) return cudaErrorUnknown;
-  } else if (mode_tile(mode)) {
-    if (a.tw * a.th * a.tn > 128 || a.tw < 1 || a.th < 1 || a.tn < 1) return cudaErrorInvalidValue;
-    if (!make_map_nhwc(&tmA, a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn)) return cudaErrorUnknown;
-    a.tiles_w = (a.dstW + a.tw - 1) / a.tw;
-    a.tiles_h = (a.dstH + a.th - 1) / a.th;
-    m_tiles = a.tiles_w * a.tiles_h * ((a.batch + a.tn - 1) / a.tn);
-  } else {
-    tmA = tmB;
-  }
   const bool stats = a.sum != nullptr;
-  switch (mode) {
-    case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmA, a, n_total, m_tiles, stats, stream);
-    case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmA, a, n_total, m_tiles, stats, stream);
-    case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmA, a, n_total, m_tiles, stats, stream);
-    case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmA, a, n_total, m_tiles, stats, stream);
-    case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(tmB, tmA, a, n_total, m_tiles, stats, stream);
-    case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(tmB, tmA, a, n_total, m_tiles, stats, stream);
-    case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(tmB, tmA, a, n_total, m_tiles, stats, stream);
-    default: return cudaErrorInvalidValue;
+  auto dispatch = [&](const ConvArgs& args, int tiles) -> cudaError_t {
+    switch (mode) {
+      case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  };
+  if (mode == kConvGemm || mode == kConvGemmDgrad) {
+    if (!make_map_2d(&tmA.m[0], a_matrix, a.M, a_cols, a_cols, 64, 128)) return cudaErrorUnknown;
+    for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
+    return dispatch(a, m_tiles);
   }
+  if (!mode_tile(mode)) {
+    for (int i = 0; i < 4; ++i) tmA.m[i] = tmB;
+    return dispatch(a, m_tiles);
+  }
+  // ---------------- tile modes ----------------
+  if (a.tw * a.th * a.tn > 128 || a.tw < 1 || a.th < 1 || a.tn < 1) return cudaErrorInvalidValue;
+  const int st = a.stride;
+  auto set_tiles = [&](ConvArgs& x) {
+    x.tiles_w = (x.dstW + x.tw - 1) / x.tw;
+    x.tiles_h = (x.dstH + x.th - 1) / x.th;
+    return x.tiles_w * x.tiles_h * ((x.batch + x.tn - 1) / x.tn);
+  };
+  if (st == 1) {
+    if (!make_map_nhwc(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+    for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
+    return dispatch(a, set_tiles(a));
+  }
+  if (st != 2 || a.R * a.S > 16) return cudaErrorInvalidValue;
+  if (mode == kConvTileFwd) {
+    // stride-2 forward: every filter tap reads a dense box of one of the four 2x2 phase sub-images of x
+    for (int pa = 0; pa < 2; ++pa)
+      for (int pb = 0; pb < 2; ++pb)
+        if (!make_map_nhwc_phase(&tmA.m[pa * 2 + pb], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, 2, pa, pb, a.tw, a.th,
+                                 a.tn))
+          return cudaErrorUnknown;
+    a.ntaps = a.R * a.S;
+    for (int r = 0; r < a.R; ++r)
+      for (int sx = 0; sx < a.S; ++sx) {
+        const int t = r * a.S + sx;
+        const int oh = r * a.dil - a.pad, ow = sx * a.dil - a.pad;
+        const int pa = ((oh % 2) + 2) % 2, pb = ((ow % 2) + 2) % 2;
+        a.tap_dh[t] = static_cast<signed char>(floor_div(oh, 2));
+        a.tap_dw[t] = static_cast<signed char>(floor_div(ow, 2));
+        a.tap_map[t] = static_cast<signed char>(pa * 2 + pb);
+        a.tap_widx[t] = static_cast<signed char>(t);
+      }
+    return dispatch(a, set_tiles(a));
+  }
+  // stride-2 data gradient: four stride-1 problems, one per output phase (pa, pb) of dx; each is a conv of dy
+  // with the subset of taps of matching parity, scattered to dx[2i+pa][2j+pb].  Phases with no tap stay as the
+  // caller initialised them (the Python wrapper zero-fills dx when such phases exist).
+  if (!make_map_nhwc(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+  for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
+  const int fullH = a.dstH, fullW = a.dstW;
+  for (int pa = 0; pa < 2; ++pa)
+    for (int pb = 0; pb < 2; ++pb) {
+      ConvArgs p = a;
+      p.dstH = (fullH - pa + 1) / 2;
+      p.dstW = (fullW - pb + 1) / 2;
+      if (p.dstH <= 0 || p.dstW <= 0) continue;
+      p.outH = fullH; p.outW = fullW; p.out_stride = 2; p.out_pa = pa; p.out_pb = pb;
+      int nt = 0;
+      for (int r = 0; r < a.R; ++r) {
+        const int th_ = pa + a.pad - r * a.dil;
+        if (((th_ % 2) + 2) % 2 != 0) continue;
+        for (int sx = 0; sx < a.S; ++sx) {
+          const int tw_ = pb + a.pad - sx * a.dil;
+          if (((tw_ % 2) + 2) % 2 != 0) continue;
+          p.tap_dh[nt] = static_cast<signed char>(floor_div(th_, 2));
+          p.tap_dw[nt] = static_cast<signed char>(floor_div(tw_, 2));
+          p.tap_map[nt] = 0;
+          p.tap_widx[nt] = static_cast<signed char>(r * a.S + sx);
+          ++nt;
+        }
+      }
+      if (nt == 0) continue;
+      p.ntaps = nt;
+      p.KB = nt * a.cchunks;
+      cudaError_t e = dispatch(p, set_tiles(p));
+      if (e != cudaSuccess) return e;
+    }
+  return cudaSuccess;
 }
 
 cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void* x_matrix, int splits,
                               cudaStream_t stream) {
   WgradArgs a = a_in;
-  CUtensorMap tmDy, tmX;
+  CUtensorMap tmDy;
+  TmaSet tmX;
   if (a.mode == kConvTileFwd) {
     if (a.tw * a.th * a.tn > 64 || a.tw < 1 || a.th < 1 || a.tn < 1) return cudaErrorInvalidValue;
     if (!make_map_nhwc(&tmDy, dy, a.batch, a.P, a.Q, a.dy_ld, a.tw, a.th, a.tn)) return cudaErrorUnknown;
-    if (!make_map_nhwc(&tmX, x_matrix, a.batch, a.H, a.W, a.C, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+    if (a.stride == 1) {
+      if (!make_map_nhwc(&tmX.m[0], x_matrix, a.batch, a.H, a.W, a.C, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+      for (int i = 1; i < 4; ++i) tmX.m[i] = tmX.m[0];
+    } else if (a.stride == 2) {
+      for (int pa = 0; pa < 2; ++pa)
+        for (int pb = 0; pb < 2; ++pb)
+          if (!make_map_nhwc_phase(&tmX.m[pa * 2 + pb], x_matrix, a.batch, a.H, a.W, a.C, 2, pa, pb, a.tw, a.th, a.tn))
+            return cudaErrorUnknown;
+    } else {
+      return cudaErrorInvalidValue;
+    }
     a.tiles_w = (a.Q + a.tw - 1) / a.tw;
     a.tiles_h = (a.P + a.th - 1) / a.th;
     a.total_kb = a.tiles_w * a.tiles_h * ((a.batch + a.tn - 1) / a.tn);
   } else {
     if (!make_map_2d(&tmDy, dy, a.M, a.dy_ld, a.dy_ld, 64, 64)) return cudaErrorUnknown;
     if (a.mode == kConvGemm) {
-      if (!make_map_2d(&tmX, x_matrix, a.M, a.ncols, a.ncols, 64, 64)) return cudaErrorUnknown;
+      if (!make_map_2d(&tmX.m[0], x_matrix, a.M, a.ncols, a.ncols, 64, 64)) return cudaErrorUnknown;
     } else {
-      tmX = tmDy;
+      tmX.m[0] = tmDy;
     }
+    for (int i = 1; i < 4; ++i) tmX.m[i] = tmX.m[0];
     a.total_kb = (a.M + 63) / 64;
   }
   if (splits < 1) splits = 1;
   if (splits > a.total_kb) splits = a.total_kb;
   a.kb_per_split = (a.total_kb + splits - 1) / splits;
   splits = (a.total_kb + a.kb_per_split - 1) / a.kb_per_split;
-  a.stages = kWgMaxStages;
-  if (g_force_stages > 0 && g_force_stages < a.stages && (a.mode == kConvGemm || a.mode == kConvTileFwd))
-    a.stages = g_force_stages;
+  // TMA-fed wgrad tiles run best with a 2-deep ring (measured: 3 CTAs/SM beat a deeper pipeline); the cp.async
+  // gather modes need depth > kLag
+  const bool tma_fed = (a.mode == kConvGemm || a.mode == kConvTileFwd);
+  a.stages = tma_fed ? 2 : kWgMaxStages;
+  if (g_force_stages > 0 && g_force_stages <= kWgMaxStages && tma_fed) a.stages = g_force_stages;
   if (a.stages > a.kb_per_split) a.stages = a.kb_per_split;
   if (a.stages < 1) a.stages = 1;
   const int smem = wg_smem_bytes(a.stages);

@@ -36,8 +36,19 @@ struct ConvArgs {
   int relu;                   // apply ReLU in the epilogue (after bias)
   int n_valid;                // output channels that really exist (bias is read only below this)
   int stages;                 // pipeline depth actually used (<= compile-time maximum)
-  // tile modes: the M tile is a tw x th x tn box of output pixels (w fastest); tw*th*tn <= 128
+  // tile modes: the M tile is a tw x th x tn box of pixels of the dstH x dstW iteration grid (w fastest);
+  // tw*th*tn <= 128.  Row (n, i, j) of the grid is written to out[n][out_stride*i + out_pa][out_stride*j + out_pb]
+  // of an outH x outW image (dense output: out_stride = 1).
   int batch, tw, th, tn, tiles_w, tiles_h;
+  int outH, outW, out_stride, out_pa, out_pb;
+  // optional explicit tap table (strided convs decomposed into stride-1 phase problems): per tap the box offset
+  // in the source map, which of the 4 source maps to read, and the weight tap index r*S+s
+  int ntaps;
+  signed char tap_dh[16], tap_dw[16], tap_map[16], tap_widx[16];
+};
+
+struct TmaSet {          // up to 4 activation maps (the 2x2 phase sub-images of a stride-2 source)
+  CUtensorMap m[4];
 };
 
 struct WgradArgs {

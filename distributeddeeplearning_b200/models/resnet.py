@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..ops.blocks import residual_block, residual_block_supported
 from .layers import BatchNorm2d, Conv2d, Linear, conv_bn, prepare_input
 
 
@@ -29,6 +30,9 @@ class BasicBlock(nn.Module):
         self.stride = stride
 
     def forward(self, x):
+        convs, bns = (self.conv1, self.conv2), (self.bn1, self.bn2)
+        if residual_block_supported(x, convs, bns, self.downsample):
+            return residual_block(x, convs, bns, self.downsample)      # one autograd node, fused input-grad sum
         identity = x
         out = conv_bn(x, self.conv1, self.bn1, relu=True)
         if self.downsample is not None:
@@ -51,6 +55,9 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
+        convs, bns = (self.conv1, self.conv2, self.conv3), (self.bn1, self.bn2, self.bn3)
+        if residual_block_supported(x, convs, bns, self.downsample):
+            return residual_block(x, convs, bns, self.downsample)      # one autograd node, fused input-grad sum
         identity = x
         out = conv_bn(x, self.conv1, self.bn1, relu=True)
         out = conv_bn(out, self.conv2, self.bn2, relu=True)

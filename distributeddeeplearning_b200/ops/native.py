@@ -68,6 +68,7 @@ def stem_geometry(R: int, S: int) -> Tuple[int, int, int, int]:
 
 
 USE_TILE_TMA = os.environ.get("DDL_DISABLE_TILE_TMA", "0") != "1"
+USE_TILE_S2 = os.environ.get("DDL_DISABLE_TILE_S2", "0") != "1"
 
 
 def tile_geometry(P: int, Q: int, N: int, max_rows: int) -> Tuple[int, int, int]:
@@ -119,11 +120,12 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
         C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, Cin // 64, Cout, H, W, Cin, P, Q,
                     1, 1, 1, 0, 1, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1],
                     Cout, x.data_ptr(), Cin, N, 0, 0, 0, _stream())
-    elif stride == 1 and USE_TILE_TMA:
-        # stride-1 window conv: the activation operand comes through ONE 4-D TMA box per filter tap
+    elif USE_TILE_TMA and (stride == 1 or (stride == 2 and R * S <= 16 and USE_TILE_S2)):
+        # window conv: the activation operand comes through ONE 4-D TMA box per filter tap (stride 2: the box is
+        # taken from the matching 2x2 phase sub-image of x)
         tw, th, tn = tile_geometry(P, Q, N, 128)
         C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64), Cout, H, W,
-                    Cin, P, Q, R, S, 1, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
+                    Cin, P, Q, R, S, stride, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
                     w_bf16.shape[1], Cout, x.data_ptr(), Cin, N, tw, th, tn, _stream())
     else:
         C.conv_gemm(C.CONV_FWD, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64),
@@ -142,7 +144,12 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
     R, S = kernel
     if Cin % 64 != 0 or Cout % 64 != 0:
         raise ValueError("conv_dgrad needs Cin, Cout multiples of 64")
-    dx = empty_act(N, Cin, H, W, dy.device)
+    s2_tile = USE_TILE_TMA and USE_TILE_S2 and stride == 2 and R * S <= 16 and dil == 1 and add is None
+    if s2_tile and (R < 2 or S < 2):
+        # some output phases receive no tap (e.g. 1x1 stride 2 only feeds even rows/cols): they stay zero
+        dx = torch.zeros((N, Cin, H, W), dtype=torch.bfloat16, device=dy.device).contiguous(memory_format=CL)
+    else:
+        dx = empty_act(N, Cin, H, W, dy.device)
     if add is not None:
         _check_act(add, "add")
     if R == 1 and S == 1 and stride == 1 and pad == 0:
@@ -153,6 +160,12 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
         tw, th, tn = tile_geometry(H, W, N, 128)
         C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin, P, Q,
                     Cout, H, W, R, S, 1, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
+                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, _stream())
+    elif s2_tile:
+        # four stride-1 phase problems (one launch each), tiles iterate the half-resolution phase grid
+        tw, th, tn = tile_geometry((H + 1) // 2, (W + 1) // 2, N, 128)
+        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin, P, Q,
+                    Cout, H, W, R, S, 2, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
                     w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, _stream())
     else:
         C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64),
@@ -195,7 +208,7 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: 
     tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
     if R == 1 and S == 1 and stride == 1 and pad == 0:
         mode, (tw, th, tn), total_kb = C.CONV_GEMM, (0, 0, 0), (M + 63) // 64
-    elif stride == 1 and USE_TILE_TMA:
+    elif USE_TILE_TMA and (stride == 1 or (stride == 2 and USE_TILE_S2)):
         mode, (tw, th, tn) = C.CONV_TILE_FWD, tile_geometry(P, Q, N, 64)
         total_kb = -(-Q // tw) * -(-P // th) * -(-N // tn)
     else:
@@ -460,3 +473,9 @@ def u8_nhwc_to_nhwc4(x_u8: torch.Tensor, mean: Optional[torch.Tensor] = None, st
     out = empty_act(N, 4, H, W, x_u8.device)
     C.nhwc_u8_to_nhwc4(x_u8.data_ptr(), out.data_ptr(), N * H * W, _ptr(mean), _ptr(std), _stream())
     return out
+
+
+def dgrad_supports_add(kernel: Tuple[int, int], stride: int) -> bool:
+    """Whether conv_dgrad can fold ``+ add`` into its epilogue for this geometry without leaving the fast path
+    (the stride-2 phase decomposition writes each output phase from a different launch, so it cannot)."""
+    return not (stride == 2 and USE_TILE_TMA and USE_TILE_S2 and kernel[0] * kernel[1] <= 16)

@@ -161,7 +161,7 @@ def g_conv_fwd():
     from distributeddeeplearning_b200.ops import native as nv
 
     dev = "cuda"
-    cases = [(3, 64, 7, 7, 64, 3, 1, 1), (5, 128, 14, 14, 128, 3, 1, 1), (2, 64, 56, 56, 128, 3, 1, 1), (2, 64, 28, 28, 64, 3, 1, 1), (2, 64, 15, 15, 64, 3, 1, 0), (1, 64, 20, 20, 64, 3, 1, 2), (2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (3, 128, 14, 14, 128, 3, 1, 1),
+    cases = [(2, 64, 56, 56, 128, 3, 2, 1), (3, 256, 14, 14, 512, 1, 2, 0), (2, 128, 13, 13, 128, 3, 2, 1), (3, 64, 7, 7, 64, 3, 1, 1), (5, 128, 14, 14, 128, 3, 1, 1), (2, 64, 56, 56, 128, 3, 1, 1), (2, 64, 28, 28, 64, 3, 1, 1), (2, 64, 15, 15, 64, 3, 1, 0), (1, 64, 20, 20, 64, 3, 1, 2), (2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (3, 128, 14, 14, 128, 3, 1, 1),
              (2, 256, 7, 7, 512, 1, 2, 0), (2, 64, 12, 12, 192, 5, 1, 2), (1, 192, 13, 13, 384, 3, 1, 1),
              (4, 64, 56, 56, 64, 3, 1, 1)]
     for (n, ci, h, w_, co, k, s, p) in cases:
@@ -194,7 +194,7 @@ def g_conv_dgrad():
     from distributeddeeplearning_b200.ops import native as nv
 
     dev = "cuda"
-    cases = [(3, 64, 7, 7, 64, 3, 1, 1), (5, 128, 14, 14, 128, 3, 1, 1), (2, 64, 56, 56, 128, 3, 1, 1), (2, 64, 28, 28, 64, 3, 1, 1), (2, 64, 15, 15, 64, 3, 1, 0), (1, 64, 20, 20, 64, 3, 1, 2), (2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (2, 128, 14, 14, 128, 3, 1, 1),
+    cases = [(2, 64, 56, 56, 128, 3, 2, 1), (3, 256, 14, 14, 512, 1, 2, 0), (2, 128, 13, 13, 128, 3, 2, 1), (3, 64, 7, 7, 64, 3, 1, 1), (5, 128, 14, 14, 128, 3, 1, 1), (2, 64, 56, 56, 128, 3, 1, 1), (2, 64, 28, 28, 64, 3, 1, 1), (2, 64, 15, 15, 64, 3, 1, 0), (1, 64, 20, 20, 64, 3, 1, 2), (2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (2, 128, 14, 14, 128, 3, 1, 1),
              (2, 256, 8, 8, 512, 1, 2, 0), (2, 256, 7, 7, 64, 1, 1, 0), (2, 64, 12, 12, 192, 5, 1, 2),
              (2, 128, 28, 28, 128, 3, 2, 1)]
     for (n, ci, h, w_, co, k, s, p) in cases:
@@ -222,7 +222,7 @@ def g_conv_wgrad():
     from distributeddeeplearning_b200.ops import native as nv
 
     dev = "cuda"
-    cases = [(3, 64, 7, 7, 64, 3, 1, 1), (5, 128, 14, 14, 128, 3, 1, 1), (2, 64, 56, 56, 128, 3, 1, 1), (2, 64, 28, 28, 64, 3, 1, 1), (2, 64, 15, 15, 64, 3, 1, 0), (1, 64, 20, 20, 64, 3, 1, 2), (2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (3, 128, 14, 14, 128, 3, 1, 1),
+    cases = [(2, 64, 56, 56, 128, 3, 2, 1), (3, 256, 14, 14, 512, 1, 2, 0), (2, 128, 13, 13, 128, 3, 2, 1), (3, 64, 7, 7, 64, 3, 1, 1), (5, 128, 14, 14, 128, 3, 1, 1), (2, 64, 56, 56, 128, 3, 1, 1), (2, 64, 28, 28, 64, 3, 1, 1), (2, 64, 15, 15, 64, 3, 1, 0), (1, 64, 20, 20, 64, 3, 1, 2), (2, 64, 8, 8, 64, 3, 1, 1), (2, 64, 9, 9, 128, 3, 2, 1), (3, 128, 14, 14, 128, 3, 1, 1),
              (2, 256, 8, 8, 512, 1, 2, 0), (4, 256, 7, 7, 64, 1, 1, 0), (2, 64, 12, 12, 192, 5, 1, 2),
              (8, 64, 56, 56, 64, 3, 1, 1), (8, 512, 7, 7, 2048, 1, 1, 0)]
     for (n, ci, h, w_, co, k, s, p) in cases:
