@@ -32,8 +32,10 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // bf16 elements = 128 bytes = one swizzle row
 constexpr int kATileBytes = kBlockM * 128;        // 16 KB
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 192;
+constexpr int kProducerThreads = 128;              // warps 0-3: gather producers (and epilogue group 0)
+constexpr int kEpiGroups = 2;                      // epilogue warp groups: group g owns columns [g*N/2, (g+1)*N/2)
+constexpr int kEpiThreads = 128 * kEpiGroups;      // warps 0-3 (+ warps 6-9)
+constexpr int kThreads = 192 + 128 * (kEpiGroups - 1);
 constexpr int kLag = 2;                           // cp.async groups kept in flight per producer
 constexpr int kMaxStages = 4;
 
@@ -46,7 +48,7 @@ struct FwdCfg {
   static constexpr int kMaxStagesN = (BLOCK_N <= 64) ? 4 : 3;
   static constexpr int smem_bytes(int stages) {
     const int pipe = stages * kStageBytes;
-    return (pipe > kEpiBytes ? pipe : kEpiBytes) + 256 /*barriers*/ + 4096 /*stats scratch*/ + 1024 /*alignment*/;
+    return (pipe > kEpiBytes ? pipe : kEpiBytes) + 256 /*barriers*/ + 8192 /*stats scratch*/ + 1024 /*alignment*/;
   }
 };
 
@@ -71,7 +73,7 @@ constexpr bool mode_tile(int mode) { return mode == kConvTileFwd || mode == kCon
 // fwd / dgrad / plain-GEMM / stem kernel
 // ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int MODE, bool STATS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmaSet tmAs, ConvArgs a) {
   const CUtensorMap& tmA = tmAs.m[0];
   using Cfg = FwdCfg<BLOCK_N>;
@@ -121,9 +123,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 4 || warp >= 6) {
+    const int egrp = warp < 4 ? 0 : 1;                 // epilogue group
+    const int qw = warp & 3;                           // TMEM lane quarter this warp may read (= warp % 4)
+    const int erow = qw * 32 + (threadIdx.x & 31);     // accumulator row owned in the epilogue
+    const int etid = egrp * 128 + erow;                // dense index over the epilogue threads
+    const int ew = egrp * 4 + qw;                      // dense epilogue warp index
     // =============================== gather producers ===================================
-    if (!kATma) {
+    if (!kATma && warp < 4) {
       const int row = threadIdx.x;
       const int m = m0 + row;
       const bool row_ok = m < a.M;
@@ -202,7 +209,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
 
     // =================================== epilogue ========================================
     // my accumulator row -> output row
-    const int row = threadIdx.x;
+    const int row = erow;
     int my_m;                     // linear output row index of this thread's accumulator row, or -1
     if (kTile) {
       const int wl = row % a.tw;
@@ -219,10 +226,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
     mbar_wait(acc_full, 0);
     tc_fence_after();
     uint8_t* stg = smem;  // pipeline buffers are free: every MMA that read them has completed
+    constexpr int kColsPerGroup = BLOCK_N / kEpiGroups;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+    for (int c0 = egrp * kColsPerGroup; c0 < (egrp + 1) * kColsPerGroup; c0 += 32) {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + c0, v);
       tmem_ld_wait();
       uint32_t packed[16];
 #pragma unroll
@@ -241,17 +249,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
       for (int j = 0; j < 4; ++j) dstp[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
     }
     // the row's destination index rides in the pad bytes of its staging row (pitch = 2*BLOCK_N + 16)
-    *reinterpret_cast<int*>(stg + row * Cfg::kPitch + BLOCK_N * 2) = my_m;
+    if (egrp == 0) *reinterpret_cast<int*>(stg + row * Cfg::kPitch + BLOCK_N * 2) = my_m;
     tc_fence_before();
-    named_bar_sync(1, kProducerThreads);
+    named_bar_sync(1, kEpiThreads);
     if (STATS) {
       // per-channel sum / sum of squares of the bf16-rounded outputs of this tile (invalid rows hold zeros).
       // thread = (column group of 8, row slice): 16-byte shared loads, fp32 accumulation.
       constexpr int kColGroups = BLOCK_N / 8;                 // 16 (N=128) or 8 (N=64)
-      constexpr int kSlices = kProducerThreads / kColGroups;  // 8 or 16 row slices
-      constexpr int kRowsPer = kBlockM / kSlices;             // 16 or 8 rows per thread
-      const int cg = threadIdx.x % kColGroups;
-      const int sl = threadIdx.x / kColGroups;
+      constexpr int kSlices = kEpiThreads / kColGroups;       // row slices
+      constexpr int kRowsPer = kBlockM / kSlices;             // rows per thread
+      const int cg = etid % kColGroups;
+      const int sl = etid / kColGroups;
       float s[8], ss[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
@@ -275,25 +283,26 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
         }
       }
       // cross-warp fold in shared memory, then ONE atomic per channel and statistic per tile
-      float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [4 warps][2][BLOCK_N]
+      float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [epi warps][2][BLOCK_N]
       if ((threadIdx.x & 31) < kColGroups) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          red[(warp * 2 + 0) * BLOCK_N + cg * 8 + i] = s[i];
-          red[(warp * 2 + 1) * BLOCK_N + cg * 8 + i] = ss[i];
+          red[(ew * 2 + 0) * BLOCK_N + cg * 8 + i] = s[i];
+          red[(ew * 2 + 1) * BLOCK_N + cg * 8 + i] = ss[i];
         }
       }
-      named_bar_sync(1, kProducerThreads);
-      for (int c = threadIdx.x; c < 2 * BLOCK_N; c += kProducerThreads) {
+      named_bar_sync(1, kEpiThreads);
+      for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
         const int which = c / BLOCK_N, col = c - which * BLOCK_N;
-        const float v = red[(0 * 2 + which) * BLOCK_N + col] + red[(1 * 2 + which) * BLOCK_N + col] +
-                        red[(2 * 2 + which) * BLOCK_N + col] + red[(3 * 2 + which) * BLOCK_N + col];
+        float v = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += red[(wq * 2 + which) * BLOCK_N + col];
         atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
       }
     }
     // coalesced stores: 16 bytes per thread, a row of the tile is BLOCK_N*2 contiguous bytes
     constexpr int kVecPerRow = BLOCK_N / 8;
-    for (int idx = threadIdx.x; idx < kBlockM * kVecPerRow; idx += kProducerThreads) {
+    for (int idx = etid; idx < kBlockM * kVecPerRow; idx += kEpiThreads) {
       const int r = idx / kVecPerRow, ch = idx - r * kVecPerRow;
       const int m = *reinterpret_cast<const int*>(stg + r * Cfg::kPitch + BLOCK_N * 2);
       if (m >= 0) {
@@ -308,6 +317,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
           p = unpack_bf16x2(val.w); q = unpack_bf16x2(o.w); val.w = pack_bf16x2(p.x + q.x, p.y + q.y);
         }
         *reinterpret_cast<uint4*>(a.out + off) = val;
+        if (kTile && a.zfill) {      // even outH/outW guaranteed by the host: all three siblings exist
+          const uint4 z = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(a.out + off + a.ldc) = z;
+          *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW) * a.ldc) = z;
+          *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW + 1) * a.ldc) = z;
+        }
       }
     }
   } else if (warp == 4) {
@@ -395,7 +410,7 @@ constexpr int wg_smem_bytes(int stages) {
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ TmaSet tmXs, WgradArgs a) {
   const CUtensorMap& tmX = tmXs.m[0];
   constexpr bool kXTma = (MODE == kConvGemm || MODE == kConvTileFwd);
@@ -446,8 +461,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    if (!kXTma) {
+  if (warp < 4 || warp >= 6) {
+    const int egrp = warp < 4 ? 0 : 1;
+    const int qw = warp & 3;
+    const int ew = egrp * 4 + qw;
+    if (!kXTma && warp < 4) {
       const int chunk = threadIdx.x >> 6;      // which 64-column half of the B tile
       const int row = threadIdx.x & 63;        // pixel row inside the k-block
       const int colc = col0 + chunk * 64;      // first k column of my chunk
@@ -517,11 +535,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     mbar_wait(acc_full, 0);
     tc_fence_after();
     float* stg = reinterpret_cast<float*>(smem);
-    const int row = threadIdx.x;
+    const int row = qw * 32 + (threadIdx.x & 31);
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 32) {
+    for (int c0 = egrp * (128 / kEpiGroups); c0 < (egrp + 1) * (128 / kEpiGroups); c0 += 32) {
       uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + c0, v);
       tmem_ld_wait();
       float4* d = reinterpret_cast<float4*>(stg + row * kWgPitch + c0);
 #pragma unroll
@@ -530,11 +548,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
                            __uint_as_float(v[4 * j + 3]));
     }
     tc_fence_before();
-    named_bar_sync(1, kProducerThreads);
+    named_bar_sync(1, kEpiThreads);
     const int lane = threadIdx.x & 31;
     const int c = col0 + lane * 4;
     if (c < a.ncols) {
-      for (int r = warp; r < 128; r += 4) {
+      for (int r = ew; r < 128; r += 4 * kEpiGroups) {
         const int co = co0 + r;
         if (co < a.Cout) {
           const float4 val = *reinterpret_cast<const float4*>(stg + r * kWgPitch + lane * 4);
@@ -767,6 +785,8 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
   }
   a.ntaps = 0;
   a.outH = a.dstH; a.outW = a.dstW; a.out_stride = 1; a.out_pa = 0; a.out_pb = 0;
+  const int want_zfill = a.zfill;
+  a.zfill = 0;
   int m_tiles = (a.M + kBlockM - 1) / kBlockM;
   const bool stats = a.sum != nullptr;
   auto dispatch = [&](const ConvArgs& args, int tiles) -> cudaError_t {
@@ -852,6 +872,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
         }
       }
       if (nt == 0) continue;
+      p.zfill = (want_zfill && pa == 0 && pb == 0 && fullH % 2 == 0 && fullW % 2 == 0) ? 1 : 0;
       p.ntaps = nt;
       p.KB = nt * a.cchunks;
       cudaError_t e = dispatch(p, set_tiles(p));

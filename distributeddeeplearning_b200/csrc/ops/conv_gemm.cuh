@@ -41,6 +41,7 @@ struct ConvArgs {
   // of an outH x outW image (dense output: out_stride = 1).
   int batch, tw, th, tn, tiles_w, tiles_h;
   int outH, outW, out_stride, out_pa, out_pb;
+  int zfill;                  // stride-2 scatter with a single live phase: also write zeros to the 3 sibling pixels
   // optional explicit tap table (strided convs decomposed into stride-1 phase problems): per tap the box offset
   // in the source map, which of the 4 source maps to read, and the weight tap index r*S+s
   int ntaps;

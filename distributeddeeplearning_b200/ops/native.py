@@ -115,22 +115,22 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
         SP, RPK, KB, RP = stem_geometry(R, S)
         C.conv_gemm(C.CONV_STEM, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, H, W, 4,
                     P, Q, R, S, stride, pad, dil, SP, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, _stream())
+                    w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, 0, _stream())
     elif R == 1 and S == 1 and stride == 1 and pad == 0:
         C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, Cin // 64, Cout, H, W, Cin, P, Q,
                     1, 1, 1, 0, 1, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1],
-                    Cout, x.data_ptr(), Cin, N, 0, 0, 0, _stream())
+                    Cout, x.data_ptr(), Cin, N, 0, 0, 0, 0, _stream())
     elif USE_TILE_TMA and (stride == 1 or (stride == 2 and R * S <= 16 and USE_TILE_S2)):
         # window conv: the activation operand comes through ONE 4-D TMA box per filter tap (stride 2: the box is
         # taken from the matching 2x2 phase sub-image of x)
         tw, th, tn = tile_geometry(P, Q, N, 128)
         C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64), Cout, H, W,
                     Cin, P, Q, R, S, stride, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cout, x.data_ptr(), Cin, N, tw, th, tn, _stream())
+                    w_bf16.shape[1], Cout, x.data_ptr(), Cin, N, tw, th, tn, 0, _stream())
     else:
         C.conv_gemm(C.CONV_FWD, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64),
                     Cout, H, W, Cin, P, Q, R, S, stride, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(),
-                    w_bf16.shape[0], w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, _stream())
+                    w_bf16.shape[0], w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, 0, _stream())
     return (y, st) if stats else y
 
 
@@ -145,32 +145,36 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
     if Cin % 64 != 0 or Cout % 64 != 0:
         raise ValueError("conv_dgrad needs Cin, Cout multiples of 64")
     s2_tile = USE_TILE_TMA and USE_TILE_S2 and stride == 2 and R * S <= 16 and dil == 1 and add is None
+    dx = empty_act(N, Cin, H, W, dy.device)
+    zfill = 0
     if s2_tile and (R < 2 or S < 2):
-        # some output phases receive no tap (e.g. 1x1 stride 2 only feeds even rows/cols): they stay zero
-        dx = torch.zeros((N, Cin, H, W), dtype=torch.bfloat16, device=dy.device).contiguous(memory_format=CL)
-    else:
-        dx = empty_act(N, Cin, H, W, dy.device)
+        # some output phases receive no tap (1x1 stride 2 only feeds even rows/cols).  Even image: the live phase's
+        # epilogue writes the zeros of its three sibling pixels; odd image: clear dx first.
+        if R == 1 and S == 1 and pad == 0 and H % 2 == 0 and W % 2 == 0:
+            zfill = 1
+        else:
+            dx.zero_()
     if add is not None:
         _check_act(add, "add")
     if R == 1 and S == 1 and stride == 1 and pad == 0:
         C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, Cout // 64, Cin, P, Q, Cout, H,
                     W, 1, 1, 1, 0, 1, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1], Cin,
-                    dy.data_ptr(), Cout, N, 0, 0, 0, _stream())
+                    dy.data_ptr(), Cout, N, 0, 0, 0, 0, _stream())
     elif stride == 1 and USE_TILE_TMA:
         tw, th, tn = tile_geometry(H, W, N, 128)
         C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin, P, Q,
                     Cout, H, W, R, S, 1, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, _stream())
+                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, 0, _stream())
     elif s2_tile:
         # four stride-1 phase problems (one launch each), tiles iterate the half-resolution phase grid
         tw, th, tn = tile_geometry((H + 1) // 2, (W + 1) // 2, N, 128)
         C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin, P, Q,
                     Cout, H, W, R, S, 2, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, _stream())
+                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, zfill, _stream())
     else:
         C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64),
                     Cin, P, Q, Cout, H, W, R, S, stride, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(),
-                    w_bf16.shape[0], w_bf16.shape[1], Cin, 0, 0, N, 0, 0, 0, _stream())
+                    w_bf16.shape[0], w_bf16.shape[1], Cin, 0, 0, N, 0, 0, 0, 0, _stream())
     return dx
 
 
@@ -232,7 +236,7 @@ def linear_fwd(x: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tenso
     Npad = (Nout + 63) // 64 * 64
     y = torch.empty((B, Npad), dtype=torch.bfloat16, device=x.device)
     C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), 0, 0, B, K // 64, Npad, 1, 1, K, 1, 1, 1, 1, 1, 0, 1,
-                K // 64, int(relu), Nout, w_bf16.data_ptr(), Nout, K, Npad, x.data_ptr(), K, B, 0, 0, 0, _stream())
+                K // 64, int(relu), Nout, w_bf16.data_ptr(), Nout, K, Npad, x.data_ptr(), K, B, 0, 0, 0, 0, _stream())
     return y
 
 
@@ -243,7 +247,7 @@ def linear_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor) -> torch.Tensor:
     Nout, K = w_bf16.shape
     dx = torch.empty((B, K), dtype=torch.bfloat16, device=dy.device)
     C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, B, Npad // 64, K, 1, 1, Npad, 1, 1, 1, 1, 1, 0,
-                1, Npad // 64, 0, K, w_bf16.data_ptr(), Nout, K, K, dy.data_ptr(), Npad, B, 0, 0, 0, _stream())
+                1, Npad // 64, 0, K, w_bf16.data_ptr(), Nout, K, K, dy.data_ptr(), Npad, B, 0, 0, 0, 0, _stream())
     return dx
 
 
