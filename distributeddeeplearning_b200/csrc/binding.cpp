@@ -34,6 +34,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a, const void* w, int w_r
 cudaError_t launch_conv_wgrad(const WgradArgs& a, const void* dy, const void* x_matrix, int splits,
                               cudaStream_t stream);
 void set_conv_force_stages(int s);
+void set_conv_persistent(int on);
 }  // namespace ddl
 
 namespace {
@@ -178,6 +179,7 @@ PYBIND11_MODULE(_C, m) {
   });
 
   // ------------------------------------------------------------------ conv / GEMM
+  m.def("set_conv_persistent", &ddl::set_conv_persistent, "tuning hook: 1 = persistent kernel for TMA-fed modes");
   m.def("set_conv_force_stages", &ddl::set_conv_force_stages, "tuning hook: force the pipeline depth (0 = policy)");
   m.def("conv_gemm",
         [](int mode, ptr_t src, ptr_t out, ptr_t add, ptr_t bias, ptr_t sum, ptr_t sumsq, int M, int KB, int ldc,

@@ -399,6 +399,277 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
 }
 
 // ---------------------------------------------------------------------------------------------
+// persistent variant for the TMA-fed modes (GEMM, TILE_FWD, TILE_DGRAD, GEMM_DGRAD)
+// ---------------------------------------------------------------------------------------------
+// One CTA per resident slot (2 per SM) walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ...  The operand ring
+// keeps streaming across tile boundaries, the accumulator is double-buffered in TMEM (2 x BLOCK_N columns) and the
+// 8 epilogue warps drain tile i while the MMA thread already accumulates tile i+1: the per-tile fixed latency
+// (TMEM alloc, barrier init, first TMA round trip, epilogue) that bounds the one-tile-per-CTA kernel on short-K
+// layers is paid once per CTA instead of once per tile.
+template <int BLOCK_N>
+struct PersistCfg {
+  static constexpr int kBTileBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kPitch = BLOCK_N * 2 + 16;
+  static constexpr int kEpiBytes = ((kBlockM * kPitch + 1023) / 1024) * 1024;
+  static constexpr int kStages = (BLOCK_N <= 64) ? 3 : 2;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 8192 + 1024;
+};
+
+template <int BLOCK_N, int MODE, bool STATS>
+__global__ void __launch_bounds__(kThreads, 2)
+conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmaSet tmAs, ConvArgs a,
+                            int n_tiles, int m_tiles) {
+  using Cfg = PersistCfg<BLOCK_N>;
+  constexpr bool kBMn = mode_b_mn(MODE);
+  constexpr bool kTile = mode_tile(MODE);
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + kStages * Cfg::kStageBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + Cfg::kEpiBytes);
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* acc_full = empty + kMaxStages;      // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int KB = a.KB;
+  const int total = n_tiles * m_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1u); mbar_init(&empty[s], 1u); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&acc_empty[b], 1u); }
+    fence_mbar_init();
+  }
+  if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmAs.m[0]);
+  }
+  if (warp == 5) tmem_alloc<2 * BLOCK_N>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int t, int& n0, int& m0, int& tq0, int& tp0, int& tn0) {
+    const int nt = t % n_tiles;
+    int mt = t / n_tiles;
+    n0 = nt * BLOCK_N;
+    m0 = mt * kBlockM;
+    tq0 = tp0 = tn0 = 0;
+    if (kTile) {
+      const int wb = mt % a.tiles_w; mt /= a.tiles_w;
+      const int hb = mt % a.tiles_h;
+      const int nb = mt / a.tiles_h;
+      tq0 = wb * a.tw; tp0 = hb * a.th; tn0 = nb * a.tn;
+      m0 = 0;
+    }
+  };
+
+  if (warp < 4 || warp >= 6) {
+    // =================================== epilogue warps =======================================
+    const int egrp = warp < 4 ? 0 : 1;
+    const int qw = warp & 3;
+    const int row = qw * 32 + (threadIdx.x & 31);
+    const int etid = egrp * 128 + row;
+    const int ew = egrp * 4 + qw;
+    constexpr int kColsPerGroup = BLOCK_N / kEpiGroups;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      int n0, m0, tq0, tp0, tn0;
+      tile_origin(t, n0, m0, tq0, tp0, tn0);
+      int my_m;
+      if (kTile) {
+        const int wl = row % a.tw;
+        const int t2 = row / a.tw;
+        const int hl = t2 % a.th;
+        const int nl = t2 / a.th;
+        const bool ok = nl < a.tn && (tn0 + nl) < a.batch && (tp0 + hl) < a.dstH && (tq0 + wl) < a.dstW;
+        my_m = ok ? ((tn0 + nl) * a.outH + (tp0 + hl) * a.out_stride + a.out_pa) * a.outW +
+                        (tq0 + wl) * a.out_stride + a.out_pb
+                  : -1;
+      } else {
+        my_m = (m0 + row) < a.M ? (m0 + row) : -1;
+      }
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = egrp * kColsPerGroup; c0 < (egrp + 1) * kColsPerGroup; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + buf * BLOCK_N + c0, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+          if (a.bias) {
+            const int cb = n0 + c0 + 2 * j;
+            if (cb < a.n_valid) x0 += a.bias[cb];
+            if (cb + 1 < a.n_valid) x1 += a.bias[cb + 1];
+          }
+          if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+          packed[j] = (kTile && my_m < 0) ? 0u : pack_bf16x2(x0, x1);
+        }
+        uint4* dstp = reinterpret_cast<uint4*>(stg + row * Cfg::kPitch + c0 * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dstp[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+      }
+      if (egrp == 0) *reinterpret_cast<int*>(stg + row * Cfg::kPitch + BLOCK_N * 2) = my_m;
+      tc_fence_before();
+      named_bar_sync(1, kEpiThreads);
+      if (etid == 0) mbar_arrive(&acc_empty[buf]);      // every epilogue thread has finished reading this TMEM buffer
+      if (STATS) {
+        constexpr int kColGroups = BLOCK_N / 8;
+        constexpr int kSlices = kEpiThreads / kColGroups;
+        constexpr int kRowsPer = kBlockM / kSlices;
+        const int cg = etid % kColGroups;
+        const int sl = etid / kColGroups;
+        float s[8], ss[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+        const uint8_t* p0 = stg + (sl * kRowsPer) * Cfg::kPitch + cg * 16;
+#pragma unroll 4
+        for (int r = 0; r < kRowsPer; ++r) {
+          const uint4 u = *reinterpret_cast<const uint4*>(p0 + r * Cfg::kPitch);
+          float2 f;
+          f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
+          f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
+          f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
+          f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
+        }
+#pragma unroll
+        for (int off = kColGroups; off < 32; off <<= 1) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+            ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
+          }
+        }
+        if ((threadIdx.x & 31) < kColGroups) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            red[(ew * 2 + 0) * BLOCK_N + cg * 8 + i] = s[i];
+            red[(ew * 2 + 1) * BLOCK_N + cg * 8 + i] = ss[i];
+          }
+        }
+        named_bar_sync(1, kEpiThreads);
+        for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
+          const int which = c / BLOCK_N, col = c - which * BLOCK_N;
+          float v = 0.f;
+#pragma unroll
+          for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += red[(wq * 2 + which) * BLOCK_N + col];
+          atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
+        }
+      }
+      constexpr int kVecPerRow = BLOCK_N / 8;
+      for (int idx = etid; idx < kBlockM * kVecPerRow; idx += kEpiThreads) {
+        const int r = idx / kVecPerRow, ch = idx - r * kVecPerRow;
+        const int m = *reinterpret_cast<const int*>(stg + r * Cfg::kPitch + BLOCK_N * 2);
+        if (m >= 0) {
+          uint4 val = *reinterpret_cast<const uint4*>(stg + r * Cfg::kPitch + ch * 16);
+          const size_t off = static_cast<size_t>(m) * a.ldc + n0 + ch * 8;
+          if (a.add) {
+            const uint4 o = *reinterpret_cast<const uint4*>(a.add + off);
+            float2 p, q;
+            p = unpack_bf16x2(val.x); q = unpack_bf16x2(o.x); val.x = pack_bf16x2(p.x + q.x, p.y + q.y);
+            p = unpack_bf16x2(val.y); q = unpack_bf16x2(o.y); val.y = pack_bf16x2(p.x + q.x, p.y + q.y);
+            p = unpack_bf16x2(val.z); q = unpack_bf16x2(o.z); val.z = pack_bf16x2(p.x + q.x, p.y + q.y);
+            p = unpack_bf16x2(val.w); q = unpack_bf16x2(o.w); val.w = pack_bf16x2(p.x + q.x, p.y + q.y);
+          }
+          *reinterpret_cast<uint4*>(a.out + off) = val;
+          if (kTile && a.zfill) {
+            const uint4 z = make_uint4(0, 0, 0, 0);
+            *reinterpret_cast<uint4*>(a.out + off + a.ldc) = z;
+            *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW) * a.ldc) = z;
+            *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW + 1) * a.ldc) = z;
+          }
+        }
+      }
+      named_bar_sync(1, kEpiThreads);      // staging (and the stats scratch) may be overwritten by the next tile
+    }
+  } else if (warp == 4) {
+    // ===================================== TMA producer =======================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : kATileBytes;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int n0, m0, tq0, tp0, tn0;
+        tile_origin(t, n0, m0, tq0, tp0, tn0);
+        int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          const uint32_t sB = smem_u32(sA + kATileBytes);
+          mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + a_bytes);
+          int widx = tap, dh = 0, dw = 0, mapi = 0;
+          if (kTile) {
+            if (a.ntaps > 0) {
+              widx = a.tap_widx[tap]; dh = a.tap_dh[tap]; dw = a.tap_dw[tap]; mapi = a.tap_map[tap];
+            } else if (MODE == kConvTileFwd) {
+              dh = tap_r * a.dil - a.pad; dw = tap_s * a.dil - a.pad;
+            } else {
+              dh = a.pad - tap_r * a.dil; dw = a.pad - tap_s * a.dil;
+            }
+          }
+          if (kBMn) {
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
+          } else {
+            tma_load_2d(sB, &tmB, (widx * a.cchunks + cc) * kBlockK, n0, &full[stage]);
+          }
+          if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
+          else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, &full[stage]);
+          if (++cc == a.cchunks) { cc = 0; ++tap; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ====================================== MMA issuer ========================================
+    constexpr uint32_t idesc = idesc_bf16(kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);     // epilogue has drained this TMEM buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+      for (int kb = 0; kb < KB; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sB = sA + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
+            const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == KB - 1) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<2 * BLOCK_N>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // wgrad kernel: dW[co][k] += sum over a pixel range of dY[m][co] * im2col(X)[m][k]
 // ---------------------------------------------------------------------------------------------
 constexpr int kWgMaxStages = 3;
@@ -731,6 +1002,34 @@ cudaError_t launch_fwd_t(const CUtensorMap& tmB, const TmaSet& tmA, const ConvAr
   return cudaGetLastError();
 }
 
+int g_persistent = 1;        // TMA-fed modes use the persistent kernel (tuning hook: set_conv_persistent)
+int g_num_sms = 0;
+
+template <int BLOCK_N, int MODE, bool STATS>
+cudaError_t launch_persistent_t(const CUtensorMap& tmB, const TmaSet& tmA, const ConvArgs& a, int n_total, int m_tiles,
+                                cudaStream_t stream) {
+  using Cfg = PersistCfg<BLOCK_N>;
+  auto kern = conv_gemm_persistent_kernel<BLOCK_N, MODE, STATS>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int n_tiles = n_total / BLOCK_N;
+  const long long total = static_cast<long long>(n_tiles) * m_tiles;
+  long long grid = 2LL * g_num_sms;
+  if (grid > total) grid = total;
+  kern<<<static_cast<unsigned>(grid), kThreads, Cfg::kSmemBytes, stream>>>(tmB, tmA, a, n_tiles, m_tiles);
+  return cudaGetLastError();
+}
+
 // Pipeline-depth policy.  Short-K tiles are dominated by per-CTA fixed latency (TMEM alloc, first TMA
 // round trip, epilogue), so they get a shallow ring -> small shared-memory footprint -> 3-4 CTAs per SM whose
 // prologues/epilogues overlap.  Long-K tiles get the deep ring.  g_force_stages (tuning hook) overrides.
@@ -752,6 +1051,15 @@ int pick_stages(int KB) {
 template <int MODE>
 cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs a, int n_total, int m_tiles,
                             bool stats, cudaStream_t stream) {
+  if (mode_a_tma(MODE) && g_persistent) {
+    if (n_total % 128 == 0)
+      return stats ? launch_persistent_t<128, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
+                   : launch_persistent_t<128, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
+    if (n_total % 64 == 0)
+      return stats ? launch_persistent_t<64, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
+                   : launch_persistent_t<64, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
+    return cudaErrorInvalidValue;
+  }
   if (n_total % 128 == 0) {
     a.stages = pick_stages<128, MODE>(a.KB);
     return stats ? launch_fwd_t<128, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
@@ -768,6 +1076,7 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs 
 }  // namespace
 
 void set_conv_force_stages(int s) { g_force_stages = s; }
+void set_conv_persistent(int on) { g_persistent = on; }
 
 // `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
 // `a_matrix`: the A operand for the TMA-A modes (2-D matrix [M][a_cols], or the NHWC tensor in tile modes).

@@ -23,7 +23,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from . import native
-from .functional import CL, grad_buffer, notify_ready, weight_bf16
+from .functional import CL, grad_buffer, notify_ready, run_wgrad, weight_bf16
 
 
 class _ResidualBlock(torch.autograd.Function):
@@ -98,7 +98,9 @@ class _ResidualBlock(torch.autograd.Function):
                     dyd, _, _ = native.bn_act_bwd(dres, yd, yd, save_d, gd, False, False, ggd, bgd)
                     add = native.conv_dgrad(dyd, wbd, x.shape, (wd.shape[2], wd.shape[3]), std, padd, dild)
                     if wd.requires_grad:
-                        native.conv_wgrad(x, dyd, grad_buffer(wd), (wd.shape[2], wd.shape[3]), std, padd, dild)
+                        gwd = grad_buffer(wd)
+                        run_wgrad(wd, lambda: native.conv_wgrad(x, dyd, gwd, (wd.shape[2], wd.shape[3]), std, padd, dild),
+                                  x, dyd)
                     for p in (gd, bd, wd):
                         if p.requires_grad:
                             notify_ready(p)
@@ -107,7 +109,9 @@ class _ResidualBlock(torch.autograd.Function):
                 else:
                     dx = native.add(native.conv_dgrad(dy, ctx.wbs[0], x.shape, kernel, st, pad, dil), add)
             if w.requires_grad:
-                native.conv_wgrad(h_in, dy, grad_buffer(w), kernel, st, pad, dil)
+                gw = grad_buffer(w)
+                run_wgrad(w, lambda h_in=h_in, dy=dy, gw=gw, kernel=kernel, st=st, pad=pad, dil=dil:
+                          native.conv_wgrad(h_in, dy, gw, kernel, st, pad, dil), h_in, dy)
             for p in (g, b, w):
                 if p.requires_grad:
                     notify_ready(p)

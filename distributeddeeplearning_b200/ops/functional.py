@@ -40,6 +40,35 @@ def grad_buffer(p: torch.Tensor) -> torch.Tensor:
     return p.grad
 
 
+# ------------------------------------------------------------------------------------------------
+# weight-gradient side stream
+# ------------------------------------------------------------------------------------------------
+# wgrad kernels feed only the optimizer, never the rest of backward.  When a fused engine is attached (it joins this
+# stream before it consumes a bucket) they are enqueued on a side stream so they overlap the dgrad -> BN-backward chain
+# of the earlier layers: the conv kernels are latency-bound per tile and the BN kernels are HBM-bound, so co-residency
+# fills otherwise idle issue slots.  DDL_ASYNC_WGRAD=0 restores single-stream execution.
+_WGRAD = {"stream": None, "enabled": os.environ.get("DDL_ASYNC_WGRAD", "1") != "0"}
+
+
+def wgrad_stream() -> Optional["torch.cuda.Stream"]:
+    return _WGRAD["stream"]
+
+
+def run_wgrad(param: torch.Tensor, fn, *tensors: torch.Tensor) -> None:
+    """Run ``fn()`` (a wgrad launch for ``param``) — on the side stream when the engine will join it."""
+    if not _WGRAD["enabled"] or getattr(param, "_ddl_ready", None) is None:
+        fn()
+        return
+    if _WGRAD["stream"] is None:
+        _WGRAD["stream"] = torch.cuda.Stream(device=param.device)
+    side = _WGRAD["stream"]
+    side.wait_stream(torch.cuda.current_stream(param.device))
+    with torch.cuda.stream(side):
+        fn()
+    for t in tensors:
+        t.record_stream(side)
+
+
 def notify_ready(p: torch.Tensor) -> None:
     cb = getattr(p, "_ddl_ready", None)
     if cb is not None:
@@ -123,7 +152,8 @@ class _ConvBnAct(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil)
         if weight.requires_grad:
-            native.conv_wgrad(x, dy, grad_buffer(weight), kernel, stride, pad, dil)
+            gw = grad_buffer(weight)
+            run_wgrad(weight, lambda: native.conv_wgrad(x, dy, gw, kernel, stride, pad, dil), x, dy)
         # LAST: a ready bucket may launch its allreduce+update kernel on the side stream now; everything
         # this layer still needed from the weight arenas (gamma, wb) has been enqueued before the event
         if gamma.requires_grad:

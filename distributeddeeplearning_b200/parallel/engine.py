@@ -234,6 +234,11 @@ class FusedSGD(torch.optim.Optimizer):
             ev = torch.cuda.Event()
             ev.record(cur)
             stream.wait_event(ev)
+        from ..ops.functional import wgrad_stream
+
+        wg = wgrad_stream()
+        if wg is not None:          # weight gradients are produced on a side stream (ops.functional.run_wgrad)
+            stream.wait_stream(wg)
         if not self._hyper_uploaded:
             self._upload_hyper(stream)
             self._hyper_uploaded = True

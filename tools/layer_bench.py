@@ -84,6 +84,11 @@ def main():
                 w_ = timeit(lambda: nv.conv_wgrad(x, dy, gw, (k, k), s, p), reps=3, flush=flush)
                 sweep[st_] = (round(f_, 4), round(d_, 4), round(w_, 4))
             C.set_conv_force_stages(0)
+        C.set_conv_persistent(0)
+        np_f = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), reps=3, flush=flush)
+        np_d = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), reps=3, flush=flush) if ci != 3 else 0.0
+        C.set_conv_persistent(1)
+        sweep["nonpersistent"] = (round(np_f, 4), round(np_d, 4))
         t_fwd = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), flush=flush)
         t_bn = timeit(lambda: nv.bn_act_fwd(y, st, gamma, beta, rm, rv, 1e-5, 0.1, True, None, True), flush=flush)
         t_dg = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), flush=flush) if ci != 3 else 0.0
