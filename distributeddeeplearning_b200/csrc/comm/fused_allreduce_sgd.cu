@@ -351,6 +351,54 @@ __global__ void __launch_bounds__(512) allreduce_kernel(CommCtx c, int channel, 
   block_barrier(c, channel, epoch + 1);
 }
 
+// Bandwidth variant of the two-shot NVLS allreduce: 4 independent 16-byte multimem.ld_reduce per thread in flight
+// before the matching multimem.st (NVLink round trips are ~2 us: bytes in flight decide the bandwidth).
+template <bool BF16>
+__global__ void __launch_bounds__(512) allreduce_mc_twoshot_kernel(CommCtx c, int channel, uint64_t off, int64_t numel,
+                                                                   float scale) {
+  const int64_t tid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t nthreads = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const uint32_t epoch = claim_epochs(c, channel, 2);
+  block_barrier(c, channel, epoch);
+  constexpr int ES = BF16 ? 2 : 4;
+  const int64_t slice_bytes = numel * ES / c.world;
+  const uint64_t base = c.mc_base + off + static_cast<uint64_t>(slice_bytes) * c.rank;
+  const int64_t n16 = slice_bytes / 16;
+  constexpr int U = 4;
+  for (int64_t i = tid; i < n16; i += U * nthreads) {
+    if (BF16) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * nthreads < n16) v[u] = multimem_ld_reduce_bf16x8(base + (i + u * nthreads) * 16);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * nthreads < n16) {
+          if (scale != 1.0f) {
+            float2 p;
+            p = unpack_bf16x2(v[u].x); v[u].x = pack_bf16x2(p.x * scale, p.y * scale);
+            p = unpack_bf16x2(v[u].y); v[u].y = pack_bf16x2(p.x * scale, p.y * scale);
+            p = unpack_bf16x2(v[u].z); v[u].z = pack_bf16x2(p.x * scale, p.y * scale);
+            p = unpack_bf16x2(v[u].w); v[u].w = pack_bf16x2(p.x * scale, p.y * scale);
+          }
+          multimem_st_u32x4(base + (i + u * nthreads) * 16, v[u]);
+        }
+    } else {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * nthreads < n16) v[u] = multimem_ld_reduce_f32x4(base + (i + u * nthreads) * 16);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (i + u * nthreads < n16) {
+          if (scale != 1.0f) { v[u].x *= scale; v[u].y *= scale; v[u].z *= scale; v[u].w *= scale; }
+          multimem_st_f32x4(base + (i + u * nthreads) * 16, v[u]);
+        }
+    }
+  }
+  block_barrier(c, channel, epoch + 1);
+}
+
 // ------------------------------------------------------------------------------------------
 // broadcast of a symmetric byte range from `root` to every replica (K16) and a pure barrier
 // ------------------------------------------------------------------------------------------
@@ -448,8 +496,13 @@ cudaError_t launch_allreduce(const CommCtx& c, int channel, uint64_t off, int64_
   if (use_mc && c.mc_base == 0) return cudaErrorInvalidValue;
 #define DDL_AR(MC, BF, OS) allreduce_kernel<MC, BF, OS><<<blocks, 512, 0, stream>>>(c, channel, off, numel, scale)
   if (use_mc) {
-    if (bf16) { if (oneshot) DDL_AR(true, true, true); else DDL_AR(true, true, false); }
-    else      { if (oneshot) DDL_AR(true, false, true); else DDL_AR(true, false, false); }
+    if (bf16) {
+      if (oneshot) DDL_AR(true, true, true);
+      else allreduce_mc_twoshot_kernel<true><<<blocks, 512, 0, stream>>>(c, channel, off, numel, scale);
+    } else {
+      if (oneshot) DDL_AR(true, false, true);
+      else allreduce_mc_twoshot_kernel<false><<<blocks, 512, 0, stream>>>(c, channel, off, numel, scale);
+    }
   } else {
     if (bf16) { if (oneshot) DDL_AR(false, true, true); else DDL_AR(false, true, false); }
     else      { if (oneshot) DDL_AR(false, false, true); else DDL_AR(false, false, false); }
