@@ -148,6 +148,30 @@ def _datastore_path() -> str:
 
 
 @task
+def create_resource_group(c):
+    """Create the root that holds run history and datastores (reference: `az group create`)."""
+    e = _env()
+    for d in (e.get("RUNS_DIR", "runs"), os.path.dirname(_datastore_path()) or "."):
+        os.makedirs(d, exist_ok=True)
+    print("resource root ready")
+
+
+@task(pre=[create_resource_group])
+def create_premium_storage(c):
+    """Reserve the datastore location (reference: BlockBlobStorage Premium_LRS account)."""
+    os.makedirs(_datastore_path(), exist_ok=True)
+    print("storage:", _datastore_path())
+
+
+@task(pre=[create_premium_storage])
+def store_key(c):
+    """Persist the datastore location in .env (reference writes ACCOUNT_KEY with set_key)."""
+    path = cfg.find_dotenv() or ".env"
+    cfg.set_key(path, "DATASTORE_ROOT", os.path.abspath(_datastore_path()))
+    print(f"DATASTORE_ROOT stored in {path}")
+
+
+@task
 def create_container(c):
     """Create the local datastore directory (reference: resource group -> storage account -> container)."""
     p = _datastore_path()
@@ -202,6 +226,18 @@ def prepare_imagenet(c, download_dir=None, target_dir=None, check_sha1=True):
 
     e = _env()
     prep.main(download_dir or e["DATA"], target_dir or e["DATA"], check_sha1)
+
+
+@task
+def upload_records(c):
+    """Copy the record shards to the datastore (reference: storage.tfrecords.upload-data via azcopy)."""
+    _copy_tree(os.path.join(_env()["DATA"], "records"), os.path.join(_datastore_path(), "records"))
+
+
+@task
+def download_records(c):
+    """Copy the record shards from the datastore (reference: storage.tfrecords.download-data)."""
+    _copy_tree(os.path.join(_datastore_path(), "records"), os.path.join(_env()["DATA"], "records"))
 
 
 @task
@@ -338,6 +374,9 @@ def build_namespace() -> Collection:
                                          {"synthetic": _template("tfexp_local_synthetic")},
                                          {"synthetic": _template("tfexp_remote_synthetic")}))
     storage = Collection("storage")
+    storage.add_task(create_resource_group, "create-resource-group")
+    storage.add_task(create_premium_storage, "create-premium-storage")
+    storage.add_task(store_key, "store-key")
     storage.add_task(create_container, "create-container")
     storage.add_task(prepare_imagenet, "prepare-imagenet")
     image = Collection("image")
@@ -349,6 +388,8 @@ def build_namespace() -> Collection:
     storage.add_collection(image)
     rec = Collection("tfrecords")
     rec.add_task(generate_records, "generate-tf-records")
+    rec.add_task(upload_records, "upload-data")
+    rec.add_task(download_records, "download-data")
     storage.add_collection(rec)
     ns.add_collection(storage)
     return ns

@@ -107,15 +107,16 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
 }
 
 // ---- backward pass 1: per-channel reductions ----------------------------------------------------
-// accumulates S1 = sum dy and S2 = sum dy * x (raw x); dbeta = S1, dgamma = invstd * (S2 - mean * S1)
+// accumulates S1 = sum dy and S2 = sum dy * x (raw x); dbeta = S1, dgamma = invstd * (S2 - mean * S1).
+// Mapping: a block owns ONE 64-channel chunk (blockIdx.y) and 32 row lanes (thread = 8 channels x 1 row lane),
+// so a block ends with 64 x 2 partial sums -> 128 atomics per block and only gridDim.x contributions per address.
+// (A block spanning all channels would issue C x 2 atomics per block: ~5 M contended atomics for C = 2048, a
+// ~100 us floor that was measured to dominate the small layers.)
 template <int MASK>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdArgs a) {
-  const int groups = a.C / 8;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = tid % groups;
-  const int row0 = tid / groups;
-  const int row_stride = (gridDim.x * blockDim.x) / groups;
-  const int c0 = g * 8;
+  const int cgl = threadIdx.x & 7;                 // channel group within the 64-channel chunk
+  const int rl = threadIdx.x >> 3;                 // row lane 0..31
+  const int c0 = blockIdx.y * 64 + cgl * 8;
   float s1[8], s2[8], msc[8], msh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; msc[i] = 0.f; msh[i] = 0.f; }
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
 #pragma unroll
     for (int i = 0; i < 8; ++i) { msc[i] = gam.v[i] * invstd.v[i]; msh[i] = bet.v[i] - mean.v[i] * msc[i]; }
   }
-  for (int r = row0; r < a.M; r += row_stride) {
+  for (int r = blockIdx.x * 32 + rl; r < a.M; r += gridDim.x * 32) {
     const size_t off = static_cast<size_t>(r) * a.C + c0;
     float dz[8], x[8];
     unpack8(ld_stream_u4(a.dz + off), dz);
@@ -145,28 +146,30 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
       s2[i] = fmaf(dz[i], x[i], s2[i]);
     }
   }
-  // fold the threads of this block that share a channel group, then 16 atomics per group per block
-  __shared__ float red[2][kBnThreads][8 + 1];
+  // lanes of a warp sharing a channel group: lane = (rl % 4) * 8 + cgl -> xor 8, 16
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s1[i]; red[1][threadIdx.x][i] = s2[i]; }
-  __syncthreads();
-  if (threadIdx.x < groups) {
-    const int per_block = blockDim.x / groups;
-    float t0[8], t1[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { t0[i] = 0.f; t1[i] = 0.f; }
-    for (int k = 0; k < per_block; ++k) {
-      const int t = threadIdx.x + k * groups;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { t0[i] += red[0][t][i]; t1[i] += red[1][t][i]; }
-    }
-    const int gc = ((blockIdx.x * blockDim.x + threadIdx.x) % groups) * 8;
-    Vec8 mean = load8_f32(a.mean + gc), invstd = load8_f32(a.invstd + gc);
+  for (int off = 8; off < 32; off <<= 1) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(a.dbeta + gc + i, t0[i]);
-      atomicAdd(a.dgamma + gc + i, invstd.v[i] * (t1[i] - mean.v[i] * t0[i]));
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
     }
+  }
+  __shared__ float red[kBnThreads / 32][8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[warp][lane][i] = s1[i]; red[warp][lane][8 + i] = s2[i]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 3, i = threadIdx.x & 7;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kBnThreads / 32; ++w) { t1 += red[w][g][i]; t2 += red[w][g][8 + i]; }
+    const int ch = blockIdx.y * 64 + g * 8 + i;
+    atomicAdd(a.dbeta + ch, t1);
+    atomicAdd(a.dgamma + ch, a.invstd[ch] * (t2 - a.mean[ch] * t1));
   }
 }
 
@@ -259,10 +262,17 @@ cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) 
   if (kBnThreads % groups != 0) return cudaErrorInvalidValue;   // groups <= 256 (C <= 2048), power of two
   const int grid = bn_grid(a.M, a.C, sms);
   const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : kMaskZ);
+  if (a.C % 64 != 0) return cudaErrorInvalidValue;
+  const int chunks = a.C / 64;
+  int gx = (a.M + 32 * 8 - 1) / (32 * 8);                 // >= 8 rows per thread
+  const int cap = (sms * 8 + chunks - 1) / chunks;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  const dim3 rgrid(gx, chunks);
   switch (mask) {
-    case kMaskNone: bn_act_bwd_reduce_kernel<kMaskNone><<<grid, kBnThreads, 0, stream>>>(a); break;
-    case kMaskZ: bn_act_bwd_reduce_kernel<kMaskZ><<<grid, kBnThreads, 0, stream>>>(a); break;
-    default: bn_act_bwd_reduce_kernel<kMaskX><<<grid, kBnThreads, 0, stream>>>(a); break;
+    case kMaskNone: bn_act_bwd_reduce_kernel<kMaskNone><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+    case kMaskZ: bn_act_bwd_reduce_kernel<kMaskZ><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+    default: bn_act_bwd_reduce_kernel<kMaskX><<<rgrid, kBnThreads, 0, stream>>>(a); break;
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

@@ -1051,7 +1051,20 @@ int pick_stages(int KB) {
 template <int MODE>
 cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs a, int n_total, int m_tiles,
                             bool stats, cudaStream_t stream) {
+  bool persistent = false;
   if (mode_a_tma(MODE) && g_persistent) {
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    // persistence pays when every CTA gets several tiles (measured crossover ~3.5 tiles per resident CTA);
+    // below that the one-tile-per-CTA kernel with 3 CTAs/SM wins.  g_persistent == 2 forces it (tuning).
+    const long long tiles = static_cast<long long>(n_total / ((n_total % 128 == 0) ? 128 : 64)) * m_tiles;
+    persistent = g_persistent == 2 || tiles * 2 >= 7LL * 2 * g_num_sms;
+  }
+  if (persistent) {
     if (n_total % 128 == 0)
       return stats ? launch_persistent_t<128, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
                    : launch_persistent_t<128, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);

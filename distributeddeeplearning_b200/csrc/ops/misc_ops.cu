@@ -112,16 +112,15 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    // windows (pp, q) covering (h, w): pp*stride - pad + r == h
-    for (int r = 0; r < p.k; ++r) {
-      const int th = h + p.pad - r;
-      if (th < 0 || th % p.stride != 0) continue;
-      const int pp = th / p.stride;
+    // windows (pp, q) covering (h, w): pp*stride - pad + r == h with 0 <= r < k  ->  at most ceil(k/stride) per axis
+    const int pp_hi = (h + p.pad) / p.stride, q_hi = (w + p.pad) / p.stride;
+    for (int pp = pp_hi; pp >= 0; --pp) {
+      const int r = h + p.pad - pp * p.stride;
+      if (r >= p.k) break;
       if (pp >= p.P) continue;
-      for (int s = 0; s < p.k; ++s) {
-        const int tw = w + p.pad - s;
-        if (tw < 0 || tw % p.stride != 0) continue;
-        const int q = tw / p.stride;
+      for (int q = q_hi; q >= 0; --q) {
+        const int s = w + p.pad - q * p.stride;
+        if (s >= p.k) break;
         if (q >= p.Q) continue;
         const size_t o = ((static_cast<size_t>(n) * p.P + pp) * p.Q + q) * p.C + g * 8;
         const uint2 am = *reinterpret_cast<const uint2*>(argmax + o);

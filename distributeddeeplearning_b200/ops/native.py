@@ -268,7 +268,7 @@ def linear_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor) -> Non
 # ------------------------------------------------------------------------------------------------
 def bn_supported(c: int) -> bool:
     g = c // 8
-    return c % 8 == 0 and g > 0 and 256 % g == 0
+    return c % 64 == 0 and g > 0 and 256 % g == 0
 
 
 def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, running_mean, running_var,

@@ -61,8 +61,9 @@ class BenchmarkSession:
     """Model + optimizer + fixed batch; ``step()`` is one full training iteration."""
 
     def __init__(self, model_name: str, batch_size: int, cuda: bool, fp16_allreduce: bool = False, lr: float = 0.01,
-                 momentum: float = 0.0, seed: int = 0):
+                 momentum: float = 0.0, seed: int = 0, profile: bool = False):
         self.cuda = cuda
+        self.profile = bool(profile) and cuda
         self.device = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
         torch.manual_seed(seed)
         self.model = models.get_model(model_name)
@@ -98,11 +99,25 @@ class BenchmarkSession:
         target = self.target if target is None else target
         maybe_inject(self.steps_done, dist.rank())
         self.steps_done += 1
-        self.optimizer.zero_grad()
-        output = self.model(data)
-        loss = self.loss_fn(output, target)
-        loss.backward()
-        self.optimizer.step()
+        if self.profile:        # NVTX ranges: forward / backward (+ overlapped bucket kernels) / step join
+            nvtx = torch.cuda.nvtx
+            self.optimizer.zero_grad()
+            nvtx.range_push("forward")
+            output = self.model(data)
+            loss = self.loss_fn(output, target)
+            nvtx.range_pop()
+            nvtx.range_push("backward+allreduce")
+            loss.backward()
+            nvtx.range_pop()
+            nvtx.range_push("optimizer.step(join)")
+            self.optimizer.step()
+            nvtx.range_pop()
+        else:
+            self.optimizer.zero_grad()
+            output = self.model(data)
+            loss = self.loss_fn(output, target)
+            loss.backward()
+            self.optimizer.step()
         self.last_loss = loss.detach()
         return self.last_loss
 
@@ -139,7 +154,8 @@ def run(args) -> Dict:
 
         os.environ["DDL_NO_CUDA"] = "1"
     dist.init()
-    session = BenchmarkSession(args.model, args.batch_size, cuda, args.fp16_allreduce, args.lr, args.momentum)
+    session = BenchmarkSession(args.model, args.batch_size, cuda, args.fp16_allreduce, args.lr, args.momentum,
+                               profile=args.profile)
     device = "GPU" if cuda else "CPU"
     log("Model: %s" % args.model)
     log("Batch size: %d" % args.batch_size)

@@ -15,7 +15,7 @@ import time
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
-GROUPS = ["elementwise", "avgdebug", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
+GROUPS = ["elementwise", "zoo", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
 RESULTS = []
 
 
@@ -396,6 +396,29 @@ def g_model():
         print(f"{name}: worst cosine(native grad, fp32 grad) = {worst[0]:.4f} at {worst[1]}; "
               f"largest deficit vs the bf16 composite = {lag[0]:.4f} at {lag[1]}")
         RESULTS.append(worst[0] > 0.80 and lag[0] < 0.08)
+
+
+def g_zoo():
+    """One short training run per remaining zoo model through the public benchmark session (fused engine included)."""
+    import torch
+
+    from distributeddeeplearning_b200.parallel import dist
+    from distributeddeeplearning_b200.workloads.benchmark import BenchmarkSession
+
+    dist.init()
+    for name, bs in [("vgg16", 32), ("alexnet", 64), ("resnet101", 16), ("resnet34", 32), ("inception_v3", 16),
+                     ("vgg11_bn", 16)]:
+        torch.manual_seed(0)
+        s = BenchmarkSession(name, bs, True, lr=0.01 if "vgg" not in name and name != "alexnet" else 0.001)
+        losses = [float(s.step()) for _ in range(6)]
+        torch.cuda.synchronize()
+        s.optimizer.check_errors()
+        finite = all(l == l and abs(l) < 1e4 for l in losses)
+        down = losses[-1] < losses[0]
+        print(f"[{'ok' if finite and down else 'FAIL'}] {name:14s} batch {bs}: loss " + " ".join(f"{l:.3f}" for l in losses), flush=True)
+        RESULTS.append(finite and down)
+        del s
+        torch.cuda.empty_cache()
 
 
 def g_avgdebug():
