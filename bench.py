@@ -115,9 +115,11 @@ def run_ours(a):
     session = BenchmarkSession(a.model, a.batch_size, True, a.fp16_allreduce)
     B, dev = a.batch_size, session.device
 
-    def region(step_fn, steps, warmup):
+    def region(step_fn, steps, warmup, tail=None):
         for _ in range(warmup):
             step_fn()
+        if tail is not None:
+            tail()
         dist.barrier()
         torch.cuda.synchronize()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -125,6 +127,8 @@ def run_ours(a):
         start.record()
         for _ in range(steps):
             step_fn()
+        if tail is not None:
+            tail()                     # host has read the result of the last timed step before the clock stops
         stop.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -151,8 +155,8 @@ def run_ours(a):
         mean = torch.tensor([0.485, 0.456, 0.406], device=dev)
         std = torch.tensor([0.229, 0.224, 0.225], device=dev)
         copy_stream = torch.cuda.Stream()
-        host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
-        state = {"i": 0, "next": None, "losses": []}
+        host_loss = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        state = {"i": 0, "next": None, "losses": [], "pending": None}
 
         def prefetch(i):
             with torch.cuda.stream(copy_stream):
@@ -173,11 +177,27 @@ def run_ours(a):
             xd.record_stream(torch.cuda.current_stream())
             yd.record_stream(torch.cuda.current_stream())
             l = session.step(x, yd)
-            host_loss.copy_(l.reshape(1), non_blocking=False)   # D2H read of this step's result
-            state["losses"].append(float(host_loss[0]))
+            # D2H read of EVERY step's loss: the copy is enqueued now, the host consumes it one step later so the
+            # CPU keeps launching step i+1 while step i drains (the last one is consumed by flush_e2e below)
+            buf = host_loss[i & 1]
+            buf.copy_(l.reshape(1), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            if state["pending"] is not None:
+                pev, pbuf = state["pending"]
+                pev.synchronize()
+                state["losses"].append(float(pbuf[0]))
+            state["pending"] = (ev, buf)
             state["i"] = i + 1
 
-        ms_e, _ = region(e2e_step, a.steps, max(3, a.warmup // 2))
+        def flush_e2e():
+            if state["pending"] is not None:
+                pev, pbuf = state["pending"]
+                pev.synchronize()
+                state["losses"].append(float(pbuf[0]))
+                state["pending"] = None
+
+        ms_e, _ = region(e2e_step, a.steps, max(3, a.warmup // 2), tail=flush_e2e)
         e2e = {"value": world * B * a.steps / (ms_e / 1e3), "unit": "images/sec",
                "h2d_bytes_per_step": world * (B * size * size * 3 + B * 8), "d2h_bytes_per_step": world * 4,
                "ms_per_step": ms_e / a.steps}
