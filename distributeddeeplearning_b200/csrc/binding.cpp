@@ -155,12 +155,17 @@ PYBIND11_MODULE(_C, m) {
                                       numel, blocks, S(stream)), "fused_sgd_local");
   });
   m.def("fused_allreduce_sgd", [](const PyCommCtx& c, int64_t start, int64_t numel, ptr_t momentum, ptr_t hyper,
-                                  int channel, bool use_mc, bool wire_bf16, int blocks, ptr_t stream) {
+                                  int channel, bool use_mc, bool wire_bf16, int blocks, ptr_t stream,
+                                  uint64_t scalar_off, ptr_t scalar_out) {
     BucketArgs b;
     b.start = start; b.numel = numel; b.momentum = P<float>(momentum); b.hyper = P<const SgdHyper>(hyper);
     b.channel = channel;
+    b.scalar_off = scalar_off; b.scalar_out = P<float>(scalar_out);
     check(ddl::launch_fused_allreduce_sgd(c.c, b, use_mc, wire_bf16, blocks, S(stream)), "fused_allreduce_sgd");
-  });
+  }, py::arg("ctx"), py::arg("start"), py::arg("numel"), py::arg("momentum"), py::arg("hyper"), py::arg("channel"),
+     py::arg("use_mc"), py::arg("wire_bf16"), py::arg("blocks"), py::arg("stream"), py::arg("scalar_off") = 0,
+     py::arg("scalar_out") = 0);
+  m.attr("SCALAR_SLOTS") = ddl::kScalarSlots;
   m.def("allreduce", [](const PyCommCtx& c, int channel, uint64_t off, int64_t numel, bool bf16, float scale,
                         bool use_mc, bool oneshot, int blocks, ptr_t stream) {
     check(ddl::launch_allreduce(c.c, channel, off, numel, bf16, scale, use_mc, oneshot, blocks, S(stream)), "allreduce");
@@ -185,9 +190,11 @@ PYBIND11_MODULE(_C, m) {
         [](int mode, ptr_t src, ptr_t out, ptr_t add, ptr_t bias, ptr_t sum, ptr_t sumsq, int M, int KB, int ldc,
            int srcH, int srcW, int srcC, int dstH, int dstW, int R, int Sx, int stride, int pad, int dil,
            int cchunks, int relu, int n_valid, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
-           int batch, int tw, int th, int tn, int zfill, ptr_t stream) {
+           int batch, int tw, int th, int tn, int zfill, ptr_t stream, int pad_w, int kstride) {
           ConvArgs a;
           a.zfill = zfill;
+          a.pad_w = pad_w < 0 ? pad : pad_w;
+          a.kstride = kstride > 0 ? kstride : cchunks * 64;
           a.src = P<const __nv_bfloat16>(src); a.out = P<__nv_bfloat16>(out); a.add = P<const __nv_bfloat16>(add);
           a.bias = P<const float>(bias); a.sum = P<float>(sum); a.sumsq = P<float>(sumsq);
           a.M = M; a.KB = KB; a.ldc = ldc; a.srcH = srcH; a.srcW = srcW; a.srcC = srcC; a.dstH = dstH; a.dstW = dstW;
@@ -195,18 +202,32 @@ PYBIND11_MODULE(_C, m) {
           a.stages = 0; a.batch = batch; a.tw = tw; a.th = th; a.tn = tn; a.tiles_w = 0; a.tiles_h = 0;
           check(ddl::launch_conv_gemm(mode, a, P<const void>(w), w_rows, w_cols, n_total, P<const void>(a_matrix),
                                       a_cols, S(stream)), "conv_gemm");
-        });
+        },
+        py::arg("mode"), py::arg("src"), py::arg("out"), py::arg("add"), py::arg("bias"), py::arg("sum"), py::arg("sumsq"),
+        py::arg("M"), py::arg("KB"), py::arg("ldc"), py::arg("srcH"), py::arg("srcW"), py::arg("srcC"), py::arg("dstH"),
+        py::arg("dstW"), py::arg("R"), py::arg("S"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("cchunks"),
+        py::arg("relu"), py::arg("n_valid"), py::arg("w"), py::arg("w_rows"), py::arg("w_cols"), py::arg("n_total"),
+        py::arg("a_matrix"), py::arg("a_cols"), py::arg("batch"), py::arg("tw"), py::arg("th"), py::arg("tn"),
+        py::arg("zfill"), py::arg("stream"), py::arg("pad_w") = -1, py::arg("kstride") = 0);
   m.def("conv_wgrad",
         [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int dy_ld, int ldw, int ncols, int H, int W, int C, int Pq,
            int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, int batch, int tw, int th, int tn,
-           ptr_t stream) {
+           ptr_t stream, int pad_w, int Cpad, int Cw) {
           WgradArgs a;
+          a.pad_w = pad_w < 0 ? pad : pad_w;
+          a.Cpad = Cpad > 0 ? Cpad : ncols;      // default: one tap spanning every column (stem scratch, GEMM)
+          a.Cw = Cw > 0 ? Cw : ncols;
           a.stages = 0; a.batch = batch; a.tw = tw; a.th = th; a.tn = tn; a.tiles_w = 0; a.tiles_h = 0;
           a.x = P<const __nv_bfloat16>(x); a.dw = P<float>(dw); a.M = M; a.Cout = Cout; a.dy_ld = dy_ld; a.ldw = ldw; a.ncols = ncols;
           a.H = H; a.W = W; a.C = C; a.P = Pq; a.Q = Q; a.R = R; a.S = Sx; a.stride = stride; a.pad = pad; a.dil = dil;
           a.cchunks = cchunks; a.kb_per_split = 0; a.total_kb = 0; a.mode = mode;
           check(ddl::launch_conv_wgrad(a, P<const void>(dy), P<const void>(x), splits, S(stream)), "conv_wgrad");
-        });
+        },
+        py::arg("mode"), py::arg("x"), py::arg("dy"), py::arg("dw"), py::arg("M"), py::arg("Cout"), py::arg("dy_ld"),
+        py::arg("ldw"), py::arg("ncols"), py::arg("H"), py::arg("W"), py::arg("C"), py::arg("P"), py::arg("Q"), py::arg("R"),
+        py::arg("S"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("cchunks"), py::arg("splits"),
+        py::arg("batch"), py::arg("tw"), py::arg("th"), py::arg("tn"), py::arg("stream"), py::arg("pad_w") = -1,
+        py::arg("Cpad") = 0, py::arg("Cw") = 0);
 
   // ------------------------------------------------------------------ BN / activation
   m.def("bn_act_fwd", [](ptr_t x, ptr_t residual, ptr_t z, ptr_t sum, ptr_t sumsq, ptr_t gamma, ptr_t beta,
@@ -317,6 +338,21 @@ PYBIND11_MODULE(_C, m) {
   m.def("dropout", [](ptr_t x, ptr_t y, int64_t n, float p, uint64_t seed, uint64_t offset, ptr_t stream) {
     check(ddl::launch_dropout(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), n, p, seed, offset, S(stream)),
           "dropout");
+  });
+  m.def("concat_channels", [](std::vector<ptr_t> parts, std::vector<int> chans, ptr_t whole, int M, bool scatter,
+                              ptr_t stream) {
+    ddl::CatArgs a;
+    if (parts.size() != chans.size() || parts.empty() || parts.size() > static_cast<size_t>(ddl::kCatMax))
+      throw std::runtime_error("concat_channels: 1..8 parts");
+    a.n = static_cast<int>(parts.size());
+    a.ctot = 0;
+    for (int i = 0; i < ddl::kCatMax; ++i) {
+      a.part[i] = i < a.n ? P<__nv_bfloat16>(parts[i]) : nullptr;
+      a.c[i] = i < a.n ? chans[i] : 0;
+      a.ctot += a.c[i];
+    }
+    a.whole = P<__nv_bfloat16>(whole); a.M = M;
+    check(ddl::launch_concat_channels(a, scatter, S(stream)), "concat_channels");
   });
   m.def("add_bf16", [](ptr_t a, ptr_t b, ptr_t y, int64_t n, ptr_t stream) {
     check(ddl::launch_add_bf16(P<const __nv_bfloat16>(a), P<const __nv_bfloat16>(b), P<__nv_bfloat16>(y), n,

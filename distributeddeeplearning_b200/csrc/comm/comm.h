@@ -45,7 +45,12 @@ struct BucketArgs {
   float* momentum;        // local momentum buffer base (indexed by arena element offset)
   const SgdHyper* hyper;  // device pointer
   int channel;
+  // scalar piggy-back: kScalarSlots fp32 values at byte offset `scalar_off` of every replica are
+  // averaged across ranks into `scalar_out` (local) by block 0 of this launch; scalar_off == 0 disables it.
+  uint64_t scalar_off;
+  float* scalar_out;
 };
+constexpr int kScalarSlots = 64;
 
 cudaError_t launch_fused_sgd_local(float* w, float* g, float* m, void* wb, const SgdHyper* hp, int64_t numel,
                                    int blocks, cudaStream_t stream);

@@ -189,6 +189,20 @@ __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, Buc
   }
   block_barrier(c, b.channel, epoch);
 
+  if (b.scalar_off != 0 && blockIdx.x == 0 && threadIdx.x < kScalarSlots / 4) {
+    // piggy-backed metrics: every rank wrote its slot before this launch (stream order) and the barrier above made the
+    // writes visible; peers overwrite their slot only after the closing barrier of this kernel.
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int p = 0; p < kMaxWorld; ++p)
+      if (p < c.world) {
+        const float4 v = ld_peer_f32x4(c.peer_base[p] + b.scalar_off + threadIdx.x * 16);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    const float s = 1.0f / static_cast<float>(c.world);
+    reinterpret_cast<float4*>(b.scalar_out)[threadIdx.x] = make_float4(acc.x * s, acc.y * s, acc.z * s, acc.w * s);
+  }
+
   const int64_t slice = b.numel / c.world;              // elements owned by each rank
   const int64_t base = b.start + slice * c.rank;        // my slice (element offset in the arena)
   constexpr int V = WIRE_BF16 ? 8 : 4;                  // elements per thread-iteration

@@ -45,14 +45,30 @@ DDL_DEVICE Vec8 load8_f32(const float* p) {
 // ---- forward --------------------------------------------------------------------------------
 // TRAIN: scale/shift derived from (sum, sumsq); also emits mean/invstd (saved for backward) and
 // updates running stats.  EVAL: scale/shift from running stats.
-template <bool TRAIN>
-__global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) {
-  const int groups = a.C / 8;                       // channel groups per row
+// Thread -> (channel group, row lane).  FLAT: threads are spread over the C/8 channel groups of consecutive rows
+// (needs C/8 to divide, or be a multiple of, the block size: the power-of-two widths of ResNet/VGG).  CHUNKED: a
+// block owns the 64-channel chunk blockIdx.y and 32 row lanes — any C that is a multiple of 8 (Inception's 48, 80,
+// 96, 160, 192, 288, 320, 384, 448, 768, 1280; DenseNet's growth steps), channel groups beyond C idle.
+template <bool CHUNKED>
+DDL_DEVICE bool bn_thread_map(int C, int& c0, int& row0, int& row_stride) {
+  if (CHUNKED) {
+    c0 = blockIdx.y * 64 + (threadIdx.x & 7) * 8;
+    row0 = blockIdx.x * 32 + (threadIdx.x >> 3);
+    row_stride = gridDim.x * 32;
+    return c0 < C;
+  }
+  const int groups = C / 8;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = tid % groups;
-  const int row0 = tid / groups;
-  const int row_stride = (gridDim.x * blockDim.x) / groups;
-  const int c0 = g * 8;
+  c0 = (tid % groups) * 8;
+  row0 = tid / groups;
+  row_stride = (gridDim.x * blockDim.x) / groups;
+  return true;
+}
+
+template <bool TRAIN, bool CHUNKED>
+__global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) {
+  int c0, row0, row_stride;
+  if (!bn_thread_map<CHUNKED>(a.C, c0, row0, row_stride)) return;
   float scale[8], shift[8];
   {
     Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
@@ -117,16 +133,17 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
   const int cgl = threadIdx.x & 7;                 // channel group within the 64-channel chunk
   const int rl = threadIdx.x >> 3;                 // row lane 0..31
   const int c0 = blockIdx.y * 64 + cgl * 8;
+  const bool live = c0 < a.C;                      // last chunk of a width that is not a multiple of 64
   float s1[8], s2[8], msc[8], msh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; msc[i] = 0.f; msh[i] = 0.f; }
-  if (MASK == kMaskX) {
+  if (MASK == kMaskX && live) {
     Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0);
     Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { msc[i] = gam.v[i] * invstd.v[i]; msh[i] = bet.v[i] - mean.v[i] * msc[i]; }
   }
-  for (int r = blockIdx.x * 32 + rl; r < a.M; r += gridDim.x * 32) {
+  for (int r = live ? blockIdx.x * 32 + rl : a.M; r < a.M; r += gridDim.x * 32) {
     const size_t off = static_cast<size_t>(r) * a.C + c0;
     float dz[8], x[8];
     unpack8(ld_stream_u4(a.dz + off), dz);
@@ -168,21 +185,19 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
 #pragma unroll
     for (int w = 0; w < kBnThreads / 32; ++w) { t1 += red[w][g][i]; t2 += red[w][g][8 + i]; }
     const int ch = blockIdx.y * 64 + g * 8 + i;
-    atomicAdd(a.dbeta + ch, t1);
-    atomicAdd(a.dgamma + ch, a.invstd[ch] * (t2 - a.mean[ch] * t1));
+    if (ch < a.C) {
+      atomicAdd(a.dbeta + ch, t1);
+      atomicAdd(a.dgamma + ch, a.invstd[ch] * (t2 - a.mean[ch] * t1));
+    }
   }
 }
 
 // ---- backward pass 2: elementwise ----------------------------------------------------------------
 // dx = k1*dy + x*B + A   with k1 = gamma*invstd, B = -k1*invstd*dgamma/M, A = -k1*dbeta/M - mean*B
-template <int MASK>
+template <int MASK, bool CHUNKED>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdArgs a) {
-  const int groups = a.C / 8;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = tid % groups;
-  const int row0 = tid / groups;
-  const int row_stride = (gridDim.x * blockDim.x) / groups;
-  const int c0 = g * 8;
+  int c0, row0, row_stride;
+  if (!bn_thread_map<CHUNKED>(a.C, c0, row0, row_stride)) return;
   float k1[8], cA[8], cB[8], msh[8];
   {
     Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0), gam = load8_f32(a.gamma + c0);
@@ -246,29 +261,39 @@ inline int bn_grid(int M, int C, int sms) {
 
 }  // namespace
 
+// chunked mapping: blocks = (row blocks, 64-channel chunks); >= 8 rows per thread, <= 8 resident waves of blocks
+inline dim3 bn_chunk_grid(int M, int C, int sms) {
+  const int chunks = (C + 63) / 64;
+  int gx = (M + 32 * 8 - 1) / (32 * 8);
+  const int cap = (sms * 8 + chunks - 1) / chunks;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3(gx, chunks);
+}
+
+inline bool bn_flat_ok(int C) {
+  const int groups = C / 8;
+  return (kBnThreads % groups == 0) || (groups % kBnThreads == 0);
+}
+
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream) {
-  if (a.C % 8 != 0) return cudaErrorInvalidValue;
-  const int groups = a.C / 8;
-  if (!((kBnThreads % groups == 0) || (groups % kBnThreads == 0))) return cudaErrorInvalidValue;
-  const int grid = bn_grid(a.M, a.C, sms);
-  if (train) bn_act_fwd_kernel<true><<<grid, kBnThreads, 0, stream>>>(a);
-  else bn_act_fwd_kernel<false><<<grid, kBnThreads, 0, stream>>>(a);
+  if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
+  if (bn_flat_ok(a.C)) {
+    const int grid = bn_grid(a.M, a.C, sms);
+    if (train) bn_act_fwd_kernel<true, false><<<grid, kBnThreads, 0, stream>>>(a);
+    else bn_act_fwd_kernel<false, false><<<grid, kBnThreads, 0, stream>>>(a);
+  } else {
+    const dim3 grid = bn_chunk_grid(a.M, a.C, sms);
+    if (train) bn_act_fwd_kernel<true, true><<<grid, kBnThreads, 0, stream>>>(a);
+    else bn_act_fwd_kernel<false, true><<<grid, kBnThreads, 0, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) {
-  if (a.C % 8 != 0) return cudaErrorInvalidValue;
-  const int groups = a.C / 8;
-  if (kBnThreads % groups != 0) return cudaErrorInvalidValue;   // groups <= 256 (C <= 2048), power of two
-  const int grid = bn_grid(a.M, a.C, sms);
+  if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
   const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : kMaskZ);
-  if (a.C % 64 != 0) return cudaErrorInvalidValue;
-  const int chunks = a.C / 64;
-  int gx = (a.M + 32 * 8 - 1) / (32 * 8);                 // >= 8 rows per thread
-  const int cap = (sms * 8 + chunks - 1) / chunks;
-  if (gx > cap) gx = cap;
-  if (gx < 1) gx = 1;
-  const dim3 rgrid(gx, chunks);
+  const dim3 rgrid = bn_chunk_grid(a.M, a.C, sms);
   switch (mask) {
     case kMaskNone: bn_act_bwd_reduce_kernel<kMaskNone><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     case kMaskZ: bn_act_bwd_reduce_kernel<kMaskZ><<<rgrid, kBnThreads, 0, stream>>>(a); break;
@@ -276,10 +301,19 @@ cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) 
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  switch (mask) {
-    case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone><<<grid, kBnThreads, 0, stream>>>(a); break;
-    case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ><<<grid, kBnThreads, 0, stream>>>(a); break;
-    default: bn_act_bwd_apply_kernel<kMaskX><<<grid, kBnThreads, 0, stream>>>(a); break;
+  if (bn_flat_ok(a.C)) {
+    const int grid = bn_grid(a.M, a.C, sms);
+    switch (mask) {
+      case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      default: bn_act_bwd_apply_kernel<kMaskX, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+    }
+  } else {
+    switch (mask) {
+      case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      default: bn_act_bwd_apply_kernel<kMaskX, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+    }
   }
   return cudaGetLastError();
 }

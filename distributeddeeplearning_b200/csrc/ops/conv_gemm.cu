@@ -69,6 +69,145 @@ constexpr bool mode_a_tma(int mode) {
 constexpr bool mode_b_mn(int mode) { return mode == kConvDgrad || mode == kConvTileDgrad || mode == kConvGemmDgrad; }
 constexpr bool mode_tile(int mode) { return mode == kConvTileFwd || mode == kConvTileDgrad; }
 
+
+// ---------------------------------------------------------------------------------------------
+// epilogue building blocks (shared by the one-tile and the persistent kernel)
+// ---------------------------------------------------------------------------------------------
+// All staging traffic uses 32-bit shared-window addresses (ld/st.shared): generic LD/ST through the aligned
+// dynamic-smem pointer cost 64-bit address arithmetic per access and showed up as ~15 % of the epilogue's
+// instruction stream in the ncu source view (profiles/ncu_summary.md).
+DDL_DEVICE void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+DDL_DEVICE uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+DDL_DEVICE void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" :: "r"(addr), "r"(v) : "memory"); }
+DDL_DEVICE uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+DDL_DEVICE float lds_f32(uint32_t addr) { return __uint_as_float(lds32(addr)); }
+
+// TMEM accumulator columns [c_begin, c_end) of this thread's row -> (bias, ReLU) -> bf16 -> staging row.
+// `stg_row`: shared address of the row's staging line; `zero_row`: the row lies outside the image (tile modes).
+template <bool BIAS_RELU>
+DDL_DEVICE void epi_tmem_to_stage(uint32_t taddr_row, uint32_t stg_row, int c_begin, int c_end, const ConvArgs& a,
+                                  int n0, bool zero_row) {
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld_32x32(taddr_row + c0, v);
+    tmem_ld_wait();
+    uint32_t packed[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+      if (BIAS_RELU) {
+        if (a.bias) {
+          const int cb = n0 + c0 + 2 * j;
+          if (cb < a.n_valid) x0 += a.bias[cb];
+          if (cb + 1 < a.n_valid) x1 += a.bias[cb + 1];
+        }
+        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+      }
+      packed[j] = zero_row ? 0u : pack_bf16x2(x0, x1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(stg_row + c0 * 2 + j * 16, packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+  }
+}
+
+// BN statistics of the staged bf16 tile (+ one atomic per valid channel and statistic), then the coalesced
+// 16-byte global stores (optional `+= add`, optional zero-fill of the three stride-2 siblings).
+// Must be entered by all kEpiThreads epilogue threads after the staging writes were made visible (named barrier 1).
+template <int BLOCK_N, bool STATS, bool TILE>
+DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, const ConvArgs& a, int n0, int m0) {
+  constexpr int kPitch = BLOCK_N * 2 + 16;
+  if (STATS) {
+    // thread = (column group of 8, row slice): 16-byte shared loads, fp32 accumulation (invalid rows hold zeros)
+    constexpr int kColGroups = BLOCK_N / 8;                 // 16 (N=128) or 8 (N=64)
+    constexpr int kSlices = kEpiThreads / kColGroups;       // row slices
+    constexpr int kRowsPer = kBlockM / kSlices;             // rows per thread
+    const int cg = etid % kColGroups;
+    const int sl = etid / kColGroups;
+    float s[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
+    const uint32_t p0 = stg + (sl * kRowsPer) * kPitch + cg * 16;
+#pragma unroll
+    for (int r = 0; r < kRowsPer; ++r) {
+      const uint4 u = lds128(p0 + r * kPitch);
+      float2 f;
+      f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
+      f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
+      f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
+      f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
+    }
+    // threads with the same column group inside a warp: lanes cg, cg+kColGroups, ... -> xor shuffles
+#pragma unroll
+    for (int off = kColGroups; off < 32; off <<= 1) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+        ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
+      }
+    }
+    // cross-warp fold in shared memory ([epi warp][2][BLOCK_N] floats), then ONE atomic per channel and statistic
+    if ((threadIdx.x & 31) < kColGroups) {
+      const uint32_t rb = red + ((ew * 2) * BLOCK_N + cg * 8) * 4;
+      sts128(rb, __float_as_uint(s[0]), __float_as_uint(s[1]), __float_as_uint(s[2]), __float_as_uint(s[3]));
+      sts128(rb + 16, __float_as_uint(s[4]), __float_as_uint(s[5]), __float_as_uint(s[6]), __float_as_uint(s[7]));
+      sts128(rb + BLOCK_N * 4, __float_as_uint(ss[0]), __float_as_uint(ss[1]), __float_as_uint(ss[2]), __float_as_uint(ss[3]));
+      sts128(rb + BLOCK_N * 4 + 16, __float_as_uint(ss[4]), __float_as_uint(ss[5]), __float_as_uint(ss[6]), __float_as_uint(ss[7]));
+    }
+    named_bar_sync(1, kEpiThreads);
+    if (etid < 2 * BLOCK_N) {
+      const int which = etid / BLOCK_N, col = etid - which * BLOCK_N;
+      float v = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += lds_f32(red + ((wq * 2 + which) * BLOCK_N + col) * 4);
+      if (n0 + col < a.n_valid) atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
+    }
+  }
+  // coalesced stores: thread = (16-byte column chunk, row phase); a tile row is BLOCK_N*2 contiguous bytes
+  constexpr int kVecPerRow = BLOCK_N / 8;
+  constexpr int kRowStep = kEpiThreads / kVecPerRow;
+  const int ch = etid % kVecPerRow;
+  const int r0 = etid / kVecPerRow;
+  if (n0 + ch * 8 >= a.ldc) return;                       // channel padding of the last N tile (ldc = row width)
+  uint32_t sp = stg + r0 * kPitch + ch * 16;
+  const size_t coff = static_cast<size_t>(n0 + ch * 8);
+#pragma unroll 4
+  for (int r = r0; r < kBlockM; r += kRowStep, sp += kRowStep * kPitch) {
+    int m;
+    if (TILE) m = static_cast<int>(lds32(sp - ch * 16 + BLOCK_N * 2));
+    else m = (m0 + r) < a.M ? (m0 + r) : -1;
+    if (m < 0) continue;
+    uint4 val = lds128(sp);
+    const size_t off = static_cast<size_t>(m) * a.ldc + coff;
+    if (a.add) {
+      const uint4 o = *reinterpret_cast<const uint4*>(a.add + off);
+      float2 p, q;
+      p = unpack_bf16x2(val.x); q = unpack_bf16x2(o.x); val.x = pack_bf16x2(p.x + q.x, p.y + q.y);
+      p = unpack_bf16x2(val.y); q = unpack_bf16x2(o.y); val.y = pack_bf16x2(p.x + q.x, p.y + q.y);
+      p = unpack_bf16x2(val.z); q = unpack_bf16x2(o.z); val.z = pack_bf16x2(p.x + q.x, p.y + q.y);
+      p = unpack_bf16x2(val.w); q = unpack_bf16x2(o.w); val.w = pack_bf16x2(p.x + q.x, p.y + q.y);
+    }
+    *reinterpret_cast<uint4*>(a.out + off) = val;
+    if (TILE && a.zfill) {      // even outH/outW guaranteed by the host: all three siblings exist
+      const uint4 z = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(a.out + off + a.ldc) = z;
+      *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW) * a.ldc) = z;
+      *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW + 1) * a.ldc) = z;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // fwd / dgrad / plain-GEMM / stem kernel
 // ---------------------------------------------------------------------------------------------
@@ -143,8 +282,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
         dw = rem - dh * a.dstW;
       }
       int hb, wb;
-      if (MODE == kConvDgrad) { hb = dh + a.pad; wb = dw + a.pad; }
-      else { hb = dh * a.stride - a.pad; wb = dw * a.stride - a.pad; }
+      if (MODE == kConvDgrad) { hb = dh + a.pad; wb = dw + a.pad_w; }
+      else { hb = dh * a.stride - a.pad; wb = dw * a.stride - a.pad_w; }
       const __nv_bfloat16* img_base = a.src + static_cast<size_t>(img) * a.srcH * a.srcW * a.srcC;
       const uint32_t row_off = row * 128u;
       const uint32_t sw = row & 7u;
@@ -190,8 +329,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
           }
           const __nv_bfloat16* src =
               ok ? img_base + (static_cast<size_t>(sh) * a.srcW + swd) * a.srcC + cc * 64 : a.src;
+          const int crem = a.srcC - cc * 64;      // channels left in this tap (last k-block of a tap may be partial)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cp_async_16(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), src + j * 8, ok);
+          for (int j = 0; j < 8; ++j) {
+            const bool okj = ok && j * 8 < crem;
+            cp_async_16(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), okj ? src + j * 8 : a.src, okj);
+          }
           if (++cc == a.cchunks) { cc = 0; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
         }
         cp_async_commit();
@@ -225,106 +368,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
     }
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    uint8_t* stg = smem;  // pipeline buffers are free: every MMA that read them has completed
+    // pipeline buffers are free (every MMA that read them has completed): the tile is staged over them
+    const uint32_t stg = smem_u32(smem);
+    const uint32_t stg_row = stg + row * Cfg::kPitch;
     constexpr int kColsPerGroup = BLOCK_N / kEpiGroups;
-#pragma unroll 1
-    for (int c0 = egrp * kColsPerGroup; c0 < (egrp + 1) * kColsPerGroup; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + c0, v);
-      tmem_ld_wait();
-      uint32_t packed[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-        if (a.bias) {
-          const int cb = n0 + c0 + 2 * j;
-          if (cb < a.n_valid) x0 += a.bias[cb];
-          if (cb + 1 < a.n_valid) x1 += a.bias[cb + 1];
-        }
-        if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-        packed[j] = (kTile && my_m < 0) ? 0u : pack_bf16x2(x0, x1);   // rows outside the image: exact zeros
-      }
-      uint4* dstp = reinterpret_cast<uint4*>(stg + row * Cfg::kPitch + c0 * 2);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) dstp[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-    }
+    const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(qw * 32) << 16);
+    const bool zero_row = kTile && my_m < 0;          // rows outside the image: exact zeros (keeps the BN sums clean)
+    if (!STATS && (a.bias != nullptr || a.relu))
+      epi_tmem_to_stage<true>(taddr_row, stg_row, egrp * kColsPerGroup, (egrp + 1) * kColsPerGroup, a, n0, zero_row);
+    else
+      epi_tmem_to_stage<false>(taddr_row, stg_row, egrp * kColsPerGroup, (egrp + 1) * kColsPerGroup, a, n0, zero_row);
     // the row's destination index rides in the pad bytes of its staging row (pitch = 2*BLOCK_N + 16)
-    if (egrp == 0) *reinterpret_cast<int*>(stg + row * Cfg::kPitch + BLOCK_N * 2) = my_m;
+    if (kTile && egrp == 0) sts32(stg_row + BLOCK_N * 2, static_cast<uint32_t>(my_m));
     tc_fence_before();
     named_bar_sync(1, kEpiThreads);
-    if (STATS) {
-      // per-channel sum / sum of squares of the bf16-rounded outputs of this tile (invalid rows hold zeros).
-      // thread = (column group of 8, row slice): 16-byte shared loads, fp32 accumulation.
-      constexpr int kColGroups = BLOCK_N / 8;                 // 16 (N=128) or 8 (N=64)
-      constexpr int kSlices = kEpiThreads / kColGroups;       // row slices
-      constexpr int kRowsPer = kBlockM / kSlices;             // rows per thread
-      const int cg = etid % kColGroups;
-      const int sl = etid / kColGroups;
-      float s[8], ss[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-      const uint8_t* p0 = stg + (sl * kRowsPer) * Cfg::kPitch + cg * 16;
-#pragma unroll 4
-      for (int r = 0; r < kRowsPer; ++r) {
-        const uint4 u = *reinterpret_cast<const uint4*>(p0 + r * Cfg::kPitch);
-        float2 f;
-        f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
-        f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
-        f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
-        f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
-      }
-      // threads with the same column group inside a warp: lanes cg, cg+kColGroups, ... -> xor shuffles
-#pragma unroll
-      for (int off = kColGroups; off < 32; off <<= 1) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
-          ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
-        }
-      }
-      // cross-warp fold in shared memory, then ONE atomic per channel and statistic per tile
-      float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);   // [epi warps][2][BLOCK_N]
-      if ((threadIdx.x & 31) < kColGroups) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          red[(ew * 2 + 0) * BLOCK_N + cg * 8 + i] = s[i];
-          red[(ew * 2 + 1) * BLOCK_N + cg * 8 + i] = ss[i];
-        }
-      }
-      named_bar_sync(1, kEpiThreads);
-      for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
-        const int which = c / BLOCK_N, col = c - which * BLOCK_N;
-        float v = 0.f;
-#pragma unroll
-        for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += red[(wq * 2 + which) * BLOCK_N + col];
-        atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
-      }
-    }
-    // coalesced stores: 16 bytes per thread, a row of the tile is BLOCK_N*2 contiguous bytes
-    constexpr int kVecPerRow = BLOCK_N / 8;
-    for (int idx = etid; idx < kBlockM * kVecPerRow; idx += kEpiThreads) {
-      const int r = idx / kVecPerRow, ch = idx - r * kVecPerRow;
-      const int m = *reinterpret_cast<const int*>(stg + r * Cfg::kPitch + BLOCK_N * 2);
-      if (m >= 0) {
-        uint4 val = *reinterpret_cast<const uint4*>(stg + r * Cfg::kPitch + ch * 16);
-        const size_t off = static_cast<size_t>(m) * a.ldc + n0 + ch * 8;
-        if (a.add) {
-          const uint4 o = *reinterpret_cast<const uint4*>(a.add + off);
-          float2 p, q;
-          p = unpack_bf16x2(val.x); q = unpack_bf16x2(o.x); val.x = pack_bf16x2(p.x + q.x, p.y + q.y);
-          p = unpack_bf16x2(val.y); q = unpack_bf16x2(o.y); val.y = pack_bf16x2(p.x + q.x, p.y + q.y);
-          p = unpack_bf16x2(val.z); q = unpack_bf16x2(o.z); val.z = pack_bf16x2(p.x + q.x, p.y + q.y);
-          p = unpack_bf16x2(val.w); q = unpack_bf16x2(o.w); val.w = pack_bf16x2(p.x + q.x, p.y + q.y);
-        }
-        *reinterpret_cast<uint4*>(a.out + off) = val;
-        if (kTile && a.zfill) {      // even outH/outW guaranteed by the host: all three siblings exist
-          const uint4 z = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(a.out + off + a.ldc) = z;
-          *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW) * a.ldc) = z;
-          *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW + 1) * a.ldc) = z;
-        }
-      }
-    }
+    epi_stats_store<BLOCK_N, STATS, kTile>(stg, smem_u32(full) + 256, etid, ew, a, n0, m0);
   } else if (warp == 4) {
     // ================================== TMA producer =====================================
     if (elect_one()) {
@@ -343,9 +401,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
           if (a.ntaps > 0) {
             widx = a.tap_widx[tap]; dh = a.tap_dh[tap]; dw = a.tap_dw[tap]; mapi = a.tap_map[tap];
           } else if (MODE == kConvTileFwd) {
-            dh = tap_r * a.dil - a.pad; dw = tap_s * a.dil - a.pad;
+            dh = tap_r * a.dil - a.pad; dw = tap_s * a.dil - a.pad_w;
           } else {
-            dh = a.pad - tap_r * a.dil; dw = a.pad - tap_s * a.dil;
+            dh = a.pad - tap_r * a.dil; dw = a.pad_w - tap_s * a.dil;
           }
         }
         if (kBMn) {
@@ -354,7 +412,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
         } else {
-          tma_load_2d(sB, &tmB, (widx * a.cchunks + cc) * kBlockK, n0, &full[stage]);
+          tma_load_2d(sB, &tmB, MODE == kConvStem ? kb * kBlockK : widx * a.kstride + cc * kBlockK, n0, &full[stage]);
         }
         if (MODE == kConvGemm || MODE == kConvGemmDgrad) {
           tma_load_2d(smem_u32(sA), &tmA, kb * kBlockK, m0, &full[stage]);
@@ -476,6 +534,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     const int etid = egrp * 128 + row;
     const int ew = egrp * 4 + qw;
     constexpr int kColsPerGroup = BLOCK_N / kEpiGroups;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const uint32_t red_u32 = smem_u32(red);
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       int n0, m0, tq0, tp0, tn0;
@@ -496,98 +556,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
       const int buf = it & 1;
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = egrp * kColsPerGroup; c0 < (egrp + 1) * kColsPerGroup; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + buf * BLOCK_N + c0, v);
-        tmem_ld_wait();
-        uint32_t packed[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-          if (a.bias) {
-            const int cb = n0 + c0 + 2 * j;
-            if (cb < a.n_valid) x0 += a.bias[cb];
-            if (cb + 1 < a.n_valid) x1 += a.bias[cb + 1];
-          }
-          if (a.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-          packed[j] = (kTile && my_m < 0) ? 0u : pack_bf16x2(x0, x1);
-        }
-        uint4* dstp = reinterpret_cast<uint4*>(stg + row * Cfg::kPitch + c0 * 2);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dstp[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
-      }
-      if (egrp == 0) *reinterpret_cast<int*>(stg + row * Cfg::kPitch + BLOCK_N * 2) = my_m;
+      const uint32_t stg_row = stg_u32 + row * Cfg::kPitch;
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + buf * BLOCK_N;
+      const bool zero_row = kTile && my_m < 0;
+      if (!STATS && (a.bias != nullptr || a.relu))
+        epi_tmem_to_stage<true>(taddr_row, stg_row, egrp * kColsPerGroup, (egrp + 1) * kColsPerGroup, a, n0, zero_row);
+      else
+        epi_tmem_to_stage<false>(taddr_row, stg_row, egrp * kColsPerGroup, (egrp + 1) * kColsPerGroup, a, n0, zero_row);
+      if (kTile && egrp == 0) sts32(stg_row + BLOCK_N * 2, static_cast<uint32_t>(my_m));
       tc_fence_before();
       named_bar_sync(1, kEpiThreads);
       if (etid == 0) mbar_arrive(&acc_empty[buf]);      // every epilogue thread has finished reading this TMEM buffer
-      if (STATS) {
-        constexpr int kColGroups = BLOCK_N / 8;
-        constexpr int kSlices = kEpiThreads / kColGroups;
-        constexpr int kRowsPer = kBlockM / kSlices;
-        const int cg = etid % kColGroups;
-        const int sl = etid / kColGroups;
-        float s[8], ss[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-        const uint8_t* p0 = stg + (sl * kRowsPer) * Cfg::kPitch + cg * 16;
-#pragma unroll 4
-        for (int r = 0; r < kRowsPer; ++r) {
-          const uint4 u = *reinterpret_cast<const uint4*>(p0 + r * Cfg::kPitch);
-          float2 f;
-          f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
-          f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
-          f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
-          f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
-        }
-#pragma unroll
-        for (int off = kColGroups; off < 32; off <<= 1) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
-            ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
-          }
-        }
-        if ((threadIdx.x & 31) < kColGroups) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            red[(ew * 2 + 0) * BLOCK_N + cg * 8 + i] = s[i];
-            red[(ew * 2 + 1) * BLOCK_N + cg * 8 + i] = ss[i];
-          }
-        }
-        named_bar_sync(1, kEpiThreads);
-        for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
-          const int which = c / BLOCK_N, col = c - which * BLOCK_N;
-          float v = 0.f;
-#pragma unroll
-          for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += red[(wq * 2 + which) * BLOCK_N + col];
-          atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
-        }
-      }
-      constexpr int kVecPerRow = BLOCK_N / 8;
-      for (int idx = etid; idx < kBlockM * kVecPerRow; idx += kEpiThreads) {
-        const int r = idx / kVecPerRow, ch = idx - r * kVecPerRow;
-        const int m = *reinterpret_cast<const int*>(stg + r * Cfg::kPitch + BLOCK_N * 2);
-        if (m >= 0) {
-          uint4 val = *reinterpret_cast<const uint4*>(stg + r * Cfg::kPitch + ch * 16);
-          const size_t off = static_cast<size_t>(m) * a.ldc + n0 + ch * 8;
-          if (a.add) {
-            const uint4 o = *reinterpret_cast<const uint4*>(a.add + off);
-            float2 p, q;
-            p = unpack_bf16x2(val.x); q = unpack_bf16x2(o.x); val.x = pack_bf16x2(p.x + q.x, p.y + q.y);
-            p = unpack_bf16x2(val.y); q = unpack_bf16x2(o.y); val.y = pack_bf16x2(p.x + q.x, p.y + q.y);
-            p = unpack_bf16x2(val.z); q = unpack_bf16x2(o.z); val.z = pack_bf16x2(p.x + q.x, p.y + q.y);
-            p = unpack_bf16x2(val.w); q = unpack_bf16x2(o.w); val.w = pack_bf16x2(p.x + q.x, p.y + q.y);
-          }
-          *reinterpret_cast<uint4*>(a.out + off) = val;
-          if (kTile && a.zfill) {
-            const uint4 z = make_uint4(0, 0, 0, 0);
-            *reinterpret_cast<uint4*>(a.out + off + a.ldc) = z;
-            *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW) * a.ldc) = z;
-            *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW + 1) * a.ldc) = z;
-          }
-        }
-      }
+      epi_stats_store<BLOCK_N, STATS, kTile>(stg_u32, red_u32, etid, ew, a, n0, m0);
       named_bar_sync(1, kEpiThreads);      // staging (and the stats scratch) may be overwritten by the next tile
     }
   } else if (warp == 4) {
@@ -610,9 +590,9 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             if (a.ntaps > 0) {
               widx = a.tap_widx[tap]; dh = a.tap_dh[tap]; dw = a.tap_dw[tap]; mapi = a.tap_map[tap];
             } else if (MODE == kConvTileFwd) {
-              dh = tap_r * a.dil - a.pad; dw = tap_s * a.dil - a.pad;
+              dh = tap_r * a.dil - a.pad; dw = tap_s * a.dil - a.pad_w;
             } else {
-              dh = a.pad - tap_r * a.dil; dw = a.pad - tap_s * a.dil;
+              dh = a.pad - tap_r * a.dil; dw = a.pad_w - tap_s * a.dil;
             }
           }
           if (kBMn) {
@@ -620,7 +600,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
           } else {
-            tma_load_2d(sB, &tmB, (widx * a.cchunks + cc) * kBlockK, n0, &full[stage]);
+            tma_load_2d(sB, &tmB, MODE == kConvStem ? kb * kBlockK : widx * a.kstride + cc * kBlockK, n0, &full[stage]);
           }
           if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
           else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, &full[stage]);
@@ -743,11 +723,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       const bool col_ok = colc < a.ncols;
       int tap_r = 0, tap_s = 0, c_off = 0;
       if (MODE != kConvStem) {
-        const int tap = colc / a.C;
-        c_off = colc - tap * a.C;
+        const int tap = colc / a.Cpad;          // columns live in the padded (tap, Cpad) space
+        c_off = colc - tap * a.Cpad;
         tap_r = tap / a.S;
         tap_s = tap - tap_r * a.S;
       }
+      const int crem = a.C - c_off;             // real channels left in this tap
       const uint32_t row_off = 16384u + chunk * 8192u + row * 128u;
       const uint32_t sw = row & 7u;
       const int pq = a.P * a.Q;
@@ -765,7 +746,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           p = rem / a.Q;
           q = rem - p * a.Q;
         }
-        const int hb = p * a.stride - a.pad, wb = q * a.stride - a.pad;
+        const int hb = p * a.stride - a.pad, wb = q * a.stride - a.pad_w;
         const __nv_bfloat16* img_base = a.x + static_cast<size_t>(img) * a.H * a.W * a.C;
         if (MODE == kConvStem) {
           const int SP = a.cchunks, RPK = 16 / SP;
@@ -787,7 +768,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           const bool ok = m_ok && h >= 0 && h < a.H && w >= 0 && w < a.W;
           const __nv_bfloat16* src = ok ? img_base + (static_cast<size_t>(h) * a.W + w) * a.C + c_off : a.x;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) cp_async_16(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), src + j * 8, ok);
+          for (int j = 0; j < 8; ++j) {
+            const bool okj = ok && j * 8 < crem;
+            cp_async_16(dst + ((static_cast<uint32_t>(j) ^ sw) << 4), okj ? src + j * 8 : a.x, okj);
+          }
         }
         cp_async_commit();
         if (i >= kLag) {
@@ -821,8 +805,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     tc_fence_before();
     named_bar_sync(1, kEpiThreads);
     const int lane = threadIdx.x & 31;
-    const int c = col0 + lane * 4;
-    if (c < a.ncols) {
+    const int vc = col0 + lane * 4;                    // column in the padded (tap, Cpad) space
+    const int vtap = vc / a.Cpad;
+    const int vch = vc - vtap * a.Cpad;
+    if (vc < a.ncols && vch < a.Cw) {                  // channel padding of a tap has no dw column
+      const int c = vtap * a.Cw + vch;
       for (int r = ew; r < 128; r += 4 * kEpiGroups) {
         const int co = co0 + r;
         if (co < a.Cout) {
@@ -839,10 +826,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int colc = col0 + j * 64;
-          const int tap = colc / a.C;
-          tc0[j] = colc - tap * a.C;
+          const int tap = colc / a.Cpad;
+          tc0[j] = colc - tap * a.Cpad;
           const int r = tap / a.S, sx = tap - r * a.S;
-          const int oh = r * a.dil - a.pad, ow = sx * a.dil - a.pad;
+          const int oh = r * a.dil - a.pad, ow = sx * a.dil - a.pad_w;
           if (a.stride == 1) {
             tdh[j] = oh; tdw[j] = ow;
           } else {               // stride-2 source: box comes from the (pa, pb) phase sub-image
@@ -1157,7 +1144,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
     for (int r = 0; r < a.R; ++r)
       for (int sx = 0; sx < a.S; ++sx) {
         const int t = r * a.S + sx;
-        const int oh = r * a.dil - a.pad, ow = sx * a.dil - a.pad;
+        const int oh = r * a.dil - a.pad, ow = sx * a.dil - a.pad_w;
         const int pa = ((oh % 2) + 2) % 2, pb = ((ow % 2) + 2) % 2;
         a.tap_dh[t] = static_cast<signed char>(floor_div(oh, 2));
         a.tap_dw[t] = static_cast<signed char>(floor_div(ow, 2));
@@ -1184,7 +1171,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
         const int th_ = pa + a.pad - r * a.dil;
         if (((th_ % 2) + 2) % 2 != 0) continue;
         for (int sx = 0; sx < a.S; ++sx) {
-          const int tw_ = pb + a.pad - sx * a.dil;
+          const int tw_ = pb + a.pad_w - sx * a.dil;
           if (((tw_ % 2) + 2) % 2 != 0) continue;
           p.tap_dh[nt] = static_cast<signed char>(floor_div(th_, 2));
           p.tap_dw[nt] = static_cast<signed char>(floor_div(tw_, 2));

@@ -31,8 +31,13 @@ struct ConvArgs {
   int ldc;                    // channels of `out` (row stride in elements)
   int srcH, srcW, srcC;       // gather-source geometry
   int dstH, dstW;             // GEMM-row geometry
-  int R, S, stride, pad, dil;
-  int cchunks;                // srcC / 64   (stem: padded taps per filter row)
+  int R, S, stride, pad, dil; // pad = padding along H
+  int pad_w;                  // padding along W (asymmetric 1x7 / 7x1 kernels)
+  int cchunks;                // ceil(srcC / 64) k-blocks per filter tap (stem: padded taps per filter row)
+  int kstride;                // K-major weights: elements between consecutive taps in a weight row (= true Cin).
+                              //   srcC need not be a multiple of 64: the last k-block of a tap is zero-filled on
+                              //   the activation side (TMA out-of-bounds / masked gather), so whatever weight
+                              //   columns the B box picks up beyond the tap contribute nothing.
   int relu;                   // apply ReLU in the epilogue (after bias)
   int n_valid;                // output channels that really exist (bias is read only below this)
   int stages;                 // pipeline depth actually used (<= compile-time maximum)
@@ -59,11 +64,14 @@ struct WgradArgs {
   int Cout;
   int dy_ld;                  // row stride (elements) of dy; >= Cout (padded FC logits)
   int ldw;                    // row stride of dw = R*S*Cin (or 256 for the stem scratch)
-  int ncols;                  // valid columns of dw
+  int ncols;                  // columns of the virtual (tap, Cpad) space = R*S*Cpad (stem / GEMM: real columns)
   int H, W, C;                // x geometry
   int P, Q;                   // dy geometry
   int R, S, stride, pad, dil;
-  int cchunks;                // C / 64
+  int pad_w;
+  int cchunks;                // stem only: padded taps per filter row
+  int Cpad;                   // virtual channels per tap = C rounded up to 64: tile columns are indexed (tap, c) in
+  int Cw;                     //   this padded space; Cw = real channels per tap of the dw row (dw col = tap*Cw + c)
   int kb_per_split;           // pixel blocks handled by one CTA
   int total_kb;               // number of pixel blocks
   int mode;                   // kConvFwd (gather), kConvGemm (x via 2-D TMA), kConvStem, kConvTileFwd (4-D TMA)

@@ -19,38 +19,47 @@ DDL_DEVICE uint4 pack8(const float (&v)[8]) {
 // ---------------------------------------------------------------------------------------------
 // channel statistics (fallback when the producer did not fuse them)
 // ---------------------------------------------------------------------------------------------
+// block = one 64-channel chunk (blockIdx.y) x 32 row lanes; thread = 8 channels of one row lane (any C % 8 == 0)
 __global__ void __launch_bounds__(256) channel_stats_kernel(const __nv_bfloat16* __restrict__ x, float* sum,
                                                             float* sumsq, int M, int C) {
-  const int groups = C / 8;
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int g = tid % groups, row0 = tid / groups;
-  const int row_stride = (gridDim.x * blockDim.x) / groups;
+  const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 64 + cgl * 8;
+  const bool live = c0 < C;
   float s[8], ss[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-  for (int r = row0; r < M; r += row_stride) {
+  for (int r = live ? blockIdx.x * 32 + rl : M; r < M; r += gridDim.x * 32) {
     float v[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * C + g * 8), v);
+    unpack8(*reinterpret_cast<const uint4*>(x + static_cast<size_t>(r) * C + c0), v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] += v[i]; ss[i] = fmaf(v[i], v[i], ss[i]); }
   }
-  __shared__ float red[2][256][9];
+  // lanes of a warp sharing a channel group: lane = (rl % 4) * 8 + cgl -> xor 8, 16
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { red[0][threadIdx.x][i] = s[i]; red[1][threadIdx.x][i] = ss[i]; }
-  __syncthreads();
-  if (threadIdx.x < groups) {
-    const int per_block = blockDim.x / groups;
-    float t0[8], t1[8];
+  for (int off = 8; off < 32; off <<= 1) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { t0[i] = 0.f; t1[i] = 0.f; }
-    for (int k = 0; k < per_block; ++k) {
-      const int t = threadIdx.x + k * groups;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { t0[i] += red[0][t][i]; t1[i] += red[1][t][i]; }
+    for (int i = 0; i < 8; ++i) {
+      s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
+      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
     }
-    const int gc = ((blockIdx.x * blockDim.x + threadIdx.x) % groups) * 8;
+  }
+  __shared__ float red[8][8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { atomicAdd(sum + gc + i, t0[i]); atomicAdd(sumsq + gc + i, t1[i]); }
+    for (int i = 0; i < 8; ++i) { red[warp][lane][i] = s[i]; red[warp][lane][8 + i] = ss[i]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 3, i = threadIdx.x & 7;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { t1 += red[w][g][i]; t2 += red[w][g][8 + i]; }
+    const int ch = blockIdx.y * 64 + g * 8 + i;
+    if (ch < C) {
+      atomicAdd(sum + ch, t1);
+      atomicAdd(sumsq + ch, t2);
+    }
   }
 }
 
@@ -509,14 +518,37 @@ inline int grid_for(int64_t work, int per_block = 256, int cap = 148 * 16) {
   return static_cast<int>(b);
 }
 
+// one thread = one 16-byte vector of the concatenated row; the part is found by walking the (<= 8) channel counts
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) concat_channels_kernel(CatArgs a) {
+  const int groups = a.ctot / 8;
+  const int64_t total = static_cast<int64_t>(a.M) * groups;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = i / groups;
+    int ch = static_cast<int>(i - row * groups) * 8;
+    int p = 0;
+#pragma unroll
+    for (int k = 0; k < kCatMax - 1; ++k)
+      if (p < a.n - 1 && ch >= a.c[p]) { ch -= a.c[p]; ++p; }
+    uint4* w = reinterpret_cast<uint4*>(a.whole) + i;
+    uint4* q = reinterpret_cast<uint4*>(a.part[p] + row * a.c[p] + ch);
+    if (SCATTER) *q = *w;
+    else *w = *q;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_channel_stats(const __nv_bfloat16* x, float* sum, float* sumsq, int M, int C, int sms,
                                  cudaStream_t stream) {
-  const int groups = C / 8;
-  if (C % 8 != 0 || 256 % groups != 0) return cudaErrorInvalidValue;
-  int blocks = grid_for(static_cast<int64_t>(M) * groups, 256, sms * 8);
-  channel_stats_kernel<<<blocks, 256, 0, stream>>>(x, sum, sumsq, M, C);
+  if (C % 8 != 0 || C <= 0) return cudaErrorInvalidValue;
+  const int chunks = (C + 63) / 64;
+  int gx = (M + 32 * 8 - 1) / (32 * 8);
+  const int cap = (sms * 8 + chunks - 1) / chunks;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  channel_stats_kernel<<<dim3(gx, chunks), 256, 0, stream>>>(x, sum, sumsq, M, C);
   return cudaGetLastError();
 }
 
@@ -622,6 +654,19 @@ cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, 
                            uint64_t offset, cudaStream_t stream) {
   if (n % 8 != 0) return cudaErrorInvalidValue;
   dropout_kernel<<<grid_for(n / 8), 256, 0, stream>>>(x, y, n / 8, p, seed, offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_concat_channels(const CatArgs& a, bool scatter, cudaStream_t stream) {
+  if (a.n < 1 || a.n > kCatMax || a.ctot % 8 != 0) return cudaErrorInvalidValue;
+  int tot = 0;
+  for (int i = 0; i < a.n; ++i) {
+    if (a.c[i] % 8 != 0 || a.c[i] <= 0) return cudaErrorInvalidValue;
+    tot += a.c[i];
+  }
+  if (tot != a.ctot) return cudaErrorInvalidValue;
+  const int64_t vecs = static_cast<int64_t>(a.M) * (a.ctot / 8);
+  if (scatter) concat_channels_kernel<true><<<grid_for(vecs), 256, 0, stream>>>(a);
+  else concat_channels_kernel<false><<<grid_for(vecs), 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, int64_t n,

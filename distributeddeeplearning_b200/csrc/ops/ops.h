@@ -108,6 +108,17 @@ cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z
 cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,
                            uint64_t offset, cudaStream_t stream);
 // y = a + b (bf16)
+// Channel concatenation of up to kCatMax NHWC tensors (Inception / DenseNet): gather = parts -> whole,
+// scatter (backward) = whole -> parts.  Every part's channel count is a multiple of 8.
+constexpr int kCatMax = 8;
+struct CatArgs {
+  __nv_bfloat16* part[kCatMax];
+  int c[kCatMax];          // channels of each part
+  int n;                   // parts
+  __nv_bfloat16* whole;    // [M][ctot]
+  int M, ctot;
+};
+cudaError_t launch_concat_channels(const CatArgs& a, bool scatter, cudaStream_t stream);
 cudaError_t launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, int64_t n,
                             cudaStream_t stream);
 

@@ -3,18 +3,21 @@
 Parity: the reference resolves ``--model`` with ``getattr(torchvision.models, name)()``
 (``pytorch_synthetic_benchmark.py:60``) / ``models.__dict__[model](pretrained=False)``
 (``imagenet_pytorch_horovod.py:383``).  North-star zoo: ResNet-50/101/152, VGG-16, Inception-v3,
-AlexNet; ResNet-18/34 and the other VGG depths come for free.
+AlexNet; ResNet-18/34, the other VGG depths, DenseNet and SqueezeNet (the rest of torchvision
+0.2.1's families) are here too.
 """
 from __future__ import annotations
 
 from .alexnet import AlexNet, alexnet  # noqa: F401
+from .densenet import DenseNet, densenet121, densenet161, densenet169, densenet201  # noqa: F401
 from .inception import Inception3, inception_v3  # noqa: F401
 from .resnet import ResNet, resnet18, resnet34, resnet50, resnet101, resnet152  # noqa: F401
+from .squeezenet import SqueezeNet, squeezenet1_0, squeezenet1_1  # noqa: F401
 from .vgg import VGG, vgg11, vgg11_bn, vgg13, vgg13_bn, vgg16, vgg16_bn, vgg19, vgg19_bn  # noqa: F401
 
 _REGISTRY = {
     f.__name__: f
-    for f in (alexnet, inception_v3, resnet18, resnet34, resnet50, resnet101, resnet152, vgg11, vgg11_bn, vgg13,
+    for f in (alexnet, densenet121, densenet161, densenet169, densenet201, squeezenet1_0, squeezenet1_1, inception_v3, resnet18, resnet34, resnet50, resnet101, resnet152, vgg11, vgg11_bn, vgg13,
               vgg13_bn, vgg16, vgg16_bn, vgg19, vgg19_bn)
 }
 

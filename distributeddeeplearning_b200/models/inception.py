@@ -5,10 +5,10 @@ Keys match ``torchvision.models.inception_v3``.  The reference cannot actually r
 SURVEY.md Q2); here the workloads size the input from ``model.input_size`` and add the 0.4-weighted
 auxiliary loss.
 
-Channel counts that are multiples of 64 go through the tcgen05 conv kernels; Inception's odd widths
-(32/48/80/96/192/288/320/448 ...) and its 1x7 / 7x1 asymmetric kernels use the PyTorch composite
-(``ops.conv_bn_act`` decides per layer).  Branch outputs are concatenated along channels (NHWC:
-a strided copy per branch).
+Every layer runs on the tcgen05 conv kernels: Inception's widths (32/48/80/96/192/288/320/448 ...) are multiples
+of 8, which is all the kernels need (partial 64-channel k-blocks are zero-filled by TMA, partial N tiles masked), and
+the 1x7 / 7x1 kernels use per-axis padding.  Branch outputs are concatenated by ``ops.concat_channels`` (one native
+gather kernel forward, one scatter kernel backward).
 """
 from __future__ import annotations
 
@@ -30,7 +30,7 @@ class BasicConv2d(nn.Module):
 
 
 def _cat(xs):
-    return torch.cat(xs, 1).contiguous(memory_format=torch.channels_last) if xs[0].is_cuda else torch.cat(xs, 1)
+    return ops.concat_channels(xs)
 
 
 class InceptionA(nn.Module):

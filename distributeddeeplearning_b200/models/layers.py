@@ -77,6 +77,12 @@ def conv_bn(x, conv: Conv2d, bn: BatchNorm2d, relu=True, residual=None):
                            conv.dilation, bn.eps, bn.momentum, relu, residual, bn.training)
 
 
+def bn_act(x, bn: BatchNorm2d, relu=True):
+    """act(BN(x)) on its own (pre-activation networks)."""
+    return ops.batch_norm_act(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu,
+                              bn.training)
+
+
 class Linear(nn.Module):
     def __init__(self, in_features, out_features, bias=True):
         super().__init__()

@@ -1,6 +1,8 @@
 """Fused ops: hand-written sm_100a kernels on CUDA, PyTorch composites on CPU (see functional.py)."""
 from .functional import (  # noqa: F401
     avg_pool2d,
+    batch_norm_act,
+    concat_channels,
     conv_bias_act,
     conv_bn_act,
     dropout,

@@ -135,14 +135,14 @@ def residual_block_supported(x: torch.Tensor, convs: Sequence, bns: Sequence, do
     mods = list(zip(convs, bns)) + ([tuple(downsample)] if downsample is not None else [])
     cin = x.shape[1]
     for conv, bn in mods:
-        if not bn.training or not isinstance(conv.padding, int):
+        if not bn.training:
             return False
         if not native.supports_conv(conv.in_channels, conv.out_channels) or not native.bn_supported(conv.out_channels):
             return False
         if conv.in_channels <= 4 or not conv.weight.is_contiguous(memory_format=CL) and conv.weight.dim() == 4 and \
                 conv.weight.shape[2] * conv.weight.shape[3] > 1:
             return False
-    return cin % 64 == 0
+    return cin % 8 == 0
 
 
 def residual_block(x: torch.Tensor, convs: Sequence, bns: Sequence, downsample=None) -> torch.Tensor:

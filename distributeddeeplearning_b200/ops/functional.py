@@ -167,7 +167,7 @@ class _ConvBnAct(torch.autograd.Function):
 def conv_bn_act(x, weight, gamma, beta, running_mean, running_var, stride=1, pad=0, dil=1, eps=1e-5, momentum=0.1,
                 relu=True, residual=None, training=True):
     """z = act(BN(conv(x, weight)) [+ residual])  — the unit every ResNet/Inception layer is made of."""
-    if use_native(x) and isinstance(pad, int) and native.supports_conv(x.shape[1], weight.shape[0]) \
+    if use_native(x) and native.supports_conv(x.shape[1], weight.shape[0]) \
             and native.bn_supported(weight.shape[0]) and _krsc(weight):
         return _ConvBnAct.apply(x, residual, weight, gamma, beta, running_mean, running_var, stride, pad, dil, eps,
                                 momentum, relu, training)
@@ -177,6 +177,43 @@ def conv_bn_act(x, weight, gamma, beta, running_mean, running_var, stride=1, pad
     z = F.batch_norm(y.float(), running_mean, running_var, gamma, beta, training, momentum, eps).to(y.dtype)
     if residual is not None:
         z = z + residual
+    return F.relu(z) if relu else z
+
+
+# ------------------------------------------------------------------------------------------------
+# standalone BN(train/eval) + ReLU on a tensor (pre-activation nets: DenseNet's norm -> relu -> conv)
+# ------------------------------------------------------------------------------------------------
+class _BnAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, relu, train):
+        z, save = native.bn_act_fwd(x, None, gamma, beta, running_mean, running_var, eps, momentum, relu, None, train)
+        ctx.relu = relu
+        ctx.params = (gamma, beta)
+        if train:
+            ctx.save_for_backward(x, z, save)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        gamma, beta = ctx.params
+        x, z, save = ctx.saved_tensors
+        if not dz.is_contiguous(memory_format=CL):
+            dz = dz.contiguous(memory_format=CL)
+        gg = grad_buffer(gamma) if gamma.requires_grad else None
+        bg = grad_buffer(beta) if beta.requires_grad else None
+        dx, _, _ = native.bn_act_bwd(dz, z, x, save, gamma, ctx.relu, False, gg, bg, beta=beta, had_residual=False)
+        if gamma.requires_grad:
+            notify_ready(gamma)
+            notify_ready(beta)
+        return (dx if ctx.needs_input_grad[0] else None,) + (None,) * 8
+
+
+def batch_norm_act(x, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, relu=True, training=True):
+    """z = act(BN(x)) with the batch statistics reduced by the native channel_stats kernel."""
+    if use_native(x) and x.dim() == 4 and x.dtype == torch.bfloat16 and native.bn_supported(x.shape[1]) \
+            and (training or not torch.is_grad_enabled()):
+        return _BnAct.apply(x, gamma, beta, running_mean, running_var, eps, momentum, relu, training)
+    z = F.batch_norm(x.float(), running_mean, running_var, gamma, beta, training, momentum, eps).to(x.dtype)
     return F.relu(z) if relu else z
 
 
@@ -216,7 +253,7 @@ class _ConvBiasAct(torch.autograd.Function):
 
 
 def conv_bias_act(x, weight, bias=None, stride=1, pad=0, dil=1, relu=True):
-    if use_native(x) and isinstance(pad, int) and native.supports_conv(x.shape[1], weight.shape[0]) and _krsc(weight):
+    if use_native(x) and native.supports_conv(x.shape[1], weight.shape[0]) and _krsc(weight):
         return _ConvBiasAct.apply(x, weight, bias, stride, pad, dil, relu)
     xi = x[:, : weight.shape[1]] if x.shape[1] != weight.shape[1] else x
     w = weight.to(xi.dtype) if x.is_cuda else weight
@@ -262,11 +299,37 @@ class _Linear(torch.autograd.Function):
 def linear(x, weight, bias=None, relu=False):
     """y = x W^T + b.  On the native path the result keeps its padded width (multiple of 64);
     use ``out_features`` aware consumers (``softmax_cross_entropy``) or slice."""
-    if use_native(x) and x.shape[1] % 64 == 0:
+    if use_native(x) and x.shape[1] % 8 == 0:
         return _Linear.apply(x.contiguous(), weight, bias, relu)
     y = F.linear(x if not x.is_cuda else x, weight.to(x.dtype) if x.is_cuda else weight,
                  (bias.to(x.dtype) if x.is_cuda else bias) if bias is not None else None)
     return F.relu(y) if relu else y
+
+
+# ------------------------------------------------------------------------------------------------
+# channel concatenation
+# ------------------------------------------------------------------------------------------------
+class _Concat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *parts):
+        ctx.chans = [int(t.shape[1]) for t in parts]
+        return native.concat_channels(parts)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if not dy.is_contiguous(memory_format=CL):
+            dy = dy.contiguous(memory_format=CL)
+        return tuple(native.split_channels(dy, ctx.chans))
+
+
+def concat_channels(parts):
+    """torch.cat(parts, 1) for NHWC activations (Inception / DenseNet branches)."""
+    parts = list(parts)
+    if use_native(parts[0]) and 1 < len(parts) <= 8 and all(t.shape[1] % 8 == 0 and t.dtype == torch.bfloat16
+                                                            and t.is_contiguous(memory_format=CL) for t in parts):
+        return _Concat.apply(*parts)
+    out = torch.cat(parts, 1)
+    return out.contiguous(memory_format=CL) if out.is_cuda and out.dim() == 4 else out
 
 
 # ------------------------------------------------------------------------------------------------

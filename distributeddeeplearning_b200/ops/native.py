@@ -50,8 +50,20 @@ def empty_act(n: int, c: int, h: int, w: int, device) -> torch.Tensor:
     return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=CL)
 
 
-def conv_out_hw(h: int, w: int, k: Tuple[int, int], stride: int, pad: int, dil: int = 1) -> Tuple[int, int]:
-    return ((h + 2 * pad - dil * (k[0] - 1) - 1) // stride + 1, (w + 2 * pad - dil * (k[1] - 1) - 1) // stride + 1)
+def _pad2(pad) -> Tuple[int, int]:
+    """Padding as (pad_h, pad_w); an int means the same on both axes."""
+    if isinstance(pad, (tuple, list)):
+        return int(pad[0]), int(pad[1])
+    return int(pad), int(pad)
+
+
+def conv_out_hw(h: int, w: int, k: Tuple[int, int], stride: int, pad, dil: int = 1) -> Tuple[int, int]:
+    ph, pw = _pad2(pad)
+    return ((h + 2 * ph - dil * (k[0] - 1) - 1) // stride + 1, (w + 2 * pw - dil * (k[1] - 1) - 1) // stride + 1)
+
+
+def _ceil_div(a: int, b: int) -> int:
+    return -(-a // b)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -85,56 +97,66 @@ def tile_geometry(P: int, Q: int, N: int, max_rows: int) -> Tuple[int, int, int]
 
 
 def supports_conv(cin: int, cout: int) -> bool:
-    """Shapes the tcgen05 implicit-GEMM kernels handle natively."""
-    return cout % 64 == 0 and (cin % 64 == 0 or cin <= 4)
+    """Shapes the tcgen05 implicit-GEMM kernels handle natively: channel counts that are multiples of 8 (one 16-byte
+    vector; partial 64-channel k-blocks / N tiles are zero-filled or masked in the kernels) or an NHWC4 stem."""
+    return cout % 8 == 0 and (cin % 8 == 0 or cin <= 4)
 
 
 # ------------------------------------------------------------------------------------------------
 # convolution forward / dgrad / wgrad
 # ------------------------------------------------------------------------------------------------
-def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], stride: int, pad: int, dil: int = 1,
+def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], stride: int, pad, dil: int = 1,
              stats: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False,
              cout: Optional[int] = None):
     """y = conv(x, w) [+ bias][ReLU]; optionally per-channel (sum, sumsq) of y for BatchNorm.
 
-    ``w_bf16``: [Cout, R*S*Cin] bf16 (or the packed stem matrix [Cout, KB*64]).
+    ``w_bf16``: [Cout, R*S*Cin] bf16 (or the packed stem matrix [Cout, KB*64]); ``pad``: int or (pad_h, pad_w).
     """
     C = _C()
     _check_act(x)
     N, Cin, H, W = x.shape
     R, S = kernel
+    ph, pw = _pad2(pad)
     Cout = cout if cout is not None else w_bf16.shape[0]
-    P, Q = conv_out_hw(H, W, kernel, stride, pad, dil)
+    if Cout % 8 != 0:
+        raise ValueError("conv_fwd: Cout must be a multiple of 8")
+    P, Q = conv_out_hw(H, W, kernel, stride, (ph, pw), dil)
     M = N * P * Q
     y = empty_act(N, Cout, P, Q, x.device)
     st = torch.zeros((2, Cout), dtype=torch.float32, device=x.device) if stats else None
     s_ptr, ss_ptr = (st[0].data_ptr(), st[1].data_ptr()) if stats else (0, 0)
+    n_total = _ceil_div(Cout, 64) * 64              # N tiles cover the padded width; stores / stats stop at Cout
+    cch = _ceil_div(Cin, 64)
+    wp, wr, wc = w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1]
     if Cin <= 4:
         if Cin != 4:
             raise ValueError("stem input must be padded to 4 channels (NHWC4)")
         SP, RPK, KB, RP = stem_geometry(R, S)
         C.conv_gemm(C.CONV_STEM, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, H, W, 4,
-                    P, Q, R, S, stride, pad, dil, SP, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, 0, _stream())
-    elif R == 1 and S == 1 and stride == 1 and pad == 0:
-        C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, Cin // 64, Cout, H, W, Cin, P, Q,
-                    1, 1, 1, 0, 1, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1],
-                    Cout, x.data_ptr(), Cin, N, 0, 0, 0, 0, _stream())
+                    P, Q, R, S, stride, ph, dil, SP, int(relu), Cout, wp, wr, wc, n_total, 0, 0, N, 0, 0, 0, 0,
+                    _stream(), pw, 0)
+        return (y, st) if stats else y
+    if Cin % 8 != 0:
+        raise ValueError("conv_fwd: Cin must be a multiple of 8 (or an NHWC4 stem)")
+    if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
+        C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, cch, Cout, H, W, Cin, P, Q,
+                    1, 1, 1, 0, 1, cch, int(relu), Cout, wp, wr, wc, n_total, x.data_ptr(), Cin, N, 0, 0, 0, 0,
+                    _stream(), 0, Cin)
     elif USE_TILE_TMA and (stride == 1 or (stride == 2 and R * S <= 16 and USE_TILE_S2)):
         # window conv: the activation operand comes through ONE 4-D TMA box per filter tap (stride 2: the box is
         # taken from the matching 2x2 phase sub-image of x)
         tw, th, tn = tile_geometry(P, Q, N, 128)
-        C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64), Cout, H, W,
-                    Cin, P, Q, R, S, stride, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cout, x.data_ptr(), Cin, N, tw, th, tn, 0, _stream())
+        C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * cch, Cout, H, W,
+                    Cin, P, Q, R, S, stride, ph, dil, cch, int(relu), Cout, wp, wr, wc, n_total, x.data_ptr(), Cin,
+                    N, tw, th, tn, 0, _stream(), pw, Cin)
     else:
-        C.conv_gemm(C.CONV_FWD, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * (Cin // 64),
-                    Cout, H, W, Cin, P, Q, R, S, stride, pad, dil, Cin // 64, int(relu), Cout, w_bf16.data_ptr(),
-                    w_bf16.shape[0], w_bf16.shape[1], Cout, 0, 0, N, 0, 0, 0, 0, _stream())
+        C.conv_gemm(C.CONV_FWD, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * cch,
+                    Cout, H, W, Cin, P, Q, R, S, stride, ph, dil, cch, int(relu), Cout, wp, wr, wc, n_total, 0, 0,
+                    N, 0, 0, 0, 0, _stream(), pw, Cin)
     return (y, st) if stats else y
 
 
-def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[int, int], stride: int, pad: int,
+def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[int, int], stride: int, pad,
                dil: int = 1, add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dx = conv_transpose(dy, w) (+ add).  ``w_bf16`` is the forward matrix [Cout, R*S*Cin]."""
     C = _C()
@@ -142,39 +164,46 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
     N, Cin, H, W = x_shape
     _, Cout, P, Q = dy.shape
     R, S = kernel
-    if Cin % 64 != 0 or Cout % 64 != 0:
-        raise ValueError("conv_dgrad needs Cin, Cout multiples of 64")
+    ph, pw = _pad2(pad)
+    if Cin % 8 != 0 or Cout % 8 != 0:
+        raise ValueError("conv_dgrad needs Cin, Cout multiples of 8")
     s2_tile = USE_TILE_TMA and USE_TILE_S2 and stride == 2 and R * S <= 16 and dil == 1 and add is None
     dx = empty_act(N, Cin, H, W, dy.device)
     zfill = 0
-    if s2_tile and (R < 2 or S < 2):
-        # some output phases receive no tap (1x1 stride 2 only feeds even rows/cols).  Even image: the live phase's
-        # epilogue writes the zeros of its three sibling pixels; odd image: clear dx first.
-        if R == 1 and S == 1 and pad == 0 and H % 2 == 0 and W % 2 == 0:
+    if s2_tile:
+        # output phases that receive no tap (e.g. 1x1 stride 2 only feeds even rows/cols; 3x3 stride 2 without
+        # padding leaves none empty) and border rows/cols no window reaches.  Even image + 1x1: the live phase's
+        # epilogue writes the zeros of its three sibling pixels; otherwise clear dx first.
+        covered_h = (P - 1) * 2 + (R - 1) * dil + 1 - ph >= H
+        covered_w = (Q - 1) * 2 + (S - 1) * dil + 1 - pw >= W
+        if R == 1 and S == 1 and ph == 0 and pw == 0 and H % 2 == 0 and W % 2 == 0:
             zfill = 1
-        else:
+        elif R < 2 or S < 2 or not (covered_h and covered_w):
             dx.zero_()
     if add is not None:
         _check_act(add, "add")
-    if R == 1 and S == 1 and stride == 1 and pad == 0:
-        C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, Cout // 64, Cin, P, Q, Cout, H,
-                    W, 1, 1, 1, 0, 1, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1], Cin,
-                    dy.data_ptr(), Cout, N, 0, 0, 0, 0, _stream())
+    n_total = _ceil_div(Cin, 64) * 64
+    cch = _ceil_div(Cout, 64)
+    wp, wr, wc = w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1]
+    if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
+        C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, cch, Cin, P, Q, Cout, H,
+                    W, 1, 1, 1, 0, 1, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, 0, 0, 0, 0, _stream(),
+                    0, 0)
     elif stride == 1 and USE_TILE_TMA:
         tw, th, tn = tile_geometry(H, W, N, 128)
-        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin, P, Q,
-                    Cout, H, W, R, S, 1, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, 0, _stream())
+        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * cch, Cin, P, Q,
+                    Cout, H, W, R, S, 1, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, tw, th, tn,
+                    0, _stream(), pw, 0)
     elif s2_tile:
         # four stride-1 phase problems (one launch each), tiles iterate the half-resolution phase grid
         tw, th, tn = tile_geometry((H + 1) // 2, (W + 1) // 2, N, 128)
-        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, N * H * W, R * S * (Cout // 64), Cin, P, Q,
-                    Cout, H, W, R, S, 2, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(), w_bf16.shape[0],
-                    w_bf16.shape[1], Cin, dy.data_ptr(), Cout, N, tw, th, tn, zfill, _stream())
+        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, N * H * W, R * S * cch, Cin, P, Q,
+                    Cout, H, W, R, S, 2, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, tw, th, tn,
+                    zfill, _stream(), pw, 0)
     else:
-        C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * (Cout // 64),
-                    Cin, P, Q, Cout, H, W, R, S, stride, pad, dil, Cout // 64, 0, Cin, w_bf16.data_ptr(),
-                    w_bf16.shape[0], w_bf16.shape[1], Cin, 0, 0, N, 0, 0, 0, 0, _stream())
+        C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * cch,
+                    Cin, P, Q, Cout, H, W, R, S, stride, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, 0, 0, N, 0, 0, 0, 0,
+                    _stream(), pw, 0)
     return dx
 
 
@@ -184,7 +213,7 @@ def _wgrad_splits(tiles: int, total_kb: int, device_index: int) -> int:
 
 
 def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: Tuple[int, int], stride: int,
-               pad: int, dil: int = 1) -> None:
+               pad, dil: int = 1) -> None:
     """grad_w[Cout][R*S*Cin] (fp32, KRSC) += dy^T * im2col(x)."""
     C = _C()
     _check_act(x)
@@ -192,6 +221,7 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: 
     N, Cin, H, W = x.shape
     _, Cout, P, Q = dy.shape
     R, S = kernel
+    ph, pw = _pad2(pad)
     M = N * P * Q
     dev = x.device.index or 0
     if grad_w.dtype != torch.float32:
@@ -202,24 +232,30 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: 
         scratch = torch.zeros((Cout, ncols), dtype=torch.float32, device=x.device)
         tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
         C.conv_wgrad(C.CONV_STEM, x.data_ptr(), dy.data_ptr(), scratch.data_ptr(), M, Cout, Cout, ncols, ncols, H, W,
-                     4, P, Q, R, S, stride, pad, dil, SP, _wgrad_splits(tiles, (M + 63) // 64, dev), N, 0, 0, 0,
-                     _stream())
+                     4, P, Q, R, S, stride, ph, dil, SP, _wgrad_splits(tiles, (M + 63) // 64, dev), N, 0, 0, 0,
+                     _stream(), pw, 0, 0)
         # grad_w is KRSC with the TRUE channel count (3): fold the packed scratch back
         cin_true = grad_w.shape[1]
         C.unpack_stem_grad(scratch.data_ptr(), grad_w.data_ptr(), Cout, R, S, cin_true, RP, SP, _stream())
         return
-    ncols = R * S * Cin
-    tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
-    if R == 1 and S == 1 and stride == 1 and pad == 0:
+    if Cin % 8 != 0 or Cout % 8 != 0:
+        raise ValueError("conv_wgrad needs Cin, Cout multiples of 8")
+    ldw = R * S * Cin
+    if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
         mode, (tw, th, tn), total_kb = C.CONV_GEMM, (0, 0, 0), (M + 63) // 64
-    elif USE_TILE_TMA and (stride == 1 or (stride == 2 and USE_TILE_S2)):
-        mode, (tw, th, tn) = C.CONV_TILE_FWD, tile_geometry(P, Q, N, 64)
-        total_kb = -(-Q // tw) * -(-P // th) * -(-N // tn)
+        cpad, ncols = Cin, Cin                       # one tap: virtual columns = real columns
     else:
-        mode, (tw, th, tn), total_kb = C.CONV_FWD, (0, 0, 0), (M + 63) // 64
+        cpad = _ceil_div(Cin, 64) * 64
+        ncols = R * S * cpad
+        if USE_TILE_TMA and (stride == 1 or (stride == 2 and USE_TILE_S2)):
+            mode, (tw, th, tn) = C.CONV_TILE_FWD, tile_geometry(P, Q, N, 64)
+            total_kb = -(-Q // tw) * -(-P // th) * -(-N // tn)
+        else:
+            mode, (tw, th, tn), total_kb = C.CONV_FWD, (0, 0, 0), (M + 63) // 64
+    tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
     splits = _wgrad_splits(tiles, total_kb, dev)
-    C.conv_wgrad(mode, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), M, Cout, Cout, ncols, ncols, H, W, Cin, P, Q,
-                 R, S, stride, pad, dil, Cin // 64, splits, N, tw, th, tn, _stream())
+    C.conv_wgrad(mode, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), M, Cout, Cout, ldw, ncols, H, W, Cin, P, Q,
+                 R, S, stride, ph, dil, 0, splits, N, tw, th, tn, _stream(), pw, cpad, Cin)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,12 +267,14 @@ def linear_fwd(x: torch.Tensor, w_bf16: torch.Tensor, bias: Optional[torch.Tenso
     _check_act(x)
     B, K = x.shape
     Nout = w_bf16.shape[0]
-    if K % 64 != 0:
-        raise ValueError("linear: in_features must be a multiple of 64")
+    if K % 8 != 0:
+        raise ValueError("linear: in_features must be a multiple of 8")
     Npad = (Nout + 63) // 64 * 64
     y = torch.empty((B, Npad), dtype=torch.bfloat16, device=x.device)
-    C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), 0, 0, B, K // 64, Npad, 1, 1, K, 1, 1, 1, 1, 1, 0, 1,
-                K // 64, int(relu), Nout, w_bf16.data_ptr(), Nout, K, Npad, x.data_ptr(), K, B, 0, 0, 0, 0, _stream())
+    kb = _ceil_div(K, 64)
+    # pad columns [Nout, Npad) are written as exact zeros (their weight rows are TMA out-of-bounds, bias is masked)
+    C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), 0, 0, B, kb, Npad, 1, 1, K, 1, 1, 1, 1, 1, 0, 1,
+                kb, int(relu), Nout, w_bf16.data_ptr(), Nout, K, Npad, x.data_ptr(), K, B, 0, 0, 0, 0, _stream())
     return y
 
 
@@ -260,15 +298,16 @@ def linear_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor) -> Non
     tiles = ((K + 127) // 128) * ((Nout + 127) // 128)
     splits = _wgrad_splits(tiles, (B + 63) // 64, x.device.index or 0)
     C.conv_wgrad(C.CONV_GEMM, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), B, Nout, Npad, K, K, 1, 1, K, 1, 1, 1,
-                 1, 1, 0, 1, K // 64, splits, B, 0, 0, 0, _stream())
+                 1, 1, 0, 1, 0, splits, B, 0, 0, 0, _stream())
 
 
 # ------------------------------------------------------------------------------------------------
 # BatchNorm + activation
 # ------------------------------------------------------------------------------------------------
 def bn_supported(c: int) -> bool:
-    g = c // 8
-    return c % 64 == 0 and g > 0 and 256 % g == 0
+    """Any channel count that is a multiple of 8 (power-of-two widths take the flat thread mapping, the rest the
+    64-channel-chunk mapping; see csrc/ops/bn_act.cu)."""
+    return c > 0 and c % 8 == 0
 
 
 def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, running_mean, running_var,
@@ -483,3 +522,27 @@ def dgrad_supports_add(kernel: Tuple[int, int], stride: int) -> bool:
     """Whether conv_dgrad can fold ``+ add`` into its epilogue for this geometry without leaving the fast path
     (the stride-2 phase decomposition writes each output phase from a different launch, so it cannot)."""
     return not (stride == 2 and USE_TILE_TMA and USE_TILE_S2 and kernel[0] * kernel[1] <= 16)
+
+
+# ------------------------------------------------------------------------------------------------
+# channel concatenation (Inception / DenseNet)
+# ------------------------------------------------------------------------------------------------
+def concat_channels(parts) -> torch.Tensor:
+    """NHWC concat along channels of up to 8 tensors (channel counts multiples of 8)."""
+    for t in parts:
+        _check_act(t, "part")
+    N, _, H, W = parts[0].shape
+    chans = [int(t.shape[1]) for t in parts]
+    out = empty_act(N, sum(chans), H, W, parts[0].device)
+    _C().concat_channels([t.data_ptr() for t in parts], chans, out.data_ptr(), N * H * W, False, _stream())
+    return out
+
+
+def split_channels(whole: torch.Tensor, chans) -> list:
+    """Inverse of :func:`concat_channels` (its backward): contiguous NHWC slices of ``whole``."""
+    _check_act(whole, "whole")
+    N, _, H, W = whole.shape
+    parts = [empty_act(N, int(c), H, W, whole.device) for c in chans]
+    _C().concat_channels([t.data_ptr() for t in parts], [int(c) for c in chans], whole.data_ptr(), N * H * W, True,
+                         _stream())
+    return parts

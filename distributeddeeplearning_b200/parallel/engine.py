@@ -174,12 +174,17 @@ class FusedSGD(torch.optim.Optimizer):
         regions = [("flags", int(self.C.SIGNAL_PAD_BYTES)), ("grad", T * 4), ("weight", T * 4), ("wbf16", T * 2)]
         if self.wire_bf16:
             regions.append(("stage", T * 2))
+        regions.append(("scalars", int(self.C.SCALAR_SLOTS) * 4))
         self.arena = SymmetricArena(regions, dev, use_multicast)
         self.use_mc = self.arena.has_multicast
         self.G = self.arena.region("grad", torch.float32, T)
         self.W = self.arena.region("weight", torch.float32, T)
         self.Wb = self.arena.region("wbf16", torch.bfloat16, T)
         self.M = torch.zeros(T, dtype=torch.float32, device=dev)
+        self._scalars_in = self.arena.region("scalars", torch.float32, int(self.C.SCALAR_SLOTS))
+        self._scalars_out = torch.zeros(int(self.C.SCALAR_SLOTS), dtype=torch.float32, device=dev)
+        self._scalars_pending = 0
+        self._scalars_last = 0
         self._epochs = torch.zeros(int(self.C.COMM_CHANNELS) * int(self.C.MAX_COMM_BLOCKS), dtype=torch.int32, device=dev)
         self._error = torch.zeros(1, dtype=torch.int32, device=dev)
         self._hyper_dev = torch.zeros(int(self.C.SGD_HYPER_BYTES), dtype=torch.uint8, device=dev)
@@ -250,8 +255,11 @@ class FusedSGD(torch.optim.Optimizer):
                                    self._hyper_dev.data_ptr(), numel, max(blocks, min(4 * self._sms, numel // 2048 + 1)),
                                    stream.cuda_stream)
         else:
+            tail = self._scalars_pending > 0 and b == self.num_buckets - 1
             self.C.fused_allreduce_sgd(self.ctx, start, numel, self.M.data_ptr(), self._hyper_dev.data_ptr(), 0,
-                                       self.use_mc, self.wire_bf16, blocks, stream.cuda_stream)
+                                       self.use_mc, self.wire_bf16, blocks, stream.cuda_stream,
+                                       self.arena.offsets["scalars"] if tail else 0,
+                                       self._scalars_out.data_ptr() if tail else 0)
 
     def _on_ready(self, idx: int) -> None:
         if self._ready_seen[idx]:
@@ -278,6 +286,9 @@ class FusedSGD(torch.optim.Optimizer):
             ev = torch.cuda.Event()
             ev.record(self._comm_stream)
             torch.cuda.current_stream(self.device).wait_event(ev)
+        if self._scalars_pending and self.world == 1:
+            self._scalars_out.copy_(self._scalars_in)
+        self._scalars_last, self._scalars_pending = self._scalars_pending, 0
         self._pending = list(self.plan["bucket_param_count"])
         self._ready_seen = [False] * len(self.params)
         self._next_bucket = 0
@@ -285,6 +296,22 @@ class FusedSGD(torch.optim.Optimizer):
         self._first_step = False
         self._steps += 1
         return loss
+
+    # ---- scalar piggy-back (reference ``PyTorch_hvd/src/imagenet_pytorch_horovod.py:246``) ----------
+    @torch.no_grad()
+    def piggyback(self, values: torch.Tensor) -> None:
+        """Queue up to SCALAR_SLOTS device scalars (loss, accuracy, ...) to be averaged across ranks by the LAST bucket
+        kernel of this step — the reference's two blocking per-step MPI allreduces ride along for free.  Call after
+        the forward pass and before ``step()``; read the result with :meth:`averaged_scalars` after ``step()``."""
+        v = values.detach().reshape(-1).to(torch.float32)
+        if v.numel() > self._scalars_in.numel():
+            raise ValueError(f"piggyback carries at most {self._scalars_in.numel()} scalars")
+        self._scalars_in[:v.numel()].copy_(v)
+        self._scalars_pending = int(v.numel())
+
+    def averaged_scalars(self) -> torch.Tensor:
+        """Cross-rank means of the values passed to :meth:`piggyback` before the last ``step()`` (device tensor)."""
+        return self._scalars_out[:self._scalars_last]
 
     def zero_grad(self, set_to_none: bool = False):
         """No-op: the fused kernel clears each gradient slot after consuming it."""

@@ -55,8 +55,11 @@ class Metric:
         self.name = name
         self._sum = torch.zeros((), dtype=torch.float64, device=device)
         self._n = 0
+        self._global = True       # every update so far was already a cross-rank mean (piggy-backed)
 
-    def update(self, val):
+    def update(self, val, averaged: bool = False):
+        """``averaged=True``: ``val`` is already the cross-rank mean (``FusedSGD.averaged_scalars``)."""
+        self._global = self._global and averaged
         if torch.is_tensor(val):
             self._sum += val.detach().to(self._sum.device, torch.float64)
         else:
@@ -68,6 +71,8 @@ class Metric:
         from ..parallel import dist
 
         local = (self._sum / max(self._n, 1)).to(torch.float32)
+        if self._global and self._n > 0:
+            return local.cpu()
         return dist.allreduce(local, average=True, name=self.name).cpu()
 
 

@@ -146,11 +146,20 @@ def main(argv=None) -> int:
                 optimizer.zero_grad()
                 output = net(data)
                 loss = criterion(output, target)
+                main_out = output[0] if isinstance(output, tuple) else output
+                acc = top1_accuracy(main_out.detach()[:, :classes].float(), target)
+                carry = hasattr(optimizer, "piggyback")
+                if carry:   # the reference's 2 blocking scalar allreduces per step ride in the last gradient bucket
+                    optimizer.piggyback(torch.stack([loss.detach().float(), acc.float()]))
                 loss.backward()
                 optimizer.step()
-                train_loss.update(loss)
-                main_out = output[0] if isinstance(output, tuple) else output
-                train_acc.update(top1_accuracy(main_out.detach()[:, :classes].float(), target))
+                if carry:
+                    avg = optimizer.averaged_scalars()
+                    train_loss.update(avg[0], averaged=True)
+                    train_acc.update(avg[1], averaged=True)
+                else:
+                    train_loss.update(loss)
+                    train_acc.update(acc)
                 t.update(1)
         if writer:
             writer.add_scalar("train/loss", float(train_loss.avg), epoch)

@@ -8,7 +8,7 @@ from distributeddeeplearning_b200.ops import native
 
 
 @pytest.mark.parametrize("name", ["resnet18", "resnet50", "resnet101", "resnet152", "vgg16", "vgg11_bn", "alexnet",
-                                  "inception_v3"])
+                                  "inception_v3", "densenet121", "densenet161", "squeezenet1_0", "squeezenet1_1"])
 def test_state_dict_matches_torchvision(name):
     m = models.get_model(name)
     kw = {"init_weights": False} if "inception" in name else {}
@@ -56,6 +56,39 @@ def test_vgg_alexnet_forward_equal_torchvision_eval():
             assert torch.allclose(m(x), tv(x), atol=1e-3, rtol=1e-3), name
 
 
+def test_densenet_squeezenet_match_torchvision():
+    torch.manual_seed(0)
+    for name in ("densenet121", "squeezenet1_1"):
+        m, tv = models.get_model(name), getattr(torchvision.models, name)()
+        m.load_state_dict(tv.state_dict())
+        m.eval(), tv.eval()
+        x = torch.randn(1, 3, 96, 96)
+        with torch.no_grad():
+            assert torch.allclose(m(x), tv(x), atol=1e-4, rtol=1e-3), name
+    # pre-activation BN + concat path in train mode: gradients equal torchvision's
+    m, tv = models.get_model("densenet121"), torchvision.models.densenet121()
+    m.load_state_dict(tv.state_dict())
+    m.train(), tv.train()
+    x, y = torch.randn(2, 3, 64, 64), torch.tensor([3, 5])
+    o1, o2 = m(x), tv(x)
+    assert torch.allclose(o1, o2, atol=1e-4, rtol=1e-3)
+    ops.softmax_cross_entropy(o1, y).backward()
+    torch.nn.functional.cross_entropy(o2, y).backward()
+    g1, g2 = dict(m.named_parameters()), dict(tv.named_parameters())
+    for k in ("features.conv0.weight", "features.denseblock2.denselayer3.conv2.weight", "features.transition1.conv.weight",
+              "features.norm5.weight", "classifier.bias"):
+        ref = g2[k].grad
+        assert (g1[k].grad - ref).abs().max() <= 1e-2 * ref.abs().max() + 1e-5, k   # 121 BN layers, batch 2: fp32 order noise
+
+
+def test_concat_channels_composite():
+    a, b = torch.randn(2, 8, 3, 3, requires_grad=True), torch.randn(2, 16, 3, 3, requires_grad=True)
+    out = ops.concat_channels([a, b])
+    assert out.shape == (2, 24, 3, 3)
+    out.sum().backward()
+    assert torch.equal(a.grad, torch.ones_like(a)) and torch.equal(b.grad, torch.ones_like(b))
+
+
 def test_inception_returns_aux_in_train_mode():
     m = models.get_model("inception_v3")
     assert models.input_size(m) == 299 and models.input_size("inception_v3") == 299
@@ -89,6 +122,9 @@ def test_stem_geometry_and_support_matrix():
     assert native.stem_geometry(7, 7) == (8, 2, 4, 8)       # ResNet stem: 4 k-blocks of 2 rows x 8 taps x 4 ch
     assert native.stem_geometry(11, 11) == (16, 1, 11, 11)  # AlexNet
     assert native.stem_geometry(3, 3) == (4, 4, 1, 4)       # VGG
-    assert native.supports_conv(64, 256) and native.supports_conv(3, 64) and not native.supports_conv(80, 192)
-    assert native.bn_supported(2048) and native.bn_supported(64) and not native.bn_supported(80)
+    # any channel count that is a multiple of 8 (Inception's 80 -> 192), or an NHWC4 stem
+    assert native.supports_conv(64, 256) and native.supports_conv(3, 64) and native.supports_conv(80, 192)
+    assert not native.supports_conv(20, 64) and not native.supports_conv(64, 1000 + 4)
+    assert native.bn_supported(2048) and native.bn_supported(64) and native.bn_supported(80) and not native.bn_supported(12)
     assert native.conv_out_hw(224, 224, (7, 7), 2, 3) == (112, 112)
+    assert native.conv_out_hw(17, 17, (1, 7), 1, (0, 3)) == (17, 17)       # asymmetric Inception kernels

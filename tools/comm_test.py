@@ -48,8 +48,14 @@ def check_engine(use_mc, wire):
                 g_avg = sum(g_all) / world
             gs.append(g_avg)
             p.grad.add_(g_all[rank].view_as(p.grad))
+            if i == 0:      # piggy-backed scalars (K19): mean over ranks of (rank + it, 10 * rank)
+                opt.piggyback(torch.tensor([float(rank + it), 10.0 * rank], device="cuda"))
             p._ddl_ready()
         opt.step()
+        want = torch.tensor([(world - 1) / 2 + it, 10.0 * (world - 1) / 2], device="cuda")
+        if not torch.allclose(opt.averaged_scalars(), want, atol=1e-5):
+            ok = False
+            log(f"  FAIL piggy-backed scalars: got {opt.averaged_scalars().tolist()} want {want.tolist()}")
         for i in range(len(ps)):
             g = gs[i] + wd * ref_w[i]
             ref_m[i] = g.clone() if it == 0 else mom * ref_m[i] + g

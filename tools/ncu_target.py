@@ -18,12 +18,12 @@ dev = torch.device("cuda")
 what = sys.argv[1] if len(sys.argv) > 1 else "conv"
 B = int(os.environ.get("NCU_BATCH", 256))
 if what == "conv":
-    for (ci, hw, co, k, s, p) in [(64, 56, 64, 3, 1, 1), (256, 56, 64, 1, 1, 0), (128, 56, 128, 3, 2, 1)]:
+    for (ci, hw, co, k, s, p) in [(64, 56, 256, 1, 1, 0), (64, 56, 64, 3, 1, 1), (256, 14, 256, 3, 1, 1), (256, 14, 1024, 1, 1, 0)]:
         x = torch.randn(B, ci, hw, hw, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
         w = torch.randn(co, ci, k, k, device=dev) * 0.05
         wb = w.permute(0, 2, 3, 1).reshape(co, -1).contiguous().to(torch.bfloat16)
         gw = torch.zeros(co, ci, k, k, device=dev).contiguous(memory_format=cl)
-        for _ in range(2):
+        for _ in range(1):
             y, st = nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co)
             dy = torch.randn_like(y)
             nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p)
