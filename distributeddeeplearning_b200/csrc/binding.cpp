@@ -72,6 +72,7 @@ PYBIND11_MODULE(_C, m) {
   m.attr("CONV_GEMM") = static_cast<int>(ddl::kConvGemm);
   m.attr("CONV_STEM") = static_cast<int>(ddl::kConvStem);
   m.attr("CONV_TILE_FWD") = static_cast<int>(ddl::kConvTileFwd);
+  m.attr("CONV_STEM_TMA") = static_cast<int>(ddl::kConvStemTma);
   m.attr("CONV_TILE_DGRAD") = static_cast<int>(ddl::kConvTileDgrad);
   m.attr("CONV_GEMM_DGRAD") = static_cast<int>(ddl::kConvGemmDgrad);
 
@@ -338,6 +339,10 @@ PYBIND11_MODULE(_C, m) {
   m.def("dropout", [](ptr_t x, ptr_t y, int64_t n, float p, uint64_t seed, uint64_t offset, ptr_t stream) {
     check(ddl::launch_dropout(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), n, p, seed, offset, S(stream)),
           "dropout");
+  });
+  m.def("pad_nhwc4", [](ptr_t in, ptr_t out, int N, int H, int W, int Hp, int Wp, int pt, int pl, int G, ptr_t stream) {
+    check(ddl::launch_pad_nhwc4(P<const __nv_bfloat16>(in), P<__nv_bfloat16>(out), N, H, W, Hp, Wp, pt, pl, G, S(stream)),
+          "pad_nhwc4");
   });
   m.def("concat_channels", [](std::vector<ptr_t> parts, std::vector<int> chans, ptr_t whole, int M, bool scatter,
                               ptr_t stream) {

@@ -101,13 +101,14 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
       }
     }
   }
-  for (int r = row0; r < a.M; r += row_stride) {
-    const size_t off = static_cast<size_t>(r) * a.C + c0;
+  // two rows per iteration: both rows' 16-byte loads are in flight before either is consumed (one load per thread
+  // leaves only ~16 KB per SM outstanding, short of the ~30 KB an HBM3e stream needs at this latency)
+  auto finish = [&](const uint4& ux, const uint4& ur, size_t off) {
     float x[8], z[8];
-    unpack8(ld_stream_u4(a.x + off), x);
+    unpack8(ux, x);
     if (a.residual) {
       float res[8];
-      unpack8(ld_stream_u4(a.residual + off), res);
+      unpack8(ur, res);
 #pragma unroll
       for (int i = 0; i < 8; ++i) z[i] = fmaf(x[i], scale[i], shift[i]) + res[i];
     } else {
@@ -119,6 +120,23 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
       for (int i = 0; i < 8; ++i) z[i] = fmaxf(z[i], 0.f);
     }
     store8_bf16(a.z + off, z);
+  };
+  int r = row0;
+  for (; r + row_stride < a.M; r += 2 * row_stride) {
+    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
+    const size_t off1 = static_cast<size_t>(r + row_stride) * a.C + c0;
+    const uint4 x0 = ld_stream_u4(a.x + off0), x1 = ld_stream_u4(a.x + off1);
+    uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+    if (a.residual) { r0 = ld_stream_u4(a.residual + off0); r1 = ld_stream_u4(a.residual + off1); }
+    finish(x0, r0, off0);
+    finish(x1, r1, off1);
+  }
+  if (r < a.M) {
+    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
+    const uint4 x0 = ld_stream_u4(a.x + off0);
+    uint4 r0 = make_uint4(0, 0, 0, 0);
+    if (a.residual) r0 = ld_stream_u4(a.residual + off0);
+    finish(x0, r0, off0);
   }
 }
 
@@ -143,14 +161,13 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
 #pragma unroll
     for (int i = 0; i < 8; ++i) { msc[i] = gam.v[i] * invstd.v[i]; msh[i] = bet.v[i] - mean.v[i] * msc[i]; }
   }
-  for (int r = live ? blockIdx.x * 32 + rl : a.M; r < a.M; r += gridDim.x * 32) {
-    const size_t off = static_cast<size_t>(r) * a.C + c0;
+  auto accumulate = [&](const uint4& udz, const uint4& ux, const uint4& uz) {
     float dz[8], x[8];
-    unpack8(ld_stream_u4(a.dz + off), dz);
-    unpack8(ld_stream_u4(a.x + off), x);
+    unpack8(udz, dz);
+    unpack8(ux, x);
     if (MASK == kMaskZ) {
       float z[8];
-      unpack8(ld_stream_u4(a.z + off), z);
+      unpack8(uz, z);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? dz[i] : 0.f;
     } else if (MASK == kMaskX) {
@@ -162,6 +179,27 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
       s1[i] += dz[i];
       s2[i] = fmaf(dz[i], x[i], s2[i]);
     }
+  };
+  // two rows per iteration so that 4 (6 with the z mask) 16-byte loads are outstanding per thread
+  const int rstep = gridDim.x * 32;
+  int r = live ? blockIdx.x * 32 + rl : a.M;
+  for (; r + rstep < a.M; r += 2 * rstep) {
+    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
+    const size_t off1 = static_cast<size_t>(r + rstep) * a.C + c0;
+    const uint4 d0 = ld_stream_u4(a.dz + off0), d1 = ld_stream_u4(a.dz + off1);
+    const uint4 x0 = ld_stream_u4(a.x + off0), x1 = ld_stream_u4(a.x + off1);
+    uint4 z0 = make_uint4(0, 0, 0, 0), z1 = z0;
+    if (MASK == kMaskZ) { z0 = ld_stream_u4(a.z + off0); z1 = ld_stream_u4(a.z + off1); }
+    accumulate(d0, x0, z0);
+    accumulate(d1, x1, z1);
+  }
+  if (r < a.M) {
+    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
+    const uint4 d0 = ld_stream_u4(a.dz + off0);
+    const uint4 x0 = ld_stream_u4(a.x + off0);
+    uint4 z0 = make_uint4(0, 0, 0, 0);
+    if (MASK == kMaskZ) z0 = ld_stream_u4(a.z + off0);
+    accumulate(d0, x0, z0);
   }
   // lanes of a warp sharing a channel group: lane = (rl % 4) * 8 + cgl -> xor 8, 16
 #pragma unroll

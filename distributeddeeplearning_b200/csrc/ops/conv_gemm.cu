@@ -63,11 +63,22 @@ DDL_DEVICE void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, int c0, int
       : "memory");
 }
 
+DDL_DEVICE void tma_load_5d(uint32_t dst_smem, const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4,
+                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+         "r"(smem_u32(bar))
+      : "memory");
+}
+
 constexpr bool mode_a_tma(int mode) {
-  return mode == kConvGemm || mode == kConvTileFwd || mode == kConvTileDgrad || mode == kConvGemmDgrad;
+  return mode == kConvGemm || mode == kConvTileFwd || mode == kConvTileDgrad || mode == kConvGemmDgrad ||
+         mode == kConvStemTma;
 }
 constexpr bool mode_b_mn(int mode) { return mode == kConvDgrad || mode == kConvTileDgrad || mode == kConvGemmDgrad; }
-constexpr bool mode_tile(int mode) { return mode == kConvTileFwd || mode == kConvTileDgrad; }
+constexpr bool mode_tile(int mode) { return mode == kConvTileFwd || mode == kConvTileDgrad || mode == kConvStemTma; }
+constexpr bool mode_stem(int mode) { return mode == kConvStem || mode == kConvStemTma; }
 
 
 // ---------------------------------------------------------------------------------------------
@@ -297,12 +308,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
           // k-block = RPK filter rows x SP taps x 4 channels, SP = a.cchunks (padded taps per row)
           const int SP = a.cchunks;
           const int RPK = 16 / SP;           // 64 elements / (SP * 4)
-          int e = 0;                          // 8-byte element index within the 128-byte row (0..15)
           for (int rr = 0; rr < RPK; ++rr) {
             const int r = kb * RPK + rr;
             const int h = hb + r * a.dil;
             const bool h_ok = row_ok && r < a.R && h >= 0 && h < a.srcH;
-            for (int s = 0; s < SP; ++s, ++e) {
+            for (int s = 0; s < SP; ++s) {
+              const int e = s * RPK + rr;     // 8-byte element index in the 128-byte row: (tap, row-in-block) order
               const int w = wb + s * a.dil;
               const bool ok = h_ok && s < a.S && w >= 0 && w < a.srcW;
               const __nv_bfloat16* src = ok ? img_base + (static_cast<size_t>(h) * a.srcW + w) * 4 : a.src;
@@ -412,10 +423,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
         } else {
-          tma_load_2d(sB, &tmB, MODE == kConvStem ? kb * kBlockK : widx * a.kstride + cc * kBlockK, n0, &full[stage]);
+          tma_load_2d(sB, &tmB, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK, n0, &full[stage]);
         }
         if (MODE == kConvGemm || MODE == kConvGemmDgrad) {
           tma_load_2d(smem_u32(sA), &tmA, kb * kBlockK, m0, &full[stage]);
+        } else if (MODE == kConvStemTma) {
+          tma_load_5d(smem_u32(sA), &tmA, 0, kb, tq0, tp0, tn0, &full[stage]);
         } else if (kTile) {
           tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
         }
@@ -600,9 +613,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
           } else {
-            tma_load_2d(sB, &tmB, MODE == kConvStem ? kb * kBlockK : widx * a.kstride + cc * kBlockK, n0, &full[stage]);
+            tma_load_2d(sB, &tmB, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK, n0, &full[stage]);
           }
-          if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
+          if (MODE == kConvStemTma) tma_load_5d(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, &full[stage]);
+          else if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
           else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, &full[stage]);
           if (++cc == a.cchunks) { cc = 0; ++tap; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -664,8 +678,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kThreads, 3)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ TmaSet tmXs, WgradArgs a) {
   const CUtensorMap& tmX = tmXs.m[0];
-  constexpr bool kXTma = (MODE == kConvGemm || MODE == kConvTileFwd);
-  constexpr bool kTile = (MODE == kConvTileFwd);
+  constexpr bool kXTma = (MODE == kConvGemm || MODE == kConvTileFwd || MODE == kConvStemTma);
+  constexpr bool kTile = (MODE == kConvTileFwd || MODE == kConvStemTma);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int nstages = a.stages;
@@ -722,7 +736,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       const int colc = col0 + chunk * 64;      // first k column of my chunk
       const bool col_ok = colc < a.ncols;
       int tap_r = 0, tap_s = 0, c_off = 0;
-      if (MODE != kConvStem) {
+      if (!mode_stem(MODE)) {
         const int tap = colc / a.Cpad;          // columns live in the padded (tap, Cpad) space
         c_off = colc - tap * a.Cpad;
         tap_r = tap / a.S;
@@ -751,12 +765,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         if (MODE == kConvStem) {
           const int SP = a.cchunks, RPK = 16 / SP;
           const int kbk = colc / 64;            // which k-block of the stem's packed K
-          int e = 0;
           for (int rr = 0; rr < RPK; ++rr) {
             const int r = kbk * RPK + rr;
             const int h = hb + r * a.dil;
             const bool h_ok = m_ok && r < a.R && h >= 0 && h < a.H;
-            for (int s = 0; s < SP; ++s, ++e) {
+            for (int s = 0; s < SP; ++s) {
+              const int e = s * RPK + rr;
               const int w = wb + s * a.dil;
               const bool ok = h_ok && s < a.S && w >= 0 && w < a.W;
               const __nv_bfloat16* src = ok ? img_base + (static_cast<size_t>(h) * a.W + w) * 4 : a.x;
@@ -822,7 +836,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     if (elect_one()) {
       // taps / channel offsets of the two 64-column chunks of the B tile (tile mode)
       int tdh[2] = {0, 0}, tdw[2] = {0, 0}, tmap[2] = {0, 0}, tc0[2] = {0, 0};
-      if (kTile) {
+      if (kTile && MODE != kConvStemTma) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int colc = col0 + j * 64;
@@ -856,8 +870,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           mbar_arrive_expect_tx(&full[stage], box_bytes * (second ? 4u : 3u));
           tma_load_4d(sA, &tmDy, co0, q0, p0, n0, &full[stage]);
           tma_load_4d(sA + 8192, &tmDy, co0 + 64, q0, p0, n0, &full[stage]);
-          tma_load_4d(sA + 16384, &tmXs.m[tmap[0]], tc0[0], q0 + tdw[0], p0 + tdh[0], n0, &full[stage]);
-          if (second) tma_load_4d(sA + 24576, &tmXs.m[tmap[1]], tc0[1], q0 + tdw[1], p0 + tdh[1], n0, &full[stage]);
+          if (MODE == kConvStemTma) {
+            // k-block (col0 / 64 + j) of the packed stem K = one box of the row-interleaved image
+            tma_load_5d(sA + 16384, &tmXs.m[0], 0, col0 / 64, q0, p0, n0, &full[stage]);
+            if (second) tma_load_5d(sA + 24576, &tmXs.m[0], 0, col0 / 64 + 1, q0, p0, n0, &full[stage]);
+          } else {
+            tma_load_4d(sA + 16384, &tmXs.m[tmap[0]], tc0[0], q0 + tdw[0], p0 + tdh[0], n0, &full[stage]);
+            if (second) tma_load_4d(sA + 24576, &tmXs.m[tmap[1]], tc0[1], q0 + tdw[1], p0 + tdh[1], n0, &full[stage]);
+          }
         } else {
           const int m = (kb_begin + i) * 64;
           mbar_arrive_expect_tx(&full[stage], 16384u + (kXTma ? 16384u : 0u));
@@ -968,6 +988,30 @@ bool make_map_nhwc_phase(CUtensorMap* map, const void* base, int N, int H, int W
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+
+// Stem operand map over the zero-padded, G-row-interleaved image [N][Hp][Wp][G][4] written by pad_nhwc4
+// (G = RPK filter rows per k-block): the k-block j of output pixel (n, p, q) is the 128 contiguous bytes at
+// (row stride*p + G*j, col stride*q).  5-D map (64 elements | k-block | out col | out row | image) whose dimensions
+// overlap in memory; box = {64, 1, tw, th, tn}.
+bool make_map_stem5d(CUtensorMap* map, const void* base, int N, int Hp, int Wp, int P, int Q, int stride, int G, int KB,
+                     int tw, int th, int tn) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t pitch = static_cast<cuuint64_t>(Wp) * G * 8;          // bytes per buffer row
+  cuuint64_t dims[5] = {64, static_cast<cuuint64_t>(KB), static_cast<cuuint64_t>(Q), static_cast<cuuint64_t>(P),
+                        static_cast<cuuint64_t>(N)};
+  cuuint64_t strides[4] = {pitch * G, static_cast<cuuint64_t>(stride) * G * 8, pitch * stride, pitch * Hp};
+  cuuint32_t box[5] = {64, 1, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tn)};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i)
+    if (strides[i] % 16 != 0) return false;
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+inline int stem_sp(int S) { return S <= 4 ? 4 : (S <= 8 ? 8 : 16); }
 
 inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
@@ -1107,6 +1151,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
       case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(tmB, tmA, args, n_total, tiles, stats, stream);
       case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
       case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvStemTma: return launch_fwd_mode<kConvStemTma>(tmB, tmA, args, n_total, tiles, stats, stream);
       default: return cudaErrorInvalidValue;
     }
   };
@@ -1127,6 +1172,16 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
     x.tiles_h = (x.dstH + x.th - 1) / x.th;
     return x.tiles_w * x.tiles_h * ((x.batch + x.tn - 1) / x.tn);
   };
+  if (mode == kConvStemTma) {
+    // a.srcH x a.srcW is the PADDED image; the k-block geometry follows from the filter width (see stem_geometry)
+    if (a.S > 16) return cudaErrorInvalidValue;
+    const int SP = stem_sp(a.S), RPK = 16 / SP;
+    if (!make_map_stem5d(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.dstH, a.dstW, st, RPK, a.KB, a.tw, a.th, a.tn))
+      return cudaErrorInvalidValue;
+    for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
+    a.cchunks = RPK;
+    return dispatch(a, set_tiles(a));
+  }
   if (st == 1) {
     if (!make_map_nhwc(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn)) return cudaErrorUnknown;
     for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
@@ -1195,10 +1250,18 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void*
   WgradArgs a = a_in;
   CUtensorMap tmDy;
   TmaSet tmX;
-  if (a.mode == kConvTileFwd) {
+  if (a.mode == kConvTileFwd || a.mode == kConvStemTma) {
     if (a.tw * a.th * a.tn > 64 || a.tw < 1 || a.th < 1 || a.tn < 1) return cudaErrorInvalidValue;
     if (!make_map_nhwc(&tmDy, dy, a.batch, a.P, a.Q, a.dy_ld, a.tw, a.th, a.tn)) return cudaErrorUnknown;
-    if (a.stride == 1) {
+    if (a.mode == kConvStemTma) {
+      // a.H x a.W is the PADDED image, a.cchunks = SP, a.ncols = KB * 64
+      if (a.cchunks < 4) return cudaErrorInvalidValue;
+      const int RPK = 16 / a.cchunks;
+      if (!make_map_stem5d(&tmX.m[0], x_matrix, a.batch, a.H, a.W, a.P, a.Q, a.stride, RPK, a.ncols / 64, a.tw, a.th,
+                           a.tn))
+        return cudaErrorInvalidValue;
+      for (int i = 1; i < 4; ++i) tmX.m[i] = tmX.m[0];
+    } else if (a.stride == 1) {
       if (!make_map_nhwc(&tmX.m[0], x_matrix, a.batch, a.H, a.W, a.C, a.tw, a.th, a.tn)) return cudaErrorUnknown;
       for (int i = 1; i < 4; ++i) tmX.m[i] = tmX.m[0];
     } else if (a.stride == 2) {
@@ -1228,7 +1291,7 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void*
   splits = (a.total_kb + a.kb_per_split - 1) / a.kb_per_split;
   // TMA-fed wgrad tiles run best with a 2-deep ring (measured: 3 CTAs/SM beat a deeper pipeline); the cp.async
   // gather modes need depth > kLag
-  const bool tma_fed = (a.mode == kConvGemm || a.mode == kConvTileFwd);
+  const bool tma_fed = (a.mode == kConvGemm || a.mode == kConvTileFwd || a.mode == kConvStemTma);
   a.stages = tma_fed ? 2 : kWgMaxStages;
   if (g_force_stages > 0 && g_force_stages <= kWgMaxStages && tma_fed) a.stages = g_force_stages;
   if (a.stages > a.kb_per_split) a.stages = a.kb_per_split;
@@ -1252,6 +1315,7 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void*
     case kConvGemm: DDL_WG(kConvGemm); break;
     case kConvStem: DDL_WG(kConvStem); break;
     case kConvTileFwd: DDL_WG(kConvTileFwd); break;
+    case kConvStemTma: DDL_WG(kConvStemTma); break;
     default: return cudaErrorInvalidValue;
   }
 #undef DDL_WG

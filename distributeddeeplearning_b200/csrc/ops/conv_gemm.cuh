@@ -17,6 +17,11 @@ enum ConvMode : int {
                        //   (padding = TMA out-of-bounds zero fill), rows = (n, h, w) of the rectangle
   kConvTileDgrad = 5,  // same for the data gradient of a stride-1 conv (source = dy, B MN-major)
   kConvGemmDgrad = 6,  // 1x1 stride-1 data gradient: A = dy matrix via 2-D TMA, B MN-major
+  kConvStemTma = 7,    // small-Cin first conv with an EVEN stride on a zero-padded NHWC4 image: the k-block of a
+                       //   row (RPK filter rows x SP taps x 4 ch = 128 B) is ONE box of a 5-D tensor map whose
+                       //   dimensions overlap in memory: (tap*ch | filter row | out col | out row | image) with
+                       //   strides (1 | Wp*4 | stride*4 | stride*Wp*4 | Hp*Wp*4) elements.  Replaces 64 8-byte
+                       //   cp.async per output pixel of kConvStem by 4 TMA requests per 128-pixel tile.
 };
 
 struct ConvArgs {

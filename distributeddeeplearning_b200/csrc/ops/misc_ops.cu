@@ -421,11 +421,17 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
                                         int Cin, int RP, int SP) {
   const int total = Cout * RP * SP * 4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // packed index = ((co * KB + j) * SP + s) * RPK*4 + g*4 + c  with filter row r = j*RPK + g: inside a k-block the
+    // order is (tap, row-in-block, channel) — the order in which the row-interleaved stem image (pad_nhwc4) lays out
+    // the 128 bytes one output pixel needs, so a single contiguous TMA box yields the operand row
+    const int RPK = 16 / SP;
     const int c = i & 3;
     int t = i >> 2;
+    const int g = t % RPK; t /= RPK;
     const int s = t % SP; t /= SP;
-    const int r = t % RP;
-    const int co = t / RP;
+    const int j = t % (RP / RPK);
+    const int co = t / (RP / RPK);
+    const int r = j * RPK + g;
     float v = 0.f;
     if (c < Cin && s < S && r < R) v = w[((co * R + r) * S + s) * Cin + c];
     packed[i] = __float2bfloat16_rn(v);
@@ -440,7 +446,8 @@ __global__ void unpack_stem_grad_kernel(const float* __restrict__ packed, float*
     const int s = t % S; t /= S;
     const int r = t % R;
     const int co = t / R;
-    gw[i] += packed[((co * RP + r) * SP + s) * 4 + c];
+    const int RPK = 16 / SP, j = r / RPK, g = r - j * RPK;
+    gw[i] += packed[(((co * (RP / RPK) + j) * SP + s) * RPK + g) * 4 + c];
   }
 }
 
@@ -516,6 +523,24 @@ inline int grid_for(int64_t work, int per_block = 256, int cap = 148 * 16) {
   if (b > cap) b = cap;
   if (b < 1) b = 1;
   return static_cast<int>(b);
+}
+
+// out[n][h][w][g][0..3] = in[n][h - pt + g][w - pl][0..3] (zero outside the source image), g < G
+__global__ void __launch_bounds__(256) pad_nhwc4_kernel(const uint2* __restrict__ in, uint2* __restrict__ out, int N,
+                                                        int H, int W, int Hp, int Wp, int pt, int pl, int G) {
+  const int64_t total = static_cast<int64_t>(N) * Hp * Wp * G;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int g = static_cast<int>(i % G);
+    int64_t t = i / G;
+    const int w = static_cast<int>(t % Wp); t /= Wp;
+    const int h = static_cast<int>(t % Hp);
+    const int64_t n = t / Hp;
+    const int sh = h - pt + g, sw = w - pl;
+    uint2 v = make_uint2(0u, 0u);
+    if (sh >= 0 && sh < H && sw >= 0 && sw < W) v = in[(n * H + sh) * W + sw];
+    out[i] = v;
+  }
 }
 
 // one thread = one 16-byte vector of the concatenated row; the part is found by walking the (<= 8) channel counts
@@ -654,6 +679,13 @@ cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, 
                            uint64_t offset, cudaStream_t stream) {
   if (n % 8 != 0) return cudaErrorInvalidValue;
   dropout_kernel<<<grid_for(n / 8), 256, 0, stream>>>(x, y, n / 8, p, seed, offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_pad_nhwc4(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int H, int W, int Hp, int Wp, int pt,
+                             int pl, int G, cudaStream_t stream) {
+  if (Hp < H + pt || Wp < W + pl || pt < 0 || pl < 0 || G < 1 || G > 4) return cudaErrorInvalidValue;
+  pad_nhwc4_kernel<<<grid_for(static_cast<int64_t>(N) * Hp * Wp * G), 256, 0, stream>>>(
+      reinterpret_cast<const uint2*>(in), reinterpret_cast<uint2*>(out), N, H, W, Hp, Wp, pt, pl, G);
   return cudaGetLastError();
 }
 cudaError_t launch_concat_channels(const CatArgs& a, bool scatter, cudaStream_t stream) {

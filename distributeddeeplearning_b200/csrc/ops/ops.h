@@ -108,6 +108,11 @@ cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z
 cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,
                            uint64_t offset, cudaStream_t stream);
 // y = a + b (bf16)
+// NHWC4 image [N][H][W] (8-byte pixels) -> zero-bordered, G-row-interleaved [N][Hp][Wp][G][4] with the source at
+// (pt, pl): position (h, w) holds the pixels of rows h .. h+G-1.  Operand layout of the TMA-fed stem convolution
+// (conv_gemm.cuh kConvStemTma): SP taps x G rows x 4 channels of one output pixel are 128 contiguous bytes.
+cudaError_t launch_pad_nhwc4(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int H, int W, int Hp, int Wp, int pt,
+                             int pl, int G, cudaStream_t stream);
 // Channel concatenation of up to kCatMax NHWC tensors (Inception / DenseNet): gather = parts -> whole,
 // scatter (backward) = whole -> parts.  Every part's channel count is a multiple of 8.
 constexpr int kCatMax = 8;

@@ -46,6 +46,45 @@ def _check_act(x: torch.Tensor, name: str = "x") -> None:
         raise ValueError(f"{name}: expected a contiguous matrix")
 
 
+class _ZeroRing:
+    """Pre-zeroed fp32 scratch handed out in stream order.
+
+    Every conv+BN unit needs a few hundred zeroed floats per step (BN sum / sum-of-squares accumulators, dgamma /
+    dbeta scratch): ~110 `torch.zeros` launches per ResNet-50 step.  Slices of one arena are handed out
+    sequentially instead and the arena is re-zeroed with ONE memset when it wraps.  Safe because every consumer of a
+    slice is enqueued on the current stream right after its producer, i.e. before the wrap-around memset."""
+
+    def __init__(self, device, numel: int = 1 << 21):
+        self.buf = torch.zeros(numel, dtype=torch.float32, device=device)
+        self.pos = 0
+
+    def take(self, numel: int) -> torch.Tensor:
+        n = (numel + 31) // 32 * 32                     # 128-byte granules
+        if n > self.buf.numel():
+            return torch.zeros(numel, dtype=torch.float32, device=self.buf.device)
+        if self.pos + n > self.buf.numel():
+            self.buf.zero_()
+            self.pos = 0
+        out = self.buf[self.pos:self.pos + numel]
+        self.pos += n
+        return out
+
+
+_zero_rings = {}
+
+
+def zeros_f32(shape, device) -> torch.Tensor:
+    """Zero-filled fp32 scratch for accumulators that are consumed on the current stream right away."""
+    key = (device.index or 0, torch.cuda.current_stream(device).cuda_stream)
+    ring = _zero_rings.get(key)
+    if ring is None:
+        ring = _zero_rings[key] = _ZeroRing(device)
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    return ring.take(numel).view(*shape)
+
+
 def empty_act(n: int, c: int, h: int, w: int, device) -> torch.Tensor:
     return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=CL)
 
@@ -79,6 +118,7 @@ def stem_geometry(R: int, S: int) -> Tuple[int, int, int, int]:
     return SP, RPK, KB, KB * RPK
 
 
+USE_STEM_TMA = os.environ.get("DDL_DISABLE_STEM_TMA", "0") != "1"
 USE_TILE_TMA = os.environ.get("DDL_DISABLE_TILE_TMA", "0") != "1"
 USE_TILE_S2 = os.environ.get("DDL_DISABLE_TILE_S2", "0") != "1"
 
@@ -94,6 +134,34 @@ def tile_geometry(P: int, Q: int, N: int, max_rows: int) -> Tuple[int, int, int]
     if th == P:
         tn = max(1, min(N, max_rows // (tw * th)))
     return tw, th, tn
+
+
+def stem_tma_geometry(H: int, W: int, kernel: Tuple[int, int], stride: int, pad) -> Optional[Tuple[int, int, int]]:
+    """(Hp, Wp, G) of the zero-padded, G-row-interleaved NHWC4 image the TMA-fed stem kernel reads (G = filter rows
+    per k-block), or None when it does not apply: the per-output-column step of the tensor map (stride*G pixels of 8
+    bytes) must be a multiple of 16 bytes."""
+    if not USE_STEM_TMA or kernel[1] > 16:
+        return None
+    ph, pw = _pad2(pad)
+    SP, RPK, KB, RP = stem_geometry(*kernel)
+    if (stride * RPK) % 2 != 0:
+        return None
+    P, Q = conv_out_hw(H, W, kernel, stride, (ph, pw))
+    Hp = max(H + 2 * ph, stride * (P - 1) + RPK * (KB - 1) + 1)
+    Wp = max(W + 2 * pw, stride * (Q - 1) + SP)
+    return Hp, Wp + (Wp % 2), RPK
+
+
+def pad_image(x4: torch.Tensor, Hp: int, Wp: int, pt: int, pl: int, G: int = 1) -> torch.Tensor:
+    """NHWC4 image -> zero-bordered [N, Hp, Wp, G, 4] copy with the source at (pt, pl); slot g of position (h, w)
+    holds the pixel of row h + g (the 128 bytes one stem k-block needs become contiguous)."""
+    _check_act(x4)
+    N, c, H, W = x4.shape
+    if c != 4:
+        raise ValueError("pad_image expects an NHWC4 tensor")
+    out = torch.empty((N, Hp, Wp, G, 4), dtype=torch.bfloat16, device=x4.device)
+    _C().pad_nhwc4(x4.data_ptr(), out.data_ptr(), N, H, W, Hp, Wp, pt, pl, G, _stream())
+    return out
 
 
 def supports_conv(cin: int, cout: int) -> bool:
@@ -123,7 +191,7 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
     P, Q = conv_out_hw(H, W, kernel, stride, (ph, pw), dil)
     M = N * P * Q
     y = empty_act(N, Cout, P, Q, x.device)
-    st = torch.zeros((2, Cout), dtype=torch.float32, device=x.device) if stats else None
+    st = zeros_f32((2, Cout), x.device) if stats else None
     s_ptr, ss_ptr = (st[0].data_ptr(), st[1].data_ptr()) if stats else (0, 0)
     n_total = _ceil_div(Cout, 64) * 64              # N tiles cover the padded width; stores / stats stop at Cout
     cch = _ceil_div(Cin, 64)
@@ -132,9 +200,19 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
         if Cin != 4:
             raise ValueError("stem input must be padded to 4 channels (NHWC4)")
         SP, RPK, KB, RP = stem_geometry(R, S)
-        C.conv_gemm(C.CONV_STEM, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, H, W, 4,
-                    P, Q, R, S, stride, ph, dil, SP, int(relu), Cout, wp, wr, wc, n_total, 0, 0, N, 0, 0, 0, 0,
-                    _stream(), pw, 0)
+        geo = stem_tma_geometry(H, W, kernel, stride, (ph, pw)) if dil == 1 else None
+        if geo is not None:
+            # even stride: copy the image into a zero-bordered buffer once (one 8-byte-per-pixel pass) and let ONE
+            # 5-D TMA box per k-block fetch what the gather path needs 64 cp.async per output pixel for
+            xp = pad_image(x, geo[0], geo[1], ph, pw, geo[2])
+            tw, th, tn = tile_geometry(P, Q, N, 128)
+            C.conv_gemm(C.CONV_STEM_TMA, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, geo[0], geo[1], 4,
+                        P, Q, R, S, stride, 0, 1, RPK, int(relu), Cout, wp, wr, wc, n_total, xp.data_ptr(), 4, N, tw, th,
+                        tn, 0, _stream(), 0, 0)
+        else:
+            C.conv_gemm(C.CONV_STEM, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, H, W, 4,
+                        P, Q, R, S, stride, ph, dil, SP, int(relu), Cout, wp, wr, wc, n_total, 0, 0, N, 0, 0, 0, 0,
+                        _stream(), pw, 0)
         return (y, st) if stats else y
     if Cin % 8 != 0:
         raise ValueError("conv_fwd: Cin must be a multiple of 8 (or an NHWC4 stem)")
@@ -231,9 +309,18 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: 
         ncols = KB * 64
         scratch = torch.zeros((Cout, ncols), dtype=torch.float32, device=x.device)
         tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
-        C.conv_wgrad(C.CONV_STEM, x.data_ptr(), dy.data_ptr(), scratch.data_ptr(), M, Cout, Cout, ncols, ncols, H, W,
-                     4, P, Q, R, S, stride, ph, dil, SP, _wgrad_splits(tiles, (M + 63) // 64, dev), N, 0, 0, 0,
-                     _stream(), pw, 0, 0)
+        geo = stem_tma_geometry(H, W, kernel, stride, (ph, pw)) if dil == 1 else None
+        if geo is not None:
+            xp = pad_image(x, geo[0], geo[1], ph, pw, geo[2])
+            tw, th, tn = tile_geometry(P, Q, N, 64)
+            total_kb = -(-Q // tw) * -(-P // th) * -(-N // tn)
+            C.conv_wgrad(C.CONV_STEM_TMA, xp.data_ptr(), dy.data_ptr(), scratch.data_ptr(), M, Cout, Cout, ncols, ncols,
+                         geo[0], geo[1], 4, P, Q, R, S, stride, 0, 1, SP, _wgrad_splits(tiles, total_kb, dev), N, tw, th,
+                         tn, _stream(), 0, 0, 0)
+        else:
+            C.conv_wgrad(C.CONV_STEM, x.data_ptr(), dy.data_ptr(), scratch.data_ptr(), M, Cout, Cout, ncols, ncols, H,
+                         W, 4, P, Q, R, S, stride, ph, dil, SP, _wgrad_splits(tiles, (M + 63) // 64, dev), N, 0, 0, 0,
+                         _stream(), pw, 0, 0)
         # grad_w is KRSC with the TRUE channel count (3): fold the packed scratch back
         cin_true = grad_w.shape[1]
         C.unpack_stem_grad(scratch.data_ptr(), grad_w.data_ptr(), Cout, R, S, cin_true, RP, SP, _stream())
@@ -319,7 +406,7 @@ def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, runn
     z = torch.empty_like(y)
     if train:
         if stats is None:
-            stats = torch.zeros((2, Ch), dtype=torch.float32, device=y.device)
+            stats = zeros_f32((2, Ch), y.device)
             C.channel_stats(y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), M, Ch, sm_count(y.device.index or 0),
                             _stream())
         save = torch.empty((2, Ch), dtype=torch.float32, device=y.device)
@@ -343,7 +430,7 @@ def bn_act_bwd(dz: torch.Tensor, z: torch.Tensor, y: torch.Tensor, save: torch.T
     M = N * H * W
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
-    scratch = torch.zeros((2, Ch), dtype=torch.float32, device=y.device)
+    scratch = zeros_f32((2, Ch), y.device)
     mask_from_x = bool(relu and beta is not None and not had_residual)     # z is not read at all in that case
     C.bn_act_bwd(dz.data_ptr(), z.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dres), save[0].data_ptr(),
                  save[1].data_ptr(), gamma.data_ptr(), _ptr(beta), scratch[0].data_ptr(), scratch[1].data_ptr(),

@@ -178,14 +178,17 @@ def g_conv_fwd():
     y = nv.conv_fwd(x, _w_bf16(w), (3, 3), 1, 1, bias=b, relu=True)
     report("conv_fwd bias+relu", y, torch.relu(_conv_ref(x, w, 1, 1) + b.view(1, -1, 1, 1)), 2e-2)
     # stems: ResNet 7x7/2, AlexNet 11x11/4, VGG 3x3/1
-    for (k, s, p, hw) in [(7, 2, 3, 32), (11, 4, 2, 63), (3, 1, 1, 16)]:
-        img = torch.randn(2, 3, hw, hw, device=dev)
-        x4 = nv.nchw_to_nhwc4(img)
-        w = torch.randn(64, 3, k, k, device=dev) * 0.1
-        wp = nv.pack_stem_weight(cl(w), k, k)
-        y, st = nv.conv_fwd(x4, wp, (k, k), s, p, stats=True, cout=64)
-        ref = _conv_ref(bf(img), bf(w), s, p)
-        report(f"stem conv k{k}s{s}p{p} {hw}x{hw}", y, ref, 2e-2)
+    for tma in (True, False):       # TMA-fed (row-interleaved padded image) and cp.async gather stems
+        nv.USE_STEM_TMA = tma
+        for (k, s, p, hw) in [(7, 2, 3, 32), (11, 4, 2, 63), (3, 1, 1, 16), (3, 2, 0, 35), (7, 2, 0, 41), (7, 2, 3, 224)]:
+            img = torch.randn(2, 3, hw, hw, device=dev)
+            x4 = nv.nchw_to_nhwc4(img)
+            w = torch.randn(64, 3, k, k, device=dev) * 0.1
+            wp = nv.pack_stem_weight(cl(w), k, k)
+            y, st = nv.conv_fwd(x4, wp, (k, k), s, p, stats=True, cout=64)
+            ref = _conv_ref(bf(img), bf(w), s, p)
+            report(f"stem conv {'tma' if tma else 'gather'} k{k}s{s}p{p} {hw}x{hw}", y, ref, 2e-2)
+    nv.USE_STEM_TMA = True
 
 
 def g_conv_generic():
@@ -292,16 +295,19 @@ def g_conv_wgrad():
         gw = cl(torch.zeros(co, ci, k, k, device=dev))
         nv.conv_wgrad(x, dy, gw, (k, k), s, p)
         report(f"conv_wgrad n{n} c{ci} {h}x{w_} ->{co} k{k}s{s}p{p}", gw, w.grad, 2e-2)
-    for (k, s, p, hw) in [(7, 2, 3, 32), (11, 4, 2, 63), (3, 1, 1, 16)]:
-        img = torch.randn(2, 3, hw, hw, device=dev)
-        x4 = nv.nchw_to_nhwc4(img)
-        w = torch.randn(64, 3, k, k, device=dev).requires_grad_(True)
-        yr = _conv_ref(bf(img), w, s, p)
-        dy = cl(bf(torch.randn_like(yr)))
-        yr.backward(dy.float())
-        gw = cl(torch.zeros(64, 3, k, k, device=dev))
-        nv.conv_wgrad(x4, dy, gw, (k, k), s, p)
-        report(f"stem wgrad k{k}s{s}p{p}", gw, w.grad, 2e-2)
+    for tma in (True, False):
+        nv.USE_STEM_TMA = tma
+        for (k, s, p, hw) in [(7, 2, 3, 32), (11, 4, 2, 63), (3, 1, 1, 16), (3, 2, 0, 35), (7, 2, 0, 41), (7, 2, 3, 224)]:
+            img = torch.randn(2, 3, hw, hw, device=dev)
+            x4 = nv.nchw_to_nhwc4(img)
+            w = torch.randn(64, 3, k, k, device=dev).requires_grad_(True)
+            yr = _conv_ref(bf(img), w, s, p)
+            dy = cl(bf(torch.randn_like(yr)))
+            yr.backward(dy.float())
+            gw = cl(torch.zeros(64, 3, k, k, device=dev))
+            nv.conv_wgrad(x4, dy, gw, (k, k), s, p)
+            report(f"stem wgrad {'tma' if tma else 'gather'} k{k}s{s}p{p}", gw, w.grad, 2e-2)
+    nv.USE_STEM_TMA = True
 
 
 def g_linear():
