@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--batch-size", type=int, default=256, help="per-GPU batch (BASELINE config: 256)")
     p.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (H2D/D2H per step) measurement")
     p.add_argument("--fp16-allreduce", action="store_true")
+    p.add_argument("--cuda-graph", choices=["on", "off"], default=os.environ.get("DDL_BENCH_GRAPH", "off"),
+                   help="replay the whole training step from one captured CUDA graph (falls back to eager if capture fails)")
     return p.parse_args()
 
 
@@ -114,6 +116,7 @@ def run_ours(a):
         raise SystemExit("bench.py needs a CUDA device (use workloads.benchmark --no-cuda for the CPU plumbing mode)")
     session = BenchmarkSession(a.model, a.batch_size, True, a.fp16_allreduce)
     B, dev = a.batch_size, session.device
+    graphed = session.enable_graph() if a.cuda_graph == "on" else False
 
     def region(step_fn, steps, warmup, tail=None):
         for _ in range(warmup):
@@ -219,6 +222,7 @@ def run_ours(a):
                "config": {"model": a.model, "global_batch": world * B, "per_gpu_batch": B, "image": "224x224x3",
                           "seq_len": None, "parallelism": f"dp{world}", "optimizer": "sgd lr=0.01 (fused allreduce+update)",
                           "weights": "random-init, fp32 master + bf16 compute", "l2": "working_set_exceeds_l2",
+                          "cuda_graph": bool(graphed),
                           "engine": session.optimizer.describe() if hasattr(session.optimizer, "describe") else "generic"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
         print(json.dumps(out), flush=True)

@@ -35,6 +35,8 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a, const void* dy, const void* x_
                               cudaStream_t stream);
 void set_conv_force_stages(int s);
 void set_conv_persistent(int on);
+void set_wgrad_swap(int on);
+void set_conv_bn256(int on);
 }  // namespace ddl
 
 namespace {
@@ -186,6 +188,8 @@ PYBIND11_MODULE(_C, m) {
 
   // ------------------------------------------------------------------ conv / GEMM
   m.def("set_conv_persistent", &ddl::set_conv_persistent, "tuning hook: 1 = persistent kernel for TMA-fed modes");
+  m.def("set_conv_bn256", &ddl::set_conv_bn256, "tuning hook: 0 = no 128x256 persistent tiles");
+  m.def("set_wgrad_swap", &ddl::set_wgrad_swap, "tuning hook: 0 = no operand-role swap for narrow-output wgrad tiles");
   m.def("set_conv_force_stages", &ddl::set_conv_force_stages, "tuning hook: force the pipeline depth (0 = policy)");
   m.def("conv_gemm",
         [](int mode, ptr_t src, ptr_t out, ptr_t add, ptr_t bias, ptr_t sum, ptr_t sumsq, int M, int KB, int ldc,

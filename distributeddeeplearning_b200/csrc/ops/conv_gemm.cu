@@ -177,8 +177,8 @@ DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, co
       sts128(rb + BLOCK_N * 4 + 16, __float_as_uint(ss[4]), __float_as_uint(ss[5]), __float_as_uint(ss[6]), __float_as_uint(ss[7]));
     }
     named_bar_sync(1, kEpiThreads);
-    if (etid < 2 * BLOCK_N) {
-      const int which = etid / BLOCK_N, col = etid - which * BLOCK_N;
+    for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
+      const int which = c / BLOCK_N, col = c - which * BLOCK_N;
       float v = 0.f;
 #pragma unroll
       for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += lds_f32(red + ((wq * 2 + which) * BLOCK_N + col) * 4);
@@ -483,8 +483,11 @@ struct PersistCfg {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kPitch = BLOCK_N * 2 + 16;
   static constexpr int kEpiBytes = ((kBlockM * kPitch + 1023) / 1024) * 1024;
+  // BLOCK_N = 256: one CTA per SM (its two accumulators fill the 512 TMEM columns); a 128 x 256 tile re-uses every
+  // activation k-block for twice the output columns, i.e. 25 % less L2 -> shared traffic per FLOP than 128 x 128
   static constexpr int kStages = (BLOCK_N <= 64) ? 3 : 2;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + 8192 + 1024;
+  static constexpr int kRedBytes = 4 * kEpiGroups * 2 * BLOCK_N * 4;      // [epi warps][2][BLOCK_N] floats
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + kRedBytes + 1024;
 };
 
 template <int BLOCK_N, int MODE, bool STATS>
@@ -613,7 +616,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
           } else {
-            tma_load_2d(sB, &tmB, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK, n0, &full[stage]);
+            // the weight map's box holds min(BLOCK_N, 128) rows
+            constexpr int kBoxRows = BLOCK_N < 128 ? BLOCK_N : 128;
+#pragma unroll
+            for (int h = 0; h < BLOCK_N / kBoxRows; ++h)
+              tma_load_2d(sB + h * kBoxRows * 128, &tmB, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
+                          n0 + h * kBoxRows, &full[stage]);
           }
           if (MODE == kConvStemTma) tma_load_5d(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, &full[stage]);
           else if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
@@ -674,7 +682,11 @@ constexpr int wg_smem_bytes(int stages) {
   return (stages * kWgStageBytes > kWgEpiBytes ? stages * kWgStageBytes : kWgEpiBytes) + 256 + 1024;
 }
 
-template <int MODE>
+// SWAP = operand roles exchanged for narrow outputs (Cout tile of 64): the 128-row MMA dimension carries the k
+// columns and N = 64 output channels, so no half of the tensor-core tile multiplies zero rows (ncu: the Cout = 64
+// layers kept the pipe ~49 % busy doing 50 % useful work).  The accumulator comes out transposed ([k col][co]) and
+// is staged transposed so the global reductions stay row-contiguous.
+template <int MODE, bool SWAP>
 __global__ void __launch_bounds__(kThreads, 3)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ TmaSet tmXs, WgradArgs a) {
   const CUtensorMap& tmX = tmXs.m[0];
@@ -691,7 +703,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int col0 = blockIdx.x * 128;          // first k column of this tile
-  const int co0 = blockIdx.y * 128;           // first output channel of this tile
+  constexpr int kCoTile = SWAP ? 64 : 128;
+  const int co0 = blockIdx.y * kCoTile;       // first output channel of this tile
   const int kb_begin = blockIdx.z * a.kb_per_split;
   const int kb_end = min(kb_begin + a.kb_per_split, a.total_kb);
   const int KB = kb_end - kb_begin;
@@ -805,16 +818,23 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     tc_fence_after();
     float* stg = reinterpret_cast<float*>(smem);
     const int row = qw * 32 + (threadIdx.x & 31);
+    constexpr int kAccCols = SWAP ? 64 : 128;
 #pragma unroll 1
-    for (int c0 = egrp * (128 / kEpiGroups); c0 < (egrp + 1) * (128 / kEpiGroups); c0 += 32) {
+    for (int c0 = egrp * (kAccCols / kEpiGroups); c0 < (egrp + 1) * (kAccCols / kEpiGroups); c0 += 32) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + c0, v);
       tmem_ld_wait();
-      float4* d = reinterpret_cast<float4*>(stg + row * kWgPitch + c0);
+      if (SWAP) {
+        // accumulator row = k column, accumulator column = output channel: stage as [co][k col]
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                           __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 32; ++j) stg[(c0 + j) * kWgPitch + row] = __uint_as_float(v[j]);
+      } else {
+        float4* d = reinterpret_cast<float4*>(stg + row * kWgPitch + c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          d[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3]));
+      }
     }
     tc_fence_before();
     named_bar_sync(1, kEpiThreads);
@@ -824,7 +844,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     const int vch = vc - vtap * a.Cpad;
     if (vc < a.ncols && vch < a.Cw) {                  // channel padding of a tap has no dw column
       const int c = vtap * a.Cw + vch;
-      for (int r = ew; r < 128; r += 4 * kEpiGroups) {
+      for (int r = ew; r < kCoTile; r += 4 * kEpiGroups) {
         const int co = co0 + r;
         if (co < a.Cout) {
           const float4 val = *reinterpret_cast<const float4*>(stg + r * kWgPitch + lane * 4);
@@ -867,9 +887,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           const int nb = t / a.tiles_h;
           const int q0 = wb * a.tw, p0 = hb * a.th, n0 = nb * a.tn;
           const bool second = (col0 + 64) < a.ncols;
-          mbar_arrive_expect_tx(&full[stage], box_bytes * (second ? 4u : 3u));
+          mbar_arrive_expect_tx(&full[stage], box_bytes * ((second ? 4u : 3u) - (SWAP ? 1u : 0u)));
           tma_load_4d(sA, &tmDy, co0, q0, p0, n0, &full[stage]);
-          tma_load_4d(sA + 8192, &tmDy, co0 + 64, q0, p0, n0, &full[stage]);
+          if (!SWAP) tma_load_4d(sA + 8192, &tmDy, co0 + 64, q0, p0, n0, &full[stage]);
           if (MODE == kConvStemTma) {
             // k-block (col0 / 64 + j) of the packed stem K = one box of the row-interleaved image
             tma_load_5d(sA + 16384, &tmXs.m[0], 0, col0 / 64, q0, p0, n0, &full[stage]);
@@ -880,9 +900,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           }
         } else {
           const int m = (kb_begin + i) * 64;
-          mbar_arrive_expect_tx(&full[stage], 16384u + (kXTma ? 16384u : 0u));
+          mbar_arrive_expect_tx(&full[stage], (SWAP ? 8192u : 16384u) + (kXTma ? 16384u : 0u));
           tma_load_2d(sA, &tmDy, co0, m, &full[stage]);
-          tma_load_2d(sA + 8192, &tmDy, co0 + 64, m, &full[stage]);
+          if (!SWAP) tma_load_2d(sA + 8192, &tmDy, co0 + 64, m, &full[stage]);
           if (kXTma) {
             tma_load_2d(sA + 16384, &tmX, col0, m, &full[stage]);
             tma_load_2d(sA + 24576, &tmX, col0 + 64, m, &full[stage]);
@@ -892,15 +912,17 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       }
     }
   } else {
-    constexpr uint32_t idesc = idesc_bf16(128, 128, 1, 1);
+    constexpr uint32_t idesc = idesc_bf16(128, SWAP ? 64 : 128, 1, 1);
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < KB; ++i) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
-        const uint32_t sB = sA + 16384;
+        const uint32_t sDy = smem_u32(smem + stage * kWgStageBytes);
+        const uint32_t sX = sDy + 16384;
+        const uint32_t sA = SWAP ? sX : sDy;      // M operand: 128 rows = two 64-wide MN-major chunks 8 KB apart
+        const uint32_t sB = SWAP ? sDy : sX;      // N operand (SWAP: one 64-channel chunk of dY)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t da = smem_desc_sw128(sA + k * 2048, 8192, 1024);
@@ -1055,7 +1077,7 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const TmaSet& tmA, const
   }
   const int n_tiles = n_total / BLOCK_N;
   const long long total = static_cast<long long>(n_tiles) * m_tiles;
-  long long grid = 2LL * g_num_sms;
+  long long grid = (BLOCK_N > 128 ? 1LL : 2LL) * g_num_sms;      // BLOCK_N = 256 owns the SM's whole TMEM
   if (grid > total) grid = total;
   kern<<<static_cast<unsigned>(grid), kThreads, Cfg::kSmemBytes, stream>>>(tmB, tmA, a, n_tiles, m_tiles);
   return cudaGetLastError();
@@ -1065,6 +1087,8 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const TmaSet& tmA, const
 // round trip, epilogue), so they get a shallow ring -> small shared-memory footprint -> 3-4 CTAs per SM whose
 // prologues/epilogues overlap.  Long-K tiles get the deep ring.  g_force_stages (tuning hook) overrides.
 int g_force_stages = 0;
+int g_bn256 = 1;            // tuning hook: 0 keeps the persistent kernel at 128 x 128 tiles
+int g_wgrad_swap = 1;       // tuning hook: 0 disables the operand-role swap of narrow-output wgrad tiles
 
 template <int BLOCK_N, int MODE>
 int pick_stages(int KB) {
@@ -1095,6 +1119,13 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs 
     const long long tiles = static_cast<long long>(n_total / ((n_total % 128 == 0) ? 128 : 64)) * m_tiles;
     persistent = g_persistent == 2 || tiles * 2 >= 7LL * 2 * g_num_sms;
   }
+  // 128 x 256 tiles: only where the main loop (operand traffic) matters (K >= 256) — with one CTA per SM the epilogue
+  // has half the warps to hide its latency, which would cost the short-K, store-bound layers
+  if (persistent && g_bn256 && n_total % 256 == 0 && a.KB >= 4 &&
+      static_cast<long long>(n_total / 256) * m_tiles >= 4LL * g_num_sms) {
+    return stats ? launch_persistent_t<256, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
+                 : launch_persistent_t<256, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
+  }
   if (persistent) {
     if (n_total % 128 == 0)
       return stats ? launch_persistent_t<128, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
@@ -1121,6 +1152,8 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs 
 
 void set_conv_force_stages(int s) { g_force_stages = s; }
 void set_conv_persistent(int on) { g_persistent = on; }
+void set_wgrad_swap(int on) { g_wgrad_swap = on; }
+void set_conv_bn256(int on) { g_bn256 = on; }
 
 // `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
 // `a_matrix`: the A operand for the TMA-A modes (2-D matrix [M][a_cols], or the NHWC tensor in tile modes).
@@ -1297,16 +1330,19 @@ cudaError_t launch_conv_wgrad(const WgradArgs& a_in, const void* dy, const void*
   if (a.stages > a.kb_per_split) a.stages = a.kb_per_split;
   if (a.stages < 1) a.stages = 1;
   const int smem = wg_smem_bytes(a.stages);
-  dim3 grid((a.ncols + 127) / 128, (a.Cout + 127) / 128, splits);
-  static bool configured[8] = {false, false, false, false, false, false, false, false};
+  // narrow outputs (the last 128-channel tile would be at most half full): swap operand roles, 64-channel tiles
+  const int co_rem = a.Cout % 128;
+  const bool swap = g_wgrad_swap && co_rem > 0 && co_rem <= 64;
+  dim3 grid((a.ncols + 127) / 128, swap ? (a.Cout + 63) / 64 : (a.Cout + 127) / 128, splits);
+  static bool configured[16] = {};
 #define DDL_WG(MODE)                                                                                          \
   do {                                                                                                        \
-    auto kern = conv_wgrad_kernel<MODE>;                                                                      \
-    if (!configured[MODE]) {                                                                                  \
+    auto kern = swap ? conv_wgrad_kernel<MODE, true> : conv_wgrad_kernel<MODE, false>;                        \
+    if (!configured[MODE * 2 + (swap ? 1 : 0)]) {                                                             \
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
                                            wg_smem_bytes(kWgMaxStages));                                      \
       if (e != cudaSuccess) return e;                                                                         \
-      configured[MODE] = true;                                                                                \
+      configured[MODE * 2 + (swap ? 1 : 0)] = true;                                                           \
     }                                                                                                         \
     kern<<<grid, kThreads, smem, stream>>>(tmDy, tmX, a);                                                     \
   } while (0)

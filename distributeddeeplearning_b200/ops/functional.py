@@ -47,11 +47,21 @@ def grad_buffer(p: torch.Tensor) -> torch.Tensor:
 # stream before it consumes a bucket) they are enqueued on a side stream so they overlap the dgrad -> BN-backward chain
 # of the earlier layers: the conv kernels are latency-bound per tile and the BN kernels are HBM-bound, so co-residency
 # fills otherwise idle issue slots.  DDL_ASYNC_WGRAD=0 restores single-stream execution.
-_WGRAD = {"stream": None, "enabled": os.environ.get("DDL_ASYNC_WGRAD", "1") != "0"}
+_WGRAD = {"stream": None, "enabled": os.environ.get("DDL_ASYNC_WGRAD", "1") != "0", "pending": False}
 
 
 def wgrad_stream() -> Optional["torch.cuda.Stream"]:
     return _WGRAD["stream"]
+
+
+def wgrad_join(consumer: "torch.cuda.Stream") -> None:
+    """Make ``consumer`` wait for the weight-gradient kernels enqueued on the side stream since the last join.
+    Skipped when nothing is pending: besides saving an event, that keeps CUDA-graph capture legal (a capturing stream
+    must not wait on a stream that has not joined the capture yet)."""
+    side = _WGRAD["stream"]
+    if side is not None and _WGRAD["pending"]:
+        consumer.wait_stream(side)
+        _WGRAD["pending"] = False
 
 
 def run_wgrad(param: torch.Tensor, fn, *tensors: torch.Tensor) -> None:
@@ -65,8 +75,10 @@ def run_wgrad(param: torch.Tensor, fn, *tensors: torch.Tensor) -> None:
     side.wait_stream(torch.cuda.current_stream(param.device))
     with torch.cuda.stream(side):
         fn()
-    for t in tensors:
-        t.record_stream(side)
+    _WGRAD["pending"] = True
+    if not torch.cuda.is_current_stream_capturing():
+        for t in tensors:
+            t.record_stream(side)
 
 
 def notify_ready(p: torch.Tensor) -> None:
@@ -412,13 +424,17 @@ class _Dropout(torch.autograd.Function):
     def forward(ctx, x, p):
         seed, off = _DROPOUT_STATE["seed"], _DROPOUT_STATE["offset"]
         _DROPOUT_STATE["offset"] = off + (x.numel() + 7) // 8
-        ctx.cfg = (p, seed, off)
-        return native.dropout(x.contiguous(), p, seed, off)
+        # the Philox mask is indexed by memory offset: keep NHWC activations in their own (dense) memory order and
+        # make the gradient follow the same order in backward
+        cl = x.dim() == 4 and x.is_contiguous(memory_format=CL)
+        ctx.cfg = (p, seed, off, cl)
+        return native.dropout(x if cl else x.contiguous(), p, seed, off)
 
     @staticmethod
     def backward(ctx, dy):
-        p, seed, off = ctx.cfg
-        return native.dropout(dy.contiguous(), p, seed, off), None
+        p, seed, off, cl = ctx.cfg
+        dy = dy.contiguous(memory_format=CL) if cl else dy.contiguous()
+        return native.dropout(dy, p, seed, off), None
 
 
 def dropout(x, p=0.5, training=True):

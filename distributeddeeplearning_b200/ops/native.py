@@ -21,7 +21,12 @@ CL = torch.channels_last
 
 @functools.lru_cache(maxsize=None)
 def _C():
-    return _ext.load()
+    C = _ext.load()
+    if os.environ.get("DDL_WGRAD_SWAP", "1") == "0":       # tuning hook (A/B runs): no operand-role swap in wgrad
+        C.set_wgrad_swap(0)
+    if os.environ.get("DDL_CONV_BN256", "1") == "0":       # tuning hook (A/B runs): 128 x 128 persistent tiles only
+        C.set_conv_bn256(0)
+    return C
 
 
 @functools.lru_cache(maxsize=None)
@@ -71,17 +76,41 @@ class _ZeroRing:
 
 
 _zero_rings = {}
+_capture_ring = {"ring": None}
+
+
+def begin_capture_scratch(device) -> None:
+    """Call right after CUDA-graph capture of a step began (on the capture stream): the step's accumulators come
+    from a dedicated arena whose memset is the first node of the graph, so every replay starts from zeros."""
+    ring = _ZeroRing.__new__(_ZeroRing)
+    ring.buf = torch.empty(1 << 21, dtype=torch.float32, device=device)
+    ring.buf.zero_()                                   # captured memset
+    ring.pos = 0
+    ring.no_wrap = True
+    _capture_ring["ring"] = ring
+
+
+def end_capture_scratch() -> None:
+    _capture_ring["ring"] = None
 
 
 def zeros_f32(shape, device) -> torch.Tensor:
     """Zero-filled fp32 scratch for accumulators that are consumed on the current stream right away."""
+    numel = 1
+    for d in shape:
+        numel *= int(d)
+    cap = _capture_ring["ring"]
+    if cap is not None:
+        n = (numel + 31) // 32 * 32
+        if cap.pos + n > cap.buf.numel():
+            return torch.zeros(numel, dtype=torch.float32, device=device).view(*shape)     # captured memset node
+        out = cap.buf[cap.pos:cap.pos + numel]
+        cap.pos += n
+        return out.view(*shape)
     key = (device.index or 0, torch.cuda.current_stream(device).cuda_stream)
     ring = _zero_rings.get(key)
     if ring is None:
         ring = _zero_rings[key] = _ZeroRing(device)
-    numel = 1
-    for d in shape:
-        numel *= int(d)
     return ring.take(numel).view(*shape)
 
 
@@ -339,7 +368,8 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: 
             total_kb = -(-Q // tw) * -(-P // th) * -(-N // tn)
         else:
             mode, (tw, th, tn), total_kb = C.CONV_FWD, (0, 0, 0), (M + 63) // 64
-    tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
+    co_tiles = _ceil_div(Cout, 64) if 0 < Cout % 128 <= 64 else _ceil_div(Cout, 128)   # narrow tail: role-swapped tiles
+    tiles = ((ncols + 127) // 128) * co_tiles
     splits = _wgrad_splits(tiles, total_kb, dev)
     C.conv_wgrad(mode, x.data_ptr(), dy.data_ptr(), grad_w.data_ptr(), M, Cout, Cout, ldw, ncols, H, W, Cin, P, Q,
                  R, S, stride, ph, dil, 0, splits, N, tw, th, tn, _stream(), pw, cpad, Cin)

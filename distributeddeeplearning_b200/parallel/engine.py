@@ -130,7 +130,7 @@ class FusedSGD(torch.optim.Optimizer):
                  weight_decay: float = 0.0, nesterov: bool = False, compression: type = Compression.none,
                  first_bucket_mb: float = 1.0, bucket_mb: float = 16.0, overlap: bool = True,
                  comm_blocks: int = 32, use_multicast: Optional[bool] = None, timeout_s: float = 30.0,
-                 broadcast_root: Optional[int] = 0):
+                 broadcast_root: Optional[int] = 0, debug: Optional[bool] = None):
         named = list(params)
         if named and isinstance(named[0], tuple):
             plist = [p for _, p in named]
@@ -155,6 +155,8 @@ class FusedSGD(torch.optim.Optimizer):
         self.compression = compression
         self.overlap = overlap
         self.comm_blocks = int(comm_blocks)
+        # debug mode: after every step verify the protocol's invariants and poison the wire staging
+        self.debug = bool(int(os.environ.get("DDL_COMM_DEBUG", "0"))) if debug is None else bool(debug)
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
 
         # ---- static plan: parameters in gradient-ready (reverse registration) order -----------
@@ -223,12 +225,18 @@ class FusedSGD(torch.optim.Optimizer):
     def _lr(self) -> float:
         return float(self.param_groups[0]["lr"])
 
-    def _upload_hyper(self, stream: torch.cuda.Stream) -> None:
+    def refresh_hyper_host(self) -> None:
+        """Pack the current hyper-parameters (lr schedule!) into the pinned staging buffer.  The H2D copy that follows
+        in every step is a memcpy node when the step is replayed from a CUDA graph, so calling this before
+        ``graph.replay()`` is all a captured step needs to follow an LR schedule."""
         g = self.param_groups[0]
         blob = self.C.pack_sgd_hyper(float(g["lr"]), float(g["momentum"]), float(g["dampening"]),
                                      float(g["weight_decay"]), 1.0 / self.world, bool(g["nesterov"]),
                                      bool(self._first_step))
         self._hyper_host.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+
+    def _upload_hyper(self, stream: torch.cuda.Stream) -> None:
+        self.refresh_hyper_host()
         with torch.cuda.stream(stream):
             self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
 
@@ -239,11 +247,9 @@ class FusedSGD(torch.optim.Optimizer):
             ev = torch.cuda.Event()
             ev.record(cur)
             stream.wait_event(ev)
-        from ..ops.functional import wgrad_stream
+        from ..ops.functional import wgrad_join
 
-        wg = wgrad_stream()
-        if wg is not None:          # weight gradients are produced on a side stream (ops.functional.run_wgrad)
-            stream.wait_stream(wg)
+        wgrad_join(stream)          # weight gradients are produced on a side stream (ops.functional.run_wgrad)
         if not self._hyper_uploaded:
             self._upload_hyper(stream)
             self._hyper_uploaded = True
@@ -295,7 +301,29 @@ class FusedSGD(torch.optim.Optimizer):
         self._hyper_uploaded = False
         self._first_step = False
         self._steps += 1
+        if self.debug:
+            self._debug_check()
         return loss
+
+    def _debug_check(self) -> None:
+        """Debug build of the step (enable with ``debug=True`` / ``DDL_COMM_DEBUG=1``): joins the device, then checks
+        that (1) no barrier timed out, (2) every gradient accumulator was cleared by its bucket kernel, (3) all blocks
+        of the bucket channel agree on the flag epoch, (4) replicas of the weights are bit-identical across ranks;
+        finally the bf16 wire staging is poisoned with NaNs so a stale read in the next step cannot go unnoticed."""
+        torch.cuda.synchronize(self.device)
+        self.check_errors()
+        if float(self.G.abs().max()) != 0.0:
+            raise RuntimeError(f"rank {self.rank}: gradient accumulators not cleared after step {self._steps}")
+        if self.world > 1:
+            # flag epochs: block 0 of the bucket channel took part in every launch on every rank -> same count everywhere
+            e0 = float(self._epochs[0])
+            if dist.allreduce_scalar(e0, op="max") != dist.allreduce_scalar(e0, op="min"):
+                raise RuntimeError(f"flag epochs differ across ranks after step {self._steps} (rank {self.rank}: {e0})")
+            for probe in (float(self.W.double().sum()), float(self.W.double().abs().sum())):
+                if dist.allreduce_scalar(probe, op="max") != dist.allreduce_scalar(probe, op="min"):
+                    raise RuntimeError(f"weight replicas diverged after step {self._steps} (rank {self.rank})")
+        if self.wire_bf16:
+            self.arena.region("stage", torch.bfloat16, self.total_elems).fill_(float("nan"))
 
     # ---- scalar piggy-back (SURVEY.md K19; reference ``PyTorch_hvd/src/imagenet_pytorch_horovod.py:246``) ----------
     @torch.no_grad()

@@ -48,6 +48,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--momentum", type=float, default=0.0)
     p.add_argument("--json", type=str, default=None, help="also write a JSON summary to this path ('-' = stdout)")
     p.add_argument("--profile", action="store_true", help="wrap phases in NVTX ranges")
+    p.add_argument("--cuda-graph", action="store_true",
+                   help="capture the training step into a CUDA graph after warm-up and replay it (small batches are "
+                        "launch-bound: ~340 kernels per ResNet-50 step)")
     return p
 
 
@@ -86,6 +89,7 @@ class BenchmarkSession:
         self.batch_size = batch_size
         self.last_loss: Optional[torch.Tensor] = None
         self.steps_done = 0
+        self._graph = None
 
     def loss_fn(self, output, target):
         if isinstance(output, tuple):           # Inception-v3 in train mode: (logits, aux)
@@ -94,11 +98,68 @@ class BenchmarkSession:
                 aux, target, self.num_classes)
         return ops.softmax_cross_entropy(output, target, self.num_classes)
 
+    # ---- CUDA-graph replay of the whole step (launch-bound regimes: small per-GPU batches) -------------------------
+    def enable_graph(self, warmup: int = 3) -> bool:
+        """Capture one full training step (forward, loss, backward with its side-stream weight gradients, the
+        per-bucket fused allreduce+SGD kernels) into a CUDA graph and replay it from then on.  ~340 kernel launches
+        and the Python autograd walk collapse into one ``cudaGraphLaunch``; the LR schedule still works because the
+        hyper-parameter upload is a memcpy node fed from a pinned buffer that ``step()`` refreshes before each replay.
+        Returns False (and stays eager) when the step cannot be captured: CPU, no fused engine, or a model with
+        dropout (its Philox offset is a launch argument, which a graph would freeze)."""
+        from ..ops import native
+        from ..parallel.engine import FusedSGD
+
+        if self._graph is not None:
+            return True
+        if not self.cuda or self.profile or not isinstance(self.optimizer, FusedSGD) or not ops.use_native(self.data):
+            return False
+        if any(float(getattr(m, "p", 0.0) or 0.0) > 0.0 for m in self.model.modules() if hasattr(m, "p")) or \
+                float(getattr(self.model, "p", 0.0) or 0.0) > 0.0:
+            return False
+        from .. import _ext
+
+        for _ in range(max(1, warmup)):          # first-use kernel configuration, momentum init, allocator warm-up
+            self._eager_step(self.data, self.target)
+        torch.cuda.synchronize()
+        self._gx, self._gy = self.data.clone(), self.target.clone()
+        graph = torch.cuda.CUDAGraph()
+        before = _ext.launch_count()
+        try:
+            with torch.cuda.graph(graph):
+                native.begin_capture_scratch(self.device)
+                self._gloss = self._eager_step(self._gx, self._gy)
+        except Exception as e:                    # stay on the eager path, say why
+            native.end_capture_scratch()
+            log("CUDA graph capture failed (%s); staying eager" % (str(e).splitlines()[0],))
+            torch.cuda.synchronize()
+            return False
+        native.end_capture_scratch()
+        self._graph_launches = _ext.launch_count() - before
+        self._graph = graph
+        return True
+
     def step(self, data=None, target=None):
+        if self._graph is not None:
+            from .. import _ext
+
+            maybe_inject(self.steps_done, dist.rank())
+            self.steps_done += 1
+            if data is not None and data is not self._gx:
+                self._gx.copy_(data, non_blocking=True)
+            if target is not None and target is not self._gy:
+                self._gy.copy_(target, non_blocking=True)
+            self.optimizer.refresh_hyper_host()
+            self._graph.replay()
+            _ext.add_launches(self._graph_launches)
+            self.last_loss = self._gloss
+            return self.last_loss
         data = self.data if data is None else data
         target = self.target if target is None else target
         maybe_inject(self.steps_done, dist.rank())
         self.steps_done += 1
+        return self._eager_step(data, target)
+
+    def _eager_step(self, data, target):
         if self.profile:        # NVTX ranges: forward / backward (+ overlapped bucket kernels) / step join
             nvtx = torch.cuda.nvtx
             self.optimizer.zero_grad()
@@ -162,6 +223,8 @@ def run(args) -> Dict:
     log("Number of %ss: %d" % (device, dist.size()))
     log("Running warmup...")
     timed_steps(session, args.num_warmup_batches)
+    if getattr(args, "cuda_graph", False) and cuda:
+        log("CUDA graph: %s" % ("captured" if session.enable_graph() else "not applicable, running eager"))
     log("Running benchmark...")
     img_secs: List[float] = []
     for x in range(args.num_iters):

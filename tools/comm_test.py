@@ -34,7 +34,7 @@ def check_engine(use_mc, wire):
     ref_m = [torch.zeros_like(p) for p in ps]
     lr, mom, wd = 0.05, 0.9, 1e-4
     opt = FusedSGD(ps, lr=lr, momentum=mom, weight_decay=wd, compression=wire, use_multicast=use_mc,
-                   first_bucket_mb=0.25, bucket_mb=2.0)
+                   first_bucket_mb=0.25, bucket_mb=2.0, debug=True)
     world, rank = dist.size(), dist.rank()
     ok = True
     for it in range(3):

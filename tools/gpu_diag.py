@@ -380,7 +380,7 @@ def g_sgd():
         torch.manual_seed(0)
         ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in [(64, 3, 7, 7), (1000, 512), (77,), (256, 64, 3, 3)]]
         ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
-        opt = FusedSGD(ps, lr=0.1, momentum=mom, weight_decay=wd, nesterov=nest)
+        opt = FusedSGD(ps, lr=0.1, momentum=mom, weight_decay=wd, nesterov=nest, debug=True)
         ropt = torch.optim.SGD(ref, lr=0.1, momentum=mom, weight_decay=wd, nesterov=nest)
         for it in range(3):
             for p, r in zip(ps, ref):
