@@ -42,7 +42,7 @@ def parse():
     p.add_argument("--batch-size", type=int, default=256, help="per-GPU batch (BASELINE config: 256)")
     p.add_argument("--no-e2e", action="store_true", help="skip the end-to-end (H2D/D2H per step) measurement")
     p.add_argument("--fp16-allreduce", action="store_true")
-    p.add_argument("--cuda-graph", choices=["on", "off"], default=os.environ.get("DDL_BENCH_GRAPH", "off"),
+    p.add_argument("--cuda-graph", choices=["on", "off"], default=os.environ.get("DDL_BENCH_GRAPH", "on"),
                    help="replay the whole training step from one captured CUDA graph (falls back to eager if capture fails)")
     return p.parse_args()
 
@@ -51,12 +51,19 @@ def parse():
 # clock sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int = 0):
         self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/ddl_clocks_{os.getpid()}.csv"
+        self.t0 = None
+
+    def mark(self):
+        """Start of the timed region: only samples taken from here on are reported.  The sampler itself is started
+        before the warm-up so that nvidia-smi's start-up (NVML attach takes driver locks for ~100 ms and was seen to
+        stall kernel launches) falls outside the timed steps."""
+        self.t0 = time.time()
 
     def start(self):
         try:
@@ -77,22 +84,30 @@ class ClockSampler:
             self.proc.kill()
         self.f.close()
         sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
                 c = [x.strip() for x in line.split(",")]
                 if len(c) < 9:
                     continue
                 try:
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+                    ts = time.mktime(time.strptime(c[0].split(".")[0], "%Y/%m/%d %H:%M:%S")) + float("0." + c[0].split(".")[1])
+                except (ValueError, IndexError):
+                    ts = None
+                rows.append((ts, c))
             os.unlink(self.path)
         except OSError:
             pass
+        inside = [c for ts, c in rows if self.t0 is None or ts is None or ts >= self.t0 - 0.2]
+        for c in (inside or [c for _, c in rows]):
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
         if sm:
             out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
         out["reasons"] = sorted(reasons)
@@ -114,17 +129,22 @@ def run_ours(a):
     rank, world = dist.rank(), dist.size()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (use workloads.benchmark --no-cuda for the CPU plumbing mode)")
+    sampler = ClockSampler(torch.cuda.current_device())
+    if rank == 0:
+        sampler.start()               # early: nvidia-smi's start-up must not overlap the timed steps (see mark())
     session = BenchmarkSession(a.model, a.batch_size, True, a.fp16_allreduce)
     B, dev = a.batch_size, session.device
     graphed = session.enable_graph() if a.cuda_graph == "on" else False
 
-    def region(step_fn, steps, warmup, tail=None):
+    def region(step_fn, steps, warmup, tail=None, on_start=None):
         for _ in range(warmup):
             step_fn()
         if tail is not None:
             tail()
         dist.barrier()
         torch.cuda.synchronize()
+        if on_start is not None:
+            on_start()
         start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = _ext.launch_count()
         start.record()
@@ -139,10 +159,7 @@ def run_ours(a):
         return ms, _ext.launch_count() - launches0
 
     # ---- device-timed headline ------------------------------------------------------------------
-    sampler = ClockSampler(torch.cuda.current_device())
-    if rank == 0:
-        sampler.start()
-    ms, launches = region(session.step, a.steps, a.warmup)
+    ms, launches = region(session.step, a.steps, a.warmup, on_start=sampler.mark)
     clocks = sampler.stop() if rank == 0 else {}
     loss = float(session.last_loss)
     value = world * B * a.steps / (ms / 1e3)

@@ -159,15 +159,16 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("fused_allreduce_sgd", [](const PyCommCtx& c, int64_t start, int64_t numel, ptr_t momentum, ptr_t hyper,
                                   int channel, bool use_mc, bool wire_bf16, int blocks, ptr_t stream,
-                                  uint64_t scalar_off, ptr_t scalar_out) {
+                                  uint64_t scalar_off, ptr_t scalar_out, bool oneshot) {
     BucketArgs b;
+    b.oneshot = oneshot ? 1 : 0;
     b.start = start; b.numel = numel; b.momentum = P<float>(momentum); b.hyper = P<const SgdHyper>(hyper);
     b.channel = channel;
     b.scalar_off = scalar_off; b.scalar_out = P<float>(scalar_out);
     check(ddl::launch_fused_allreduce_sgd(c.c, b, use_mc, wire_bf16, blocks, S(stream)), "fused_allreduce_sgd");
   }, py::arg("ctx"), py::arg("start"), py::arg("numel"), py::arg("momentum"), py::arg("hyper"), py::arg("channel"),
      py::arg("use_mc"), py::arg("wire_bf16"), py::arg("blocks"), py::arg("stream"), py::arg("scalar_off") = 0,
-     py::arg("scalar_out") = 0);
+     py::arg("scalar_out") = 0, py::arg("oneshot") = false);
   m.attr("SCALAR_SLOTS") = ddl::kScalarSlots;
   m.def("allreduce", [](const PyCommCtx& c, int channel, uint64_t off, int64_t numel, bool bf16, float scale,
                         bool use_mc, bool oneshot, int blocks, ptr_t stream) {

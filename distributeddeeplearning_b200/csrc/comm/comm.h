@@ -49,6 +49,7 @@ struct BucketArgs {
   // averaged across ranks into `scalar_out` (local) by block 0 of this launch; scalar_off == 0 disables it.
   uint64_t scalar_off;
   float* scalar_out;
+  int oneshot;            // small bucket: every rank reduces and updates the whole bucket (no broadcast phase)
 };
 constexpr int kScalarSlots = 64;
 

@@ -165,7 +165,10 @@ __global__ void __launch_bounds__(512) fused_sgd_local_kernel(float* __restrict_
 // world > 1: two-shot fused allreduce + SGD.  MC = NVLS multicast path, else P2P loads/stores.
 // WIRE_BF16 = gradients travel as bfloat16 (the --fp16-allreduce analogue).
 // ------------------------------------------------------------------------------------------
-template <bool MC, bool WIRE_BF16>
+// ONESHOT (small buckets): every rank reduces the WHOLE bucket from all replicas (peer loads in rank order, so all
+// ranks compute bit-identical sums) and updates only its own replica — no broadcast stores, one data phase instead of
+// reduce-scatter + all-gather.  Two-shot (large buckets): rank r reduces slice r and broadcasts the new weights.
+template <bool MC, bool WIRE_BF16, bool ONESHOT>
 __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, BucketArgs b) {
   const SgdHyper h = *b.hyper;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,8 +206,10 @@ __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, Buc
     reinterpret_cast<float4*>(b.scalar_out)[threadIdx.x] = make_float4(acc.x * s, acc.y * s, acc.z * s, acc.w * s);
   }
 
-  const int64_t slice = b.numel / c.world;              // elements owned by each rank
-  const int64_t base = b.start + slice * c.rank;        // my slice (element offset in the arena)
+  const int64_t slice = ONESHOT ? b.numel : b.numel / c.world;           // elements this rank reduces and updates
+  const int64_t base = ONESHOT ? b.start : b.start + slice * c.rank;     // (element offset in the arena)
+  constexpr bool kSwitchReduce = MC && !ONESHOT;        // in-switch reduction order is not guaranteed identical
+                                                        // for different requesters: one-shot sums peers itself
   constexpr int V = WIRE_BF16 ? 8 : 4;                  // elements per thread-iteration
   const int64_t nvec = slice / V;
   for (int64_t i = tid; i < nvec; i += nthreads) {
@@ -212,7 +217,7 @@ __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, Buc
     float gsum[V];
     if (WIRE_BF16) {
       uint4 r;
-      if (MC) {
+      if (kSwitchReduce) {
         r = multimem_ld_reduce_bf16x8(c.mc_base + c.stage_off + e * 2);
         float2 p0 = unpack_bf16x2(r.x), p1 = unpack_bf16x2(r.y), p2 = unpack_bf16x2(r.z), p3 = unpack_bf16x2(r.w);
         gsum[0] = p0.x; gsum[1] = p0.y; gsum[2] = p1.x; gsum[3] = p1.y;
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, Buc
       }
     } else {
       float4 r;
-      if (MC) {
+      if (kSwitchReduce) {
         r = multimem_ld_reduce_f32x4(c.mc_base + c.grad_off + e * 4);
       } else {
         float4 rr[kMaxWorld];
@@ -269,7 +274,10 @@ __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, Buc
       const float4 wn = make_float4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
       const uint2 wbn = make_uint2(pack_bf16x2(wn.x, wn.y), pack_bf16x2(wn.z, wn.w));
       const int64_t eo = e + 4 * q;
-      if (MC) {
+      if (ONESHOT) {
+        *reinterpret_cast<float4*>(self + c.weight_off + eo * 4) = wn;
+        *reinterpret_cast<uint2*>(self + c.wbf16_off + eo * 2) = wbn;
+      } else if (MC) {
         multimem_st_f32x4(c.mc_base + c.weight_off + eo * 4, wn);
         multimem_st_u32x2(c.mc_base + c.wbf16_off + eo * 2, wbn);
       } else {
@@ -492,13 +500,15 @@ cudaError_t launch_fused_allreduce_sgd(const CommCtx& c, const BucketArgs& b, bo
   if (b.numel % (static_cast<int64_t>(c.world) * 8) != 0) return cudaErrorInvalidValue;
   blocks = clamp_blocks(blocks);
   if (use_mc && c.mc_base == 0) return cudaErrorInvalidValue;
-  if (use_mc) {
-    if (wire_bf16) fused_allreduce_sgd_kernel<true, true><<<blocks, 512, 0, stream>>>(c, b);
-    else fused_allreduce_sgd_kernel<true, false><<<blocks, 512, 0, stream>>>(c, b);
+#define DDL_FUSED(MCV, WB, OS) fused_allreduce_sgd_kernel<MCV, WB, OS><<<blocks, 512, 0, stream>>>(c, b)
+  if (b.oneshot) {
+    if (wire_bf16) DDL_FUSED(false, true, true); else DDL_FUSED(false, false, true);
+  } else if (use_mc) {
+    if (wire_bf16) DDL_FUSED(true, true, false); else DDL_FUSED(true, false, false);
   } else {
-    if (wire_bf16) fused_allreduce_sgd_kernel<false, true><<<blocks, 512, 0, stream>>>(c, b);
-    else fused_allreduce_sgd_kernel<false, false><<<blocks, 512, 0, stream>>>(c, b);
+    if (wire_bf16) DDL_FUSED(false, true, false); else DDL_FUSED(false, false, false);
   }
+#undef DDL_FUSED
   return cudaGetLastError();
 }
 

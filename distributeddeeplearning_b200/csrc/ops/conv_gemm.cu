@@ -1087,7 +1087,8 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const TmaSet& tmA, const
 // round trip, epilogue), so they get a shallow ring -> small shared-memory footprint -> 3-4 CTAs per SM whose
 // prologues/epilogues overlap.  Long-K tiles get the deep ring.  g_force_stages (tuning hook) overrides.
 int g_force_stages = 0;
-int g_bn256 = 1;            // tuning hook: 0 keeps the persistent kernel at 128 x 128 tiles
+int g_bn256 = 0;            // tuning hook: 1 lets long-K layers use 128 x 256 persistent tiles (measured 1.7 % SLOWER on
+                            // ResNet-50: one CTA per SM leaves the epilogue half the warps; kept for A/B runs)
 int g_wgrad_swap = 1;       // tuning hook: 0 disables the operand-role swap of narrow-output wgrad tiles
 
 template <int BLOCK_N, int MODE>

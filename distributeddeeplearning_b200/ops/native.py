@@ -24,8 +24,8 @@ def _C():
     C = _ext.load()
     if os.environ.get("DDL_WGRAD_SWAP", "1") == "0":       # tuning hook (A/B runs): no operand-role swap in wgrad
         C.set_wgrad_swap(0)
-    if os.environ.get("DDL_CONV_BN256", "1") == "0":       # tuning hook (A/B runs): 128 x 128 persistent tiles only
-        C.set_conv_bn256(0)
+    if os.environ.get("DDL_CONV_BN256", "0") == "1":       # tuning hook (A/B runs): 128 x 256 persistent tiles
+        C.set_conv_bn256(1)
     return C
 
 

@@ -130,7 +130,7 @@ class FusedSGD(torch.optim.Optimizer):
                  weight_decay: float = 0.0, nesterov: bool = False, compression: type = Compression.none,
                  first_bucket_mb: float = 1.0, bucket_mb: float = 16.0, overlap: bool = True,
                  comm_blocks: int = 32, use_multicast: Optional[bool] = None, timeout_s: float = 30.0,
-                 broadcast_root: Optional[int] = 0, debug: Optional[bool] = None):
+                 broadcast_root: Optional[int] = 0, debug: Optional[bool] = None, oneshot_kb: float = 512.0):
         named = list(params)
         if named and isinstance(named[0], tuple):
             plist = [p for _, p in named]
@@ -155,6 +155,7 @@ class FusedSGD(torch.optim.Optimizer):
         self.compression = compression
         self.overlap = overlap
         self.comm_blocks = int(comm_blocks)
+        self.oneshot_bytes = int(oneshot_kb * 1024)       # buckets up to this size skip the broadcast phase
         # debug mode: after every step verify the protocol's invariants and poison the wire staging
         self.debug = bool(int(os.environ.get("DDL_COMM_DEBUG", "0"))) if debug is None else bool(debug)
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -262,10 +263,13 @@ class FusedSGD(torch.optim.Optimizer):
                                    stream.cuda_stream)
         else:
             tail = self._scalars_pending > 0 and b == self.num_buckets - 1
+            oneshot = numel * 4 <= self.oneshot_bytes
+            if oneshot:
+                blocks = max(1, min(self.comm_blocks, (numel + 2047) // 2048))
             self.C.fused_allreduce_sgd(self.ctx, start, numel, self.M.data_ptr(), self._hyper_dev.data_ptr(), 0,
                                        self.use_mc, self.wire_bf16, blocks, stream.cuda_stream,
                                        self.arena.offsets["scalars"] if tail else 0,
-                                       self._scalars_out.data_ptr() if tail else 0)
+                                       self._scalars_out.data_ptr() if tail else 0, oneshot)
 
     def _on_ready(self, idx: int) -> None:
         if self._ready_seen[idx]:

@@ -59,3 +59,72 @@ def test_bench_contract_small():
         assert key in out, key
     assert out["value"] > 0 and out["gpu_launches"] > 0 and out["e2e"]["value"] > 0
     assert out["e2e"]["h2d_bytes_per_step"] == 32 * 224 * 224 * 3 + 32 * 8
+
+
+def _launch(module, argv, gpus, env=None, timeout=900):
+    import io
+
+    sys.path.insert(0, ROOT)
+    from distributeddeeplearning_b200.cli import launcher
+
+    out, err = io.StringIO(), io.StringIO()
+    e = {"PYTHONPATH": ROOT}
+    e.update(env or {})
+    res = launcher.launch(module, argv, gpus=gpus, record=False, stdout=out, stderr=err, timeout=timeout, env=e)
+    return res, out.getvalue(), err.getvalue()
+
+
+def test_imagenet_trainer_synthetic_gpu(tmp_path):
+    """Reference PyTorch_imagenet trainer surface on the native kernels: LR warm-up, epoch log lines, checkpoint."""
+    res, out, err = _launch("distributeddeeplearning_b200.workloads.imagenet",
+                            ["--epochs", "1", "--batch_size", "16", "--model", "resnet50",
+                             "--save_filepath", str(tmp_path / "ck-{epoch}.pt")], gpus=1, env={"FAKE_DATA_LENGTH": "64"})
+    assert res.returncode == 0, (out + err)[-3000:]
+    assert "Training epoch 0 took" in out and "Total images/sec:" in out
+    assert (tmp_path / "ck-1.pt").exists()
+
+
+def test_hvd_trainer_checkpoint_resume_gpu(tmp_path):
+    """Reference PyTorch_hvd trainer: checkpoints every epoch, second launch resumes from the latest one; the per-step
+    metric allreduces ride in the last gradient bucket (FusedSGD.piggyback)."""
+    fmt = str(tmp_path / "checkpoint-{epoch}.pth.tar")
+    common = ["--batch-size", "16", "--model", "resnet50", "--synthetic-length", "32", "--checkpoint-format", fmt,
+              "--log-dir", str(tmp_path / "logs")]
+    for epochs in ("1", "2"):
+        res, out, err = _launch("distributeddeeplearning_b200.workloads.hvd_imagenet", ["--epochs", epochs] + common, gpus=1)
+        assert res.returncode == 0, (out + err)[-3000:]
+    assert os.path.exists(fmt.format(epoch=1)) and os.path.exists(fmt.format(epoch=2))
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured step (forward, backward with side-stream weight gradients, fused SGD buckets) replays to the same
+    loss trajectory as the eager step."""
+    code = ("import sys, torch; sys.path.insert(0, %r)\n"
+            "from distributeddeeplearning_b200.parallel import dist\n"
+            "from distributeddeeplearning_b200.workloads.benchmark import BenchmarkSession\n"
+            "dist.init()\n"
+            "def run(graph):\n"
+            "    torch.manual_seed(0)\n"
+            "    s = BenchmarkSession('resnet18', 16, True, lr=0.05, momentum=0.9)\n"
+            "    out = [float(s.step()) for _ in range(3)]\n"
+            "    if graph: assert s.enable_graph(warmup=1), 'capture failed'\n"
+            "    else: out.append(float(s.step()))\n"
+            "    out += [float(s.step()) for _ in range(4)]\n"
+            "    return out[-4:]\n"
+            "a, b = run(False), run(True)\n"
+            "print(a, b)\n"
+            "assert all(abs(x - y) < 2e-2 * max(1.0, abs(x)) for x, y in zip(a, b)), (a, b)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+
+
+def test_two_rank_fused_engine():
+    """NVLink peer-memory engine (P2P + NVLS, fp32 + bf16 wire, piggy-backed scalars, debug checks) on 2 GPUs."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(ROOT, "tools", "comm_test.py"),
+                        "--no-sweep"], cwd=ROOT, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ENGINE CHECKS: all ok" in r.stdout, (r.stdout + r.stderr)[-3000:]

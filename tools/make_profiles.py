@@ -70,6 +70,22 @@ def ncu_reports():
     open(os.path.join(P, "ncu_summary.md"), "w").write("\n".join(L) + "\n")
 
 
+def sanitizer():
+    logs = sorted(glob.glob(os.path.join(G, "sanitize_*.log")))
+    if not logs:
+        return
+    L = ["# compute-sanitizer passes (tools/sanitize.sh <tool> <gpu_diag group>, 1 GPU)", "",
+         "| tool | kernel group (tools/gpu_diag.py) | summary |", "|---|---|---|"]
+    for f in logs:
+        name = os.path.basename(f)[len("sanitize_"):-len(".log")]
+        tool, group = name.split("_", 1)
+        txt = open(f, errors="replace").read()
+        summ = [l.strip("= ").strip() for l in txt.splitlines() if "SUMMARY" in l]
+        rc = [l for l in txt.splitlines() if l.startswith("compute-sanitizer")]
+        L.append(f"| {tool} | {group} | {'; '.join(summ) or 'n/a'} ({rc[-1].split()[-1] if rc else 'rc=?'}) |")
+    open(os.path.join(P, "sanitizer.md"), "w").write("\n".join(L) + "\n")
+
+
 def comm():
     for p in sorted(glob.glob(os.path.join(G, "comm_sweep_N*.json"))):
         d = json.load(open(p))
@@ -113,6 +129,7 @@ if __name__ == "__main__":
     layer_bench()
     launches()
     ncu_reports()
+    sanitizer()
     comm()
     bench_lines()
     print(sorted(os.listdir(P)))
