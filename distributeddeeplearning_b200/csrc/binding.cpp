@@ -196,8 +196,9 @@ PYBIND11_MODULE(_C, m) {
         [](int mode, ptr_t src, ptr_t out, ptr_t add, ptr_t bias, ptr_t sum, ptr_t sumsq, int M, int KB, int ldc,
            int srcH, int srcW, int srcC, int dstH, int dstW, int R, int Sx, int stride, int pad, int dil,
            int cchunks, int relu, int n_valid, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
-           int batch, int tw, int th, int tn, int zfill, ptr_t stream, int pad_w, int kstride) {
+           int batch, int tw, int th, int tn, int zfill, ptr_t stream, int pad_w, int kstride, ptr_t add_mask) {
           ConvArgs a;
+          a.add_mask = P<const uint8_t>(add_mask);
           a.zfill = zfill;
           a.pad_w = pad_w < 0 ? pad : pad_w;
           a.kstride = kstride > 0 ? kstride : cchunks * 64;
@@ -214,7 +215,7 @@ PYBIND11_MODULE(_C, m) {
         py::arg("dstW"), py::arg("R"), py::arg("S"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("cchunks"),
         py::arg("relu"), py::arg("n_valid"), py::arg("w"), py::arg("w_rows"), py::arg("w_cols"), py::arg("n_total"),
         py::arg("a_matrix"), py::arg("a_cols"), py::arg("batch"), py::arg("tw"), py::arg("th"), py::arg("tn"),
-        py::arg("zfill"), py::arg("stream"), py::arg("pad_w") = -1, py::arg("kstride") = 0);
+        py::arg("zfill"), py::arg("stream"), py::arg("pad_w") = -1, py::arg("kstride") = 0, py::arg("add_mask") = 0);
   m.def("conv_wgrad",
         [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int dy_ld, int ldw, int ncols, int H, int W, int C, int Pq,
            int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, int batch, int tw, int th, int tn,
@@ -238,26 +239,33 @@ PYBIND11_MODULE(_C, m) {
   // ------------------------------------------------------------------ BN / activation
   m.def("bn_act_fwd", [](ptr_t x, ptr_t residual, ptr_t z, ptr_t sum, ptr_t sumsq, ptr_t gamma, ptr_t beta,
                          ptr_t mean, ptr_t invstd, ptr_t rmean, ptr_t rvar, float eps, float momentum, int M, int C,
-                         int relu, bool train, int sms, ptr_t stream) {
+                         int relu, bool train, int sms, ptr_t stream, ptr_t mask) {
     BnFwdArgs a;
+    a.mask = P<uint8_t>(mask);
     a.x = P<const __nv_bfloat16>(x); a.residual = P<const __nv_bfloat16>(residual); a.z = P<__nv_bfloat16>(z);
     a.sum = P<const float>(sum); a.sumsq = P<const float>(sumsq); a.gamma = P<const float>(gamma);
     a.beta = P<const float>(beta); a.mean = P<float>(mean); a.invstd = P<float>(invstd);
     a.running_mean = P<float>(rmean); a.running_var = P<float>(rvar); a.eps = eps; a.momentum = momentum;
     a.M = M; a.C = C; a.relu = relu;
     check(ddl::launch_bn_act_fwd(a, train, sms, S(stream)), "bn_act_fwd");
-  });
+  }, py::arg("x"), py::arg("residual"), py::arg("z"), py::arg("sum"), py::arg("sumsq"), py::arg("gamma"), py::arg("beta"),
+     py::arg("mean"), py::arg("invstd"), py::arg("rmean"), py::arg("rvar"), py::arg("eps"), py::arg("momentum"),
+     py::arg("M"), py::arg("C"), py::arg("relu"), py::arg("train"), py::arg("sms"), py::arg("stream"), py::arg("mask") = 0);
   m.def("bn_act_bwd", [](ptr_t dz, ptr_t z, ptr_t x, ptr_t dx, ptr_t dres, ptr_t mean, ptr_t invstd, ptr_t gamma,
                          ptr_t beta, ptr_t dgamma, ptr_t dbeta, ptr_t gamma_grad, ptr_t beta_grad, int M, int C,
-                         int relu, int mask_from_x, int sms, ptr_t stream) {
+                         int relu, int mask_from_x, int sms, ptr_t stream, ptr_t zmask) {
     BnBwdArgs a;
+    a.zmask = P<const uint8_t>(zmask);
     a.dz = P<const __nv_bfloat16>(dz); a.z = P<const __nv_bfloat16>(z); a.x = P<const __nv_bfloat16>(x);
     a.dx = P<__nv_bfloat16>(dx); a.dres = P<__nv_bfloat16>(dres); a.mean = P<const float>(mean);
     a.invstd = P<const float>(invstd); a.gamma = P<const float>(gamma); a.dgamma = P<float>(dgamma);
     a.dbeta = P<float>(dbeta); a.gamma_grad = P<float>(gamma_grad); a.beta_grad = P<float>(beta_grad);
     a.M = M; a.C = C; a.relu = relu; a.beta = P<const float>(beta); a.mask_from_x = mask_from_x;
     check(ddl::launch_bn_act_bwd(a, sms, S(stream)), "bn_act_bwd");
-  });
+  }, py::arg("dz"), py::arg("z"), py::arg("x"), py::arg("dx"), py::arg("dres"), py::arg("mean"), py::arg("invstd"),
+     py::arg("gamma"), py::arg("beta"), py::arg("dgamma"), py::arg("dbeta"), py::arg("gamma_grad"), py::arg("beta_grad"),
+     py::arg("M"), py::arg("C"), py::arg("relu"), py::arg("mask_from_x"), py::arg("sms"), py::arg("stream"),
+     py::arg("zmask") = 0);
   m.def("channel_stats", [](ptr_t x, ptr_t sum, ptr_t sumsq, int M, int C, int sms, ptr_t stream) {
     check(ddl::launch_channel_stats(P<const __nv_bfloat16>(x), P<float>(sum), P<float>(sumsq), M, C, sms, S(stream)),
           "channel_stats");

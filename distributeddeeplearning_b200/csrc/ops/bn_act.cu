@@ -22,7 +22,7 @@ namespace ddl {
 namespace {
 
 constexpr int kBnThreads = 256;
-enum { kMaskNone = 0, kMaskZ = 1, kMaskX = 2 };
+enum { kMaskNone = 0, kMaskZ = 1, kMaskX = 2, kMaskBits = 3 };
 
 struct Vec8 {
   float v[8];
@@ -116,6 +116,12 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
       for (int i = 0; i < 8; ++i) z[i] = fmaf(x[i], scale[i], shift[i]);
     }
     if (a.relu) {
+      if (a.mask) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bits |= (z[i] > 0.f ? 1u : 0u) << i;
+        a.mask[off >> 3] = static_cast<uint8_t>(bits);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) z[i] = fmaxf(z[i], 0.f);
     }
@@ -170,6 +176,9 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
       unpack8(uz, z);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? dz[i] : 0.f;
+    } else if (MASK == kMaskBits) {        // uz.x carries the 8 mask bits of this (row, channel group)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = ((uz.x >> i) & 1u) ? dz[i] : 0.f;
     } else if (MASK == kMaskX) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = fmaf(x[i], msc[i], msh[i]) > 0.f ? dz[i] : 0.f;
@@ -190,6 +199,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
     const uint4 x0 = ld_stream_u4(a.x + off0), x1 = ld_stream_u4(a.x + off1);
     uint4 z0 = make_uint4(0, 0, 0, 0), z1 = z0;
     if (MASK == kMaskZ) { z0 = ld_stream_u4(a.z + off0); z1 = ld_stream_u4(a.z + off1); }
+    if (MASK == kMaskBits) { z0.x = a.zmask[off0 >> 3]; z1.x = a.zmask[off1 >> 3]; }
     accumulate(d0, x0, z0);
     accumulate(d1, x1, z1);
   }
@@ -199,6 +209,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
     const uint4 x0 = ld_stream_u4(a.x + off0);
     uint4 z0 = make_uint4(0, 0, 0, 0);
     if (MASK == kMaskZ) z0 = ld_stream_u4(a.z + off0);
+    if (MASK == kMaskBits) z0.x = a.zmask[off0 >> 3];
     accumulate(d0, x0, z0);
   }
   // lanes of a warp sharing a channel group: lane = (rl % 4) * 8 + cgl -> xor 8, 16
@@ -271,6 +282,10 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdAr
       unpack8(ld_stream_u4(a.z + off), z);
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = z[i] > 0.f ? dz[i] : 0.f;
+    } else if (MASK == kMaskBits) {
+      const uint32_t bits = a.zmask[off >> 3];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) dz[i] = ((bits >> i) & 1u) ? dz[i] : 0.f;
     } else if (MASK == kMaskX) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) dz[i] = fmaf(x[i], k1[i], msh[i]) > 0.f ? dz[i] : 0.f;
@@ -330,11 +345,12 @@ cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStrea
 
 cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) {
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
-  const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : kMaskZ);
+  const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : (a.zmask ? kMaskBits : kMaskZ));
   const dim3 rgrid = bn_chunk_grid(a.M, a.C, sms);
   switch (mask) {
     case kMaskNone: bn_act_bwd_reduce_kernel<kMaskNone><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     case kMaskZ: bn_act_bwd_reduce_kernel<kMaskZ><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+    case kMaskBits: bn_act_bwd_reduce_kernel<kMaskBits><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     default: bn_act_bwd_reduce_kernel<kMaskX><<<rgrid, kBnThreads, 0, stream>>>(a); break;
   }
   cudaError_t e = cudaGetLastError();
@@ -344,12 +360,14 @@ cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) 
     switch (mask) {
       case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone, false><<<grid, kBnThreads, 0, stream>>>(a); break;
       case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskBits: bn_act_bwd_apply_kernel<kMaskBits, false><<<grid, kBnThreads, 0, stream>>>(a); break;
       default: bn_act_bwd_apply_kernel<kMaskX, false><<<grid, kBnThreads, 0, stream>>>(a); break;
     }
   } else {
     switch (mask) {
       case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
       case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskBits: bn_act_bwd_apply_kernel<kMaskBits, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
       default: bn_act_bwd_apply_kernel<kMaskX, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     }
   }

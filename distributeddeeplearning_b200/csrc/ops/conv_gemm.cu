@@ -202,7 +202,14 @@ DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, co
     uint4 val = lds128(sp);
     const size_t off = static_cast<size_t>(m) * a.ldc + coff;
     if (a.add) {
-      const uint4 o = *reinterpret_cast<const uint4*>(a.add + off);
+      uint4 o = *reinterpret_cast<const uint4*>(a.add + off);
+      if (a.add_mask) {
+        const uint32_t bits = a.add_mask[off >> 3];
+        o.x &= ((bits & 1u) ? 0x0000ffffu : 0u) | ((bits & 2u) ? 0xffff0000u : 0u);
+        o.y &= ((bits & 4u) ? 0x0000ffffu : 0u) | ((bits & 8u) ? 0xffff0000u : 0u);
+        o.z &= ((bits & 16u) ? 0x0000ffffu : 0u) | ((bits & 32u) ? 0xffff0000u : 0u);
+        o.w &= ((bits & 64u) ? 0x0000ffffu : 0u) | ((bits & 128u) ? 0xffff0000u : 0u);
+      }
       float2 p, q;
       p = unpack_bf16x2(val.x); q = unpack_bf16x2(o.x); val.x = pack_bf16x2(p.x + q.x, p.y + q.y);
       p = unpack_bf16x2(val.y); q = unpack_bf16x2(o.y); val.y = pack_bf16x2(p.x + q.x, p.y + q.y);

@@ -28,6 +28,9 @@ struct ConvArgs {
   const __nv_bfloat16* src;   // gather source (x for fwd / stem, dy for dgrad); unused for TMA-A modes
   __nv_bfloat16* out;         // [M][ldc] (NHWC activations / gradients)
   const __nv_bfloat16* add;   // optional: out = acc + add   (same layout as out)
+  const uint8_t* add_mask;    // optional with `add`: bit i of byte [m][c/8] gates add[m][c + i] (the ReLU bit mask
+                              //   of the block output: the shortcut gradient dz * (z > 0) is formed here instead
+                              //   of being written by the BN-backward kernel and read back)
   const float* bias;          // optional: per output channel
   float* sum;                 // optional BN statistics: sum[c]   += sum_m out[m][c]   (of the bf16-rounded value)
   float* sumsq;               //                         sumsq[c] += sum_m out[m][c]^2

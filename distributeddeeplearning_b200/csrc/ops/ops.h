@@ -21,6 +21,8 @@ struct BnFwdArgs {
   float* running_var;
   float eps, momentum;
   int M, C, relu;
+  uint8_t* mask;                  // optional [M][C/8]: bit i of byte (row, group) = (z[row][8*group + i] > 0).  Written
+                                  //   for residual layers so that backward reads 1 bit instead of 16 bits per element
 };
 
 struct BnBwdArgs {
@@ -39,6 +41,7 @@ struct BnBwdArgs {
   const float* beta;              // needed when the ReLU mask is recomputed from x (mask_from_x)
   int M, C, relu;
   int mask_from_x;                // no residual: z > 0  <=>  x*scale + shift > 0, so z is never read
+  const uint8_t* zmask;           // residual layers: the bit mask written by the forward kernel (z is never read)
 };
 
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream);

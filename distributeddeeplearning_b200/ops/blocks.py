@@ -50,7 +50,10 @@ class _ResidualBlock(torch.autograd.Function):
             wb = weight_bf16(w)
             y, stats = native.conv_fwd(h, wb, (w.shape[2], w.shape[3]), st, pad, dil, stats=True, cout=w.shape[0])
             last = i == n_main - 1
-            z, save = native.bn_act_fwd(y, stats, g, b, rm, rv, eps, mom, True, identity if last else None, True)
+            if last:      # residual layer: backward masks with 1 bit per element instead of re-reading the block output
+                z, save, zmask = native.bn_act_fwd(y, stats, g, b, rm, rv, eps, mom, True, identity, True, want_mask=True)
+            else:
+                z, save = native.bn_act_fwd(y, stats, g, b, rm, rv, eps, mom, True, None, True)
             saved += [h, y, save]
             wbs.append(wb)
             h = z
@@ -58,14 +61,14 @@ class _ResidualBlock(torch.autograd.Function):
         ctx.layers = layers
         ctx.wbs = wbs
         ctx.ds_pack = ds_pack if has_ds else None
-        ctx.save_for_backward(x, h, *saved)
+        ctx.save_for_backward(x, zmask, *saved)
         return h
 
     @staticmethod
     def backward(ctx, dout):
         cfg, layers = ctx.cfg, ctx.layers
         n_main, has_ds = cfg["n_main"], cfg["has_ds"]
-        x, out = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        x, zmask = ctx.saved_tensors[0], ctx.saved_tensors[1]
         saved = ctx.saved_tensors[2:]
         if not dout.is_contiguous(memory_format=CL):
             dout = dout.contiguous(memory_format=CL)
@@ -73,6 +76,7 @@ class _ResidualBlock(torch.autograd.Function):
         d = dout
         dres = None
         dx = None
+        gated_add = None
         for i in range(n_main - 1, -1, -1):
             w, g, b, _, _ = layers[i]
             st, pad, dil, _, _ = cfg["layers"][i]
@@ -81,8 +85,16 @@ class _ResidualBlock(torch.autograd.Function):
             last = i == n_main - 1
             gg = grad_buffer(g) if g.requires_grad else None
             bg = grad_buffer(b) if b.requires_grad else None
-            z = out if last else saved[3 * (i + 1)]            # this layer's output = next layer's input
-            dy, dr, _ = native.bn_act_bwd(d, z, y, save, g, True, last, gg, bg, beta=b, had_residual=last)
+            z = None if last else saved[3 * (i + 1)]           # this layer's output = next layer's input (unused: the
+            #                                                    mask is recomputed from y; last layer: bit mask)
+            # identity shortcut + a dgrad that can add in its epilogue: the shortcut gradient dout * (out > 0) is
+            # formed there from dout and the bit mask, so the BN-backward kernel need not write (and dgrad re-read) it
+            gate = last and not has_ds and need_dx and native.dgrad_supports_add(
+                (layers[0][0].shape[2], layers[0][0].shape[3]), cfg["layers"][0][0])
+            dy, dr, _ = native.bn_act_bwd(d, z, y, save, g, True, last and not gate, gg, bg, beta=b, had_residual=last,
+                                          zmask=zmask if last else None)
+            if gate:
+                gated_add = (dout, zmask)
             if last:
                 dres = dr
             if i > 0:
@@ -104,7 +116,10 @@ class _ResidualBlock(torch.autograd.Function):
                     for p in (gd, bd, wd):
                         if p.requires_grad:
                             notify_ready(p)
-                if native.dgrad_supports_add(kernel, st):
+                if gated_add is not None:
+                    dx = native.conv_dgrad(dy, ctx.wbs[0], x.shape, kernel, st, pad, dil, add=gated_add[0],
+                                           add_mask=gated_add[1])
+                elif native.dgrad_supports_add(kernel, st):
                     dx = native.conv_dgrad(dy, ctx.wbs[0], x.shape, kernel, st, pad, dil, add=add)
                 else:
                     dx = native.add(native.conv_dgrad(dy, ctx.wbs[0], x.shape, kernel, st, pad, dil), add)

@@ -136,8 +136,14 @@ class _ConvBnAct(torch.autograd.Function):
         wb = weight_bf16(weight)
         y, stats = native.conv_fwd(x, wb, (R, S), stride, pad, dil, stats=train, cout=weight.shape[0]) if train else (
             native.conv_fwd(x, wb, (R, S), stride, pad, dil, cout=weight.shape[0]), None)
-        z, save = native.bn_act_fwd(y, stats, gamma, beta, running_mean, running_var, eps, momentum, relu, residual,
-                                    train)
+        use_bits = train and relu and residual is not None
+        if use_bits:      # residual layer: 1-bit ReLU mask for backward instead of re-reading z
+            z, save, zmask = native.bn_act_fwd(y, stats, gamma, beta, running_mean, running_var, eps, momentum, relu,
+                                               residual, train, want_mask=True)
+        else:
+            z, save = native.bn_act_fwd(y, stats, gamma, beta, running_mean, running_var, eps, momentum, relu, residual,
+                                        train)
+            zmask = None
         ctx.cfg = (stride, pad, dil, relu, residual is not None, (R, S))
         ctx.params = (weight, gamma, beta)
         if train:
@@ -145,7 +151,7 @@ class _ConvBnAct(torch.autograd.Function):
             # version check) — the arena is only rewritten by the bucket kernel, which is ordered after
             # this layer's backward (see notify_ready at the end of backward)
             ctx.wb = wb
-            ctx.save_for_backward(x, y, z, save)
+            ctx.save_for_backward(x, y, zmask if use_bits else z, save)
         return z
 
     @staticmethod
@@ -153,13 +159,15 @@ class _ConvBnAct(torch.autograd.Function):
         stride, pad, dil, relu, has_res, kernel = ctx.cfg
         weight, gamma, beta = ctx.params
         x, y, z, save = ctx.saved_tensors
+        zmask = z if (z is not None and z.dtype == torch.uint8) else None     # residual layers saved the bit mask
         wb = ctx.wb
         if not dz.is_contiguous(memory_format=CL):
             dz = dz.contiguous(memory_format=CL)
         gg = grad_buffer(gamma) if gamma.requires_grad else None
         bg = grad_buffer(beta) if beta.requires_grad else None
-        dy, dres, _ = native.bn_act_bwd(dz, z, y, save, gamma, relu, has_res and ctx.needs_input_grad[1], gg, bg,
-                                        beta=beta, had_residual=has_res)
+        dy, dres, _ = native.bn_act_bwd(dz, None if zmask is not None else z, y, save, gamma, relu,
+                                        has_res and ctx.needs_input_grad[1], gg, bg, beta=beta, had_residual=has_res,
+                                        zmask=zmask)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil)

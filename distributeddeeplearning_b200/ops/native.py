@@ -264,8 +264,9 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
 
 
 def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[int, int], stride: int, pad,
-               dil: int = 1, add: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """dx = conv_transpose(dy, w) (+ add).  ``w_bf16`` is the forward matrix [Cout, R*S*Cin]."""
+               dil: int = 1, add: Optional[torch.Tensor] = None, add_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dx = conv_transpose(dy, w) (+ add [gated by the bit mask ``add_mask``: uint8 [M, Cin/8]]).
+    ``w_bf16`` is the forward matrix [Cout, R*S*Cin]."""
     C = _C()
     _check_act(dy, "dy")
     N, Cin, H, W = x_shape
@@ -289,18 +290,20 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
             dx.zero_()
     if add is not None:
         _check_act(add, "add")
+    if add_mask is not None and (add is None or add_mask.dtype != torch.uint8 or add_mask.numel() != N * H * W * (Cin // 8)):
+        raise ValueError("add_mask: expected a uint8 [N*H*W, Cin/8] bit mask accompanying `add`")
     n_total = _ceil_div(Cin, 64) * 64
     cch = _ceil_div(Cout, 64)
     wp, wr, wc = w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1]
     if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
         C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, cch, Cin, P, Q, Cout, H,
                     W, 1, 1, 1, 0, 1, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, 0, 0, 0, 0, _stream(),
-                    0, 0)
+                    0, 0, _ptr(add_mask))
     elif stride == 1 and USE_TILE_TMA:
         tw, th, tn = tile_geometry(H, W, N, 128)
         C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * cch, Cin, P, Q,
                     Cout, H, W, R, S, 1, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, tw, th, tn,
-                    0, _stream(), pw, 0)
+                    0, _stream(), pw, 0, _ptr(add_mask))
     elif s2_tile:
         # four stride-1 phase problems (one launch each), tiles iterate the half-resolution phase grid
         tw, th, tn = tile_geometry((H + 1) // 2, (W + 1) // 2, N, 128)
@@ -310,7 +313,7 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
     else:
         C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * cch,
                     Cin, P, Q, Cout, H, W, R, S, stride, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, 0, 0, N, 0, 0, 0, 0,
-                    _stream(), pw, 0)
+                    _stream(), pw, 0, _ptr(add_mask))
     return dx
 
 
@@ -428,7 +431,10 @@ def bn_supported(c: int) -> bool:
 
 
 def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, running_mean, running_var,
-               eps: float, momentum: float, relu: bool, residual: Optional[torch.Tensor], train: bool):
+               eps: float, momentum: float, relu: bool, residual: Optional[torch.Tensor], train: bool,
+               want_mask: bool = False):
+    """z = act(BN(y) [+ residual]).  Returns (z, save) — with ``want_mask`` (train + ReLU) (z, save, mask): one bit per
+    element telling whether z > 0, which lets the backward of residual layers skip reading z (16x less mask traffic)."""
     C = _C()
     _check_act(y, "y")
     N, Ch, H, W = y.shape
@@ -440,20 +446,25 @@ def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, runn
             C.channel_stats(y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(), M, Ch, sm_count(y.device.index or 0),
                             _stream())
         save = torch.empty((2, Ch), dtype=torch.float32, device=y.device)
+        mask = torch.empty((M, Ch // 8), dtype=torch.uint8, device=y.device) if (want_mask and relu) else None
         C.bn_act_fwd(y.data_ptr(), _ptr(residual), z.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
                      gamma.data_ptr(), beta.data_ptr(), save[0].data_ptr(), save[1].data_ptr(), _ptr(running_mean),
-                     _ptr(running_var), eps, momentum, M, Ch, int(relu), True, sm_count(y.device.index or 0), _stream())
-        return z, save
+                     _ptr(running_var), eps, momentum, M, Ch, int(relu), True, sm_count(y.device.index or 0), _stream(),
+                     _ptr(mask))
+        return (z, save, mask) if want_mask else (z, save)
     C.bn_act_fwd(y.data_ptr(), _ptr(residual), z.data_ptr(), 0, 0, gamma.data_ptr(), beta.data_ptr(), 0, 0,
                  running_mean.data_ptr(), running_var.data_ptr(), eps, momentum, M, Ch, int(relu), False,
-                 sm_count(y.device.index or 0), _stream())
-    return z, None
+                 sm_count(y.device.index or 0), _stream(), 0)
+    return (z, None, None) if want_mask else (z, None)
 
 
-def bn_act_bwd(dz: torch.Tensor, z: torch.Tensor, y: torch.Tensor, save: torch.Tensor, gamma: torch.Tensor,
+def bn_act_bwd(dz: torch.Tensor, z: Optional[torch.Tensor], y: torch.Tensor, save: torch.Tensor, gamma: torch.Tensor,
                relu: bool, want_dres: bool, gamma_grad: Optional[torch.Tensor], beta_grad: Optional[torch.Tensor],
-               beta: Optional[torch.Tensor] = None, had_residual: bool = True):
-    """Returns (dy, dres|None); accumulates into gamma_grad / beta_grad (fp32) when given."""
+               beta: Optional[torch.Tensor] = None, had_residual: bool = True, zmask: Optional[torch.Tensor] = None):
+    """Returns (dy, dres|None, scratch); accumulates into gamma_grad / beta_grad (fp32) when given.
+
+    ReLU mask source: recomputed from y when the layer had no residual (``beta`` given), else the bit mask written by
+    the forward (``zmask``), else the saved output ``z``."""
     C = _C()
     _check_act(dz, "dz")
     N, Ch, H, W = y.shape
@@ -462,10 +473,12 @@ def bn_act_bwd(dz: torch.Tensor, z: torch.Tensor, y: torch.Tensor, save: torch.T
     dres = torch.empty_like(y) if want_dres else None
     scratch = zeros_f32((2, Ch), y.device)
     mask_from_x = bool(relu and beta is not None and not had_residual)     # z is not read at all in that case
-    C.bn_act_bwd(dz.data_ptr(), z.data_ptr(), y.data_ptr(), dy.data_ptr(), _ptr(dres), save[0].data_ptr(),
+    if relu and not mask_from_x and zmask is None and z is None:
+        raise ValueError("bn_act_bwd: need z or zmask for the ReLU mask of a residual layer")
+    C.bn_act_bwd(dz.data_ptr(), _ptr(z), y.data_ptr(), dy.data_ptr(), _ptr(dres), save[0].data_ptr(),
                  save[1].data_ptr(), gamma.data_ptr(), _ptr(beta), scratch[0].data_ptr(), scratch[1].data_ptr(),
                  _ptr(gamma_grad), _ptr(beta_grad), M, Ch, int(relu), int(mask_from_x), sm_count(y.device.index or 0),
-                 _stream())
+                 _stream(), _ptr(zmask) if (relu and not mask_from_x) else 0)
     return dy, dres, scratch
 
 

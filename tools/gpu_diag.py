@@ -275,6 +275,19 @@ def g_conv_dgrad():
     yr.backward(dy.float())
     dx = nv.conv_dgrad(dy, _w_bf16(w), x.shape, (3, 3), 1, 1, add=add)
     report("conv_dgrad + add", dx, x.grad + add.float(), 2e-2)
+    # epilogue add gated by a ReLU bit mask (shortcut gradient of an identity residual block)
+    zpos = torch.rand(2, 64, 8, 8, device=dev) > 0.5
+    bits = cl(zpos.to(torch.uint8)).permute(0, 2, 3, 1).reshape(-1, 8, 8)       # [M, C/8, 8]
+    mask = (bits.to(torch.int32) << torch.arange(8, device=dev, dtype=torch.int32)).sum(-1).to(torch.uint8).contiguous()
+    dx = nv.conv_dgrad(dy, _w_bf16(w), x.shape, (3, 3), 1, 1, add=add, add_mask=mask)
+    report("conv_dgrad + masked add", dx, x.grad + add.float() * zpos.float(), 2e-2)
+    x1 = torch.randn(2, 64, 8, 8, device=dev).requires_grad_(True)
+    w1 = bf(torch.randn(128, 64, 1, 1, device=dev) * 0.1)
+    y1 = _conv_ref(x1, w1, 1, 0)
+    dy1 = cl(bf(torch.randn_like(y1)))
+    y1.backward(dy1.float())
+    dx1 = nv.conv_dgrad(dy1, _w_bf16(w1), x1.shape, (1, 1), 1, 0, add=add, add_mask=mask)
+    report("conv_dgrad 1x1 + masked add", dx1, x1.grad + add.float() * zpos.float(), 2e-2)
 
 
 def g_conv_wgrad():
@@ -367,6 +380,30 @@ def g_bn():
         report("  bwd dbeta", bg, br.grad, 2e-2)
         if res:
             report("  bwd dres", dres, rr.grad, 2e-2)
+        if res and relu:
+            # 1-bit ReLU mask path (what the residual blocks use): identical results without reading z in backward
+            rm3, rv3 = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+            z2, save2, zmask = nv.bn_act_fwd(y, None, gamma, beta, rm3, rv3, 1e-5, 0.1, relu, r, True, want_mask=True)
+            report("  bitmask fwd z", z2, z, 1e-6)
+            gg2, bg2 = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+            dy2, dres2, _ = nv.bn_act_bwd(dz, None, y, save2, gamma, relu, True, gg2, bg2, zmask=zmask)
+            report("  bitmask bwd dy", dy2, dy, 1e-6)
+            report("  bitmask bwd dres", dres2, dres, 1e-6)
+            report("  bitmask bwd dgamma", gg2, gg, 1e-5)
+    # odd widths (chunked thread mapping) with the bit mask
+    for c in (96, 320):
+        y = cl(bf(torch.randn(2, c, 6, 6, device=dev)))
+        r = cl(bf(torch.randn(2, c, 6, 6, device=dev)))
+        gamma, beta = torch.rand(c, device=dev) + 0.5, torch.randn(c, device=dev)
+        rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        z, save = nv.bn_act_fwd(y, None, gamma, beta, rm.clone(), rv.clone(), 1e-5, 0.1, True, r, True)
+        z2, save2, zmask = nv.bn_act_fwd(y, None, gamma, beta, rm, rv, 1e-5, 0.1, True, r, True, want_mask=True)
+        dz = cl(bf(torch.randn_like(z.float())))
+        g1, b1, g2, b2 = (torch.zeros(c, device=dev) for _ in range(4))
+        dy, dres, _ = nv.bn_act_bwd(dz, z, y, save, gamma, True, True, g1, b1)
+        dy2, dres2, _ = nv.bn_act_bwd(dz, None, y, save2, gamma, True, True, g2, b2, zmask=zmask)
+        report(f"  bitmask C={c} dy", dy2, dy, 1e-6)
+        report(f"  bitmask C={c} dres", dres2, dres, 1e-6)
 
 
 def g_sgd():
