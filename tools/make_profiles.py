@@ -106,8 +106,8 @@ def comm():
 
 
 def bench_lines():
-    L = ["# bench.py JSON lines collected this round (gpurun_out/*.json)", ""]
-    for p in sorted(glob.glob(os.path.join(G, "*.json"))):
+    L = ["# bench.py JSON lines collected this round (gpurun_out/*.json, oldest first: the progression of the build)", ""]
+    for p in sorted(glob.glob(os.path.join(G, "*.json")), key=os.path.getmtime):
         if os.path.basename(p).startswith((".", "layer_bench", "comm_sweep")):
             continue
         try:
@@ -121,7 +121,7 @@ def bench_lines():
         e2e = d.get("e2e") or {}
         L.append(f"* `{os.path.basename(p)}`: impl={d.get('impl')} n_gpus={d.get('n_gpus')} value={d['value']:.1f} {d.get('unit')} "
                  f"ms/step={d.get('ms_per_step'):.2f} e2e={e2e.get('value', float('nan')):.1f} launches={d.get('gpu_launches')} "
-                 f"clocks={d.get('clocks')}")
+                 f"graph={(d.get('config') or {}).get('cuda_graph')} clocks={d.get('clocks')}")
     open(os.path.join(P, "bench_lines.md"), "w").write("\n".join(L) + "\n")
 
 
