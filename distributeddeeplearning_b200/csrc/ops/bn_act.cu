@@ -343,11 +343,11 @@ cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStrea
   return cudaGetLastError();
 }
 
-cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream) {
+cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream, bool skip_reduce) {
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
   const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : (a.zmask ? kMaskBits : kMaskZ));
   const dim3 rgrid = bn_chunk_grid(a.M, a.C, sms);
-  switch (mask) {
+  if (!skip_reduce) switch (mask) {
     case kMaskNone: bn_act_bwd_reduce_kernel<kMaskNone><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     case kMaskZ: bn_act_bwd_reduce_kernel<kMaskZ><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     case kMaskBits: bn_act_bwd_reduce_kernel<kMaskBits><<<rgrid, kBnThreads, 0, stream>>>(a); break;

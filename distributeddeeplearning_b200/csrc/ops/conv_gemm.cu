@@ -150,14 +150,60 @@ DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, co
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
     const uint32_t p0 = stg + (sl * kRowsPer) * kPitch + cg * 16;
+    if (a.bnr_y == nullptr) {
 #pragma unroll
-    for (int r = 0; r < kRowsPer; ++r) {
-      const uint4 u = lds128(p0 + r * kPitch);
-      float2 f;
-      f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
-      f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
-      f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
-      f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
+      for (int r = 0; r < kRowsPer; ++r) {
+        const uint4 u = lds128(p0 + r * kPitch);
+        float2 f;
+        f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
+        f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
+        f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
+        f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
+      }
+    } else {
+      // fused BN-backward reduction (see ConvArgs::bnr_y): S1 = sum dm, S2 = sum dm * y with the ReLU mask of the BN
+      // recomputed from y.  The y tile is read with the same coalesced 16-byte accesses the stores below use.
+      const int c0 = n0 + cg * 8;
+      const bool cols_ok = c0 < a.n_valid;
+      float sc[8], sh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sc[i] = 0.f; sh[i] = 0.f; }
+      if (cols_ok) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const float4 g4 = reinterpret_cast<const float4*>(a.bnr_gamma + c0)[q];
+          const float4 b4 = reinterpret_cast<const float4*>(a.bnr_beta + c0)[q];
+          const float4 m4 = reinterpret_cast<const float4*>(a.bnr_mean + c0)[q];
+          const float4 i4 = reinterpret_cast<const float4*>(a.bnr_invstd + c0)[q];
+          sc[4 * q + 0] = g4.x * i4.x; sh[4 * q + 0] = b4.x - m4.x * sc[4 * q + 0];
+          sc[4 * q + 1] = g4.y * i4.y; sh[4 * q + 1] = b4.y - m4.y * sc[4 * q + 1];
+          sc[4 * q + 2] = g4.z * i4.z; sh[4 * q + 2] = b4.z - m4.z * sc[4 * q + 2];
+          sc[4 * q + 3] = g4.w * i4.w; sh[4 * q + 3] = b4.w - m4.w * sc[4 * q + 3];
+        }
+      }
+#pragma unroll 2
+      for (int r = 0; r < kRowsPer; ++r) {
+        const int row = sl * kRowsPer + r;
+        int m;
+        if (TILE) m = static_cast<int>(lds32(stg + row * kPitch + BLOCK_N * 2));
+        else m = (m0 + row) < a.M ? (m0 + row) : -1;
+        if (m < 0 || !cols_ok) continue;
+        const uint4 u = lds128(p0 + r * kPitch);
+        const uint4 yv = *reinterpret_cast<const uint4*>(a.bnr_y + static_cast<size_t>(m) * a.ldc + c0);
+        float2 d, y;
+        d = unpack_bf16x2(u.x); y = unpack_bf16x2(yv.x);
+        d.x = fmaf(y.x, sc[0], sh[0]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[1], sh[1]) > 0.f ? d.y : 0.f;
+        s[0] += d.x; ss[0] = fmaf(d.x, y.x, ss[0]); s[1] += d.y; ss[1] = fmaf(d.y, y.y, ss[1]);
+        d = unpack_bf16x2(u.y); y = unpack_bf16x2(yv.y);
+        d.x = fmaf(y.x, sc[2], sh[2]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[3], sh[3]) > 0.f ? d.y : 0.f;
+        s[2] += d.x; ss[2] = fmaf(d.x, y.x, ss[2]); s[3] += d.y; ss[3] = fmaf(d.y, y.y, ss[3]);
+        d = unpack_bf16x2(u.z); y = unpack_bf16x2(yv.z);
+        d.x = fmaf(y.x, sc[4], sh[4]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[5], sh[5]) > 0.f ? d.y : 0.f;
+        s[4] += d.x; ss[4] = fmaf(d.x, y.x, ss[4]); s[5] += d.y; ss[5] = fmaf(d.y, y.y, ss[5]);
+        d = unpack_bf16x2(u.w); y = unpack_bf16x2(yv.w);
+        d.x = fmaf(y.x, sc[6], sh[6]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[7], sh[7]) > 0.f ? d.y : 0.f;
+        s[6] += d.x; ss[6] = fmaf(d.x, y.x, ss[6]); s[7] += d.y; ss[7] = fmaf(d.y, y.y, ss[7]);
+      }
     }
     // threads with the same column group inside a warp: lanes cg, cg+kColGroups, ... -> xor shuffles
 #pragma unroll
@@ -177,12 +223,28 @@ DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, co
       sts128(rb + BLOCK_N * 4 + 16, __float_as_uint(ss[4]), __float_as_uint(ss[5]), __float_as_uint(ss[6]), __float_as_uint(ss[7]));
     }
     named_bar_sync(1, kEpiThreads);
-    for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
-      const int which = c / BLOCK_N, col = c - which * BLOCK_N;
-      float v = 0.f;
+    if (a.bnr_y == nullptr) {
+      for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
+        const int which = c / BLOCK_N, col = c - which * BLOCK_N;
+        float v = 0.f;
 #pragma unroll
-      for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += lds_f32(red + ((wq * 2 + which) * BLOCK_N + col) * 4);
-      if (n0 + col < a.n_valid) atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
+        for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += lds_f32(red + ((wq * 2 + which) * BLOCK_N + col) * 4);
+        if (n0 + col < a.n_valid) atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
+      }
+    } else {
+      for (int col = etid; col < BLOCK_N; col += kEpiThreads) {      // dbeta += S1, dgamma += invstd * (S2 - mean * S1)
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int wq = 0; wq < 4 * kEpiGroups; ++wq) {
+          t1 += lds_f32(red + ((wq * 2 + 0) * BLOCK_N + col) * 4);
+          t2 += lds_f32(red + ((wq * 2 + 1) * BLOCK_N + col) * 4);
+        }
+        const int ch = n0 + col;
+        if (ch < a.n_valid) {
+          atomicAdd(a.sum + ch, t1);
+          atomicAdd(a.sumsq + ch, a.bnr_invstd[ch] * (t2 - a.bnr_mean[ch] * t1));
+        }
+      }
     }
   }
   // coalesced stores: thread = (16-byte column chunk, row phase); a tile row is BLOCK_N*2 contiguous bytes

@@ -34,6 +34,16 @@ struct ConvArgs {
   const float* bias;          // optional: per output channel
   float* sum;                 // optional BN statistics: sum[c]   += sum_m out[m][c]   (of the bf16-rounded value)
   float* sumsq;               //                         sumsq[c] += sum_m out[m][c]^2
+  // optional (dgrad launches): fuse the BatchNorm-backward reduction of the layer whose output gradient this kernel
+  // produces.  With bnr_y != nullptr the statistics epilogue accumulates, per channel of `out`,
+  //   sum[c] += S1 = sum_m dm,   sumsq[c] += invstd[c] * (S2 - mean[c] * S1),  S2 = sum_m dm * y[m][c]
+  // where dm = out[m][c] * [gamma*invstd*(y - mean) + beta > 0] — i.e. dbeta and dgamma of that BN (ReLU mask
+  // recomputed from its saved input y), so the separate reduce pass over (d, y) is not needed.
+  const __nv_bfloat16* bnr_y;
+  const float* bnr_gamma;
+  const float* bnr_beta;
+  const float* bnr_mean;
+  const float* bnr_invstd;
   int M;                      // GEMM rows (= batch * dstH * dstW)
   int KB;                     // number of 64-element k-blocks
   int ldc;                    // channels of `out` (row stride in elements)

@@ -45,7 +45,8 @@ struct BnBwdArgs {
 };
 
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream);
-cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream);
+// skip_reduce: dgamma / dbeta scratch already hold this layer's sums (fused into the producing dgrad kernel's epilogue)
+cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream, bool skip_reduce = false);
 
 // per-channel sum / sumsq of a bf16 [M][C] tensor (used when the producer had no fused stats)
 cudaError_t launch_channel_stats(const __nv_bfloat16* x, float* sum, float* sumsq, int M, int C, int sms,

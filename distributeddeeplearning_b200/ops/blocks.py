@@ -18,12 +18,16 @@ the backward is scheduled.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
 from . import native
 from .functional import CL, grad_buffer, notify_ready, run_wgrad, weight_bf16
+
+
+FUSE_BN_REDUCE = os.environ.get("DDL_FUSE_BN_REDUCE", "0") != "0"      # tuning hook (A/B runs)
 
 
 class _ResidualBlock(torch.autograd.Function):
@@ -77,6 +81,7 @@ class _ResidualBlock(torch.autograd.Function):
         dres = None
         dx = None
         gated_add = None
+        pre = None
         for i in range(n_main - 1, -1, -1):
             w, g, b, _, _ = layers[i]
             st, pad, dil, _, _ = cfg["layers"][i]
@@ -92,13 +97,20 @@ class _ResidualBlock(torch.autograd.Function):
             gate = last and not has_ds and need_dx and native.dgrad_supports_add(
                 (layers[0][0].shape[2], layers[0][0].shape[3]), cfg["layers"][0][0])
             dy, dr, _ = native.bn_act_bwd(d, z, y, save, g, True, last and not gate, gg, bg, beta=b, had_residual=last,
-                                          zmask=zmask if last else None)
+                                          zmask=zmask if last else None, pre_reduced=pre)
             if gate:
                 gated_add = (dout, zmask)
             if last:
                 dres = dr
+            pre = None
             if i > 0:
-                d = native.conv_dgrad(dy, ctx.wbs[i], h_in.shape, kernel, st, pad, dil)
+                # the dgrad that produces d_{i-1} also reduces dbeta / dgamma of BN_{i-1} in its epilogue (it holds the
+                # gradient tile anyway and only has to read the y tile): BN_{i-1}'s backward is then one pass, not two
+                gp, bp = layers[i - 1][1], layers[i - 1][2]
+                pre = native.zeros_f32((2, h_in.shape[1]), h_in.device) if FUSE_BN_REDUCE else None
+                d = native.conv_dgrad(dy, ctx.wbs[i], h_in.shape, kernel, st, pad, dil,
+                                      bn_reduce=(saved[3 * (i - 1) + 1], gp, bp, saved[3 * (i - 1) + 2], pre)
+                                      if pre is not None else None)
             elif need_dx:
                 add = dres
                 if has_ds:

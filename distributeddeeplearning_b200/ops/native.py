@@ -264,9 +264,14 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
 
 
 def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[int, int], stride: int, pad,
-               dil: int = 1, add: Optional[torch.Tensor] = None, add_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+               dil: int = 1, add: Optional[torch.Tensor] = None, add_mask: Optional[torch.Tensor] = None,
+               bn_reduce: Optional[tuple] = None) -> torch.Tensor:
     """dx = conv_transpose(dy, w) (+ add [gated by the bit mask ``add_mask``: uint8 [M, Cin/8]]).
-    ``w_bf16`` is the forward matrix [Cout, R*S*Cin]."""
+    ``w_bf16`` is the forward matrix [Cout, R*S*Cin].
+
+    ``bn_reduce = (y, gamma, beta, save, scratch)``: dx is the output gradient of a BN+ReLU layer whose saved input is
+    ``y``; the kernel's epilogue then also accumulates that BN's dbeta / dgamma sums into ``scratch`` (fp32 [2, Cin],
+    zeroed), so ``bn_act_bwd(..., pre_reduced=scratch)`` can skip its reduction pass over (dx, y)."""
     C = _C()
     _check_act(dy, "dy")
     N, Cin, H, W = x_shape
@@ -295,25 +300,37 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
     n_total = _ceil_div(Cin, 64) * 64
     cch = _ceil_div(Cout, 64)
     wp, wr, wc = w_bf16.data_ptr(), w_bf16.shape[0], w_bf16.shape[1]
+    bnr = {}
+    s1 = s2 = 0
+    if bn_reduce is not None:
+        by, bgam, bbeta, bsave, bscr = bn_reduce
+        if add is not None:
+            raise ValueError("bn_reduce cannot be combined with add (the sums are taken before the epilogue add)")
+        if tuple(by.shape) != (N, Cin, H, W) or bscr.shape != (2, Cin):
+            raise ValueError("bn_reduce: y / scratch do not match dx")
+        _check_act(by, "bn_reduce.y")
+        bnr = dict(bnr_y=by.data_ptr(), bnr_gamma=bgam.data_ptr(), bnr_beta=bbeta.data_ptr(),
+                   bnr_mean=bsave[0].data_ptr(), bnr_invstd=bsave[1].data_ptr())
+        s1, s2 = bscr[0].data_ptr(), bscr[1].data_ptr()
     if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
-        C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, cch, Cin, P, Q, Cout, H,
+        C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, cch, Cin, P, Q, Cout, H,
                     W, 1, 1, 1, 0, 1, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, 0, 0, 0, 0, _stream(),
-                    0, 0, _ptr(add_mask))
+                    0, 0, _ptr(add_mask), **bnr)
     elif stride == 1 and USE_TILE_TMA:
         tw, th, tn = tile_geometry(H, W, N, 128)
-        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * cch, Cin, P, Q,
+        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, R * S * cch, Cin, P, Q,
                     Cout, H, W, R, S, 1, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, tw, th, tn,
-                    0, _stream(), pw, 0, _ptr(add_mask))
+                    0, _stream(), pw, 0, _ptr(add_mask), **bnr)
     elif s2_tile:
         # four stride-1 phase problems (one launch each), tiles iterate the half-resolution phase grid
         tw, th, tn = tile_geometry((H + 1) // 2, (W + 1) // 2, N, 128)
-        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, N * H * W, R * S * cch, Cin, P, Q,
+        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, s1, s2, N * H * W, R * S * cch, Cin, P, Q,
                     Cout, H, W, R, S, 2, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, tw, th, tn,
-                    zfill, _stream(), pw, 0)
+                    zfill, _stream(), pw, 0, 0, **bnr)
     else:
-        C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, R * S * cch,
+        C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, R * S * cch,
                     Cin, P, Q, Cout, H, W, R, S, stride, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, 0, 0, N, 0, 0, 0, 0,
-                    _stream(), pw, 0, _ptr(add_mask))
+                    _stream(), pw, 0, _ptr(add_mask), **bnr)
     return dx
 
 
@@ -460,8 +477,11 @@ def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, runn
 
 def bn_act_bwd(dz: torch.Tensor, z: Optional[torch.Tensor], y: torch.Tensor, save: torch.Tensor, gamma: torch.Tensor,
                relu: bool, want_dres: bool, gamma_grad: Optional[torch.Tensor], beta_grad: Optional[torch.Tensor],
-               beta: Optional[torch.Tensor] = None, had_residual: bool = True, zmask: Optional[torch.Tensor] = None):
+               beta: Optional[torch.Tensor] = None, had_residual: bool = True, zmask: Optional[torch.Tensor] = None,
+               pre_reduced: Optional[torch.Tensor] = None):
     """Returns (dy, dres|None, scratch); accumulates into gamma_grad / beta_grad (fp32) when given.
+    ``pre_reduced``: fp32 [2, C] holding (dbeta, dgamma) already (``conv_dgrad(..., bn_reduce=...)``): only the
+    elementwise pass runs.
 
     ReLU mask source: recomputed from y when the layer had no residual (``beta`` given), else the bit mask written by
     the forward (``zmask``), else the saved output ``z``."""
@@ -471,14 +491,16 @@ def bn_act_bwd(dz: torch.Tensor, z: Optional[torch.Tensor], y: torch.Tensor, sav
     M = N * H * W
     dy = torch.empty_like(y)
     dres = torch.empty_like(y) if want_dres else None
-    scratch = zeros_f32((2, Ch), y.device)
+    scratch = pre_reduced if pre_reduced is not None else zeros_f32((2, Ch), y.device)
     mask_from_x = bool(relu and beta is not None and not had_residual)     # z is not read at all in that case
+    if pre_reduced is not None and not mask_from_x:
+        raise ValueError("pre_reduced sums are only defined for BN+ReLU layers without residual")
     if relu and not mask_from_x and zmask is None and z is None:
         raise ValueError("bn_act_bwd: need z or zmask for the ReLU mask of a residual layer")
     C.bn_act_bwd(dz.data_ptr(), _ptr(z), y.data_ptr(), dy.data_ptr(), _ptr(dres), save[0].data_ptr(),
                  save[1].data_ptr(), gamma.data_ptr(), _ptr(beta), scratch[0].data_ptr(), scratch[1].data_ptr(),
                  _ptr(gamma_grad), _ptr(beta_grad), M, Ch, int(relu), int(mask_from_x), sm_count(y.device.index or 0),
-                 _stream(), _ptr(zmask) if (relu and not mask_from_x) else 0)
+                 _stream(), _ptr(zmask) if (relu and not mask_from_x) else 0, pre_reduced is not None)
     return dy, dres, scratch
 
 

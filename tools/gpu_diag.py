@@ -275,6 +275,27 @@ def g_conv_dgrad():
     yr.backward(dy.float())
     dx = nv.conv_dgrad(dy, _w_bf16(w), x.shape, (3, 3), 1, 1, add=add)
     report("conv_dgrad + add", dx, x.grad + add.float(), 2e-2)
+    # BN-backward reduction fused into the dgrad epilogue: dbeta / dgamma sums equal the stand-alone reduce kernel's
+    for (n, ci, h, co, k, s_, p_) in [(2, 64, 12, 128, 3, 1, 1), (3, 128, 9, 256, 1, 1, 0), (2, 64, 16, 64, 3, 2, 1),
+                                      (2, 96, 10, 160, 1, 1, 0), (4, 256, 14, 64, 1, 1, 0)]:
+        xs = (n, ci, h, h)
+        w_ = bf(torch.randn(co, ci, k, k, device=dev) * (1.0 / (co * k * k) ** 0.5))
+        ho = (h + 2 * p_ - k) // s_ + 1
+        dyv = cl(bf(torch.randn(n, co, ho, ho, device=dev)))
+        ybn = cl(bf(torch.randn(*xs, device=dev) * 1.5 + 0.3))
+        gam, bet = torch.rand(ci, device=dev) + 0.5, torch.randn(ci, device=dev) * 0.3
+        save = torch.stack([ybn.float().mean((0, 2, 3)), 1.0 / (ybn.float().var((0, 2, 3), unbiased=False) + 1e-5).sqrt()]).contiguous()
+        pre = torch.zeros(2, ci, device=dev)
+        d_fused = nv.conv_dgrad(dyv, _w_bf16(w_), xs, (k, k), s_, p_, bn_reduce=(ybn, gam, bet, save, pre))
+        d_plain = nv.conv_dgrad(dyv, _w_bf16(w_), xs, (k, k), s_, p_)
+        report(f"dgrad+bn-reduce c{ci}<-{co} k{k}s{s_}: dx unchanged", d_fused, d_plain, 1e-6)
+        zdummy = torch.empty_like(ybn)
+        dy_a, _, scr = nv.bn_act_bwd(d_plain, zdummy, ybn, save, gam, True, False, None, None, beta=bet, had_residual=False)
+        report("   dbeta", pre[0], scr[0], 2e-3, atol=2e-3)
+        report("   dgamma", pre[1], scr[1], 2e-3, atol=2e-3)
+        dy_b, _, _ = nv.bn_act_bwd(d_plain, zdummy, ybn, save, gam, True, False, None, None, beta=bet, had_residual=False,
+                                   pre_reduced=pre)
+        report("   bn apply from fused sums", dy_b, dy_a, 2e-3)
     # epilogue add gated by a ReLU bit mask (shortcut gradient of an identity residual block)
     zpos = torch.rand(2, 64, 8, 8, device=dev) > 0.5
     bits = cl(zpos.to(torch.uint8)).permute(0, 2, 3, 1).reshape(-1, 8, 8)       # [M, C/8, 8]
