@@ -272,6 +272,30 @@ PYBIND11_MODULE(_C, m) {
      py::arg("gamma"), py::arg("beta"), py::arg("dgamma"), py::arg("dbeta"), py::arg("gamma_grad"), py::arg("beta_grad"),
      py::arg("M"), py::arg("C"), py::arg("relu"), py::arg("mask_from_x"), py::arg("sms"), py::arg("stream"),
      py::arg("zmask") = 0, py::arg("skip_reduce") = false);
+  m.def("bn_relu_maxpool_fwd", [](ptr_t x, ptr_t pooled, ptr_t argmax, ptr_t sum, ptr_t sumsq, ptr_t gamma, ptr_t beta,
+                                  ptr_t mean, ptr_t invstd, ptr_t rmean, ptr_t rvar, float eps, float momentum, int N, int H,
+                                  int W, int C, int Pq, int Q, int k, int stride, int pad, int sms, ptr_t stream) {
+    BnFwdArgs a;
+    a.x = P<const __nv_bfloat16>(x); a.residual = nullptr; a.z = nullptr; a.mask = nullptr;
+    a.sum = P<const float>(sum); a.sumsq = P<const float>(sumsq); a.gamma = P<const float>(gamma);
+    a.beta = P<const float>(beta); a.mean = P<float>(mean); a.invstd = P<float>(invstd);
+    a.running_mean = P<float>(rmean); a.running_var = P<float>(rvar); a.eps = eps; a.momentum = momentum;
+    a.M = N * H * W; a.C = C; a.relu = 1;
+    check(ddl::launch_bn_relu_maxpool_fwd(a, pool_args(N, H, W, C, Pq, Q, k, stride, pad), P<__nv_bfloat16>(pooled),
+                                          P<uint8_t>(argmax), sms, S(stream)), "bn_relu_maxpool_fwd");
+  });
+  m.def("bn_pool_bwd", [](ptr_t dy_pooled, ptr_t argmax, ptr_t x, ptr_t dx, ptr_t mean, ptr_t invstd, ptr_t gamma, ptr_t beta,
+                          ptr_t dgamma, ptr_t dbeta, ptr_t gamma_grad, ptr_t beta_grad, int N, int H, int W, int C, int Pq,
+                          int Q, int k, int stride, int pad, int sms, ptr_t stream) {
+    BnBwdArgs a;
+    a.dz = nullptr; a.z = nullptr; a.x = P<const __nv_bfloat16>(x); a.dx = P<__nv_bfloat16>(dx); a.dres = nullptr;
+    a.mean = P<const float>(mean); a.invstd = P<const float>(invstd); a.gamma = P<const float>(gamma);
+    a.beta = P<const float>(beta); a.dgamma = P<float>(dgamma); a.dbeta = P<float>(dbeta);
+    a.gamma_grad = P<float>(gamma_grad); a.beta_grad = P<float>(beta_grad); a.M = N * H * W; a.C = C; a.relu = 1;
+    a.mask_from_x = 1; a.zmask = nullptr;
+    check(ddl::launch_bn_pool_bwd(a, pool_args(N, H, W, C, Pq, Q, k, stride, pad), P<const __nv_bfloat16>(dy_pooled),
+                                  P<const uint8_t>(argmax), sms, S(stream)), "bn_pool_bwd");
+  });
   m.def("channel_stats", [](ptr_t x, ptr_t sum, ptr_t sumsq, int M, int C, int sms, ptr_t stream) {
     check(ddl::launch_channel_stats(P<const __nv_bfloat16>(x), P<float>(sum), P<float>(sumsq), M, C, sms, S(stream)),
           "channel_stats");

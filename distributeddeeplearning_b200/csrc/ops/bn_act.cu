@@ -297,6 +297,215 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdAr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// stem fusion: conv -> BN -> ReLU -> max-pool (ResNet / DenseNet first layers)
+// ---------------------------------------------------------------------------------------------
+// forward: the BN+ReLU output (the largest activation of the network, 112 x 112 x 64 per image) is never written —
+// each pooled pixel applies scale/shift to its window of the raw conv output and keeps max + arg-max code.
+// backward: BN's input gradient dz is rebuilt on the fly from the pooled gradient and the arg-max codes (the
+// gather of maxpool_bwd_kernel), so neither max-pool backward's 112 x 112 output nor its two re-reads exist.
+template <bool CHUNKED_UNUSED = false>
+DDL_DEVICE void bn_scale_shift(const BnFwdArgs& a, int c0, bool writer, float (&scale)[8], float (&shift)[8]) {
+  Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
+  Vec8 s = load8_f32(a.sum + c0), ss = load8_f32(a.sumsq + c0);
+  const float inv_n = 1.f / static_cast<float>(a.M);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float mean = s.v[i] * inv_n;
+    const float var = fmaxf(ss.v[i] * inv_n - mean * mean, 0.f);
+    const float invstd = rsqrtf(var + a.eps);
+    scale[i] = gam.v[i] * invstd;
+    shift[i] = bet.v[i] - mean * scale[i];
+    if (writer) {
+      a.mean[c0 + i] = mean;
+      a.invstd[c0 + i] = invstd;
+      if (a.running_mean) {
+        const float unbiased = a.M > 1 ? var * static_cast<float>(a.M) / static_cast<float>(a.M - 1) : var;
+        a.running_mean[c0 + i] = (1.f - a.momentum) * a.running_mean[c0 + i] + a.momentum * mean;
+        a.running_var[c0 + i] = (1.f - a.momentum) * a.running_var[c0 + i] + a.momentum * unbiased;
+      }
+    }
+  }
+}
+
+// block = one 64-channel chunk x 32 pooled-pixel lanes (same mapping as the reduce kernel: any C % 8 == 0)
+__global__ void __launch_bounds__(kBnThreads, 4)
+bn_relu_maxpool_fwd_kernel(BnFwdArgs a, PoolArgs p, __nv_bfloat16* pooled, uint8_t* argmax) {
+  const int c0 = blockIdx.y * 64 + (threadIdx.x & 7) * 8;
+  if (c0 >= a.C) return;
+  const int lane = blockIdx.x * 32 + (threadIdx.x >> 3);
+  float scale[8], shift[8];
+  bn_scale_shift(a, c0, lane == 0, scale, shift);
+  const int total = p.N * p.P * p.Q;
+  for (int o = lane; o < total; o += gridDim.x * 32) {
+    const int q = o % p.Q;
+    const int t = o / p.Q;
+    const int pp = t % p.P;
+    const int n = t / p.P;
+    float best[8];
+    uint32_t code[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; code[i] = 0; }
+    for (int r = 0; r < p.k; ++r) {
+      const int h = pp * p.stride - p.pad + r;
+      if (h < 0 || h >= p.H) continue;
+      for (int sx = 0; sx < p.k; ++sx) {
+        const int w = q * p.stride - p.pad + sx;
+        if (w < 0 || w >= p.W) continue;
+        float v[8];
+        unpack8(ld_stream_u4(a.x + ((static_cast<size_t>(n) * p.H + h) * p.W + w) * a.C + c0), v);
+        const uint32_t cd = r * p.k + sx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float z = bf16_round(fmaf(v[i], scale[i], shift[i]));     // the value the unfused path would store
+          if (z > best[i]) { best[i] = z; code[i] = cd; }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) best[i] = fmaxf(best[i], 0.f);           // ReLU commutes with max
+    const size_t off = static_cast<size_t>(o) * a.C + c0;
+    store8_bf16(pooled + off, best);
+    uint2 am;
+    am.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+    am.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+    *reinterpret_cast<uint2*>(argmax + off) = am;
+  }
+}
+
+// gradient of the max-pool input pixel (n, h, w), channels [c0, c0+8): sum of the pooled gradients of the windows
+// whose arg-max is this pixel
+DDL_DEVICE void pool_gather(const __nv_bfloat16* __restrict__ dyp, const uint8_t* __restrict__ argmax, const PoolArgs& p,
+                            int C, int n, int h, int w, int c0, float (&acc)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const int pp_hi = (h + p.pad) / p.stride, q_hi = (w + p.pad) / p.stride;
+  for (int pp = pp_hi; pp >= 0; --pp) {
+    const int r = h + p.pad - pp * p.stride;
+    if (r >= p.k) break;
+    if (pp >= p.P) continue;
+    for (int q = q_hi; q >= 0; --q) {
+      const int sx = w + p.pad - q * p.stride;
+      if (sx >= p.k) break;
+      if (q >= p.Q) continue;
+      const size_t o = ((static_cast<size_t>(n) * p.P + pp) * p.Q + q) * C + c0;
+      const uint2 am = *reinterpret_cast<const uint2*>(argmax + o);
+      float v[8];
+      unpack8(*reinterpret_cast<const uint4*>(dyp + o), v);
+      const uint32_t code = r * p.k + sx;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t ai = ((i < 4 ? am.x : am.y) >> (8 * (i & 3))) & 0xffu;
+        if (ai == code) acc[i] += v[i];
+      }
+    }
+  }
+}
+
+// pass 1 of the fused stem backward: S1 = sum dm, S2 = sum dm * x with dm = pool_gather(...) * [x*scale + shift > 0]
+__global__ void __launch_bounds__(kBnThreads, 4)
+bn_pool_bwd_reduce_kernel(BnBwdArgs a, PoolArgs p, const __nv_bfloat16* __restrict__ dyp,
+                          const uint8_t* __restrict__ argmax) {
+  const int cgl = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.y * 64 + cgl * 8;
+  const bool live = c0 < a.C;
+  float s1[8], s2[8], msc[8], msh[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s1[i] = 0.f; s2[i] = 0.f; msc[i] = 0.f; msh[i] = 0.f; }
+  if (live) {
+    Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0);
+    Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { msc[i] = gam.v[i] * invstd.v[i]; msh[i] = bet.v[i] - mean.v[i] * msc[i]; }
+  }
+  for (int r = live ? blockIdx.x * 32 + rl : a.M; r < a.M; r += gridDim.x * 32) {
+    const int w = r % p.W;
+    const int t = r / p.W;
+    const int h = t % p.H;
+    const int n = t / p.H;
+    float dz[8], x[8];
+    unpack8(ld_stream_u4(a.x + static_cast<size_t>(r) * a.C + c0), x);
+    pool_gather(dyp, argmax, p, a.C, n, h, w, c0, dz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dm = fmaf(x[i], msc[i], msh[i]) > 0.f ? dz[i] : 0.f;
+      s1[i] += dm;
+      s2[i] = fmaf(dm, x[i], s2[i]);
+    }
+  }
+#pragma unroll
+  for (int off = 8; off < 32; off <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+      s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+    }
+  }
+  __shared__ float red[kBnThreads / 32][8][16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[warp][lane][i] = s1[i]; red[warp][lane][8 + i] = s2[i]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int g = threadIdx.x >> 3, i = threadIdx.x & 7;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < kBnThreads / 32; ++wv) { t1 += red[wv][g][i]; t2 += red[wv][g][8 + i]; }
+    const int ch = blockIdx.y * 64 + g * 8 + i;
+    if (ch < a.C) {
+      atomicAdd(a.dbeta + ch, t1);
+      atomicAdd(a.dgamma + ch, a.invstd[ch] * (t2 - a.mean[ch] * t1));
+    }
+  }
+}
+
+// pass 2: dx = k1*dm + x*B + A (see bn_act_bwd_apply_kernel) with dm rebuilt from the pooled gradient
+__global__ void __launch_bounds__(kBnThreads, 4)
+bn_pool_bwd_apply_kernel(BnBwdArgs a, PoolArgs p, const __nv_bfloat16* __restrict__ dyp,
+                         const uint8_t* __restrict__ argmax) {
+  const int c0 = blockIdx.y * 64 + (threadIdx.x & 7) * 8;
+  if (c0 >= a.C) return;
+  const int row0 = blockIdx.x * 32 + (threadIdx.x >> 3);
+  float k1[8], cA[8], cB[8], msh[8];
+  {
+    Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0), gam = load8_f32(a.gamma + c0);
+    Vec8 db = load8_f32(a.dbeta + c0), dg = load8_f32(a.dgamma + c0), bet = load8_f32(a.beta + c0);
+    const float inv_n = 1.f / static_cast<float>(a.M);
+    if (row0 == 0 && a.gamma_grad) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a.gamma_grad[c0 + i] += dg.v[i];
+        a.beta_grad[c0 + i] += db.v[i];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      k1[i] = gam.v[i] * invstd.v[i];
+      cB[i] = -k1[i] * invstd.v[i] * dg.v[i] * inv_n;
+      cA[i] = -k1[i] * db.v[i] * inv_n - mean.v[i] * cB[i];
+      msh[i] = bet.v[i] - mean.v[i] * k1[i];
+    }
+  }
+  for (int r = row0; r < a.M; r += gridDim.x * 32) {
+    const int w = r % p.W;
+    const int t = r / p.W;
+    const int h = t % p.H;
+    const int n = t / p.H;
+    const size_t off = static_cast<size_t>(r) * a.C + c0;
+    float dz[8], x[8];
+    unpack8(ld_stream_u4(a.x + off), x);
+    pool_gather(dyp, argmax, p, a.C, n, h, w, c0, dz);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float dm = fmaf(x[i], k1[i], msh[i]) > 0.f ? dz[i] : 0.f;
+      x[i] = fmaf(dm, k1[i], fmaf(x[i], cB[i], cA[i]));
+    }
+    store8_bf16(a.dx + off, x);
+  }
+}
+
 // grid: every block must hold a whole number of channel groups AND total threads % groups == 0
 inline int bn_grid(int M, int C, int sms) {
   const int groups = C / 8;
@@ -371,6 +580,26 @@ cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream, 
       default: bn_act_bwd_apply_kernel<kMaskX, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     }
   }
+  return cudaGetLastError();
+}
+
+
+cudaError_t launch_bn_relu_maxpool_fwd(const BnFwdArgs& a, const PoolArgs& p, __nv_bfloat16* pooled, uint8_t* argmax,
+                                       int sms, cudaStream_t stream) {
+  if (a.C % 8 != 0 || a.C <= 0 || a.M != p.N * p.H * p.W || a.C != p.C || p.k * p.k > 255) return cudaErrorInvalidValue;
+  const dim3 grid = bn_chunk_grid(p.N * p.P * p.Q, a.C, sms);
+  bn_relu_maxpool_fwd_kernel<<<grid, kBnThreads, 0, stream>>>(a, p, pooled, argmax);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bn_pool_bwd(const BnBwdArgs& a, const PoolArgs& p, const __nv_bfloat16* dy_pooled, const uint8_t* argmax,
+                               int sms, cudaStream_t stream) {
+  if (a.C % 8 != 0 || a.C <= 0 || a.M != p.N * p.H * p.W || a.C != p.C) return cudaErrorInvalidValue;
+  const dim3 grid = bn_chunk_grid(a.M, a.C, sms);
+  bn_pool_bwd_reduce_kernel<<<grid, kBnThreads, 0, stream>>>(a, p, dy_pooled, argmax);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  bn_pool_bwd_apply_kernel<<<grid, kBnThreads, 0, stream>>>(a, p, dy_pooled, argmax);
   return cudaGetLastError();
 }
 

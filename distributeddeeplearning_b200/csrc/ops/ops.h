@@ -56,6 +56,12 @@ cudaError_t launch_channel_stats(const __nv_bfloat16* x, float* sum, float* sums
 struct PoolArgs {
   int N, H, W, C, P, Q, k, stride, pad;
 };
+// stem fusion (conv -> BN -> ReLU -> max-pool): forward writes only the pooled activation + arg-max codes, backward
+// rebuilds BN's input gradient from the pooled gradient (train mode; a.x = raw conv output [N*H*W][C])
+cudaError_t launch_bn_relu_maxpool_fwd(const BnFwdArgs& a, const PoolArgs& p, __nv_bfloat16* pooled, uint8_t* argmax,
+                                       int sms, cudaStream_t stream);
+cudaError_t launch_bn_pool_bwd(const BnBwdArgs& a, const PoolArgs& p, const __nv_bfloat16* dy_pooled, const uint8_t* argmax,
+                               int sms, cudaStream_t stream);
 cudaError_t launch_maxpool_fwd(const __nv_bfloat16* x, __nv_bfloat16* y, uint8_t* argmax, const PoolArgs& p,
                                cudaStream_t stream);
 cudaError_t launch_maxpool_bwd(const __nv_bfloat16* dy, const uint8_t* argmax, __nv_bfloat16* dx, const PoolArgs& p,

@@ -12,7 +12,7 @@ from __future__ import annotations
 import torch.nn as nn
 
 from .. import ops
-from .layers import BatchNorm2d, Conv2d, Linear, bn_act, conv_bn, prepare_input
+from .layers import BatchNorm2d, Conv2d, Linear, bn_act, conv_bn, conv_bn_pool, prepare_input
 
 
 class _DenseLayer(nn.Module):
@@ -68,8 +68,7 @@ class _Features(nn.Module):
         self.out_channels = c
 
     def forward(self, x):
-        x = conv_bn(x, self.conv0, self.norm0, relu=True)
-        x = ops.max_pool2d(x, 3, 2, 1)
+        x = conv_bn_pool(x, self.conv0, self.norm0, 3, 2, 1)
         for name, m in self.named_children():
             if name.startswith(("denseblock", "transition")):
                 x = m(x)

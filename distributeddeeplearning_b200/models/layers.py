@@ -77,6 +77,12 @@ def conv_bn(x, conv: Conv2d, bn: BatchNorm2d, relu=True, residual=None):
                            conv.dilation, bn.eps, bn.momentum, relu, residual, bn.training)
 
 
+def conv_bn_pool(x, conv: Conv2d, bn: BatchNorm2d, kernel=3, stride=2, padding=1):
+    """maxpool(relu(BN(conv(x)))) — stem unit (fused on the native training path)."""
+    return ops.conv_bn_act_maxpool(x, conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, conv.stride,
+                                   conv.padding, conv.dilation, bn.eps, bn.momentum, bn.training, kernel, stride, padding)
+
+
 def bn_act(x, bn: BatchNorm2d, relu=True):
     """act(BN(x)) on its own (pre-activation networks)."""
     return ops.batch_norm_act(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, relu,

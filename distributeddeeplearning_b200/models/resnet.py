@@ -14,7 +14,7 @@ import torch.nn as nn
 
 from .. import ops
 from ..ops.blocks import residual_block, residual_block_supported
-from .layers import BatchNorm2d, Conv2d, Linear, conv_bn, prepare_input
+from .layers import BatchNorm2d, Conv2d, Linear, conv_bn, prepare_input, conv_bn_pool
 
 
 class BasicBlock(nn.Module):
@@ -103,8 +103,7 @@ class ResNet(nn.Module):
 
     def forward(self, x):
         x = prepare_input(x)
-        x = conv_bn(x, self.conv1, self.bn1, relu=True)
-        x = ops.max_pool2d(x, 3, 2, 1)
+        x = conv_bn_pool(x, self.conv1, self.bn1, 3, 2, 1)      # conv1 + bn1 + relu + maxpool as one unit
         x = self.layer1(x)
         x = self.layer2(x)
         x = self.layer3(x)

@@ -5,6 +5,7 @@ from .functional import (  # noqa: F401
     concat_channels,
     conv_bias_act,
     conv_bn_act,
+    conv_bn_act_maxpool,
     dropout,
     global_avg_pool,
     linear,

@@ -201,6 +201,61 @@ def conv_bn_act(x, weight, gamma, beta, running_mean, running_var, stride=1, pad
 
 
 # ------------------------------------------------------------------------------------------------
+# stem: conv + BN(train) + ReLU + max-pool as one unit (ResNet / DenseNet first layers)
+# ------------------------------------------------------------------------------------------------
+class _ConvBnActPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, stride, pad, dil, eps, momentum, pk, ps, pp):
+        R, S = weight.shape[2], weight.shape[3]
+        wb = weight_bf16(weight)
+        y, stats = native.conv_fwd(x, wb, (R, S), stride, pad, dil, stats=True, cout=weight.shape[0])
+        pooled, arg, save = native.bn_relu_maxpool_fwd(y, stats, gamma, beta, running_mean, running_var, eps, momentum,
+                                                       pk, ps, pp)
+        ctx.cfg = (stride, pad, dil, (R, S), (pk, ps, pp))
+        ctx.params = (weight, gamma, beta)
+        ctx.wb = wb
+        ctx.save_for_backward(x, y, arg, save)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, dpooled):
+        stride, pad, dil, kernel, (pk, ps, pp) = ctx.cfg
+        weight, gamma, beta = ctx.params
+        x, y, arg, save = ctx.saved_tensors
+        if not dpooled.is_contiguous(memory_format=CL):
+            dpooled = dpooled.contiguous(memory_format=CL)
+        gg = grad_buffer(gamma) if gamma.requires_grad else None
+        bg = grad_buffer(beta) if beta.requires_grad else None
+        dy = native.bn_pool_bwd(dpooled, arg, y, save, gamma, beta, gg, bg, pk, ps, pp)
+        dx = native.conv_dgrad(dy, ctx.wb, x.shape, kernel, stride, pad, dil) if ctx.needs_input_grad[0] else None
+        if weight.requires_grad:
+            gw = grad_buffer(weight)
+            run_wgrad(weight, lambda: native.conv_wgrad(x, dy, gw, kernel, stride, pad, dil), x, dy)
+        if gamma.requires_grad:
+            notify_ready(gamma)
+            notify_ready(beta)
+        if weight.requires_grad:
+            notify_ready(weight)
+        return (dx,) + (None,) * 13
+
+
+FUSE_STEM_POOL = os.environ.get("DDL_FUSE_STEM_POOL", "1") != "0"      # tuning hook (A/B runs)
+
+
+def conv_bn_act_maxpool(x, weight, gamma, beta, running_mean, running_var, stride=1, pad=0, dil=1, eps=1e-5,
+                        momentum=0.1, training=True, pool_kernel=3, pool_stride=2, pool_pad=1):
+    """maxpool(relu(BN(conv(x)))) — the stem of ResNet / DenseNet.  In training on the native path the BN output (the
+    largest activation of the network) is never materialised; everywhere else this is conv_bn_act + max_pool2d."""
+    if FUSE_STEM_POOL and training and use_native(x) and native.supports_conv(x.shape[1], weight.shape[0]) \
+            and native.bn_supported(weight.shape[0]) and _krsc(weight) and torch.is_grad_enabled():
+        return _ConvBnActPool.apply(x, weight, gamma, beta, running_mean, running_var, stride, pad, dil, eps, momentum,
+                                    pool_kernel, pool_stride, pool_pad)
+    z = conv_bn_act(x, weight, gamma, beta, running_mean, running_var, stride, pad, dil, eps, momentum, True, None,
+                    training)
+    return max_pool2d(z, pool_kernel, pool_stride, pool_pad)
+
+
+# ------------------------------------------------------------------------------------------------
 # standalone BN(train/eval) + ReLU on a tensor (pre-activation nets: DenseNet's norm -> relu -> conv)
 # ------------------------------------------------------------------------------------------------
 class _BnAct(torch.autograd.Function):

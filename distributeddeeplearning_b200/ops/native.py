@@ -505,6 +505,41 @@ def bn_act_bwd(dz: torch.Tensor, z: Optional[torch.Tensor], y: torch.Tensor, sav
 
 
 # ------------------------------------------------------------------------------------------------
+# stem fusion: BN(train) + ReLU + max-pool on a raw conv output, and its backward
+# ------------------------------------------------------------------------------------------------
+def bn_relu_maxpool_fwd(y: torch.Tensor, stats: torch.Tensor, gamma, beta, running_mean, running_var, eps: float,
+                        momentum: float, k: int, stride: int, pad: int):
+    """pooled = maxpool(relu(BN_train(y))) without materialising the BN output.  Returns (pooled, argmax, save)."""
+    C = _C()
+    _check_act(y, "y")
+    N, Ch, H, W = y.shape
+    P, Q = _pool_out(H, k, stride, pad, False), _pool_out(W, k, stride, pad, False)
+    pooled = empty_act(N, Ch, P, Q, y.device)
+    arg = torch.empty((N, P, Q, Ch), dtype=torch.uint8, device=y.device)
+    save = torch.empty((2, Ch), dtype=torch.float32, device=y.device)
+    C.bn_relu_maxpool_fwd(y.data_ptr(), pooled.data_ptr(), arg.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                          gamma.data_ptr(), beta.data_ptr(), save[0].data_ptr(), save[1].data_ptr(), _ptr(running_mean),
+                          _ptr(running_var), eps, momentum, N, H, W, Ch, P, Q, k, stride, pad, sm_count(y.device.index or 0),
+                          _stream())
+    return pooled, arg, save
+
+
+def bn_pool_bwd(dy_pooled: torch.Tensor, arg: torch.Tensor, y: torch.Tensor, save: torch.Tensor, gamma, beta,
+                gamma_grad: Optional[torch.Tensor], beta_grad: Optional[torch.Tensor], k: int, stride: int, pad: int):
+    """Gradient wrt the raw conv output y of maxpool(relu(BN(y))) given the pooled gradient (2 kernels: reduce, apply)."""
+    C = _C()
+    _check_act(dy_pooled, "dy_pooled")
+    N, Ch, H, W = y.shape
+    P, Q = dy_pooled.shape[2], dy_pooled.shape[3]
+    dy = torch.empty_like(y)
+    scratch = zeros_f32((2, Ch), y.device)
+    C.bn_pool_bwd(dy_pooled.data_ptr(), arg.data_ptr(), y.data_ptr(), dy.data_ptr(), save[0].data_ptr(), save[1].data_ptr(),
+                  gamma.data_ptr(), beta.data_ptr(), scratch[1].data_ptr(), scratch[0].data_ptr(), _ptr(gamma_grad),
+                  _ptr(beta_grad), N, H, W, Ch, P, Q, k, stride, pad, sm_count(y.device.index or 0), _stream())
+    return dy
+
+
+# ------------------------------------------------------------------------------------------------
 # pooling
 # ------------------------------------------------------------------------------------------------
 def maxpool_fwd(x: torch.Tensor, k: int, stride: int, pad: int, ceil_mode: bool = False):

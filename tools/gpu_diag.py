@@ -411,6 +411,26 @@ def g_bn():
             report("  bitmask bwd dy", dy2, dy, 1e-6)
             report("  bitmask bwd dres", dres2, dres, 1e-6)
             report("  bitmask bwd dgamma", gg2, gg, 1e-5)
+    # fused stem: maxpool(relu(BN(y))) forward without the BN output, backward rebuilt from the pooled gradient
+    for (n, c, h, w_) in [(2, 64, 16, 16), (3, 96, 11, 13), (2, 64, 112, 112)]:
+        y = cl(bf(torch.randn(n, c, h, w_, device=dev) * 2 + 0.5))
+        gamma, beta = torch.rand(c, device=dev) + 0.5, torch.randn(c, device=dev) * 0.5
+        rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        stats = torch.stack([y.float().sum((0, 2, 3)), (y.float() ** 2).sum((0, 2, 3))]).contiguous()
+        pooled, arg, save = nv.bn_relu_maxpool_fwd(y, stats, gamma, beta, rm, rv, 1e-5, 0.1, 3, 2, 1)
+        yr = y.float().contiguous().requires_grad_(True)
+        gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        rm2, rv2 = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+        pr = F.max_pool2d(torch.relu(F.batch_norm(yr, rm2, rv2, gr, br, True, 0.1, 1e-5)), 3, 2, 1)
+        report(f"stem bn+relu+maxpool fwd c{c} {h}x{w_}", pooled, pr.detach(), 2e-2)
+        report("  running_var", rv, rv2, 1e-2)
+        dp = cl(bf(torch.randn_like(pr)))
+        pr.backward(dp.float().contiguous())
+        gg, bg = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
+        dyv = nv.bn_pool_bwd(dp, arg, y, save, gamma, beta, gg, bg, 3, 2, 1)
+        report("  stem bwd dy", dyv, yr.grad, 3e-2)
+        report("  stem bwd dgamma", gg, gr.grad, 2e-2, atol=1e-1)
+        report("  stem bwd dbeta", bg, br.grad, 2e-2, atol=1e-1)
     # odd widths (chunked thread mapping) with the bit mask
     for c in (96, 320):
         y = cl(bf(torch.randn(2, c, 6, 6, device=dev)))
