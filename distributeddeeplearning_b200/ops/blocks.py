@@ -27,7 +27,10 @@ from . import native
 from .functional import CL, grad_buffer, notify_ready, run_wgrad, weight_bf16
 
 
-FUSE_BN_REDUCE = os.environ.get("DDL_FUSE_BN_REDUCE", "0") != "0"      # tuning hook (A/B runs)
+# Measured on B200 (ResNet-50, batch 256): folding the BN-backward reduction into the producing dgrad's epilogue removes
+# 32 launches and one read of each inner gradient tensor but makes those (already epilogue-bound) dgrads slower: net
+# +0.4 ms/step.  Off unless DDL_FUSE_BN_REDUCE=1.
+FUSE_BN_REDUCE = os.environ.get("DDL_FUSE_BN_REDUCE", "0") != "0"
 
 
 class _ResidualBlock(torch.autograd.Function):

@@ -311,7 +311,7 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
         _check_act(by, "bn_reduce.y")
         bnr = dict(bnr_y=by.data_ptr(), bnr_gamma=bgam.data_ptr(), bnr_beta=bbeta.data_ptr(),
                    bnr_mean=bsave[0].data_ptr(), bnr_invstd=bsave[1].data_ptr())
-        s1, s2 = bscr[0].data_ptr(), bscr[1].data_ptr()
+        s1, s2 = bscr[1].data_ptr(), bscr[0].data_ptr()      # scratch layout of bn_act_bwd: [0] = dgamma, [1] = dbeta
     if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
         C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, cch, Cin, P, Q, Cout, H,
                     W, 1, 1, 1, 0, 1, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, 0, 0, 0, 0, _stream(),
