@@ -101,62 +101,29 @@ class BenchmarkSession:
     # ---- CUDA-graph replay of the whole step (launch-bound regimes: small per-GPU batches) -------------------------
     def enable_graph(self, warmup: int = 3) -> bool:
         """Capture one full training step (forward, loss, backward with its side-stream weight gradients, the
-        per-bucket fused allreduce+SGD kernels) into a CUDA graph and replay it from then on.  ~340 kernel launches
-        and the Python autograd walk collapse into one ``cudaGraphLaunch``; the LR schedule still works because the
-        hyper-parameter upload is a memcpy node fed from a pinned buffer that ``step()`` refreshes before each replay.
-        Returns False (and stays eager) when the step cannot be captured: CPU, no fused engine, or a model with
-        dropout (its Philox offset is a launch argument, which a graph would freeze)."""
-        from ..ops import native
-        from ..parallel.engine import FusedSGD
+        per-bucket fused allreduce+SGD kernels) into a CUDA graph and replay it from then on (``graph_step.py``).
+        Returns False (and stays eager) when the step cannot be captured: CPU, no fused engine, NVTX profiling, or a
+        model with dropout."""
+        from .graph_step import GraphedStep
 
         if self._graph is not None:
             return True
-        if not self.cuda or self.profile or not isinstance(self.optimizer, FusedSGD) or not ops.use_native(self.data):
+        if not self.cuda or self.profile or not GraphedStep.applicable(self.model, self.optimizer, self.data):
             return False
-        if any(float(getattr(m, "p", 0.0) or 0.0) > 0.0 for m in self.model.modules() if hasattr(m, "p")) or \
-                float(getattr(self.model, "p", 0.0) or 0.0) > 0.0:
+        g = GraphedStep(self._eager_step, self.optimizer, log)
+        if not g.capture((self.data, self.target), warmup):
             return False
-        from .. import _ext
-
-        for _ in range(max(1, warmup)):          # first-use kernel configuration, momentum init, allocator warm-up
-            self._eager_step(self.data, self.target)
-        torch.cuda.synchronize()
-        self._gx, self._gy = self.data.clone(), self.target.clone()
-        graph = torch.cuda.CUDAGraph()
-        before = _ext.launch_count()
-        try:
-            with torch.cuda.graph(graph):
-                native.begin_capture_scratch(self.device)
-                self._gloss = self._eager_step(self._gx, self._gy)
-        except Exception as e:                    # stay on the eager path, say why
-            native.end_capture_scratch()
-            log("CUDA graph capture failed (%s); staying eager" % (str(e).splitlines()[0],))
-            torch.cuda.synchronize()
-            return False
-        native.end_capture_scratch()
-        self._graph_launches = _ext.launch_count() - before
-        self._graph = graph
+        self._graph = g
         return True
 
     def step(self, data=None, target=None):
-        if self._graph is not None:
-            from .. import _ext
-
-            maybe_inject(self.steps_done, dist.rank())
-            self.steps_done += 1
-            if data is not None and data is not self._gx:
-                self._gx.copy_(data, non_blocking=True)
-            if target is not None and target is not self._gy:
-                self._gy.copy_(target, non_blocking=True)
-            self.optimizer.refresh_hyper_host()
-            self._graph.replay()
-            _ext.add_launches(self._graph_launches)
-            self.last_loss = self._gloss
-            return self.last_loss
         data = self.data if data is None else data
         target = self.target if target is None else target
         maybe_inject(self.steps_done, dist.rank())
         self.steps_done += 1
+        if self._graph is not None:
+            self.last_loss = self._graph(data, target)
+            return self.last_loss
         return self._eager_step(data, target)
 
     def _eager_step(self, data, target):

@@ -49,6 +49,8 @@ def build_parser():
     p.add_argument("--model", default="resnet50")
     p.add_argument("--synthetic-length", type=int, default=int(os.getenv("FAKE_DATA_LENGTH", 1281167)))
     p.add_argument("--num-workers", type=int, default=4)
+    p.add_argument("--no-cuda-graph", action="store_true", default=False,
+                   help="launch every kernel of the training step eagerly instead of replaying a captured CUDA graph")
     return p
 
 
@@ -129,6 +131,26 @@ def main(argv=None) -> int:
                 output[1], target, classes)
         return ops.softmax_cross_entropy(output, target, classes)
 
+    carry = hasattr(optimizer, "piggyback")
+
+    def train_step(data, target):
+        """One optimisation step; returns (loss, accuracy) — cross-rank means when the fused engine carries them."""
+        optimizer.zero_grad()
+        output = net(data)
+        loss = criterion(output, target)
+        main_out = output[0] if isinstance(output, tuple) else output
+        acc = top1_accuracy(main_out.detach()[:, :classes].float(), target)
+        if carry:   # the reference's 2 blocking scalar allreduces per step ride in the last gradient bucket
+            optimizer.piggyback(torch.stack([loss.detach().float(), acc.float()]))
+        loss.backward()
+        optimizer.step()
+        if carry:
+            avg = optimizer.averaged_scalars()
+            return avg[0], avg[1]
+        return loss.detach(), acc
+
+    graph_state = {}
+
     def train(epoch):
         net.train()
         if hasattr(train_sampler, "set_epoch"):
@@ -143,23 +165,17 @@ def main(argv=None) -> int:
                 data, target = data.to(device, non_blocking=True), target.to(device, non_blocking=True)
                 if prepare is not None:
                     data = prepare(data)
-                optimizer.zero_grad()
-                output = net(data)
-                loss = criterion(output, target)
-                main_out = output[0] if isinstance(output, tuple) else output
-                acc = top1_accuracy(main_out.detach()[:, :classes].float(), target)
-                carry = hasattr(optimizer, "piggyback")
-                if carry:   # the reference's 2 blocking scalar allreduces per step ride in the last gradient bucket
-                    optimizer.piggyback(torch.stack([loss.detach().float(), acc.float()]))
-                loss.backward()
-                optimizer.step()
-                if carry:
-                    avg = optimizer.averaged_scalars()
-                    train_loss.update(avg[0], averaged=True)
-                    train_acc.update(avg[1], averaged=True)
-                else:
-                    train_loss.update(loss)
-                    train_acc.update(acc)
+                if "step" not in graph_state:
+                    from .graph_step import GraphedStep
+
+                    graph_state["step"] = train_step
+                    if not args.no_cuda_graph and GraphedStep.applicable(net, optimizer, data):
+                        g = GraphedStep(train_step, optimizer)
+                        if g.capture((data, target), warmup=2):
+                            graph_state["step"] = g
+                l, a = graph_state["step"](data, target)
+                train_loss.update(l, averaged=carry)
+                train_acc.update(a, averaged=carry)
                 t.update(1)
         if writer:
             writer.add_scalar("train/loss", float(train_loss.avg), epoch)

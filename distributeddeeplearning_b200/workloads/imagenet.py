@@ -80,8 +80,21 @@ class _DeviceMetrics:
         return {"loss": float(self.loss_sum) / max(self.steps, 1), "acc": 100.0 * c[0] / n, "acc5": 100.0 * c[1] / n}
 
 
+def _train_step_fn(model, criterion, optimizer):
+    def step(data, target):
+        optimizer.zero_grad()
+        output = model(data)
+        loss = criterion(output, target)
+        loss.backward()
+        optimizer.step()
+        return loss.detach(), (output[0] if isinstance(output, tuple) else output).detach()
+    return step
+
+
 def train(train_loader, model, criterion, optimizer, base_lr, warmup_epochs, epoch, device, classes, world,
-          prepare=None):
+          prepare=None, graph=None):
+    """One epoch.  ``graph``: an (initially empty) dict — when given, the training step is captured into a CUDA graph on
+    the first full batch and replayed for every batch of that shape (``graph_step.GraphedStep``)."""
     logger = logging.getLogger(__name__)
     batch_time = AverageMeter()
     metrics = _DeviceMetrics(device)
@@ -94,11 +107,24 @@ def train(train_loader, model, criterion, optimizer, base_lr, warmup_epochs, epo
         data, target = data.to(device, non_blocking=True), target.to(device, non_blocking=True)
         if prepare is not None:
             data = prepare(data)
-        optimizer.zero_grad()
-        output = model(data)
-        loss = criterion(output, target)
-        loss.backward()
-        optimizer.step()
+        if graph is not None and "step" not in graph:
+            from .graph_step import GraphedStep
+
+            fn = _train_step_fn(model, criterion, optimizer)
+            graph["step"] = fn
+            if GraphedStep.applicable(model, optimizer, data):
+                g = GraphedStep(fn, optimizer, logger.info)
+                if g.capture((data, target), warmup=2):
+                    graph["step"] = g
+                    logger.info("training step captured into a CUDA graph (%d kernels per replay)" % g.launches)
+        if graph is not None:
+            loss, output = graph["step"](data, target)
+        else:
+            optimizer.zero_grad()
+            output = model(data)
+            loss = criterion(output, target)
+            loss.backward()
+            optimizer.step()
         metrics.update(loss, output, target, classes)
         last_loss = loss
         if i % _LOG_INTERVAL == 0:
@@ -132,9 +158,12 @@ def validate(val_loader, model, criterion, device, classes, prepare=None):
 
 def main(training_data_path=None, validation_data_path=None, use_gpu=False, save_filepath=None, model="resnet50",
          epochs=_EPOCHS, batch_size=_BATCHSIZE, fp16_allreduce=False, base_lr=0.0125, warmup_epochs=5,
-         num_workers=5, host_data=False):
+         num_workers=5, host_data=False, cuda_graph=True):
+    """``cuda_graph``: on a GPU with the fused engine, replay the training step from a captured CUDA graph (the
+    reference's default batch of 64 per GPU is launch-bound: ~340 kernels per ResNet-50 step)."""
     logger = logging.getLogger(__name__)
     epochs = int(epochs)
+    cuda_graph = _str_to_bool(cuda_graph) if isinstance(cuda_graph, str) else bool(cuda_graph)
     use_gpu = _str_to_bool(use_gpu) if isinstance(use_gpu, str) else bool(use_gpu)
     use_gpu = use_gpu and torch.cuda.is_available()
     if not use_gpu:
@@ -207,13 +236,14 @@ def main(training_data_path=None, validation_data_path=None, use_gpu=False, save
 
     logger.info("Training ...")
     total_time = 0.0
+    graph_state = {} if (cuda_graph and use_gpu) else None
     for epoch in range(epochs):
         with Timer(output=logger.info, prefix=f"Training epoch {epoch} ") as t:
             net.train()
             if hasattr(train_sampler, "set_epoch"):
                 train_sampler.set_epoch(epoch)
             metrics = train(train_loader, net, criterion, optimizer, base_lr, warmup_epochs, epoch, device, classes,
-                            world, prepare)
+                            world, prepare, graph=graph_state)
             if use_gpu:
                 torch.cuda.synchronize()
         total_time += t.elapsed
