@@ -134,8 +134,10 @@ class _ConvBnAct(torch.autograd.Function):
                 relu, train):
         R, S = weight.shape[2], weight.shape[3]
         wb = weight_bf16(weight)
-        y, stats = native.conv_fwd(x, wb, (R, S), stride, pad, dil, stats=train, cout=weight.shape[0]) if train else (
-            native.conv_fwd(x, wb, (R, S), stride, pad, dil, cout=weight.shape[0]), None)
+        # stem: the padded / row-interleaved image the TMA kernels read is built once and shared with the wgrad kernel
+        xp = native.stem_prepare(x, (R, S), stride, pad, dil) if (train and x.shape[1] == 4) else None
+        y, stats = native.conv_fwd(x, wb, (R, S), stride, pad, dil, stats=train, cout=weight.shape[0], prepadded=xp) \
+            if train else (native.conv_fwd(x, wb, (R, S), stride, pad, dil, cout=weight.shape[0]), None)
         use_bits = train and relu and residual is not None
         if use_bits:      # residual layer: 1-bit ReLU mask for backward instead of re-reading z
             z, save, zmask = native.bn_act_fwd(y, stats, gamma, beta, running_mean, running_var, eps, momentum, relu,
@@ -151,6 +153,7 @@ class _ConvBnAct(torch.autograd.Function):
             # version check) — the arena is only rewritten by the bucket kernel, which is ordered after
             # this layer's backward (see notify_ready at the end of backward)
             ctx.wb = wb
+            ctx.xp = xp
             ctx.save_for_backward(x, y, zmask if use_bits else z, save)
         return z
 
@@ -173,7 +176,9 @@ class _ConvBnAct(torch.autograd.Function):
             dx = native.conv_dgrad(dy, wb, x.shape, kernel, stride, pad, dil)
         if weight.requires_grad:
             gw = grad_buffer(weight)
-            run_wgrad(weight, lambda: native.conv_wgrad(x, dy, gw, kernel, stride, pad, dil), x, dy)
+            xp = ctx.xp
+            run_wgrad(weight, lambda: native.conv_wgrad(x, dy, gw, kernel, stride, pad, dil, prepadded=xp), x, dy,
+                      *((xp,) if xp is not None else ()))
         # LAST: a ready bucket may launch its allreduce+update kernel on the side stream now; everything
         # this layer still needed from the weight arenas (gamma, wb) has been enqueued before the event
         if gamma.requires_grad:

@@ -193,6 +193,18 @@ def pad_image(x4: torch.Tensor, Hp: int, Wp: int, pt: int, pl: int, G: int = 1) 
     return out
 
 
+def stem_prepare(x4: torch.Tensor, kernel: Tuple[int, int], stride: int, pad, dil: int = 1) -> Optional[torch.Tensor]:
+    """The zero-padded, row-interleaved copy of an NHWC4 image batch that the TMA-fed stem kernels read, or None when
+    that path does not apply.  Forward and weight-gradient kernels of the same layer can share it (``prepadded=``)."""
+    if x4.shape[1] != 4 or dil != 1:
+        return None
+    ph, pw = _pad2(pad)
+    geo = stem_tma_geometry(x4.shape[2], x4.shape[3], kernel, stride, (ph, pw))
+    if geo is None:
+        return None
+    return pad_image(x4, geo[0], geo[1], ph, pw, geo[2])
+
+
 def supports_conv(cin: int, cout: int) -> bool:
     """Shapes the tcgen05 implicit-GEMM kernels handle natively: channel counts that are multiples of 8 (one 16-byte
     vector; partial 64-channel k-blocks / N tiles are zero-filled or masked in the kernels) or an NHWC4 stem."""
@@ -204,8 +216,9 @@ def supports_conv(cin: int, cout: int) -> bool:
 # ------------------------------------------------------------------------------------------------
 def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], stride: int, pad, dil: int = 1,
              stats: bool = False, bias: Optional[torch.Tensor] = None, relu: bool = False,
-             cout: Optional[int] = None):
+             cout: Optional[int] = None, prepadded: Optional[torch.Tensor] = None):
     """y = conv(x, w) [+ bias][ReLU]; optionally per-channel (sum, sumsq) of y for BatchNorm.
+    ``prepadded``: result of :func:`stem_prepare` for this (x, geometry) — skips the internal padding copy.
 
     ``w_bf16``: [Cout, R*S*Cin] bf16 (or the packed stem matrix [Cout, KB*64]); ``pad``: int or (pad_h, pad_w).
     """
@@ -233,7 +246,7 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
         if geo is not None:
             # even stride: copy the image into a zero-bordered buffer once (one 8-byte-per-pixel pass) and let ONE
             # 5-D TMA box per k-block fetch what the gather path needs 64 cp.async per output pixel for
-            xp = pad_image(x, geo[0], geo[1], ph, pw, geo[2])
+            xp = prepadded if prepadded is not None else pad_image(x, geo[0], geo[1], ph, pw, geo[2])
             tw, th, tn = tile_geometry(P, Q, N, 128)
             C.conv_gemm(C.CONV_STEM_TMA, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, KB, Cout, geo[0], geo[1], 4,
                         P, Q, R, S, stride, 0, 1, RPK, int(relu), Cout, wp, wr, wc, n_total, xp.data_ptr(), 4, N, tw, th,
@@ -340,8 +353,8 @@ def _wgrad_splits(tiles: int, total_kb: int, device_index: int) -> int:
 
 
 def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: Tuple[int, int], stride: int,
-               pad, dil: int = 1) -> None:
-    """grad_w[Cout][R*S*Cin] (fp32, KRSC) += dy^T * im2col(x)."""
+               pad, dil: int = 1, prepadded: Optional[torch.Tensor] = None) -> None:
+    """grad_w[Cout][R*S*Cin] (fp32, KRSC) += dy^T * im2col(x).  ``prepadded``: see :func:`stem_prepare`."""
     C = _C()
     _check_act(x)
     _check_act(dy, "dy")
@@ -360,7 +373,7 @@ def conv_wgrad(x: torch.Tensor, dy: torch.Tensor, grad_w: torch.Tensor, kernel: 
         tiles = ((ncols + 127) // 128) * ((Cout + 127) // 128)
         geo = stem_tma_geometry(H, W, kernel, stride, (ph, pw)) if dil == 1 else None
         if geo is not None:
-            xp = pad_image(x, geo[0], geo[1], ph, pw, geo[2])
+            xp = prepadded if prepadded is not None else pad_image(x, geo[0], geo[1], ph, pw, geo[2])
             tw, th, tn = tile_geometry(P, Q, N, 64)
             total_kb = -(-Q // tw) * -(-P // th) * -(-N // tn)
             C.conv_wgrad(C.CONV_STEM_TMA, xp.data_ptr(), dy.data_ptr(), scratch.data_ptr(), M, Cout, Cout, ncols, ncols,
