@@ -87,6 +87,15 @@ def g_elementwise():
         dy = cl(bf(torch.randn_like(yr)))
         yr.backward(dy.float())
         report(f"maxpool bwd k{k}s{s}p{p}", nv.maxpool_bwd(dy, arg, x.shape, k, s, p), xr.grad, 1e-2)
+    # even image, 3x3 / s2 / p1: the 2x2-patch specialisation (ResNet stem geometry)
+    for (n_, c_, h_, w_) in [(2, 64, 16, 12), (3, 24, 112, 112)]:
+        xe = cl(bf(torch.randn(n_, c_, h_, w_, device=dev)))
+        yk, arg = nv.maxpool_fwd(xe, 3, 2, 1)
+        xr = xe.float().requires_grad_(True)
+        yr = F.max_pool2d(xr, 3, 2, 1)
+        dy = cl(bf(torch.randn_like(yr)))
+        yr.backward(dy.float())
+        report(f"maxpool bwd k3s2p1 even {h_}x{w_} c{c_}", nv.maxpool_bwd(dy, arg, xe.shape, 3, 2, 1), xr.grad, 1e-2)
     for cip in (True, False):
         ya = nv.avgpool_fwd(x, 3, 1, 1, cip)
         xr = x.float().contiguous().requires_grad_(True)      # NCHW-contiguous oracle (torch's channels_last
