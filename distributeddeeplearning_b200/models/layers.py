@@ -107,10 +107,6 @@ class Linear(nn.Module):
         return f"in_features={self.in_features}, out_features={self.out_features}"
 
 
-class Logits(torch.Tensor):
-    """Marker subclass is avoided on purpose: heads return plain tensors plus `num_classes`."""
-
-
 def prepare_input(x: torch.Tensor) -> torch.Tensor:
     """Bring an image batch into the layout/dtype the active device path expects.
 

@@ -128,3 +128,37 @@ def test_stem_geometry_and_support_matrix():
     assert native.bn_supported(2048) and native.bn_supported(64) and native.bn_supported(80) and not native.bn_supported(12)
     assert native.conv_out_hw(224, 224, (7, 7), 2, 3) == (112, 112)
     assert native.conv_out_hw(17, 17, (1, 7), 1, (0, 3)) == (17, 17)       # asymmetric Inception kernels
+
+
+def test_stem_tma_geometry_and_padding_rules():
+    # ResNet stem 7x7/2 pad 3 on 224: 2 filter rows per k-block -> 2-row interleave, 230x230 padded image
+    assert native.stem_tma_geometry(224, 224, (7, 7), 2, 3) == (230, 230, 2)
+    # AlexNet 11x11/4 pad 2: one row per k-block, width padded so the last window's 16 taps stay in bounds (even width)
+    hp, wp, g = native.stem_tma_geometry(224, 224, (11, 11), 4, 2)
+    assert g == 1 and wp % 2 == 0 and wp >= 4 * 54 + 16 and hp >= 228
+    # 3x3/1 (VGG): 4-row interleave makes the per-pixel step 32 bytes -> TMA-eligible
+    assert native.stem_tma_geometry(224, 224, (3, 3), 1, 1)[2] == 4
+    # 11x11 stride 1 would need an 8-byte column step: gather path
+    assert native.stem_tma_geometry(64, 64, (11, 11), 1, 5) is None
+    assert native._pad2(3) == (3, 3) and native._pad2((0, 3)) == (0, 3)
+
+
+def test_graphed_step_not_applicable_on_cpu_and_dropout_detection():
+    from distributeddeeplearning_b200.workloads.graph_step import GraphedStep, model_has_dropout
+
+    m = models.get_model("resnet18")
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    assert not GraphedStep.applicable(m, opt, torch.zeros(1, 3, 8, 8))
+    assert not model_has_dropout(m) and model_has_dropout(models.get_model("alexnet"))
+    g = GraphedStep(lambda a: a + 1, opt)
+    assert not g.matches((torch.zeros(2),))
+    assert torch.equal(g(torch.zeros(2)), torch.ones(2))          # falls back to the eager function
+
+
+def test_batch_norm_act_composite_matches_torch():
+    x = torch.randn(4, 8, 5, 5, requires_grad=True)
+    g, b = torch.rand(8) + 0.5, torch.randn(8)
+    rm, rv = torch.zeros(8), torch.ones(8)
+    z = ops.batch_norm_act(x, g, b, rm, rv, 1e-5, 0.1, True, True)
+    ref = torch.relu(torch.nn.functional.batch_norm(x, torch.zeros(8), torch.ones(8), g, b, True, 0.1, 1e-5))
+    assert torch.allclose(z, ref, atol=1e-5)

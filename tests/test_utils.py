@@ -113,3 +113,14 @@ def test_run_history(tmp_path):
         assert runs.Run.get_context().id == r.id
     finally:
         del os.environ["DDL_RUN_DIR"]
+
+
+def test_metric_skips_collective_when_values_are_already_averaged():
+    from distributeddeeplearning_b200.utils.meters import Metric
+
+    m = Metric("loss")
+    m.update(torch.tensor(2.0), averaged=True)
+    m.update(torch.tensor(4.0), averaged=True)
+    assert m._global and float(m.avg) == 3.0
+    m.update(torch.tensor(6.0))                 # a local value: the mean must go through the allreduce again
+    assert not m._global and float(m.avg) == 4.0
