@@ -10,11 +10,11 @@ so = os.path.join(ROOT, "distributeddeeplearning_b200", "_C.so")
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 pats = [("UTCHMMA", r"UTCHMMA"), ("LDTM", r"\bLDTM"), ("UTMALDG", r"UTMALDG"), ("UTCBAR", r"UTCBAR"), ("SYNCS", r"SYNCS"),
-        ("LDGSTS", r"LDGSTS"), ("LDGMC (multimem.ld_reduce)", r"LDGMC"), ("STG/RED .MC (multimem.st)", r"(STG|REDG?|STGMC)\.[A-Z0-9_.]*MC|STGMC"),
+        ("LDGSTS", r"LDGSTS"), ("LDGMC (multimem.ld_reduce)", r"LDGMC"), ("STG.E.{64,128}.STRONG.SYS (multimem.st)", r"STG\.E\.(64|128)\.STRONG\.SYS"),
         ("REDG/ATOMG", r"\bREDG|\bATOMG")]
 lines = ["# SASS evidence (`cuobjdump -sass distributeddeeplearning_b200/_C.so`, sm_100a)", "",
          "UTCHMMA = tcgen05.mma · LDTM = tcgen05.ld · UTMALDG = cp.async.bulk.tensor (TMA) · UTCBAR = tcgen05.commit · SYNCS = mbarrier ·",
-         "LDGSTS = cp.async · LDGMC = multimem.ld_reduce (NVLS in-switch reduction) · .MC stores = multimem.st", "",
+         "LDGSTS = cp.async · LDGMC = multimem.ld_reduce (NVLS in-switch reduction) · multimem.st lowers to a system-scope vector store on the multicast address (STG.E.128.STRONG.SYS)", "",
          "| kernel | " + " | ".join(n for n, _ in pats) + " |", "|---|" + "---|" * len(pats)]
 for f in funcs:
     name = f.split("\n", 1)[0].strip()
