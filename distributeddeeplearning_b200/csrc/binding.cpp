@@ -379,10 +379,11 @@ PYBIND11_MODULE(_C, m) {
     check(ddl::launch_bias_relu_bwd(P<const __nv_bfloat16>(dy), P<const __nv_bfloat16>(z), P<__nv_bfloat16>(dx),
                                     P<float>(dbias), M, C, c_valid, relu, sms, S(stream)), "bias_relu_bwd");
   });
-  m.def("dropout", [](ptr_t x, ptr_t y, int64_t n, float p, uint64_t seed, uint64_t offset, ptr_t stream) {
-    check(ddl::launch_dropout(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), n, p, seed, offset, S(stream)),
-          "dropout");
-  });
+  m.def("dropout", [](ptr_t x, ptr_t y, int64_t n, float p, uint64_t seed, uint64_t offset, ptr_t stream, ptr_t step) {
+    check(ddl::launch_dropout(P<const __nv_bfloat16>(x), P<__nv_bfloat16>(y), n, p, seed, offset, P<const int64_t>(step),
+                              S(stream)), "dropout");
+  }, py::arg("x"), py::arg("y"), py::arg("n"), py::arg("p"), py::arg("seed"), py::arg("offset"), py::arg("stream"),
+     py::arg("step") = 0);
   m.def("pad_nhwc4", [](ptr_t in, ptr_t out, int N, int H, int W, int Hp, int Wp, int pt, int pl, int G, ptr_t stream) {
     check(ddl::launch_pad_nhwc4(P<const __nv_bfloat16>(in), P<__nv_bfloat16>(out), N, H, W, Hp, Wp, pt, pl, G, S(stream)),
           "pad_nhwc4");

@@ -541,9 +541,13 @@ __global__ void __launch_bounds__(256) bias_relu_bwd_kernel(const __nv_bfloat16*
 }
 
 __global__ void __launch_bounds__(256) dropout_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* y,
-                                                      int64_t n8, float p, uint64_t seed, uint64_t offset) {
-  // mask is a pure function of (seed, offset, element index): backward recomputes it (no mask tensor)
-  const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+                                                      int64_t n8, float p, uint64_t seed, uint64_t offset,
+                                                      const int64_t* __restrict__ step) {
+  // mask is a pure function of (seed, step, offset, element index): backward recomputes it (no mask tensor).
+  // `step` is an optional device-resident counter advanced once per training step: it keeps the masks fresh when the
+  // whole step — launch arguments included — is replayed from a CUDA graph.
+  const uint64_t sd = seed + (step ? static_cast<uint64_t>(*step) * 0x9E3779B97F4A7C15ull : 0ull);
+  const uint2 key = make_uint2(static_cast<uint32_t>(sd), static_cast<uint32_t>(sd >> 32));
   const float scale = 1.f / (1.f - p);
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -736,9 +740,9 @@ cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z
   return cudaGetLastError();
 }
 cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,
-                           uint64_t offset, cudaStream_t stream) {
+                           uint64_t offset, const int64_t* step, cudaStream_t stream) {
   if (n % 8 != 0) return cudaErrorInvalidValue;
-  dropout_kernel<<<grid_for(n / 8), 256, 0, stream>>>(x, y, n / 8, p, seed, offset);
+  dropout_kernel<<<grid_for(n / 8), 256, 0, stream>>>(x, y, n / 8, p, seed, offset, step);
   return cudaGetLastError();
 }
 cudaError_t launch_pad_nhwc4(const __nv_bfloat16* in, __nv_bfloat16* out, int N, int H, int W, int Hp, int Wp, int pt,

@@ -116,7 +116,7 @@ cudaError_t launch_unpack_stem_grad(const float* packed, float* gw, int Cout, in
 cudaError_t launch_bias_relu_bwd(const __nv_bfloat16* dy, const __nv_bfloat16* z, __nv_bfloat16* dx, float* dbias,
                                  int M, int C, int c_valid, int relu, int sms, cudaStream_t stream);
 cudaError_t launch_dropout(const __nv_bfloat16* x, __nv_bfloat16* y, int64_t n, float p, uint64_t seed,
-                           uint64_t offset, cudaStream_t stream);
+                           uint64_t offset, const int64_t* step, cudaStream_t stream);
 // y = a + b (bf16)
 // NHWC4 image [N][H][W] (8-byte pixels) -> zero-bordered, G-row-interleaved [N][Hp][Wp][G][4] with the source at
 // (pt, pl): position (h, w) holds the pixels of rows h .. h+G-1.  Operand layout of the TMA-fed stem convolution

@@ -1,5 +1,6 @@
 """Fused ops: hand-written sm_100a kernels on CUDA, PyTorch composites on CPU (see functional.py)."""
 from .functional import (  # noqa: F401
+    advance_dropout_step,
     avg_pool2d,
     batch_norm_act,
     concat_channels,

@@ -481,12 +481,29 @@ def global_avg_pool(x):
 # ------------------------------------------------------------------------------------------------
 # dropout (Philox mask recomputed in backward)
 # ------------------------------------------------------------------------------------------------
-_DROPOUT_STATE = {"seed": 0x5EED, "offset": 0}
+_DROPOUT_STATE = {"seed": 0x5EED, "offset": 0, "step": {}}
 
 
 def seed_dropout(seed: int) -> None:
     _DROPOUT_STATE["seed"] = int(seed)
     _DROPOUT_STATE["offset"] = 0
+
+
+def _dropout_step(device) -> torch.Tensor:
+    """Device-resident step counter mixed into the Philox key (one per device, created on first use)."""
+    key = device.index or 0
+    t = _DROPOUT_STATE["step"].get(key)
+    if t is None:
+        t = _DROPOUT_STATE["step"][key] = torch.zeros((), dtype=torch.int64, device=device)
+    return t
+
+
+def advance_dropout_step() -> None:
+    """Advance the device-side dropout step counters (no-op when no dropout layer ran on a GPU yet).  The host-side
+    offset already makes eager steps draw fresh masks; a step replayed from a CUDA graph freezes every launch
+    argument, so ``GraphedStep`` ends each captured step with this one-element increment instead."""
+    for t in _DROPOUT_STATE["step"].values():
+        t.add_(1)
 
 
 class _Dropout(torch.autograd.Function):
@@ -497,14 +514,15 @@ class _Dropout(torch.autograd.Function):
         # the Philox mask is indexed by memory offset: keep NHWC activations in their own (dense) memory order and
         # make the gradient follow the same order in backward
         cl = x.dim() == 4 and x.is_contiguous(memory_format=CL)
-        ctx.cfg = (p, seed, off, cl)
-        return native.dropout(x if cl else x.contiguous(), p, seed, off)
+        step = _dropout_step(x.device)
+        ctx.cfg = (p, seed, off, cl, step)
+        return native.dropout(x if cl else x.contiguous(), p, seed, off, step)
 
     @staticmethod
     def backward(ctx, dy):
-        p, seed, off, cl = ctx.cfg
+        p, seed, off, cl, step = ctx.cfg
         dy = dy.contiguous(memory_format=CL) if cl else dy.contiguous()
-        return native.dropout(dy, p, seed, off), None
+        return native.dropout(dy, p, seed, off, step), None
 
 
 def dropout(x, p=0.5, training=True):

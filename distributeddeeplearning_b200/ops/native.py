@@ -695,9 +695,11 @@ def bias_relu_bwd(dy: torch.Tensor, z: torch.Tensor, dbias: Optional[torch.Tenso
     return dx
 
 
-def dropout(x: torch.Tensor, p: float, seed: int, offset: int) -> torch.Tensor:
+def dropout(x: torch.Tensor, p: float, seed: int, offset: int, step: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Philox dropout; ``step``: optional int64 device scalar mixed into the key (advanced once per training step so a
+    step replayed from a CUDA graph still draws fresh masks)."""
     y = torch.empty_like(x)
-    _C().dropout(x.data_ptr(), y.data_ptr(), x.numel(), p, seed, offset, _stream())
+    _C().dropout(x.data_ptr(), y.data_ptr(), x.numel(), p, seed, offset, _stream(), _ptr(step))
     return y
 
 

@@ -102,8 +102,7 @@ class BenchmarkSession:
     def enable_graph(self, warmup: int = 3) -> bool:
         """Capture one full training step (forward, loss, backward with its side-stream weight gradients, the
         per-bucket fused allreduce+SGD kernels) into a CUDA graph and replay it from then on (``graph_step.py``).
-        Returns False (and stays eager) when the step cannot be captured: CPU, no fused engine, NVTX profiling, or a
-        model with dropout."""
+        Returns False (and stays eager) when the step cannot be captured: CPU, no fused engine, NVTX profiling."""
         from .graph_step import GraphedStep
 
         if self._graph is not None:

@@ -8,8 +8,9 @@ hyper-parameter blob (so LR schedules keep working — the upload is a memcpy no
 ``cudaGraphLaunch``.
 
 Capture rules the framework follows: accumulators come from an arena whose memset is the first
-graph node (``native.begin_capture_scratch``); streams only join what is pending (``functional.wgrad_join``); models
-with dropout are not captured (the Philox offset is a launch argument and would be frozen).
+graph node (``native.begin_capture_scratch``); streams only join what is pending (``functional.wgrad_join``); dropout
+masks stay fresh because their Philox key mixes in a device-resident step counter that the captured step increments
+(``ops.advance_dropout_step``) — launch arguments such as the host-side offset are frozen by a graph.
 """
 from __future__ import annotations
 
@@ -32,7 +33,12 @@ class GraphedStep:
     """``fn(*inputs) -> tensor | tuple of tensors`` replayed from a CUDA graph for inputs of the captured shapes."""
 
     def __init__(self, fn: Callable, optimizer, log: Optional[Callable[[str], None]] = None):
-        self.fn, self.optimizer, self.log = fn, optimizer, log or (lambda s: None)
+        def stepped(*inputs):
+            out = fn(*inputs)
+            ops.advance_dropout_step()          # part of the captured step: replays draw fresh dropout masks
+            return out
+
+        self.fn, self.optimizer, self.log = stepped, optimizer, log or (lambda s: None)
         self.graph = None
         self.static_in: Tuple[torch.Tensor, ...] = ()
         self.static_out = None
@@ -43,8 +49,7 @@ class GraphedStep:
     def applicable(model: torch.nn.Module, optimizer, example: torch.Tensor) -> bool:
         from ..parallel.engine import FusedSGD
 
-        return bool(example.is_cuda and isinstance(optimizer, FusedSGD) and ops.use_native(example)
-                    and not model_has_dropout(model))
+        return bool(example.is_cuda and isinstance(optimizer, FusedSGD) and ops.use_native(example))
 
     def capture(self, inputs: Sequence[torch.Tensor], warmup: int = 3) -> bool:
         """Warm up eagerly on ``inputs`` (kernel configuration, momentum init, allocator), then capture one step."""

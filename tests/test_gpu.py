@@ -20,7 +20,7 @@ def _group(name, timeout=600):
     assert "FAIL" not in r.stdout, tail
 
 
-@pytest.mark.parametrize("group", ["elementwise", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "zoo", "zoograd", "conv_generic"])
+@pytest.mark.parametrize("group", ["elementwise", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "zoo", "zoograd", "conv_generic", "graph"])
 def test_kernel_group(group):
     _group(group)
 

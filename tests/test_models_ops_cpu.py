@@ -150,6 +150,7 @@ def test_graphed_step_not_applicable_on_cpu_and_dropout_detection():
     opt = torch.optim.SGD(m.parameters(), lr=0.1)
     assert not GraphedStep.applicable(m, opt, torch.zeros(1, 3, 8, 8))
     assert not model_has_dropout(m) and model_has_dropout(models.get_model("alexnet"))
+    ops.advance_dropout_step()                                     # no GPU dropout ran: a no-op
     g = GraphedStep(lambda a: a + 1, opt)
     assert not g.matches((torch.zeros(2),))
     assert torch.equal(g(torch.zeros(2)), torch.ones(2))          # falls back to the eager function

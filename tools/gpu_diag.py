@@ -15,7 +15,7 @@ import time
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
-GROUPS = ["elementwise", "zoo", "zoograd", "gemm", "conv_generic", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
+GROUPS = ["elementwise", "zoo", "graph", "zoograd", "gemm", "conv_generic", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
 RESULTS = []
 
 
@@ -124,6 +124,15 @@ def g_elementwise():
     keep = (d != 0).float().mean().item()
     print(f"dropout keep={keep:.4f} scale={d.max().item()}")
     RESULTS.append(abs(keep - 0.5) < 0.02 and d.max().item() == 2.0)
+    # device-resident step counter (CUDA-graph replays): same step -> same mask, next step -> a fresh mask
+    ones = bf(torch.ones(1 << 16, device=dev))
+    step = torch.zeros((), dtype=torch.int64, device=dev)
+    m0, m0b = nv.dropout(ones, 0.5, 1, 0, step), nv.dropout(ones, 0.5, 1, 0, step)
+    step.add_(1)
+    m1 = nv.dropout(ones, 0.5, 1, 0, step)
+    same, frac = bool((m0 == m0b).all()), float((m0 != m1).float().mean())
+    print(f"dropout step counter: repeatable={same} changed fraction after advance={frac:.3f}")
+    RESULTS.append(same and 0.4 < frac < 0.6)
     dz, z = cl(bf(torch.randn(2, 192, 5, 5, device=dev))), cl(bf(torch.randn(2, 192, 5, 5, device=dev)))
     db = torch.zeros(192, device=dev)
     dx = nv.bias_relu_bwd(dz, z, db, True)
@@ -577,6 +586,28 @@ def g_zoo():
         down = losses[-1] < losses[0] + (0.02 if name in ("alexnet", "vgg16", "squeezenet1_1") else 0.0)
         print(f"[{'ok' if finite and down else 'FAIL'}] {name:14s} batch {bs}: loss " + " ".join(f"{l:.3f}" for l in losses), flush=True)
         RESULTS.append(finite and down)
+        del s
+        torch.cuda.empty_cache()
+
+
+def g_graph():
+    """Whole-step CUDA-graph replay, incl. a dropout model (device-side step counter) and a BN/residual model."""
+    import torch
+
+    from distributeddeeplearning_b200.parallel import dist
+    from distributeddeeplearning_b200.workloads.benchmark import BenchmarkSession
+
+    dist.init()
+    for name, bs in [("alexnet", 32), ("resnet18", 16), ("squeezenet1_1", 16)]:
+        torch.manual_seed(0)
+        s = BenchmarkSession(name, bs, True, lr=0.01 if name == "resnet18" else 0.001)
+        ok = s.enable_graph(warmup=2)
+        losses = [float(s.step()) for _ in range(5)]
+        torch.cuda.synchronize()
+        s.optimizer.check_errors()
+        finite = all(l == l and abs(l) < 1e4 for l in losses)
+        print(f"[{'ok' if ok and finite else 'FAIL'}] graph replay {name:14s}: captured={ok} loss " + " ".join(f"{l:.3f}" for l in losses), flush=True)
+        RESULTS.append(ok and finite)
         del s
         torch.cuda.empty_cache()
 
