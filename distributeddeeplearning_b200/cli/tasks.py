@@ -54,18 +54,20 @@ def _submit(module, argv, gpus, experiment, no_cuda=False, env=None):
 
 # ------------------------------------------------------------------ pytorch-benchmark
 @task(help={"no_cuda": "CPU/gloo plumbing mode", "model": "torchvision model name", "batch_size": "per-GPU batch"})
-def benchmark_local(c, model="resnet50", batch_size=64, no_cuda=False):
+def benchmark_local(c, model="resnet50", batch_size=64, no_cuda=False, eager=False):
     """Submit the synthetic benchmark for local execution (one rank)."""
     argv = ["--model", model, "--batch-size", str(batch_size)] + (["--no-cuda"] if no_cuda else [])
+    argv += [] if (eager or no_cuda) else ["--cuda-graph"]     # batch 64 is launch-bound: replay the step from a graph
     _submit(_BENCH, argv, 1, "synthetic_benchmark_local", no_cuda)
 
 
 @task(help={"node_count": "number of ranks (GPUs of this box)"})
-def benchmark_remote(c, node_count=None, model="resnet50", batch_size=64, no_cuda=False, fp16_allreduce=False):
+def benchmark_remote(c, node_count=None, model="resnet50", batch_size=64, no_cuda=False, fp16_allreduce=False,
+                     eager=False):
     """Submit the synthetic benchmark on --node-count ranks."""
     n = int(node_count or _max_nodes())
     argv = ["--model", model, "--batch-size", str(batch_size)]
-    argv += ["--no-cuda"] if no_cuda else []
+    argv += ["--no-cuda"] if no_cuda else ([] if eager else ["--cuda-graph"])
     argv += ["--fp16-allreduce"] if fp16_allreduce else []
     _submit(_BENCH, argv, n, "synthetic_benchmark_remote", no_cuda)
 
