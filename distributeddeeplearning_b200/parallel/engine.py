@@ -430,6 +430,8 @@ class FusedSGD(torch.optim.Optimizer):
     # ---------------------------------------------------------------------------------------------
     def describe(self) -> str:
         mb = self.total_elems * 4 / (1 << 20)
-        return (f"FusedSGD(world={self.world}, params={len(self.params)}, buckets={self.num_buckets}, "
+        one = sum(1 for n in self.plan["bucket_numel"] if int(n) * 4 <= self.oneshot_bytes) if self.world > 1 else 0
+        return (f"FusedSGD(world={self.world}, params={len(self.params)}, buckets={self.num_buckets}"
+                f"{f' ({one} one-shot)' if one else ''}, "
                 f"arena={mb:.1f} MiB fp32, wire={'bf16' if self.wire_bf16 else 'fp32'}, "
                 f"transport={'nvls-multicast' if self.use_mc else ('p2p' if self.world > 1 else 'local')})")
