@@ -37,6 +37,7 @@ void set_conv_force_stages(int s);
 void set_conv_persistent(int on);
 void set_wgrad_swap(int on);
 void set_conv_bn256(int on);
+void set_conv_cluster(int on);
 }  // namespace ddl
 
 namespace {
@@ -189,6 +190,7 @@ PYBIND11_MODULE(_C, m) {
 
   // ------------------------------------------------------------------ conv / GEMM
   m.def("set_conv_persistent", &ddl::set_conv_persistent, "tuning hook: 1 = persistent kernel for TMA-fed modes");
+  m.def("set_conv_cluster", &ddl::set_conv_cluster, "tuning hook: 1 = CTA pairs with TMA-multicast weight tiles");
   m.def("set_conv_bn256", &ddl::set_conv_bn256, "tuning hook: 0 = no 128x256 persistent tiles");
   m.def("set_wgrad_swap", &ddl::set_wgrad_swap, "tuning hook: 0 = no operand-role swap for narrow-output wgrad tiles");
   m.def("set_conv_force_stages", &ddl::set_conv_force_stages, "tuning hook: force the pipeline depth (0 = policy)");

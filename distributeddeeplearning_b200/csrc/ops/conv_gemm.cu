@@ -559,10 +559,14 @@ struct PersistCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 256 + kRedBytes + 1024;
 };
 
-template <int BLOCK_N, int MODE, bool STATS>
+// CLUSTER = launched as thread-block clusters of 2 CTAs that work on the SAME N tile and adjacent M tiles: each CTA
+// fetches half of the weight tile and TMA-multicasts it into both CTAs' shared memory, so the B operand crosses
+// L2 -> SM once per pair (operand traffic per 128 x 128 tile: 32 KB -> 24 KB).  A stage may be refilled only when
+// BOTH CTAs' MMAs have consumed it: `empty` counts two arrivals, delivered by a multicast tcgen05.commit.
+template <int BLOCK_N, int MODE, bool STATS, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads, 2)
-conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ TmaSet tmAs, ConvArgs a,
-                            int n_tiles, int m_tiles) {
+conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
+                            const __grid_constant__ TmaSet tmAs, ConvArgs a, int n_tiles, int m_tiles) {
   using Cfg = PersistCfg<BLOCK_N>;
   constexpr bool kBMn = mode_b_mn(MODE);
   constexpr bool kTile = mode_tile(MODE);
@@ -579,10 +583,15 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int KB = a.KB;
-  const int total = n_tiles * m_tiles;
+  // work items: tiles (t -> n tile fastest), or with CLUSTER pairs of M tiles: item -> (n tile, M tiles 2j and 2j+1)
+  const int crank = CLUSTER ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_items = CLUSTER ? (m_tiles + 1) / 2 : m_tiles;
+  const int total = n_tiles * m_items;
+  const int item0 = CLUSTER ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = CLUSTER ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1u); mbar_init(&empty[s], 1u); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1u); mbar_init(&empty[s], CLUSTER ? 2u : 1u); }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&acc_empty[b], 1u); }
     fence_mbar_init();
   }
@@ -593,12 +602,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
   if (warp == 5) tmem_alloc<2 * BLOCK_N>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();      // the peer's mbarriers exist before any multicast can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  auto tile_origin = [&](int t, int& n0, int& m0, int& tq0, int& tp0, int& tn0) {
+  // returns false for the padding tile of an odd M-tile count (its CTA still runs loads and MMAs in lock-step with
+  // the peer, on the clamped last tile, but writes nothing)
+  auto tile_origin = [&](int t, int& n0, int& m0, int& tq0, int& tp0, int& tn0) -> bool {
     const int nt = t % n_tiles;
     int mt = t / n_tiles;
+    bool valid = true;
+    if (CLUSTER) {
+      mt = 2 * mt + crank;
+      valid = mt < m_tiles;
+      if (!valid) mt = m_tiles - 1;
+    }
     n0 = nt * BLOCK_N;
     m0 = mt * kBlockM;
     tq0 = tp0 = tn0 = 0;
@@ -609,6 +627,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
       tq0 = wb * a.tw; tp0 = hb * a.th; tn0 = nb * a.tn;
       m0 = 0;
     }
+    return valid;
   };
 
   if (warp < 4 || warp >= 6) {
@@ -622,9 +641,18 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     const uint32_t stg_u32 = smem_u32(stg);
     const uint32_t red_u32 = smem_u32(red);
     int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int t = item0; t < total; t += item_step, ++it) {
       int n0, m0, tq0, tp0, tn0;
-      tile_origin(t, n0, m0, tq0, tp0, tn0);
+      const bool valid = tile_origin(t, n0, m0, tq0, tp0, tn0);
+      if (CLUSTER && !valid) {          // padding tile: keep the accumulator hand-shake going, write nothing
+        const int pbuf = it & 1;
+        mbar_wait(&acc_full[pbuf], (it >> 1) & 1);
+        tc_fence_after();
+        tc_fence_before();
+        named_bar_sync(1, kEpiThreads);
+        if (etid == 0) mbar_arrive(&acc_empty[pbuf]);
+        continue;
+      }
       int my_m;
       if (kTile) {
         const int wl = row % a.tw;
@@ -661,7 +689,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : kATileBytes;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int t = item0; t < total; t += item_step) {
         int n0, m0, tq0, tp0, tn0;
         tile_origin(t, n0, m0, tq0, tp0, tn0);
         int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
@@ -680,7 +708,16 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
               dh = a.pad - tap_r * a.dil; dw = a.pad_w - tap_s * a.dil;
             }
           }
-          if (kBMn) {
+          if (CLUSTER) {
+            // my half of the weight tile, delivered to both CTAs of the pair (each CTA's `full` barrier sees both halves)
+            if (kBMn) {       // BLOCK_N = 128: the two 64-column boxes are the halves
+              tma_load_2d_multicast(sB + crank * 8192, &tmB, widx * a.ldc + n0 + crank * 64, cc * 64, &full[stage], 0x3);
+            } else {          // K-major: rows [crank * BLOCK_N/2, +BLOCK_N/2) through the half-height box map
+              tma_load_2d_multicast(sB + crank * (BLOCK_N / 2) * 128, &tmBh,
+                                    mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
+                                    n0 + crank * (BLOCK_N / 2), &full[stage], 0x3);
+            }
+          } else if (kBMn) {
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j)
               tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
@@ -706,7 +743,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int t = item0; t < total; t += item_step, ++it) {
       const int buf = it & 1;
       mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);     // epilogue has drained this TMEM buffer
       tc_fence_after();
@@ -723,7 +760,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
             const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
             umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty[stage]);
+          if (CLUSTER) umma_commit_multicast(&empty[stage], 0x3);     // frees the stage in BOTH CTAs of the pair
+          else umma_commit(&empty[stage]);
           if (kb == KB - 1) umma_commit(&acc_full[buf]);
         }
         __syncwarp();
@@ -734,6 +772,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (CLUSTER) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / signal its barriers
   if (warp == 5) {
     tc_fence_after();
     tmem_dealloc<2 * BLOCK_N>(tmem_base);
@@ -1127,11 +1166,11 @@ cudaError_t launch_fwd_t(const CUtensorMap& tmB, const TmaSet& tmA, const ConvAr
 int g_persistent = 1;        // TMA-fed modes use the persistent kernel (tuning hook: set_conv_persistent)
 int g_num_sms = 0;
 
-template <int BLOCK_N, int MODE, bool STATS>
-cudaError_t launch_persistent_t(const CUtensorMap& tmB, const TmaSet& tmA, const ConvArgs& a, int n_total, int m_tiles,
-                                cudaStream_t stream) {
+template <int BLOCK_N, int MODE, bool STATS, bool CLUSTER>
+cudaError_t launch_persistent_t(const CUtensorMap& tmB, const CUtensorMap& tmBh, const TmaSet& tmA, const ConvArgs& a,
+                                int n_total, int m_tiles, cudaStream_t stream) {
   using Cfg = PersistCfg<BLOCK_N>;
-  auto kern = conv_gemm_persistent_kernel<BLOCK_N, MODE, STATS>;
+  auto kern = conv_gemm_persistent_kernel<BLOCK_N, MODE, STATS, CLUSTER>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -1145,10 +1184,27 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const TmaSet& tmA, const
     if (g_num_sms <= 0) g_num_sms = 148;
   }
   const int n_tiles = n_total / BLOCK_N;
-  const long long total = static_cast<long long>(n_tiles) * m_tiles;
+  const long long items = static_cast<long long>(n_tiles) * (CLUSTER ? (m_tiles + 1) / 2 : m_tiles);
   long long grid = (BLOCK_N > 128 ? 1LL : 2LL) * g_num_sms;      // BLOCK_N = 256 owns the SM's whole TMEM
-  if (grid > total) grid = total;
-  kern<<<static_cast<unsigned>(grid), kThreads, Cfg::kSmemBytes, stream>>>(tmB, tmA, a, n_tiles, m_tiles);
+  if (CLUSTER) {
+    if (grid > 2 * items) grid = 2 * items;
+    grid &= ~1LL;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, tmB, tmBh, tmA, a, n_tiles, m_tiles);
+  }
+  if (grid > items) grid = items;
+  kern<<<static_cast<unsigned>(grid), kThreads, Cfg::kSmemBytes, stream>>>(tmB, tmBh, tmA, a, n_tiles, m_tiles);
   return cudaGetLastError();
 }
 
@@ -1156,6 +1212,7 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const TmaSet& tmA, const
 // round trip, epilogue), so they get a shallow ring -> small shared-memory footprint -> 3-4 CTAs per SM whose
 // prologues/epilogues overlap.  Long-K tiles get the deep ring.  g_force_stages (tuning hook) overrides.
 int g_force_stages = 0;
+int g_cluster = 0;          // tuning hook: 1 = CTA pairs with TMA-multicast weight tiles in the persistent kernel
 int g_bn256 = 0;            // tuning hook: 1 lets long-K layers use 128 x 256 persistent tiles (measured 1.7 % SLOWER on
                             // ResNet-50: one CTA per SM leaves the epilogue half the warps; kept for A/B runs)
 int g_wgrad_swap = 1;       // tuning hook: 0 disables the operand-role swap of narrow-output wgrad tiles
@@ -1174,8 +1231,8 @@ int pick_stages(int KB) {
 }
 
 template <int MODE>
-cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs a, int n_total, int m_tiles,
-                            bool stats, cudaStream_t stream) {
+cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, bool have_half_map, const TmaSet& tmA,
+                            ConvArgs a, int n_total, int m_tiles, bool stats, cudaStream_t stream) {
   bool persistent = false;
   if (mode_a_tma(MODE) && g_persistent) {
     if (g_num_sms == 0) {
@@ -1193,16 +1250,28 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const TmaSet& tmA, ConvArgs 
   // has half the warps to hide its latency, which would cost the short-K, store-bound layers
   if (persistent && g_bn256 && n_total % 256 == 0 && a.KB >= 4 &&
       static_cast<long long>(n_total / 256) * m_tiles >= 4LL * g_num_sms) {
-    return stats ? launch_persistent_t<256, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
-                 : launch_persistent_t<256, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
+    return stats ? launch_persistent_t<256, MODE, true, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                 : launch_persistent_t<256, MODE, false, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
   }
   if (persistent) {
-    if (n_total % 128 == 0)
-      return stats ? launch_persistent_t<128, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
-                   : launch_persistent_t<128, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
-    if (n_total % 64 == 0)
-      return stats ? launch_persistent_t<64, MODE, true>(tmB, tmA, a, n_total, m_tiles, stream)
-                   : launch_persistent_t<64, MODE, false>(tmB, tmA, a, n_total, m_tiles, stream);
+    // CTA pairs sharing the weight tile through TMA multicast: where operand traffic matters (K >= 128) and the half
+    // tile is loadable (K-major: half-height box map; MN-major: the two 64-column boxes of a 128-wide tile)
+    const bool pair = g_cluster && m_tiles >= 2 && a.KB >= 2 &&
+                      (mode_b_mn(MODE) ? (n_total % 128 == 0) : have_half_map);
+    if (n_total % 128 == 0) {
+      if (pair)
+        return stats ? launch_persistent_t<128, MODE, true, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                     : launch_persistent_t<128, MODE, false, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+      return stats ? launch_persistent_t<128, MODE, true, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                   : launch_persistent_t<128, MODE, false, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+    }
+    if (n_total % 64 == 0) {
+      if (pair && !mode_b_mn(MODE))
+        return stats ? launch_persistent_t<64, MODE, true, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                     : launch_persistent_t<64, MODE, false, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+      return stats ? launch_persistent_t<64, MODE, true, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                   : launch_persistent_t<64, MODE, false, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+    }
     return cudaErrorInvalidValue;
   }
   if (n_total % 128 == 0) {
@@ -1224,6 +1293,7 @@ void set_conv_force_stages(int s) { g_force_stages = s; }
 void set_conv_persistent(int on) { g_persistent = on; }
 void set_wgrad_swap(int on) { g_wgrad_swap = on; }
 void set_conv_bn256(int on) { g_bn256 = on; }
+void set_conv_cluster(int on) { g_cluster = on; }
 
 // `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
 // `a_matrix`: the A operand for the TMA-A modes (2-D matrix [M][a_cols], or the NHWC tensor in tile modes).
@@ -1234,10 +1304,15 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
   TmaSet tmA;
   const int bn = (n_total % 128 == 0) ? 128 : 64;
   if (n_total % 64 != 0) return cudaErrorInvalidValue;
+  CUtensorMap tmBh;                 // K-major weights: half-height box (one CTA's share of a multicast pair)
+  bool have_half = false;
   if (mode_b_mn(mode)) {
     if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, 64)) return cudaErrorUnknown;
+    tmBh = tmB;
   } else {
     if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, bn)) return cudaErrorUnknown;
+    have_half = g_cluster && make_map_2d(&tmBh, w, w_rows, w_cols, w_cols, 64, bn / 2);
+    if (!have_half) tmBh = tmB;
   }
   a.ntaps = 0;
   a.outH = a.dstH; a.outW = a.dstW; a.out_stride = 1; a.out_pa = 0; a.out_pb = 0;
@@ -1247,14 +1322,14 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
   const bool stats = a.sum != nullptr;
   auto dispatch = [&](const ConvArgs& args, int tiles) -> cudaError_t {
     switch (mode) {
-      case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmA, args, n_total, tiles, stats, stream);
-      case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
-      case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmA, args, n_total, tiles, stats, stream);
-      case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmA, args, n_total, tiles, stats, stream);
-      case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(tmB, tmA, args, n_total, tiles, stats, stream);
-      case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
-      case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(tmB, tmA, args, n_total, tiles, stats, stream);
-      case kConvStemTma: return launch_fwd_mode<kConvStemTma>(tmB, tmA, args, n_total, tiles, stats, stream);
+      case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvStemTma: return launch_fwd_mode<kConvStemTma>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
       default: return cudaErrorInvalidValue;
     }
   };

@@ -65,6 +65,32 @@ DDL_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// ---- thread-block cluster helpers (CTA pairs sharing the weight tile by TMA multicast) ------------------------
+DDL_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+DDL_DEVICE void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D TMA load delivered to the same shared-memory offset of every CTA in `cta_mask`; each destination CTA's mbarrier
+// at the same offset receives the complete_tx for the bytes written into that CTA.
+DDL_DEVICE void tma_load_2d_multicast(uint32_t dst_smem, const CUtensorMap* m, int x, int y, uint64_t* bar,
+                                      uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%2, %3}], [%4], %5;"
+      :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(x), "r"(y), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `cta_mask`
+DDL_DEVICE void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 DDL_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- cp.async (16 B, zero-fill when !valid) ---------------------------------------------------

@@ -24,6 +24,10 @@ def _C():
     C = _ext.load()
     if os.environ.get("DDL_WGRAD_SWAP", "1") == "0":       # tuning hook (A/B runs): no operand-role swap in wgrad
         C.set_wgrad_swap(0)
+    if os.environ.get("DDL_CONV_PERSISTENT", "") in ("0", "2"):    # tuning hook: 0 = never, 2 = always persistent
+        C.set_conv_persistent(int(os.environ["DDL_CONV_PERSISTENT"]))
+    if os.environ.get("DDL_CONV_CLUSTER", "0") == "1":     # tuning hook (A/B runs): CTA pairs + TMA multicast of weights
+        C.set_conv_cluster(1)
     if os.environ.get("DDL_CONV_BN256", "0") == "1":       # tuning hook (A/B runs): 128 x 256 persistent tiles
         C.set_conv_bn256(1)
     return C
