@@ -5,6 +5,13 @@ N=${1:-2}
 mkdir -p gpurun_out
 T0=$(date +%s)
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+if [ "$2" = "benchonly" ]; then     # just the headline line (one scaling point)
+  timeout 600 $TR --master-port 29612 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/oursg_N$N.json 2> gpurun_out/oursg_N$N.err
+  echo "ours(graph) rc=$?" >> gpurun_out/oursg_N$N.err
+  grep -o '"value": [0-9.]*, "unit": "images/sec", "n_gpus": [0-9]*, "steps": 30, "warmup": 5, "ms_per_step": [0-9.]*' gpurun_out/oursg_N$N.json
+  tail -2 gpurun_out/oursg_N$N.err
+  exit 0
+fi
 timeout 600 $TR --master-port 29611 tools/comm_test.py --no-sweep > gpurun_out/commlean_N$N.log 2>&1
 echo "comm rc=$?" >> gpurun_out/commlean_N$N.log
 timeout 600 $TR --master-port 29612 bench.py --gpus $N --steps 30 --warmup 5 > gpurun_out/oursg_N$N.json 2> gpurun_out/oursg_N$N.err
