@@ -9,7 +9,6 @@ copy carries uint8-range floats only once and no fp32 normalised copy is materia
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
 
 import torch
 

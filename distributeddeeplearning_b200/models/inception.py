@@ -12,7 +12,6 @@ gather kernel forward, one scatter kernel backward).
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 
 from .. import ops

@@ -9,7 +9,6 @@ BN statistics in its epilogue, then a single BN-apply/ReLU/add pass.
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 
 from .. import ops

@@ -6,7 +6,6 @@ layers are the same GEMM kernel; dropout recomputes its Philox mask in backward.
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 
 from .. import ops

@@ -19,7 +19,7 @@ the backward is scheduled.
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import Sequence
 
 import torch
 

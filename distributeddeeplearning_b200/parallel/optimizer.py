@@ -15,7 +15,7 @@ with allreduce-averaged gradients — behind Horovod's call shap
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Tuple
+from typing import List, Optional, Tuple
 
 import torch
 import torch.distributed as td

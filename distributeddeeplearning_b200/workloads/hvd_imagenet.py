@@ -14,7 +14,6 @@ data-free mode); ``--model``; ``--synthetic-length``.
 from __future__ import annotations
 
 import argparse
-import math
 import os
 import sys
 

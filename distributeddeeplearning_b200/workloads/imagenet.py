@@ -17,8 +17,6 @@ from __future__ import annotations
 import logging
 import os
 import shutil
-import sys
-from typing import Optional
 
 import torch
 

@@ -3,7 +3,6 @@
 import os
 import re
 import subprocess
-import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "distributeddeeplearning_b200", "_C.so")
