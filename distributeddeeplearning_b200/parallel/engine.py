@@ -154,7 +154,7 @@ class FusedSGD(torch.optim.Optimizer):
         self.wire_bf16 = compression is not Compression.none and compression is not Compressor
         self.compression = compression
         self.overlap = overlap
-        self.comm_blocks = int(comm_blocks)
+        self.comm_blocks = int(os.environ.get("DDL_COMM_BLOCKS", comm_blocks))      # env: tuning hook (A/B runs)
         self.oneshot_bytes = int(oneshot_kb * 1024)       # buckets up to this size skip the broadcast phase
         # debug mode: after every step verify the protocol's invariants and poison the wire staging
         self.debug = bool(int(os.environ.get("DDL_COMM_DEBUG", "0"))) if debug is None else bool(debug)
@@ -163,6 +163,7 @@ class FusedSGD(torch.optim.Optimizer):
         # ---- static plan: parameters in gradient-ready (reverse registration) order -----------
         self.params: List[torch.Tensor] = list(reversed(plist))
         numels = [p.numel() for p in self.params]
+        bucket_mb = float(os.environ.get("DDL_BUCKET_MB", bucket_mb))                 # env: tuning hook (A/B runs)
         plan = self.C.plan_buckets(numels, max(2048, int(first_bucket_mb * (1 << 20) / 4)),
                                    max(2048, int(bucket_mb * (1 << 20) / 4)), 64, 2048)
         self.plan = plan
