@@ -129,7 +129,7 @@ class FusedSGD(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 0.01, momentum: float = 0.0, dampening: float = 0.0,
                  weight_decay: float = 0.0, nesterov: bool = False, compression: type = Compression.none,
                  first_bucket_mb: float = 1.0, bucket_mb: float = 16.0, overlap: bool = True,
-                 comm_blocks: int = 32, use_multicast: Optional[bool] = None, timeout_s: float = 30.0,
+                 comm_blocks: int = 64, use_multicast: Optional[bool] = None, timeout_s: float = 30.0,
                  broadcast_root: Optional[int] = 0, debug: Optional[bool] = None, oneshot_kb: float = 512.0):
         named = list(params)
         if named and isinstance(named[0], tuple):
