@@ -563,7 +563,12 @@ struct PersistCfg {
 // fetches half of the weight tile and TMA-multicasts it into both CTAs' shared memory, so the B operand crosses
 // L2 -> SM once per pair (operand traffic per 128 x 128 tile: 32 KB -> 24 KB).  A stage may be refilled only when
 // BOTH CTAs' MMAs have consumed it: `empty` counts two arrivals, delivered by a multicast tcgen05.commit.
-template <int BLOCK_N, int MODE, bool STATS, bool CLUSTER>
+// CL: 0 = independent CTAs, 1 = the multicast pairs described above, 2 = CTA pairs sharing ONE MMA (cta_group::2,
+// M = 256): each CTA loads its 128 rows of A and only HALF of the weight tile; the leader CTA issues the MMAs, which
+// read both SMs' shared memory and write both SMs' TMEM.  Bytes entering each SM per 128 x 128 outputs: 32 KB -> 24 KB.
+//   barriers (CL = 2): leader.full[s] = own producer + the peer's forwarded arrive (the peer's MMA warp relays its local
+//   `full`); empty[s] / acc_full[b] in both CTAs = the leader's multicast commit; leader.acc_empty[b] = both epilogues.
+template <int BLOCK_N, int MODE, bool STATS, int CL>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
                             const __grid_constant__ TmaSet tmAs, ConvArgs a, int n_tiles, int m_tiles) {
@@ -571,6 +576,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
   constexpr bool kBMn = mode_b_mn(MODE);
   constexpr bool kTile = mode_tile(MODE);
   constexpr int kStages = Cfg::kStages;
+  constexpr bool CLUSTER = CL != 0;
+  constexpr bool PAIR = CL == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg = smem + kStages * Cfg::kStageBytes;
@@ -591,15 +598,21 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
   const int item_step = CLUSTER ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1u); mbar_init(&empty[s], CLUSTER ? 2u : 1u); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&acc_empty[b], 1u); }
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], (PAIR && crank == 0) ? 2u : 1u);
+      mbar_init(&empty[s], CL == 1 ? 2u : 1u);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&acc_empty[b], PAIR ? 2u : 1u); }
     fence_mbar_init();
   }
   if (warp == 4 && elect_one()) {
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmAs.m[0]);
   }
-  if (warp == 5) tmem_alloc<2 * BLOCK_N>(tmem_slot);
+  if (warp == 5) {
+    if (PAIR) tmem_alloc_pair<2 * BLOCK_N>(tmem_slot);
+    else tmem_alloc<2 * BLOCK_N>(tmem_slot);
+  }
   tc_fence_before();
   __syncthreads();
   if (CLUSTER) cluster_sync_all();      // the peer's mbarriers exist before any multicast can signal them
@@ -650,7 +663,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         tc_fence_after();
         tc_fence_before();
         named_bar_sync(1, kEpiThreads);
-        if (etid == 0) mbar_arrive(&acc_empty[pbuf]);
+        if (etid == 0) {
+          if (PAIR && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[pbuf]), 0));
+          else mbar_arrive(&acc_empty[pbuf]);
+        }
         continue;
       }
       int my_m;
@@ -679,7 +695,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
       if (kTile && egrp == 0) sts32(stg_row + BLOCK_N * 2, static_cast<uint32_t>(my_m));
       tc_fence_before();
       named_bar_sync(1, kEpiThreads);
-      if (etid == 0) mbar_arrive(&acc_empty[buf]);      // every epilogue thread has finished reading this TMEM buffer
+      if (etid == 0) {                                  // every epilogue thread has finished reading this TMEM buffer
+        if (PAIR && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));   // the leader issues the MMAs
+        else mbar_arrive(&acc_empty[buf]);
+      }
       epi_stats_store<BLOCK_N, STATS, kTile>(stg_u32, red_u32, etid, ew, a, n0, m0);
       named_bar_sync(1, kEpiThreads);      // staging (and the stats scratch) may be overwritten by the next tile
     }
@@ -697,7 +716,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           const uint32_t sB = smem_u32(sA + kATileBytes);
-          mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + a_bytes);
+          mbar_arrive_expect_tx(&full[stage], (PAIR ? Cfg::kBTileBytes / 2 : Cfg::kBTileBytes) + a_bytes);
           int widx = tap, dh = 0, dw = 0, mapi = 0;
           if (kTile) {
             if (a.ntaps > 0) {
@@ -708,7 +727,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
               dh = a.pad - tap_r * a.dil; dw = a.pad_w - tap_s * a.dil;
             }
           }
-          if (CLUSTER) {
+          if (PAIR) {
+            // my half of the weight tile into MY shared memory only: the pair MMA reads the other half from the peer
+            if (kBMn) tma_load_2d(sB, &tmB, widx * a.ldc + n0 + crank * (BLOCK_N / 2), cc * 64, &full[stage]);
+            else tma_load_2d(sB, &tmBh, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
+                             n0 + crank * (BLOCK_N / 2), &full[stage]);
+          } else if (CLUSTER) {
             // my half of the weight tile, delivered to both CTAs of the pair (each CTA's `full` barrier sees both halves)
             if (kBMn) {       // BLOCK_N = 128: the two 64-column boxes are the halves
               tma_load_2d_multicast(sB + crank * 8192, &tmB, widx * a.ldc + n0 + crank * 64, cc * 64, &full[stage], 0x3);
@@ -739,33 +763,51 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     }
   } else {
     // ====================================== MMA issuer ========================================
-    constexpr uint32_t idesc = idesc_bf16(kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = item0; t < total; t += item_step, ++it) {
-      const int buf = it & 1;
-      mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);     // epilogue has drained this TMEM buffer
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
-      for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sB = sA + kATileBytes;
-#pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
-            const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
-          }
-          if (CLUSTER) umma_commit_multicast(&empty[stage], 0x3);     // frees the stage in BOTH CTAs of the pair
-          else umma_commit(&empty[stage]);
-          if (kb == KB - 1) umma_commit(&acc_full[buf]);
+    if (PAIR && crank != 0) {
+      // peer CTA of a pair: no MMAs to issue — relay "my operands of this stage have landed" to the leader's barrier
+      for (int t = item0; t < total; t += item_step) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (elect_one()) mbar_arrive_cluster(mapa_shared(smem_u32(&full[stage]), 0));
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        __syncwarp();
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    } else {
+      for (int t = item0; t < total; t += item_step, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);     // epilogue(s) have drained this TMEM buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sB = sA + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
+              const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+              if (PAIR) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+              else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            }
+            if (PAIR) {
+              umma_commit_pair_multicast(&empty[stage], 0x3);          // frees the stage in both CTAs
+              if (kb == KB - 1) umma_commit_pair_multicast(&acc_full[buf], 0x3);
+            } else {
+              if (CLUSTER) umma_commit_multicast(&empty[stage], 0x3);  // frees the stage in BOTH CTAs of the pair
+              else umma_commit(&empty[stage]);
+              if (kb == KB - 1) umma_commit(&acc_full[buf]);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   }
@@ -775,7 +817,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
   if (CLUSTER) cluster_sync_all();      // no CTA leaves while its peer may still multicast into it / signal its barriers
   if (warp == 5) {
     tc_fence_after();
-    tmem_dealloc<2 * BLOCK_N>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<2 * BLOCK_N>(tmem_base);
+    else tmem_dealloc<2 * BLOCK_N>(tmem_base);
   }
 }
 
@@ -1166,11 +1209,12 @@ cudaError_t launch_fwd_t(const CUtensorMap& tmB, const TmaSet& tmA, const ConvAr
 int g_persistent = 1;        // TMA-fed modes use the persistent kernel (tuning hook: set_conv_persistent)
 int g_num_sms = 0;
 
-template <int BLOCK_N, int MODE, bool STATS, bool CLUSTER>
+template <int BLOCK_N, int MODE, bool STATS, int CL>
 cudaError_t launch_persistent_t(const CUtensorMap& tmB, const CUtensorMap& tmBh, const TmaSet& tmA, const ConvArgs& a,
                                 int n_total, int m_tiles, cudaStream_t stream) {
   using Cfg = PersistCfg<BLOCK_N>;
-  auto kern = conv_gemm_persistent_kernel<BLOCK_N, MODE, STATS, CLUSTER>;
+  constexpr bool CLUSTER = CL != 0;
+  auto kern = conv_gemm_persistent_kernel<BLOCK_N, MODE, STATS, CL>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -1212,7 +1256,7 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const CUtensorMap& tmBh,
 // round trip, epilogue), so they get a shallow ring -> small shared-memory footprint -> 3-4 CTAs per SM whose
 // prologues/epilogues overlap.  Long-K tiles get the deep ring.  g_force_stages (tuning hook) overrides.
 int g_force_stages = 0;
-int g_cluster = 0;          // tuning hook: 1 = CTA pairs with TMA-multicast weight tiles in the persistent kernel
+int g_cluster = 0;          // tuning hook: 1 = CTA pairs with TMA-multicast weight tiles, 2 = cta_group::2 pair MMAs
 int g_bn256 = 0;            // tuning hook: 1 lets long-K layers use 128 x 256 persistent tiles (measured 1.7 % SLOWER on
                             // ResNet-50: one CTA per SM leaves the epilogue half the warps; kept for A/B runs)
 int g_wgrad_swap = 1;       // tuning hook: 0 disables the operand-role swap of narrow-output wgrad tiles
@@ -1250,8 +1294,8 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, boo
   // has half the warps to hide its latency, which would cost the short-K, store-bound layers
   if (persistent && g_bn256 && n_total % 256 == 0 && a.KB >= 4 &&
       static_cast<long long>(n_total / 256) * m_tiles >= 4LL * g_num_sms) {
-    return stats ? launch_persistent_t<256, MODE, true, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
-                 : launch_persistent_t<256, MODE, false, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+    return stats ? launch_persistent_t<256, MODE, true, 0>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                 : launch_persistent_t<256, MODE, false, 0>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
   }
   if (persistent) {
     // CTA pairs sharing the weight tile through TMA multicast: where operand traffic matters (K >= 128) and the half
@@ -1259,18 +1303,24 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, boo
     const bool pair = g_cluster && m_tiles >= 2 && a.KB >= 2 &&
                       (mode_b_mn(MODE) ? (n_total % 128 == 0) : have_half_map);
     if (n_total % 128 == 0) {
+      if (pair && g_cluster == 2)
+        return stats ? launch_persistent_t<128, MODE, true, 2>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                     : launch_persistent_t<128, MODE, false, 2>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
       if (pair)
-        return stats ? launch_persistent_t<128, MODE, true, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
-                     : launch_persistent_t<128, MODE, false, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
-      return stats ? launch_persistent_t<128, MODE, true, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
-                   : launch_persistent_t<128, MODE, false, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+        return stats ? launch_persistent_t<128, MODE, true, 1>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                     : launch_persistent_t<128, MODE, false, 1>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+      return stats ? launch_persistent_t<128, MODE, true, 0>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                   : launch_persistent_t<128, MODE, false, 0>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
     }
     if (n_total % 64 == 0) {
+      if (pair && !mode_b_mn(MODE) && g_cluster == 2)
+        return stats ? launch_persistent_t<64, MODE, true, 2>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                     : launch_persistent_t<64, MODE, false, 2>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
       if (pair && !mode_b_mn(MODE))
-        return stats ? launch_persistent_t<64, MODE, true, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
-                     : launch_persistent_t<64, MODE, false, true>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
-      return stats ? launch_persistent_t<64, MODE, true, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
-                   : launch_persistent_t<64, MODE, false, false>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+        return stats ? launch_persistent_t<64, MODE, true, 1>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                     : launch_persistent_t<64, MODE, false, 1>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
+      return stats ? launch_persistent_t<64, MODE, true, 0>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+                   : launch_persistent_t<64, MODE, false, 0>(tmB, tmBh, tmA, a, n_total, m_tiles, stream);
     }
     return cudaErrorInvalidValue;
   }

@@ -91,6 +91,40 @@ DDL_DEVICE void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
                :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
 }
 
+// ---- CTA pair (cta_group::2): one MMA spans two SMs, each SM holding its 128 rows of A and HALF of B ---------------
+template <int COLS>
+DDL_DEVICE void tmem_alloc_pair(uint32_t* slot_in_smem) {      // one whole warp in EACH CTA of the pair
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(slot_in_smem)), "n"(COLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <int COLS>
+DDL_DEVICE void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(COLS) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 per CTA] * B[N columns: N/2 per CTA]; issued by ONE thread of the leader CTA
+DDL_DEVICE void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+DDL_DEVICE void umma_commit_pair_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// address of `local` (a shared::cta address) in CTA `rank` of this cluster
+DDL_DEVICE uint32_t mapa_shared(uint32_t local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
+  return r;
+}
+DDL_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+
 DDL_DEVICE void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- cp.async (16 B, zero-fill when !valid) ---------------------------------------------------

@@ -26,8 +26,8 @@ def _C():
         C.set_wgrad_swap(0)
     if os.environ.get("DDL_CONV_PERSISTENT", "") in ("0", "2"):    # tuning hook: 0 = never, 2 = always persistent
         C.set_conv_persistent(int(os.environ["DDL_CONV_PERSISTENT"]))
-    if os.environ.get("DDL_CONV_CLUSTER", "0") == "1":     # tuning hook (A/B runs): CTA pairs + TMA multicast of weights
-        C.set_conv_cluster(1)
+    if os.environ.get("DDL_CONV_CLUSTER", "0") in ("1", "2"):     # tuning hook: 1 = CTA pairs + TMA multicast of the
+        C.set_conv_cluster(int(os.environ["DDL_CONV_CLUSTER"]))       #   weights, 2 = cta_group::2 pair MMAs
     if os.environ.get("DDL_CONV_BN256", "0") == "1":       # tuning hook (A/B runs): 128 x 256 persistent tiles
         C.set_conv_bn256(1)
     return C
