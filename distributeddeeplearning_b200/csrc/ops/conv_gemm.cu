@@ -566,8 +566,9 @@ struct PersistCfg {
 // CL: 0 = independent CTAs, 1 = the multicast pairs described above, 2 = CTA pairs sharing ONE MMA (cta_group::2,
 // M = 256): each CTA loads its 128 rows of A and only HALF of the weight tile; the leader CTA issues the MMAs, which
 // read both SMs' shared memory and write both SMs' TMEM.  Bytes entering each SM per 128 x 128 outputs: 32 KB -> 24 KB.
-//   barriers (CL = 2): leader.full[s] = own producer + the peer's forwarded arrive (the peer's MMA warp relays its local
-//   `full`); empty[s] / acc_full[b] in both CTAs = the leader's multicast commit; leader.acc_empty[b] = both epilogues.
+//   barriers (CL = 2): leader.full[s] = expect_tx of BOTH CTAs' operand bytes (the peer's TMA loads complete on the
+//   leader's barrier: cp.async.bulk.tensor.cta_group::2); empty[s] / acc_full[b] in both CTAs = the leader's multicast
+//   commit; leader.acc_empty[b] = both epilogues (the peer arrives remotely).
 template <int BLOCK_N, int MODE, bool STATS, int CL>
 __global__ void __launch_bounds__(kThreads, 2)
 conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
@@ -599,7 +600,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], (PAIR && crank == 0) ? 2u : 1u);
+      mbar_init(&full[s], 1u);
       mbar_init(&empty[s], CL == 1 ? 2u : 1u);
     }
     for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&acc_empty[b], PAIR ? 2u : 1u); }
@@ -716,7 +717,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
           mbar_wait(&empty[stage], phase ^ 1u);
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           const uint32_t sB = smem_u32(sA + kATileBytes);
-          mbar_arrive_expect_tx(&full[stage], (PAIR ? Cfg::kBTileBytes / 2 : Cfg::kBTileBytes) + a_bytes);
+          // CTA pair: every load of BOTH CTAs completes on the LEADER's barrier (it alone waits for operands), which
+          // therefore expects the bytes of the whole pair; the peer CTA arrives nowhere.
+          const uint32_t pair_bar = PAIR ? mapa_shared(smem_u32(&full[stage]), 0) : 0u;
+          if (!PAIR) mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + a_bytes);
+          else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (Cfg::kBTileBytes / 2 + a_bytes));
           int widx = tap, dh = 0, dw = 0, mapi = 0;
           if (kTile) {
             if (a.ntaps > 0) {
@@ -729,33 +734,38 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
           }
           if (PAIR) {
             // my half of the weight tile into MY shared memory only: the pair MMA reads the other half from the peer
-            if (kBMn) tma_load_2d(sB, &tmB, widx * a.ldc + n0 + crank * (BLOCK_N / 2), cc * 64, &full[stage]);
-            else tma_load_2d(sB, &tmBh, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
-                             n0 + crank * (BLOCK_N / 2), &full[stage]);
-          } else if (CLUSTER) {
-            // my half of the weight tile, delivered to both CTAs of the pair (each CTA's `full` barrier sees both halves)
-            if (kBMn) {       // BLOCK_N = 128: the two 64-column boxes are the halves
-              tma_load_2d_multicast(sB + crank * 8192, &tmB, widx * a.ldc + n0 + crank * 64, cc * 64, &full[stage], 0x3);
-            } else {          // K-major: rows [crank * BLOCK_N/2, +BLOCK_N/2) through the half-height box map
-              tma_load_2d_multicast(sB + crank * (BLOCK_N / 2) * 128, &tmBh,
-                                    mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
-                                    n0 + crank * (BLOCK_N / 2), &full[stage], 0x3);
-            }
-          } else if (kBMn) {
-#pragma unroll
-            for (int j = 0; j < BLOCK_N / 64; ++j)
-              tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
+            if (kBMn) tma_load_2d_pair(sB, &tmB, widx * a.ldc + n0 + crank * (BLOCK_N / 2), cc * 64, pair_bar);
+            else tma_load_2d_pair(sB, &tmBh, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
+                                  n0 + crank * (BLOCK_N / 2), pair_bar);
+            if (MODE == kConvStemTma) tma_load_5d_pair(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, pair_bar);
+            else if (kTile) tma_load_4d_pair(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, pair_bar);
+            else tma_load_2d_pair(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, pair_bar);
           } else {
-            // the weight map's box holds min(BLOCK_N, 128) rows
-            constexpr int kBoxRows = BLOCK_N < 128 ? BLOCK_N : 128;
+            if (CLUSTER) {
+              // my half of the weight tile, delivered to both CTAs of the pair (each CTA's `full` barrier sees both halves)
+              if (kBMn) {       // BLOCK_N = 128: the two 64-column boxes are the halves
+                tma_load_2d_multicast(sB + crank * 8192, &tmB, widx * a.ldc + n0 + crank * 64, cc * 64, &full[stage], 0x3);
+              } else {          // K-major: rows [crank * BLOCK_N/2, +BLOCK_N/2) through the half-height box map
+                tma_load_2d_multicast(sB + crank * (BLOCK_N / 2) * 128, &tmBh,
+                                      mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
+                                      n0 + crank * (BLOCK_N / 2), &full[stage], 0x3);
+              }
+            } else if (kBMn) {
 #pragma unroll
-            for (int h = 0; h < BLOCK_N / kBoxRows; ++h)
-              tma_load_2d(sB + h * kBoxRows * 128, &tmB, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
-                          n0 + h * kBoxRows, &full[stage]);
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
+            } else {
+              // the weight map's box holds min(BLOCK_N, 128) rows
+              constexpr int kBoxRows = BLOCK_N < 128 ? BLOCK_N : 128;
+#pragma unroll
+              for (int h = 0; h < BLOCK_N / kBoxRows; ++h)
+                tma_load_2d(sB + h * kBoxRows * 128, &tmB, mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK,
+                            n0 + h * kBoxRows, &full[stage]);
+            }
+            if (MODE == kConvStemTma) tma_load_5d(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, &full[stage]);
+            else if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
+            else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, &full[stage]);
           }
-          if (MODE == kConvStemTma) tma_load_5d(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, &full[stage]);
-          else if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
-          else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, &full[stage]);
           if (++cc == a.cchunks) { cc = 0; ++tap; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -768,15 +778,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     uint32_t phase = 0;
     int it = 0;
     if (PAIR && crank != 0) {
-      // peer CTA of a pair: no MMAs to issue — relay "my operands of this stage have landed" to the leader's barrier
-      for (int t = item0; t < total; t += item_step) {
-        for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[stage], phase);
-          if (elect_one()) mbar_arrive_cluster(mapa_shared(smem_u32(&full[stage]), 0));
-          __syncwarp();
-          if (++stage == kStages) { stage = 0; phase ^= 1u; }
-        }
-      }
+      // peer CTA of a pair: the leader issues the MMAs for both (its operands' arrival is signalled to the leader directly)
     } else {
       for (int t = item0; t < total; t += item_step, ++it) {
         const int buf = it & 1;

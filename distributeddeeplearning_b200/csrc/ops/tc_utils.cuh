@@ -121,6 +121,28 @@ DDL_DEVICE uint32_t mapa_shared(uint32_t local, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(rank));
   return r;
 }
+// TMA loads of a CTA pair: data lands in the ISSUING CTA's shared memory, the complete_tx goes to `bar_cluster_addr`,
+// which may be the peer (leader) CTA's mbarrier (shared::cluster address from mapa_shared).
+DDL_DEVICE void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* m, int x, int y, uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(x), "r"(y), "r"(bar_cluster_addr) : "memory");
+}
+DDL_DEVICE void tma_load_4d_pair(uint32_t dst_smem, const CUtensorMap* m, int c0, int c1, int c2, int c3,
+                                 uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_cluster_addr)
+      : "memory");
+}
+DDL_DEVICE void tma_load_5d_pair(uint32_t dst_smem, const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4,
+                                 uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4),
+         "r"(bar_cluster_addr)
+      : "memory");
+}
 DDL_DEVICE void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
