@@ -92,3 +92,16 @@ def test_fd_exchange_between_processes():
 
 def test_driver_probe_does_not_raise(C):
     assert C.driver_available() in (True, False)
+
+
+def test_launch_accounting_table_matches_module(C):
+    """Every entry of the kernel-launch accounting table names a real binding (bench.py's gpu_launches relies on it)."""
+    from distributeddeeplearning_b200 import _ext
+
+    missing = [k for k in _ext.KERNEL_LAUNCHES if not hasattr(C, k)]
+    assert not missing, missing
+    for hook in ("set_conv_persistent", "set_conv_cluster", "set_conv_bn256", "set_wgrad_swap", "set_conv_force_stages"):
+        assert hasattr(C, hook), hook
+    n0 = _ext.launch_count()
+    _ext.add_launches(7)
+    assert _ext.launch_count() == n0 + 7
