@@ -12,9 +12,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _group(name, timeout=600):
+def _group(name, timeout=600, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_diag.py"), "--group", name], cwd=ROOT,
-                       capture_output=True, text=True, timeout=timeout)
+                       capture_output=True, text=True, timeout=timeout, env=e)
     tail = (r.stdout + r.stderr)[-4000:]
     assert r.returncode == 0, tail
     assert "FAIL" not in r.stdout, tail
@@ -23,6 +25,14 @@ def _group(name, timeout=600):
 @pytest.mark.parametrize("group", ["elementwise", "gemm", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "zoo", "zoograd", "conv_generic", "graph"])
 def test_kernel_group(group):
     _group(group)
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+def test_cluster_pair_kernels(mode):
+    """Thread-block-cluster variants of the persistent conv kernel, forced onto every TMA-fed shape: 1 = CTA pairs that
+    TMA-multicast the weight tile, 2 = cta_group::2 pair MMAs (M = 256 across two SMs, half of B per SM)."""
+    for group in ("gemm", "conv_dgrad"):
+        _group(group, timeout=300, env={"DDL_CONV_CLUSTER": mode, "DDL_CONV_PERSISTENT": "2"})
 
 
 def test_whole_model_gradients():
