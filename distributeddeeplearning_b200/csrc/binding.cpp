@@ -125,7 +125,7 @@ PYBIND11_MODULE(_C, m) {
   py::class_<PyCommCtx>(m, "CommCtx")
       .def(py::init([](const std::vector<uint64_t>& peers, uint64_t mc_base, int rank, int world, uint64_t flag_off,
                        uint64_t grad_off, uint64_t weight_off, uint64_t wbf16_off, uint64_t stage_off,
-                       ptr_t epoch_ctr, ptr_t error_flag, uint64_t timeout_ns) {
+                       ptr_t epoch_ctr, ptr_t error_flag, uint64_t timeout_ns, uint32_t debug_skew_ns) {
              if (world < 1 || world > ddl::kCommMaxWorld || static_cast<int>(peers.size()) < world)
                throw std::invalid_argument("CommCtx: bad world / peers");
              PyCommCtx x;
@@ -141,11 +141,12 @@ PYBIND11_MODULE(_C, m) {
              x.c.epoch_ctr = P<uint32_t>(epoch_ctr);
              x.c.error_flag = P<uint32_t>(error_flag);
              x.c.timeout_ns = timeout_ns;
+             x.c.debug_skew_ns = debug_skew_ns;
              return x;
            }),
            py::arg("peers"), py::arg("mc_base"), py::arg("rank"), py::arg("world"), py::arg("flag_off"),
            py::arg("grad_off"), py::arg("weight_off"), py::arg("wbf16_off"), py::arg("stage_off"),
-           py::arg("epoch_ctr"), py::arg("error_flag"), py::arg("timeout_ns"))
+           py::arg("epoch_ctr"), py::arg("error_flag"), py::arg("timeout_ns"), py::arg("debug_skew_ns") = 0)
       .def_property_readonly("has_multicast", [](const PyCommCtx& x) { return x.c.mc_base != 0; });
 
   m.def("pack_sgd_hyper", [](float lr, float momentum, float dampening, float wd, float grad_scale, bool nesterov,
@@ -160,16 +161,17 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("fused_allreduce_sgd", [](const PyCommCtx& c, int64_t start, int64_t numel, ptr_t momentum, ptr_t hyper,
                                   int channel, bool use_mc, bool wire_bf16, int blocks, ptr_t stream,
-                                  uint64_t scalar_off, ptr_t scalar_out, bool oneshot) {
+                                  uint64_t scalar_off, ptr_t scalar_out, bool oneshot, bool closing) {
     BucketArgs b;
     b.oneshot = oneshot ? 1 : 0;
+    b.closing = closing ? 1 : 0;
     b.start = start; b.numel = numel; b.momentum = P<float>(momentum); b.hyper = P<const SgdHyper>(hyper);
     b.channel = channel;
     b.scalar_off = scalar_off; b.scalar_out = P<float>(scalar_out);
     check(ddl::launch_fused_allreduce_sgd(c.c, b, use_mc, wire_bf16, blocks, S(stream)), "fused_allreduce_sgd");
   }, py::arg("ctx"), py::arg("start"), py::arg("numel"), py::arg("momentum"), py::arg("hyper"), py::arg("channel"),
      py::arg("use_mc"), py::arg("wire_bf16"), py::arg("blocks"), py::arg("stream"), py::arg("scalar_off") = 0,
-     py::arg("scalar_out") = 0, py::arg("oneshot") = false);
+     py::arg("scalar_out") = 0, py::arg("oneshot") = false, py::arg("closing") = true);
   m.attr("SCALAR_SLOTS") = ddl::kScalarSlots;
   m.def("allreduce", [](const PyCommCtx& c, int channel, uint64_t off, int64_t numel, bool bf16, float scale,
                         bool use_mc, bool oneshot, int blocks, ptr_t stream) {

@@ -24,6 +24,7 @@ struct CommCtx {
   uint32_t* epoch_ctr;                // local: [kCommChannels][kMaxCommBlocks]
   uint32_t* error_flag;               // local: set to 1+peer on barrier timeout
   uint64_t timeout_ns;
+  uint32_t debug_skew_ns;             // test hook: block b idles (b % 4) * skew ns before its data phase / prologue
   int rank;
   int world;
 };
@@ -50,6 +51,8 @@ struct BucketArgs {
   uint64_t scalar_off;
   float* scalar_out;
   int oneshot;            // small bucket: every rank reduces and updates the whole bucket (no broadcast phase)
+  int closing;            // end the kernel with a cross-rank barrier (the LAST bucket kernel of a step must: it is what
+                          // makes every peer's weight stores / accumulator clears of the whole step visible locally)
 };
 constexpr int kScalarSlots = 64;
 

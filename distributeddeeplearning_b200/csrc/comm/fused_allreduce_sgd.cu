@@ -12,8 +12,8 @@
 //   update           g/N (+wd*w), momentum, w -= lr*m on the fp32 master slice   [K15]
 //   all-gather       updated fp32 weights AND their bf16 compute copy are written to every
 //                    replica with multimem.st (or 8 peer stores)                 [K14/K16]
-//   barrier-out      all peers are done reading my gradients / writing my weights
-//   clear            zero my fp32 gradient accumulators for the next step        [K12]
+//   clear            the reader of a gradient vector zeroes it on every replica   [K12]
+//   barrier-out      (last bucket of the step only) every peer's stores have landed
 //
 // Cross-rank barriers are per-block flag exchanges in the symmetric signal pad with
 // st.release.sys / ld.acquire.sys, epochs kept in device memory (CUDA-graph safe) and a bounded
@@ -89,7 +89,9 @@ DDL_DEVICE uint32_t ld_acquire_sys(uint64_t addr) {
 // Signal pad layout (uint32), identical on every rank:  pad[channel][block][src_rank].
 // Block b of rank r stores `epoch` into pad[ch][b][r] of EVERY rank, then waits until its own
 // pad[ch][b][*] all reached `epoch`.  Epochs only grow, so a late reader never misses one.
-DDL_DEVICE void block_barrier(const CommCtx& c, int channel, uint32_t epoch) {
+DDL_DEVICE bool block_barrier(const CommCtx& c, int channel, uint32_t epoch) {
+  __shared__ int s_timed_out;
+  if (threadIdx.x == 0) s_timed_out = 0;
   __syncthreads();
   if (threadIdx.x < static_cast<unsigned>(c.world)) {
     const int peer = threadIdx.x;
@@ -102,11 +104,15 @@ DDL_DEVICE void block_barrier(const CommCtx& c, int channel, uint32_t epoch) {
     while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
       if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > c.timeout_ns) {
         atomicExch(c.error_flag, 1u + static_cast<uint32_t>(peer));  // which peer never arrived
+        s_timed_out = 1;
         break;
       }
     }
   }
   __syncthreads();
+  // Block-uniform verdict.  A caller that sees `false` must NOT touch weights, momentum or gradients any more: a
+  // peer's data is incomplete, and the host (FusedSGD.check_errors, polled by the trainers) aborts the job.
+  return s_timed_out == 0;
 }
 
 // Each (channel, block) owns an epoch counter in local device memory; thread 0 bumps it by
@@ -168,33 +174,67 @@ __global__ void __launch_bounds__(512) fused_sgd_local_kernel(float* __restrict_
 // ONESHOT (small buckets): every rank reduces the WHOLE bucket from all replicas (peer loads in rank order, so all
 // ranks compute bit-identical sums) and updates only its own replica — no broadcast stores, one data phase instead of
 // reduce-scatter + all-gather.  Two-shot (large buckets): rank r reduces slice r and broadcasts the new weights.
+//
+// Producer/consumer block identity (two-shot).  The cross-rank flag barrier pairs block b with block b of every
+// peer, so every datum that crosses ranks must be produced, consumed and recycled by the SAME block index on all
+// ranks.  The consumer of element e = start + slice*q + i*V (slice q, vector i) is thread (i mod nthreads) of rank
+// q; therefore the bf16 staging prologue walks "for q: for i = tid; i < nvec; i += nthreads" (not a flat sweep of
+// the bucket), and the gradient accumulators are recycled by their READER: after rank q has pulled vector i of all
+// replicas it stores zeros to that vector of all replicas (multimem.st, or one peer store each) — the store carries a
+// register dependence on the load's result, so it cannot overtake the read.  No block ever clears data a different
+// block of a peer may still be reading, and no closing barrier is needed for the accumulators.
+//
+// Closing barrier.  What remains to be ordered is visibility of the peers' weight stores in MY replica before my
+// next forward pass reads them.  Kernels of one rank run in stream order and every barrier-in executes a
+// fence.sys (cumulative), so it is enough that the LAST bucket kernel of a step ends with a barrier
+// (`b.closing`): when it completes locally, every block of every peer has fenced and signalled after the stores
+// of all its earlier bucket kernels.  The other kernels return right after their data phase — they neither wait for
+// the slowest peer a second time nor hold their SM slots while doing so.
 template <bool MC, bool WIRE_BF16, bool ONESHOT>
 __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, BucketArgs b) {
   const SgdHyper h = *b.hyper;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
-  const uint32_t epoch = claim_epochs(c, b.channel, 2);
+  const bool closing = ONESHOT || b.closing != 0;
+  const uint32_t epoch = claim_epochs(c, b.channel, closing ? 2 : 1);
   const uint64_t self = c.peer_base[c.rank];
+  constexpr int V = WIRE_BF16 ? 8 : 4;                  // elements per vector
+  const int64_t slice = ONESHOT ? b.numel : b.numel / c.world;           // elements this rank reduces and updates
+  const int64_t nvec = slice / V;
+  const int nslices = ONESHOT ? 1 : c.world;
 
+  auto debug_skew = [&]() {       // test hook: de-synchronise the blocks of a rank (and the ranks) on purpose
+    if (c.debug_skew_ns != 0) {
+      const uint64_t t0 = globaltimer_ns();
+      const uint64_t wait = static_cast<uint64_t>((blockIdx.x + c.rank) % 4) * c.debug_skew_ns;
+      while (globaltimer_ns() - t0 < wait) __nanosleep(200);
+    }
+  };
   if (WIRE_BF16) {
-    // cast-and-scale prologue: fp32 accumulators -> symmetric bf16 staging, clear accumulators
-    const int64_t n8 = b.numel / 8;
+    debug_skew();
+    // cast-and-scale prologue: fp32 accumulators -> symmetric bf16 staging, clear accumulators (local data only).
+    // Same (slice, vector) -> thread mapping as the consumer loop below.
     const float s = h.grad_scale;
-    for (int64_t i = tid; i < n8; i += nthreads) {
-      float4* gp = reinterpret_cast<float4*>(self + c.grad_off + (b.start + i * 8) * 4);
-      float4 a = gp[0], d = gp[1];
-      uint4 o = make_uint4(pack_bf16x2(a.x * s, a.y * s), pack_bf16x2(a.z * s, a.w * s),
-                           pack_bf16x2(d.x * s, d.y * s), pack_bf16x2(d.z * s, d.w * s));
-      *reinterpret_cast<uint4*>(self + c.stage_off + (b.start + i * 8) * 2) = o;
-      gp[0] = make_float4(0, 0, 0, 0);
-      gp[1] = make_float4(0, 0, 0, 0);
+    for (int q = 0; q < nslices; ++q) {
+      const int64_t sbase = b.start + slice * q;
+      for (int64_t i = tid; i < nvec; i += nthreads) {
+        const int64_t e = sbase + i * 8;
+        float4* gp = reinterpret_cast<float4*>(self + c.grad_off + e * 4);
+        float4 a = gp[0], d = gp[1];
+        uint4 o = make_uint4(pack_bf16x2(a.x * s, a.y * s), pack_bf16x2(a.z * s, a.w * s),
+                             pack_bf16x2(d.x * s, d.y * s), pack_bf16x2(d.z * s, d.w * s));
+        *reinterpret_cast<uint4*>(self + c.stage_off + e * 2) = o;
+        gp[0] = make_float4(0, 0, 0, 0);
+        gp[1] = make_float4(0, 0, 0, 0);
+      }
     }
   }
-  block_barrier(c, b.channel, epoch);
+  if (!block_barrier(c, b.channel, epoch)) return;      // timeout: leave weights / momentum / gradients alone
 
   if (b.scalar_off != 0 && blockIdx.x == 0 && threadIdx.x < kScalarSlots / 4) {
     // piggy-backed metrics: every rank wrote its slot before this launch (stream order) and the barrier above made the
-    // writes visible; peers overwrite their slot only after the closing barrier of this kernel.
+    // writes visible; peers overwrite their slot only after the closing barrier of this kernel (the engine puts the
+    // scalars on the closing bucket).
     float4 acc = make_float4(0, 0, 0, 0);
 #pragma unroll
     for (int p = 0; p < kMaxWorld; ++p)
@@ -206,93 +246,122 @@ __global__ void __launch_bounds__(512) fused_allreduce_sgd_kernel(CommCtx c, Buc
     reinterpret_cast<float4*>(b.scalar_out)[threadIdx.x] = make_float4(acc.x * s, acc.y * s, acc.z * s, acc.w * s);
   }
 
-  const int64_t slice = ONESHOT ? b.numel : b.numel / c.world;           // elements this rank reduces and updates
+  debug_skew();
   const int64_t base = ONESHOT ? b.start : b.start + slice * c.rank;     // (element offset in the arena)
   constexpr bool kSwitchReduce = MC && !ONESHOT;        // in-switch reduction order is not guaranteed identical
                                                         // for different requesters: one-shot sums peers itself
-  constexpr int V = WIRE_BF16 ? 8 : 4;                  // elements per thread-iteration
-  const int64_t nvec = slice / V;
-  for (int64_t i = tid; i < nvec; i += nthreads) {
-    const int64_t e = base + i * V;
-    float gsum[V];
-    if (WIRE_BF16) {
-      uint4 r;
-      if (kSwitchReduce) {
-        r = multimem_ld_reduce_bf16x8(c.mc_base + c.stage_off + e * 2);
-        float2 p0 = unpack_bf16x2(r.x), p1 = unpack_bf16x2(r.y), p2 = unpack_bf16x2(r.z), p3 = unpack_bf16x2(r.w);
-        gsum[0] = p0.x; gsum[1] = p0.y; gsum[2] = p1.x; gsum[3] = p1.y;
-        gsum[4] = p2.x; gsum[5] = p2.y; gsum[6] = p3.x; gsum[7] = p3.y;
+  // NVLink round trips are ~2-3 us: bytes in flight decide the bandwidth.  The in-switch path keeps U independent
+  // 16-byte multimem.ld_reduce per thread outstanding, so a small grid (few SM slots taken from the backward pass
+  // running next to this kernel) still fills the links; the peer-load path already has `world` loads per vector.
+  constexpr int U = kSwitchReduce ? 4 : 1;
+  for (int64_t i0 = tid; i0 < nvec; i0 += static_cast<int64_t>(U) * nthreads) {
+    float gsum[U][V];
+    uint32_t dep[U];                                     // 0, but data-dependent on the loads (orders the clears)
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * nthreads;
+      dep[u] = 0;
+      if (i >= nvec) continue;
+      const int64_t e = base + i * V;
+      if (WIRE_BF16) {
+        if (kSwitchReduce) {
+          const uint4 r = multimem_ld_reduce_bf16x8(c.mc_base + c.stage_off + e * 2);
+          float2 p0 = unpack_bf16x2(r.x), p1 = unpack_bf16x2(r.y), p2 = unpack_bf16x2(r.z), p3 = unpack_bf16x2(r.w);
+          gsum[u][0] = p0.x; gsum[u][1] = p0.y; gsum[u][2] = p1.x; gsum[u][3] = p1.y;
+          gsum[u][V - 4] = p2.x; gsum[u][V - 3] = p2.y; gsum[u][V - 2] = p3.x; gsum[u][V - 1] = p3.y;
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) gsum[u][k] = 0.f;
+          uint4 rr[kMaxWorld];
+#pragma unroll
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) rr[p] = ld_peer_u32x4(c.peer_base[p] + c.stage_off + e * 2);
+#pragma unroll
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) {
+              float2 p0 = unpack_bf16x2(rr[p].x), p1 = unpack_bf16x2(rr[p].y), p2 = unpack_bf16x2(rr[p].z),
+                     p3 = unpack_bf16x2(rr[p].w);
+              gsum[u][0] += p0.x; gsum[u][1] += p0.y; gsum[u][2] += p1.x; gsum[u][3] += p1.y;
+              gsum[u][V - 4] += p2.x; gsum[u][V - 3] += p2.y; gsum[u][V - 2] += p3.x; gsum[u][V - 1] += p3.y;
+            }
+        }
       } else {
+        float4 r;
+        if (kSwitchReduce) {
+          r = multimem_ld_reduce_f32x4(c.mc_base + c.grad_off + e * 4);
+        } else {
+          float4 rr[kMaxWorld];
 #pragma unroll
-        for (int k = 0; k < V; ++k) gsum[k] = 0.f;
-        uint4 rr[kMaxWorld];
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) rr[p] = ld_peer_f32x4(c.peer_base[p] + c.grad_off + e * 4);
+          r = make_float4(0, 0, 0, 0);
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-          if (p < c.world) rr[p] = ld_peer_u32x4(c.peer_base[p] + c.stage_off + e * 2);
-#pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-          if (p < c.world) {
-            float2 p0 = unpack_bf16x2(rr[p].x), p1 = unpack_bf16x2(rr[p].y), p2 = unpack_bf16x2(rr[p].z),
-                   p3 = unpack_bf16x2(rr[p].w);
-            gsum[0] += p0.x; gsum[1] += p0.y; gsum[2] += p1.x; gsum[3] += p1.y;
-            gsum[4] += p2.x; gsum[5] += p2.y; gsum[6] += p3.x; gsum[7] += p3.y;
-          }
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) { r.x += rr[p].x; r.y += rr[p].y; r.z += rr[p].z; r.w += rr[p].w; }
+        }
+        asm volatile("and.b32 %0, %1, 0;" : "=r"(dep[u]) : "r"(__float_as_uint(r.x)));
+        const float s = h.grad_scale;
+        gsum[u][0] = r.x * s; gsum[u][1] = r.y * s; gsum[u][2] = r.z * s; gsum[u][3] = r.w * s;
       }
-    } else {
-      float4 r;
-      if (kSwitchReduce) {
-        r = multimem_ld_reduce_f32x4(c.mc_base + c.grad_off + e * 4);
-      } else {
-        float4 rr[kMaxWorld];
-#pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-          if (p < c.world) rr[p] = ld_peer_f32x4(c.peer_base[p] + c.grad_off + e * 4);
-        r = make_float4(0, 0, 0, 0);
-#pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-          if (p < c.world) { r.x += rr[p].x; r.y += rr[p].y; r.z += rr[p].z; r.w += rr[p].w; }
-      }
-      const float s = h.grad_scale;
-      gsum[0] = r.x * s; gsum[1] = r.y * s; gsum[2] = r.z * s; gsum[3] = r.w * s;
-    }
-    // fp32 master weights + momentum of my slice live in my own replica
-    float wv[V], mv[V];
-    const float4* wp = reinterpret_cast<const float4*>(self + c.weight_off + e * 4);
-    float4* mp = reinterpret_cast<float4*>(b.momentum + e);
-#pragma unroll
-    for (int q = 0; q < V / 4; ++q) {
-      float4 t = wp[q];
-      wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
-      float4 u = (h.momentum != 0.f && !h.first_step) ? mp[q] : make_float4(0, 0, 0, 0);
-      mv[4 * q] = u.x; mv[4 * q + 1] = u.y; mv[4 * q + 2] = u.z; mv[4 * q + 3] = u.w;
     }
 #pragma unroll
-    for (int k = 0; k < V; ++k) sgd_update(wv[k], mv[k], gsum[k], h);
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + static_cast<int64_t>(u) * nthreads;
+      if (i >= nvec) continue;
+      const int64_t e = base + i * V;
+      if (!WIRE_BF16 && !ONESHOT) {
+        // recycle the accumulators of this vector on every replica (I am their only cross-rank reader)
+        const float z = __uint_as_float(dep[u]);
+        const float4 z4 = make_float4(z, z, z, z);
+        if (MC) {
+          multimem_st_f32x4(c.mc_base + c.grad_off + e * 4, z4);
+        } else {
 #pragma unroll
-    for (int q = 0; q < V / 4; ++q) {
-      if (h.momentum != 0.f) mp[q] = make_float4(mv[4 * q], mv[4 * q + 1], mv[4 * q + 2], mv[4 * q + 3]);
-      const float4 wn = make_float4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
-      const uint2 wbn = make_uint2(pack_bf16x2(wn.x, wn.y), pack_bf16x2(wn.z, wn.w));
-      const int64_t eo = e + 4 * q;
-      if (ONESHOT) {
-        *reinterpret_cast<float4*>(self + c.weight_off + eo * 4) = wn;
-        *reinterpret_cast<uint2*>(self + c.wbf16_off + eo * 2) = wbn;
-      } else if (MC) {
-        multimem_st_f32x4(c.mc_base + c.weight_off + eo * 4, wn);
-        multimem_st_u32x2(c.mc_base + c.wbf16_off + eo * 2, wbn);
-      } else {
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) st_peer_f32x4(c.peer_base[p] + c.grad_off + e * 4, z4);
+        }
+      }
+      // fp32 master weights + momentum of my slice live in my own replica
+      float wv[V], mv[V];
+      const float4* wp = reinterpret_cast<const float4*>(self + c.weight_off + e * 4);
+      float4* mp = reinterpret_cast<float4*>(b.momentum + e);
 #pragma unroll
-        for (int p = 0; p < kMaxWorld; ++p)
-          if (p < c.world) {
-            st_peer_f32x4(c.peer_base[p] + c.weight_off + eo * 4, wn);
-            st_peer_u32x2(c.peer_base[p] + c.wbf16_off + eo * 2, wbn);
-          }
+      for (int q = 0; q < V / 4; ++q) {
+        float4 t = wp[q];
+        wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
+        float4 m4 = (h.momentum != 0.f && !h.first_step) ? mp[q] : make_float4(0, 0, 0, 0);
+        mv[4 * q] = m4.x; mv[4 * q + 1] = m4.y; mv[4 * q + 2] = m4.z; mv[4 * q + 3] = m4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) sgd_update(wv[k], mv[k], gsum[u][k], h);
+#pragma unroll
+      for (int q = 0; q < V / 4; ++q) {
+        if (h.momentum != 0.f) mp[q] = make_float4(mv[4 * q], mv[4 * q + 1], mv[4 * q + 2], mv[4 * q + 3]);
+        const float4 wn = make_float4(wv[4 * q], wv[4 * q + 1], wv[4 * q + 2], wv[4 * q + 3]);
+        const uint2 wbn = make_uint2(pack_bf16x2(wn.x, wn.y), pack_bf16x2(wn.z, wn.w));
+        const int64_t eo = e + 4 * q;
+        if (ONESHOT) {
+          *reinterpret_cast<float4*>(self + c.weight_off + eo * 4) = wn;
+          *reinterpret_cast<uint2*>(self + c.wbf16_off + eo * 2) = wbn;
+        } else if (MC) {
+          multimem_st_f32x4(c.mc_base + c.weight_off + eo * 4, wn);
+          multimem_st_u32x2(c.mc_base + c.wbf16_off + eo * 2, wbn);
+        } else {
+#pragma unroll
+          for (int p = 0; p < kMaxWorld; ++p)
+            if (p < c.world) {
+              st_peer_f32x4(c.peer_base[p] + c.weight_off + eo * 4, wn);
+              st_peer_u32x2(c.peer_base[p] + c.wbf16_off + eo * 2, wbn);
+            }
+        }
       }
     }
   }
-  block_barrier(c, b.channel, epoch + 1);
-  if (!WIRE_BF16) {
-    // every peer has consumed my accumulators: clear them for the next step's wgrad atomics
+  if (!closing) return;
+  if (!block_barrier(c, b.channel, epoch + 1)) return;
+  if (ONESHOT && !WIRE_BF16) {
+    // one-shot: every rank read every replica; the identical flat mapping on all ranks makes block b the only
+    // cross-rank reader of the vectors block b clears here
     const int64_t n4 = b.numel / 4;
     float4* gp = reinterpret_cast<float4*>(self + c.grad_off + b.start * 4);
     for (int64_t i = tid; i < n4; i += nthreads) gp[i] = make_float4(0, 0, 0, 0);
@@ -308,7 +377,7 @@ __global__ void __launch_bounds__(512) allreduce_kernel(CommCtx c, int channel, 
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const uint32_t epoch = claim_epochs(c, channel, 2);
-  block_barrier(c, channel, epoch);
+  if (!block_barrier(c, channel, epoch)) return;
   constexpr int V = BF16 ? 8 : 4;
   constexpr int ES = BF16 ? 2 : 4;
   const int64_t slice = ONESHOT ? numel : numel / c.world;

@@ -108,13 +108,22 @@ int recv_fd(int sock, int32_t* tag, int timeout_ms) {
   throw std::runtime_error("fd_channel: message carried no descriptor");
 }
 
+// Accept one connection from a process of OUR user (SO_PEERCRED): the socket lives in the abstract namespace, which
+// any local process can reach, so connections of other users are dropped instead of being trusted (their bogus
+// descriptor or source rank would otherwise poison / abort the arena set-up).  The socket name itself carries a random
+// token agreed over the process group (see SymmetricArena), so a foreign process of the same user cannot guess it.
 int accept_timeout(int server, int timeout_ms) {
-  pollfd p{server, POLLIN, 0};
-  int pr = ::poll(&p, 1, timeout_ms);
-  if (pr <= 0) throw std::runtime_error("fd_channel: timed out in accept");
-  int c = ::accept4(server, nullptr, nullptr, SOCK_CLOEXEC);
-  if (c < 0) throw std::runtime_error(std::string("fd_channel: accept(): ") + std::strerror(errno));
-  return c;
+  for (;;) {
+    pollfd p{server, POLLIN, 0};
+    int pr = ::poll(&p, 1, timeout_ms);
+    if (pr <= 0) throw std::runtime_error("fd_channel: timed out in accept");
+    int c = ::accept4(server, nullptr, nullptr, SOCK_CLOEXEC);
+    if (c < 0) throw std::runtime_error(std::string("fd_channel: accept(): ") + std::strerror(errno));
+    ucred cred{};
+    socklen_t len = sizeof(cred);
+    if (::getsockopt(c, SOL_SOCKET, SO_PEERCRED, &cred, &len) == 0 && cred.uid == ::geteuid()) return c;
+    ::close(c);     // not one of ours: ignore and keep waiting for the real peer
+  }
 }
 
 }  // namespace

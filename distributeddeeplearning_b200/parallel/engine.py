@@ -21,7 +21,7 @@ With world_size == 1 the same class runs the local fused SGD kernel per bucket.
 from __future__ import annotations
 
 import os
-import time
+import secrets
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -50,9 +50,9 @@ class SymmetricArena:
     """One symmetric allocation per rank carved into named regions (byte offsets identical everywhere)."""
 
     def __init__(self, regions: List[Tuple[str, int]], device: torch.device, want_multicast: Optional[bool] = None,
-                 session: Optional[str] = None):
+                 session: Optional[str] = None, local: bool = False):
         self.C = _ext.load()
-        self.rank, self.world = dist.rank(), dist.size()
+        self.rank, self.world = (0, 1) if local else (dist.rank(), dist.size())
         self.device = device
         self.offsets: Dict[str, int] = {}
         cur = 0
@@ -74,7 +74,7 @@ class SymmetricArena:
             dev_index = device.index if device.index is not None else torch.cuda.current_device()
             self.native = self.C.SymmArena(self.rank, self.world, dev_index, self.nbytes)
             self.native.alloc()
-            tag = session or dist.broadcast_object(f"ddl{os.getpid()}-{int(time.time() * 1e3) & 0xffffff}", 0)
+            tag = session or dist.broadcast_object(f"ddl{os.getpid()}-{secrets.token_hex(12)}", 0)   # unguessable socket name
             SymmetricArena._seq = getattr(SymmetricArena, "_seq", 0) + 1
             tag = f"{tag}-{SymmetricArena._seq}"
             self.native.exchange(tag + "-x", 60000)
@@ -129,8 +129,11 @@ class FusedSGD(torch.optim.Optimizer):
     def __init__(self, params, lr: float = 0.01, momentum: float = 0.0, dampening: float = 0.0,
                  weight_decay: float = 0.0, nesterov: bool = False, compression: type = Compression.none,
                  first_bucket_mb: float = 1.0, bucket_mb: float = 16.0, overlap: bool = True,
-                 comm_blocks: int = 64, use_multicast: Optional[bool] = None, timeout_s: float = 30.0,
-                 broadcast_root: Optional[int] = 0, debug: Optional[bool] = None, oneshot_kb: float = 512.0):
+                 comm_blocks: int = 32, use_multicast: Optional[bool] = None, timeout_s: float = 30.0,
+                 broadcast_root: Optional[int] = 0, debug: Optional[bool] = None, oneshot_kb: float = 0.0,
+                 local: bool = False):
+        """``local=True`` builds a single-rank engine inside a multi-rank job (no peers, no averaging): the oracle of
+        ``selfcheck.step_equivalence``."""
         named = list(params)
         if named and isinstance(named[0], tuple):
             plist = [p for _, p in named]
@@ -150,12 +153,14 @@ class FusedSGD(torch.optim.Optimizer):
             raise ValueError("FusedSGD keeps fp32 master weights; parameters must be fp32")
         self.C = _ext.load()
         self.device = dev
-        self.world, self.rank = dist.size(), dist.rank()
+        self.world, self.rank = (1, 0) if local else (dist.size(), dist.rank())
         self.wire_bf16 = compression is not Compression.none and compression is not Compressor
         self.compression = compression
         self.overlap = overlap
         self.comm_blocks = int(os.environ.get("DDL_COMM_BLOCKS", comm_blocks))      # env: tuning hook (A/B runs)
-        self.oneshot_bytes = int(oneshot_kb * 1024)       # buckets up to this size skip the broadcast phase
+        # one-shot buckets (every rank reduces everything, no broadcast phase) always need their own closing barrier;
+        # since the two-shot kernels no longer end with one, two-shot wins at every size and one-shot is opt-in
+        self.oneshot_bytes = int(float(os.environ.get("DDL_ONESHOT_KB", oneshot_kb)) * 1024)
         # debug mode: after every step verify the protocol's invariants and poison the wire staging
         self.debug = bool(int(os.environ.get("DDL_COMM_DEBUG", "0"))) if debug is None else bool(debug)
         self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
@@ -168,7 +173,7 @@ class FusedSGD(torch.optim.Optimizer):
                                    max(2048, int(bucket_mb * (1 << 20) / 4)), 64, 2048)
         self.plan = plan
         h = float(plan["hash"] % (1 << 52))
-        if dist.is_distributed() and (dist.allreduce_scalar(h, op="max") != h or dist.allreduce_scalar(h, op="min") != h):
+        if dist.is_distributed() and not local and (dist.allreduce_scalar(h, op="max") != h or dist.allreduce_scalar(h, op="min") != h):
             raise RuntimeError("bucket plan differs across ranks (models are not identical)")
         T = int(plan["total_elems"])
         self.total_elems = T
@@ -179,7 +184,7 @@ class FusedSGD(torch.optim.Optimizer):
         if self.wire_bf16:
             regions.append(("stage", T * 2))
         regions.append(("scalars", int(self.C.SCALAR_SLOTS) * 4))
-        self.arena = SymmetricArena(regions, dev, use_multicast)
+        self.arena = SymmetricArena(regions, dev, use_multicast, local=local)
         self.use_mc = self.arena.has_multicast
         self.G = self.arena.region("grad", torch.float32, T)
         self.W = self.arena.region("weight", torch.float32, T)
@@ -193,10 +198,13 @@ class FusedSGD(torch.optim.Optimizer):
         self._error = torch.zeros(1, dtype=torch.int32, device=dev)
         self._hyper_dev = torch.zeros(int(self.C.SGD_HYPER_BYTES), dtype=torch.uint8, device=dev)
         self._hyper_host = torch.zeros(int(self.C.SGD_HYPER_BYTES), dtype=torch.uint8).pin_memory()
+        self._hyper_blob = None
+        self._hyper_event = None
         off = self.arena.offsets
         self.ctx = self.C.CommCtx(self.arena.peer_ptrs, self.arena.mc_ptr, self.rank, self.world, off["flags"],
                                   off["grad"], off["weight"], off["wbf16"], off.get("stage", 0),
-                                  self._epochs.data_ptr(), self._error.data_ptr(), int(timeout_s * 1e9))
+                                  self._epochs.data_ptr(), self._error.data_ptr(), int(timeout_s * 1e9),
+                                  int(os.environ.get("DDL_COMM_SKEW_NS", "0")))
 
         # ---- move parameters into the arena ----------------------------------------------------
         self._index = {}
@@ -230,17 +238,34 @@ class FusedSGD(torch.optim.Optimizer):
     def refresh_hyper_host(self) -> None:
         """Pack the current hyper-parameters (lr schedule!) into the pinned staging buffer.  The H2D copy that follows
         in every step is a memcpy node when the step is replayed from a CUDA graph, so calling this before
-        ``graph.replay()`` is all a captured step needs to follow an LR schedule."""
+        ``graph.replay()`` is all a captured step needs to follow an LR schedule.
+
+        The blob is rewritten only when its contents change, and only after the device has consumed the previous
+        contents (``mark_hyper_consumed`` records an event behind the last enqueued copy): the host may run several
+        steps ahead of the GPU, and a queued step must not pick up a later step's lr / first_step."""
         g = self.param_groups[0]
         blob = self.C.pack_sgd_hyper(float(g["lr"]), float(g["momentum"]), float(g["dampening"]),
                                      float(g["weight_decay"]), 1.0 / self.world, bool(g["nesterov"]),
                                      bool(self._first_step))
+        if blob == self._hyper_blob:
+            return
+        if self._hyper_event is not None:
+            self._hyper_event.synchronize()
         self._hyper_host.copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        self._hyper_blob = blob
+
+    def mark_hyper_consumed(self, stream: Optional[torch.cuda.Stream] = None) -> None:
+        """Record that every copy of the pinned hyper blob enqueued so far precedes this point of ``stream``."""
+        if self._hyper_event is None:
+            self._hyper_event = torch.cuda.Event()
+        self._hyper_event.record(stream if stream is not None else torch.cuda.current_stream(self.device))
 
     def _upload_hyper(self, stream: torch.cuda.Stream) -> None:
         self.refresh_hyper_host()
         with torch.cuda.stream(stream):
             self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
+        if not torch.cuda.is_current_stream_capturing():
+            self.mark_hyper_consumed(stream)
 
     def _launch_bucket(self, b: int) -> None:
         cur = torch.cuda.current_stream(self.device)
@@ -270,7 +295,8 @@ class FusedSGD(torch.optim.Optimizer):
             self.C.fused_allreduce_sgd(self.ctx, start, numel, self.M.data_ptr(), self._hyper_dev.data_ptr(), 0,
                                        self.use_mc, self.wire_bf16, blocks, stream.cuda_stream,
                                        self.arena.offsets["scalars"] if tail else 0,
-                                       self._scalars_out.data_ptr() if tail else 0, oneshot)
+                                       self._scalars_out.data_ptr() if tail else 0, oneshot,
+                                       b == self.num_buckets - 1)
 
     def _on_ready(self, idx: int) -> None:
         if self._ready_seen[idx]:
@@ -406,26 +432,62 @@ class FusedSGD(torch.optim.Optimizer):
         return self.M
 
     def state_dict(self):
+        """``torch.optim.SGD.state_dict()`` layout: ``state`` keyed by REGISTRATION-order parameter index,
+        ``param_groups[0]['params'] = [0..N-1]``, momentum under ``momentum_buffer`` — so checkpoints are
+        interchangeable with the reference's ``optimizer.state_dict()``
+        (``PyTorch_hvd/src/imagenet_pytorch_horovod.py:228-235``) and with this repo's CPU optimizer.  The engine's
+        own bookkeeping rides in an extra ``ddl`` key that ``torch.optim.SGD.load_state_dict`` ignores."""
         mom = self.full_momentum()
+        n = len(self.params)
         state = {}
-        for i, p in enumerate(self.params):
-            o, n = int(self.plan["param_offset"][i]), p.numel()
-            state[i] = {"momentum_buffer": _param_view(mom[o:o + n], p).detach().clone().cpu()}
-        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
-        return {"state": state, "param_groups": groups, "first_step": self._first_step, "fused": True,
-                "order": "reverse_registration"}
+        g0 = self.param_groups[0]
+        if float(g0["momentum"]) != 0.0 and not self._first_step:
+            for i, p in enumerate(self.params):               # self.params is reverse registration order
+                o, cnt = int(self.plan["param_offset"][i]), p.numel()
+                state[n - 1 - i] = {"momentum_buffer": _param_view(mom[o:o + cnt], p).detach().clone().cpu()}
+        groups = []
+        for g in self.param_groups:
+            d = {k: v for k, v in g.items() if k != "params"}
+            d["params"] = list(range(n))
+            groups.append(d)
+        return {"state": state, "param_groups": groups, "ddl": {"fused": True, "first_step": self._first_step}}
 
     def load_state_dict(self, sd):
+        """Accepts the torch layout written by :meth:`state_dict` / ``torch.optim.SGD`` (registration order) and the
+        round-1 private layout (``order == 'reverse_registration'``); shapes are validated before anything is copied."""
+        n = len(self.params)
+        legacy = sd.get("order") == "reverse_registration"
+        st = sd.get("state", {})
+
+        def entry(reg_index: int):
+            key = (n - 1 - reg_index) if legacy else reg_index
+            return st.get(key, st.get(str(key)))
+
+        plan = []
+        for i, p in enumerate(self.params):
+            ent = entry(n - 1 - i)
+            buf = None if ent is None else ent.get("momentum_buffer")
+            if buf is None:
+                continue
+            if tuple(buf.shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state for parameter {n - 1 - i} has shape {tuple(buf.shape)}, "
+                                 f"expected {tuple(p.shape)} (checkpoint from a different model or parameter order)")
+            plan.append((i, buf))
         for g, src in zip(self.param_groups, sd["param_groups"]):
             g.update({k: v for k, v in src.items() if k != "params"})
         with torch.no_grad():
-            for i, p in enumerate(self.params):
-                ent = sd["state"].get(i, sd["state"].get(str(i)))
-                if ent is None or ent.get("momentum_buffer") is None:
-                    continue
-                o, n = int(self.plan["param_offset"][i]), p.numel()
-                _param_view(self.M[o:o + n], p).copy_(ent["momentum_buffer"].to(self.device))
-        self._first_step = bool(sd.get("first_step", False))
+            for i, buf in plan:
+                p = self.params[i]
+                o, cnt = int(self.plan["param_offset"][i]), p.numel()
+                _param_view(self.M[o:o + cnt], p).copy_(buf.to(self.device))
+        meta = sd.get("ddl", {})
+        if "first_step" in meta:
+            self._first_step = bool(meta["first_step"])
+        elif "first_step" in sd:
+            self._first_step = bool(sd["first_step"])
+        else:
+            self._first_step = len(plan) == 0 and float(self.param_groups[0]["momentum"]) != 0.0
+        self._hyper_blob = None
         self.refresh_bf16()
 
     # ---------------------------------------------------------------------------------------------

@@ -1,0 +1,190 @@
+"""Runtime self-checks of the multi-GPU engine — cheap enough to run before every multi-rank benchmark, strict enough
+to catch protocol bugs (dropped contributions, stale staging, diverged replicas, wrong averaging).
+
+The reference has no equivalent (it trusts Horovod: ``hvd.DistributedOptimizer`` at
+``PyTorch_benchmark/src/pytorch_synthetic_benchmark.py:72-74``); these checks pin down the semantics this repo's
+hand-written kernels must reproduce: sum over ranks, divide by size, SGD(+momentum, +wd) on fp32 masters, replicas
+bit-identical, gradient accumulators recycled.
+
+* ``check_engine``      synthetic parameters, per-rank DIFFERENT gradients, 3 steps, against the same maths in torch;
+                        optional block skew (``skew_ns``) de-synchronises blocks and ranks on purpose.
+* ``step_equivalence``  a real model: one step on N ranks fed IDENTICAL data must move the weights exactly like one
+                        step of a single-rank engine (the average of N identical gradients is that gradient).
+* ``replica_checksum``  cross-rank equality of the fp32 master weights (sum and |sum| in float64).
+"""
+from __future__ import annotations
+
+import os
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+
+from . import dist
+from .compression import Compression
+
+
+def _max_over_ranks(t: torch.Tensor) -> torch.Tensor:
+    import torch.distributed as td
+
+    out = t.detach().clone()
+    if dist.is_distributed():
+        td.all_reduce(out, op=td.ReduceOp.MAX)
+    return out
+
+
+def check_engine(use_mc: Optional[bool] = None, wire=Compression.none, skew_ns: int = 0, steps: int = 3,
+                 log: Optional[Callable[[str], None]] = None) -> Tuple[bool, bool, str]:
+    """Returns (ok, used_multicast, description).  Collective: every rank must call."""
+    from .engine import FusedSGD
+
+    log = log or (lambda s: None)
+    torch.manual_seed(1234)               # same init everywhere
+    # slices of these buckets are NOT multiples of (blocks x 512 threads x vector): the consumer of a vector on the
+    # owner rank and its producer / recycler on the source rank must still be the same block index
+    shapes = [(64, 3, 7, 7), (1000, 512), (77,), (256, 64, 3, 3), (512, 512, 3, 3), (2048,), (1000,), (333, 65)]
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    ref_w = [p.detach().clone() for p in ps]
+    ref_m = [torch.zeros_like(p) for p in ps]
+    lr, mom, wd = 0.05, 0.9, 1e-4
+    old = os.environ.get("DDL_COMM_SKEW_NS")
+    os.environ["DDL_COMM_SKEW_NS"] = str(int(skew_ns))
+    try:
+        opt = FusedSGD(ps, lr=lr, momentum=mom, weight_decay=wd, compression=wire, use_multicast=use_mc,
+                       first_bucket_mb=0.25, bucket_mb=2.0, debug=True)
+    finally:
+        if old is None:
+            os.environ.pop("DDL_COMM_SKEW_NS", None)
+        else:
+            os.environ["DDL_COMM_SKEW_NS"] = old
+    world, rank = dist.size(), dist.rank()
+    bf16_wire = wire is not Compression.none
+    ok = True
+    for it in range(steps):
+        gs = []
+        for i, p in enumerate(ps):
+            g_all = [torch.randn(p.shape, device="cuda",
+                                 generator=torch.Generator("cuda").manual_seed(100 * it + 10 * r + i))
+                     for r in range(world)]
+            if bf16_wire:
+                g_avg = sum((g / world).to(torch.bfloat16).float() for g in g_all)
+            else:
+                g_avg = sum(g_all) / world
+            gs.append(g_avg)
+            p.grad.add_(g_all[rank].view_as(p.grad))
+            if i == 0:      # piggy-backed scalars (K19): mean over ranks of (rank + it, 10 * rank)
+                opt.piggyback(torch.tensor([float(rank + it), 10.0 * rank], device="cuda"))
+            p._ddl_ready()
+        opt.step()
+        want = torch.tensor([(world - 1) / 2 + it, 10.0 * (world - 1) / 2], device="cuda")
+        if not torch.allclose(opt.averaged_scalars(), want, atol=1e-5):
+            ok = False
+            log(f"  FAIL piggy-backed scalars: got {opt.averaged_scalars().tolist()} want {want.tolist()}")
+        for i in range(len(ps)):
+            g = gs[i] + wd * ref_w[i]
+            ref_m[i] = g.clone() if it == 0 else mom * ref_m[i] + g
+            ref_w[i] = ref_w[i] - lr * ref_m[i]
+    torch.cuda.synchronize()
+    opt.check_errors()
+    tol = 2e-2 if bf16_wire else 1e-5
+    for i, p in enumerate(ps):
+        err = (p.detach() - ref_w[i]).abs().max().item() / (ref_w[i].abs().max().item() + 1e-9)
+        same = bool((_max_over_ranks(p) == p.detach()).all())
+        cleared = float(p.grad.abs().max()) == 0.0
+        bf_ok = bool((p._ddl_bf16.float().reshape(-1) == p.detach().to(torch.bfloat16).float().reshape(-1)).all())
+        if err > tol or not same or not cleared or not bf_ok:
+            ok = False
+            log(f"  FAIL param {i}: rel_err={err:.3e} replicas_identical={same} grads_cleared={cleared} "
+                f"bf16_copy={bf_ok}")
+    # checkpoint path: sharded momentum gather, then the broadcast kernel
+    full = opt.full_momentum()
+    for i, p in enumerate(ps):
+        o = int(opt.plan["param_offset"][len(ps) - 1 - i])
+        got = full[o:o + p.numel()]
+        from .engine import _param_view
+
+        merr = (_param_view(got, p) - ref_m[i]).abs().max().item() / (ref_m[i].abs().max().item() + 1e-9)
+        if merr > tol:
+            ok = False
+            log(f"  FAIL momentum {i}: rel_err={merr:.3e}")
+    with torch.no_grad():
+        if rank == 1:
+            for p in ps:
+                p.add_(1.0)
+    opt.broadcast_parameters(0)
+    torch.cuda.synchronize()
+    for i, p in enumerate(ps):
+        if not bool((_max_over_ranks(p) == p.detach()).all()):
+            ok = False
+            log(f"  FAIL broadcast param {i}")
+    name = (f"fused engine transport={'nvls' if opt.use_mc else 'p2p'} wire={'bf16' if bf16_wire else 'fp32'}"
+            f"{f' skew={skew_ns}ns' if skew_ns else ''}")
+    ok = dist.allreduce_scalar(1.0 if ok else 0.0, op="min") > 0
+    log(f"[{'ok' if ok else 'FAIL'}] {name}  ({opt.describe()})")
+    return ok, bool(opt.use_mc), name
+
+
+def replica_checksum(optimizer) -> Dict[str, object]:
+    """(sum, abs-sum) of the fp32 master weights in float64 + whether every rank holds the same values."""
+    W = getattr(optimizer, "W", None)
+    if W is None:
+        ws = [p.detach().double() for g in optimizer.param_groups for p in g["params"]]
+        s = float(sum(w.sum() for w in ws))
+        a = float(sum(w.abs().sum() for w in ws))
+    else:
+        s, a = float(W.double().sum()), float(W.double().abs().sum())
+    same = True
+    if dist.is_distributed():
+        same = (dist.allreduce_scalar(s, op="max") == dist.allreduce_scalar(s, op="min") and
+                dist.allreduce_scalar(a, op="max") == dist.allreduce_scalar(a, op="min"))
+    return {"sum": s, "abs_sum": a, "replicas_identical": bool(same)}
+
+
+def step_equivalence(model_name: str = "resnet50", batch_size: int = 32, lr: float = 0.01, wire=Compression.none,
+                     seed: int = 7) -> Dict[str, float]:
+    """One training step on ``dist.size()`` ranks that all hold the SAME batch must equal one step of a single-rank
+    engine: the allreduce-average of N identical gradients is that gradient, so
+
+        || (w_N - w_0) - (w_1 - w_0) || / || w_1 - w_0 ||
+
+    measures nothing but the engine (wire rounding, dropped / doubled contributions, wrong scale).  The two models are
+    built from the same seed; kernels with fp32 atomics make the two gradients agree to rounding noise only, which
+    the bound (1e-3, bf16 wire: 1e-2) leaves room for.  Collective: every rank must call."""
+    from .. import models, ops
+    from ..data import fixed_synthetic_batch
+    from .engine import FusedSGD
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def build(local: bool):
+        torch.manual_seed(seed)
+        m = models.get_model(model_name).cuda().train()
+        opt = FusedSGD(m.named_parameters(), lr=lr, compression=wire, local=local)
+        return m, opt
+
+    size = models.input_size(models.get_model(model_name))
+    data, target = fixed_synthetic_batch(batch_size, size, 1000, dev, seed=seed + 17)    # identical on every rank
+
+    def one_step(m, opt):
+        w0 = opt.W.detach().clone()
+        out = m(data)
+        if isinstance(out, tuple):
+            loss = ops.softmax_cross_entropy(out[0], target, 1000) + 0.4 * ops.softmax_cross_entropy(out[1], target, 1000)
+        else:
+            loss = ops.softmax_cross_entropy(out, target, 1000)
+        loss.backward()
+        opt.step()
+        torch.cuda.synchronize()
+        opt.check_errors()
+        return (opt.W.detach() - w0).double(), float(loss)
+
+    m1, o1 = build(local=True)
+    d1, loss1 = one_step(m1, o1)
+    mn, on = build(local=False)
+    dn, lossn = one_step(mn, on)
+    # the two engines lay parameters out identically (same plan for the same model)
+    rel = float((dn - d1).norm() / d1.norm().clamp_min(1e-30))
+    scale = float((dn * d1).sum() / (d1 * d1).sum().clamp_min(1e-30))      # least-squares step-size ratio
+    rel = dist.allreduce_scalar(rel, op="max")
+    return {"rel_delta_error": rel, "step_scale": scale, "loss_single": loss1, "loss_multi": lossn,
+            "world": dist.size(), "ok": bool(rel < (1e-2 if wire is not Compression.none else 1e-3)),
+            "replicas_identical": replica_checksum(on)["replicas_identical"]}

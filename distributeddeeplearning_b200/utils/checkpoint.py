@@ -33,7 +33,10 @@ def agreed_resume_epoch(checkpoint_format: str, max_epochs: int, root_rank: int 
 
 def save_checkpoint(path: str, model: torch.nn.Module, optimizer, epoch: int = 0, step: int = 0,
                     extra: Optional[Dict[str, Any]] = None, root_rank: int = 0) -> Optional[str]:
-    """All ranks must call (sharded optimizer state is gathered collectively); rank 0 writes."""
+    """All ranks must call (sharded optimizer state is gathered collectively); rank 0 writes.  A pending
+    communication error (fused-engine barrier timeout) aborts BEFORE anything is written."""
+    if optimizer is not None and hasattr(optimizer, "check_errors"):
+        optimizer.check_errors()
     opt_state = optimizer.state_dict() if optimizer is not None else None
     if dist.rank() != root_rank:
         return None

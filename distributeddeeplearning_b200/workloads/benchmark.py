@@ -64,7 +64,7 @@ class BenchmarkSession:
     """Model + optimizer + fixed batch; ``step()`` is one full training iteration."""
 
     def __init__(self, model_name: str, batch_size: int, cuda: bool, fp16_allreduce: bool = False, lr: float = 0.01,
-                 momentum: float = 0.0, seed: int = 0, profile: bool = False):
+                 momentum: float = 0.0, seed: int = 0, profile: bool = False, data_seed_offset: Optional[int] = None):
         self.cuda = cuda
         self.profile = bool(profile) and cuda
         self.device = torch.device("cuda", torch.cuda.current_device()) if cuda else torch.device("cpu")
@@ -85,7 +85,12 @@ class BenchmarkSession:
             dist.broadcast_parameters({k: v for k, v in self.model.named_buffers()}, root_rank=0)
             dist.broadcast_optimizer_state(self.optimizer, root_rank=0)
         size = models.input_size(self.model)
-        self.data, self.target = fixed_synthetic_batch(batch_size, size, self.num_classes, self.device, seed=seed + 17)
+        # every rank draws its OWN fixed batch (the reference draws unseeded per-process data,
+        # pytorch_synthetic_benchmark.py:81-84), so the allreduce averages genuinely different gradients
+        if data_seed_offset is None:
+            data_seed_offset = dist.rank()
+        self.data, self.target = fixed_synthetic_batch(batch_size, size, self.num_classes, self.device,
+                                                       seed=seed + 17 + 1000 * int(data_seed_offset))
         self.batch_size = batch_size
         self.last_loss: Optional[torch.Tensor] = None
         self.steps_done = 0

@@ -93,5 +93,7 @@ class GraphedStep:
         if hasattr(self.optimizer, "refresh_hyper_host"):
             self.optimizer.refresh_hyper_host()
         self.graph.replay()
+        if hasattr(self.optimizer, "mark_hyper_consumed"):
+            self.optimizer.mark_hyper_consumed()       # the replay's memcpy node read the pinned hyper blob
         _ext.add_launches(self.launches)
         return self.static_out

@@ -16,7 +16,6 @@ from __future__ import annotations
 
 import logging
 import os
-import shutil
 
 import torch
 
@@ -129,6 +128,8 @@ def train(train_loader, model, criterion, optimizer, base_lr, warmup_epochs, epo
             t.stop()
             batch_time.update(t.elapsed, n=_LOG_INTERVAL)
             logger.info(msg.format(t.elapsed, float(last_loss), i * int(target.shape[0])))
+            if hasattr(optimizer, "check_errors"):
+                optimizer.check_errors()          # a barrier timeout must stop the job before more steps / checkpoints
             t.start()
     out = metrics.read()
     out["batch_time"] = batch_time.avg
@@ -181,9 +182,10 @@ def main(training_data_path=None, validation_data_path=None, use_gpu=False, save
     if rank == 0:
         run = Run.get_context("pytorch_imagenet")
         run.tag("model", value=model)
-        logs_dir = os.path.join(os.curdir, "logs")
-        if os.path.exists(logs_dir):
-            shutil.rmtree(logs_dir, ignore_errors=True)
+        # the reference wipes and rewrites ./logs of the job's private working directory (``:324-329``); a local
+        # run keeps its event files inside its own run directory instead (DDL_LOG_DIR overrides), so nothing in
+        # the caller's cwd is deleted or littered
+        logs_dir = os.getenv("DDL_LOG_DIR") or os.path.join(run.dir, "logs")
         writer = summary_writer(logs_dir)
 
     net = models.get_model(model)

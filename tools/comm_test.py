@@ -18,7 +18,8 @@ import torch.distributed as td
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from distributeddeeplearning_b200 import _ext  # noqa: E402
 from distributeddeeplearning_b200.parallel import Compression, dist  # noqa: E402
-from distributeddeeplearning_b200.parallel.engine import FusedSGD, SymmetricArena  # noqa: E402
+from distributeddeeplearning_b200.parallel import selfcheck  # noqa: E402
+from distributeddeeplearning_b200.parallel.engine import SymmetricArena  # noqa: E402
 
 
 def log(*a):
@@ -26,73 +27,9 @@ def log(*a):
         print(*a, flush=True)
 
 
-def check_engine(use_mc, wire):
-    torch.manual_seed(1234)               # same init everywhere
-    shapes = [(64, 3, 7, 7), (1000, 512), (77,), (256, 64, 3, 3), (512, 512, 3, 3), (2048,)]
-    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
-    ref_w = [p.detach().clone() for p in ps]
-    ref_m = [torch.zeros_like(p) for p in ps]
-    lr, mom, wd = 0.05, 0.9, 1e-4
-    opt = FusedSGD(ps, lr=lr, momentum=mom, weight_decay=wd, compression=wire, use_multicast=use_mc,
-                   first_bucket_mb=0.25, bucket_mb=2.0, debug=True)
-    world, rank = dist.size(), dist.rank()
-    ok = True
-    for it in range(3):
-        gs = []
-        for i, p in enumerate(ps):
-            g_all = [torch.randn(p.shape, device="cuda", generator=torch.Generator("cuda").manual_seed(100 * it + 10 * r + i))
-                     for r in range(world)]
-            if wire is not Compression.none:
-                g_avg = sum((g / world).to(torch.bfloat16).float() for g in g_all)
-            else:
-                g_avg = sum(g_all) / world
-            gs.append(g_avg)
-            p.grad.add_(g_all[rank].view_as(p.grad))
-            if i == 0:      # piggy-backed scalars (K19): mean over ranks of (rank + it, 10 * rank)
-                opt.piggyback(torch.tensor([float(rank + it), 10.0 * rank], device="cuda"))
-            p._ddl_ready()
-        opt.step()
-        want = torch.tensor([(world - 1) / 2 + it, 10.0 * (world - 1) / 2], device="cuda")
-        if not torch.allclose(opt.averaged_scalars(), want, atol=1e-5):
-            ok = False
-            log(f"  FAIL piggy-backed scalars: got {opt.averaged_scalars().tolist()} want {want.tolist()}")
-        for i in range(len(ps)):
-            g = gs[i] + wd * ref_w[i]
-            ref_m[i] = g.clone() if it == 0 else mom * ref_m[i] + g
-            ref_w[i] = ref_w[i] - lr * ref_m[i]
-    torch.cuda.synchronize()
-    opt.check_errors()
-    tol = 2e-2 if wire is not Compression.none else 1e-5
-    for i, p in enumerate(ps):
-        err = (p.detach() - ref_w[i]).abs().max().item() / (ref_w[i].abs().max().item() + 1e-9)
-        # replicas identical?
-        mx = p.detach().clone()
-        td.all_reduce(mx, op=td.ReduceOp.MAX)
-        same = bool((mx == p.detach()).all())
-        cleared = float(p.grad.abs().max()) == 0.0
-        bf_ok = bool((p._ddl_bf16.float().reshape(-1) == p.detach().to(torch.bfloat16).float().reshape(-1)).all())
-        if err > tol or not same or not cleared or not bf_ok:
-            ok = False
-            log(f"  FAIL param {i}: rel_err={err:.3e} replicas_identical={same} grads_cleared={cleared} bf16_copy={bf_ok}")
-    # momentum gather + broadcast kernel
-    full = opt.full_momentum()
-    for i, p in enumerate(ps):
-        o = int(opt.plan["param_offset"][i])
-    with torch.no_grad():
-        if rank == 1:
-            for p in ps:
-                p.add_(1.0)
-    opt.broadcast_parameters(0)
-    torch.cuda.synchronize()
-    for i, p in enumerate(ps):
-        mx = p.detach().clone()
-        td.all_reduce(mx, op=td.ReduceOp.MAX)
-        if not bool((mx == p.detach()).all()):
-            ok = False
-            log(f"  FAIL broadcast param {i}")
-    name = f"fused engine transport={'nvls' if opt.use_mc else 'p2p'} wire={'bf16' if wire is not Compression.none else 'fp32'}"
-    log(f"[{'ok' if ok else 'FAIL'}] {name}  ({opt.describe()})")
-    return ok, opt.use_mc
+def check_engine(use_mc, wire, skew_ns=0):
+    ok, used_mc, _ = selfcheck.check_engine(use_mc, wire, skew_ns=skew_ns, log=log)
+    return ok, used_mc
 
 
 def sweep(max_bytes):
@@ -198,6 +135,15 @@ def main():
     if had_mc:
         oks.append(check_engine(False, Compression.none)[0])
         oks.append(check_engine(False, Compression.bf16)[0])
+    # de-synchronised blocks / ranks: a producer-consumer block mismatch in the protocol shows up as wrong sums here
+    for wire in (Compression.none, Compression.bf16):
+        oks.append(check_engine(None, wire, skew_ns=30000)[0])
+        if had_mc:
+            oks.append(check_engine(False, wire, skew_ns=30000)[0])
+    if "--model-check" in sys.argv:
+        eq = selfcheck.step_equivalence("resnet50", 32)
+        log("STEP EQUIVALENCE:", json.dumps(eq))
+        oks.append(eq["ok"])
     max_bytes = int(os.environ.get("SWEEP_MAX", 1 << 30))
     res = [] if "--no-sweep" in sys.argv else sweep(max_bytes)
     if dist.rank() == 0 and res:
