@@ -40,10 +40,6 @@ def _max_nodes() -> int:
     return int(_env().get("CLUSTER_MAX_NODES", 8))
 
 
-def _gpu_flag(no_cuda: bool) -> bool:
-    return bool(no_cuda)
-
-
 def _submit(module, argv, gpus, experiment, no_cuda=False, env=None):
     res = launcher.launch(module, argv, gpus=gpus, no_cuda=no_cuda, experiment=experiment, env=env)
     print(res)
@@ -109,6 +105,23 @@ def imagenet_images_remote(c, node_count=None, epochs=1, no_cuda=False):
     store = _datastore_path()
     _submit(_IMAGENET, _imagenet_argv(epochs, not no_cuda, os.path.join(store, "train"), os.path.join(store, "validation")),
             int(node_count or _max_nodes()), "real_images_remote", no_cuda)
+
+
+@task
+def imagenet_records_local(c, epochs=1, no_cuda=False):
+    """ImageNet trainer on the record shards under $DATA/records (reference: tf-imagenet ... tfrecords), one rank."""
+    rec = os.path.join(_env()["DATA"], "records")
+    _submit(_IMAGENET, _imagenet_argv(epochs, not no_cuda, os.path.join(rec, "train"), os.path.join(rec, "validation"),
+                                      ["--data_type", "records"]), 1, "records_local", no_cuda)
+
+
+@task
+def imagenet_records_remote(c, node_count=None, epochs=1, no_cuda=False):
+    """ImageNet trainer on the datastore's record shards, --node-count ranks (file-level sharding across ranks)."""
+    rec = os.path.join(_datastore_path(), "records")
+    _submit(_IMAGENET, _imagenet_argv(epochs, not no_cuda, os.path.join(rec, "train"), os.path.join(rec, "validation"),
+                                      ["--data_type", "records"]), int(node_count or _max_nodes()), "records_remote",
+            no_cuda)
 
 
 # ------------------------------------------------------------------ pytorch-hvd (orphan in the reference; wired here)
@@ -353,28 +366,67 @@ def _submit_collection(name, local=None, remote=None):
     return col
 
 
+# template type (cookiecutter ``type`` variable, ``cookiecutter.json:18-26``) -> the workload collections it keeps; the
+# reference's post-gen hook was meant to delete the other project directories (``hooks/post_gen_project.py:19-33``)
+WORKLOAD_TYPES = {
+    "pytorch_benchmark": ("pytorch_benchmark",),
+    "pytorch_imagenet": ("pytorch_imagenet",),
+    "pytorch_hvd": ("pytorch_hvd",),
+    "pytorch_template": ("pytorch_experiment",),
+    "tensorflow_benchmark": ("tf_benchmark",),
+    "tensorflow_imagenet": ("tf_imagenet",),
+    "tensorflow_template": ("tf_experiment",),
+}
+
+
+def enabled_workloads():
+    """Collections the project keeps: ``ENABLED_WORKLOADS`` (process env, else the project's .env; written by
+    ``control.template.render_project`` when ``_remove_unused_projects`` is set) — None = everything."""
+    raw = os.environ.get("ENABLED_WORKLOADS")
+    if raw is None:
+        try:
+            raw = cfg.load_config(required=False).get("ENABLED_WORKLOADS")
+        except Exception:
+            raw = None
+    if not raw or raw.strip().lower() == "all":
+        return None
+    keep = set()
+    for t in raw.replace(";", ",").split(","):
+        t = t.strip()
+        if t:
+            keep.update(WORKLOAD_TYPES.get(t, (t,)))
+    return keep
+
+
 def build_namespace() -> Collection:
     ns = Collection(setup, login, select_subscription, experiments, runs, tensorboard, delete, interactive, new_project)
-    ns.add_collection(_submit_collection("pytorch_benchmark", {"synthetic": benchmark_local},
-                                         {"synthetic": benchmark_remote}))
-    ns.add_collection(_submit_collection("pytorch_imagenet",
-                                         {"synthetic": imagenet_synthetic_local, "images": imagenet_images_local},
-                                         {"synthetic": imagenet_synthetic_remote, "images": imagenet_images_remote}))
-    ns.add_collection(_submit_collection("pytorch_hvd", {"synthetic": hvd_synthetic_local},
-                                         {"synthetic": hvd_synthetic_remote, "images": hvd_images_remote}))
-    ns.add_collection(_submit_collection("pytorch_experiment",
-                                         {"synthetic": _template("exp_local_synthetic"), "images": _template("exp_local_images")},
-                                         {"synthetic": _template("exp_remote_synthetic"), "images": _template("exp_remote_images")}))
+    keep = enabled_workloads()
+
+    def add(col):
+        if keep is None or str(col.name).replace("-", "_") in keep:
+            ns.add_collection(col)
+
+    add(_submit_collection("pytorch_benchmark", {"synthetic": benchmark_local}, {"synthetic": benchmark_remote}))
+    add(_submit_collection("pytorch_imagenet",
+                           {"synthetic": imagenet_synthetic_local, "images": imagenet_images_local,
+                            "records": imagenet_records_local},
+                           {"synthetic": imagenet_synthetic_remote, "images": imagenet_images_remote,
+                            "records": imagenet_records_remote}))
+    add(_submit_collection("pytorch_hvd", {"synthetic": hvd_synthetic_local},
+                           {"synthetic": hvd_synthetic_remote, "images": hvd_images_remote}))
+    add(_submit_collection("pytorch_experiment",
+                           {"synthetic": _template("exp_local_synthetic"), "images": _template("exp_local_images")},
+                           {"synthetic": _template("exp_remote_synthetic"), "images": _template("exp_remote_images")}))
     # TensorFlow twins collapse onto the PyTorch workloads (BASELINE.json north-star)
-    ns.add_collection(_submit_collection("tf_benchmark", {"synthetic": benchmark_local}, {"synthetic": benchmark_remote}))
-    ns.add_collection(_submit_collection("tf_imagenet",
-                                         {"synthetic": imagenet_synthetic_local, "images": imagenet_images_local,
-                                          "tfrecords": imagenet_images_local},
-                                         {"synthetic": imagenet_synthetic_remote, "images": imagenet_images_remote,
-                                          "tfrecords": imagenet_images_remote}))
-    ns.add_collection(_submit_collection("tf_experiment",
-                                         {"synthetic": _template("tfexp_local_synthetic")},
-                                         {"synthetic": _template("tfexp_remote_synthetic")}))
+    add(_submit_collection("tf_benchmark", {"synthetic": benchmark_local}, {"synthetic": benchmark_remote}))
+    add(_submit_collection("tf_imagenet",
+                           {"synthetic": imagenet_synthetic_local, "images": imagenet_images_local,
+                            "tfrecords": imagenet_records_local},
+                           {"synthetic": imagenet_synthetic_remote, "images": imagenet_images_remote,
+                            "tfrecords": imagenet_records_remote}))
+    add(_submit_collection("tf_experiment",
+                           {"synthetic": _template("tfexp_local_synthetic")},
+                           {"synthetic": _template("tfexp_remote_synthetic")}))
     storage = Collection("storage")
     storage.add_task(create_resource_group, "create-resource-group")
     storage.add_task(create_premium_storage, "create-premium-storage")

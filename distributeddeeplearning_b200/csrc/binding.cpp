@@ -38,6 +38,7 @@ void set_conv_persistent(int on);
 void set_wgrad_swap(int on);
 void set_conv_bn256(int on);
 void set_conv_cluster(int on);
+void set_conv_deep(int on);
 }  // namespace ddl
 
 namespace {
@@ -193,6 +194,7 @@ PYBIND11_MODULE(_C, m) {
   // ------------------------------------------------------------------ conv / GEMM
   m.def("set_conv_persistent", &ddl::set_conv_persistent, "tuning hook: 1 = persistent kernel for TMA-fed modes");
   m.def("set_conv_cluster", &ddl::set_conv_cluster, "tuning hook: 1 = CTA pairs with TMA-multicast weight tiles");
+  m.def("set_conv_deep", &ddl::set_conv_deep, "tuning hook: 0 = never the deep-ring kernel, 1 = policy, 2 = always");
   m.def("set_conv_bn256", &ddl::set_conv_bn256, "tuning hook: 0 = no 128x256 persistent tiles");
   m.def("set_wgrad_swap", &ddl::set_wgrad_swap, "tuning hook: 0 = no operand-role swap for narrow-output wgrad tiles");
   m.def("set_conv_force_stages", &ddl::set_conv_force_stages, "tuning hook: force the pipeline depth (0 = policy)");
@@ -201,8 +203,9 @@ PYBIND11_MODULE(_C, m) {
            int srcH, int srcW, int srcC, int dstH, int dstW, int R, int Sx, int stride, int pad, int dil,
            int cchunks, int relu, int n_valid, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
            int batch, int tw, int th, int tn, int zfill, ptr_t stream, int pad_w, int kstride, ptr_t add_mask,
-           ptr_t bnr_y, ptr_t bnr_gamma, ptr_t bnr_beta, ptr_t bnr_mean, ptr_t bnr_invstd) {
+           ptr_t bnr_y, ptr_t bnr_gamma, ptr_t bnr_beta, ptr_t bnr_mean, ptr_t bnr_invstd, int variant) {
           ConvArgs a;
+          a.variant = variant;
           a.bnr_y = P<const __nv_bfloat16>(bnr_y); a.bnr_gamma = P<const float>(bnr_gamma);
           a.bnr_beta = P<const float>(bnr_beta); a.bnr_mean = P<const float>(bnr_mean);
           a.bnr_invstd = P<const float>(bnr_invstd);
@@ -225,7 +228,7 @@ PYBIND11_MODULE(_C, m) {
         py::arg("a_matrix"), py::arg("a_cols"), py::arg("batch"), py::arg("tw"), py::arg("th"), py::arg("tn"),
         py::arg("zfill"), py::arg("stream"), py::arg("pad_w") = -1, py::arg("kstride") = 0, py::arg("add_mask") = 0,
         py::arg("bnr_y") = 0, py::arg("bnr_gamma") = 0, py::arg("bnr_beta") = 0, py::arg("bnr_mean") = 0,
-        py::arg("bnr_invstd") = 0);
+        py::arg("bnr_invstd") = 0, py::arg("variant") = 0);
   m.def("conv_wgrad",
         [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int dy_ld, int ldw, int ncols, int H, int W, int C, int Pq,
            int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, int batch, int tw, int th, int tn,

@@ -825,6 +825,286 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
 }
 
 // ---------------------------------------------------------------------------------------------
+// deep-ring persistent kernel: ONE CTA per SM (or one cta_group::2 CTA pair per SM pair)
+// ---------------------------------------------------------------------------------------------
+// What bounds the long-K layers is operand delivery, L2 -> shared memory: a 128 x 128 x 64 step needs 32 KB per 256
+// tensor-pipe cycles = 128 B/cycle/SM, while the chip sustains ~45 B/cycle/SM out of L2 (cuBLAS's own bf16 peak with
+// 256 x 256 pair tiles sits right at that limit).  This variant therefore
+//   * spends the whole SM on one CTA: the ring is as deep as 227 KB allow (5 x 32 KB for 128 x 128, 3 x 48 KB for
+//     128 x 256, 5 x 32 KB for a 256 x 256 pair tile), so TMA round trips (~1-1.5 k cycles under load) stay covered;
+//   * supports 256-wide tiles (A is re-used for twice the columns: 96 B/cycle) and CTA pairs with ONE M = 256 MMA
+//     (tcgen05.mma.cta_group::2: each SM loads its 128 rows of A and HALF of the weight tile: 64 B/cycle at N = 256);
+//   * drains the accumulator in 64-column chunks through two small staging buffers (2 x 18 KB instead of one
+//     34-68 KB tile image), which is what frees the shared memory for the ring.
+// TMEM: 2 x BLOCK_N columns (double-buffered accumulator; N = 256 uses all 512 columns — fine with one CTA per SM).
+template <int BLOCK_N, bool PAIR>
+struct DeepCfg {
+  static constexpr int kBLoadRows = PAIR ? BLOCK_N / 2 : BLOCK_N;   // weight rows (K-major) / columns (MN-major) per CTA
+  static constexpr int kBTileBytes = kBLoadRows * 128;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kChunk = 64;                                  // accumulator columns drained per epilogue pass
+  static constexpr int kChunkPitch = kChunk * 2 + 16;
+  static constexpr int kChunkBytes = kBlockM * kChunkPitch;          // 18,432
+  static constexpr int kRedBytes = 4 * kEpiGroups * 2 * kChunk * 4;  // [epi warps][2][64] floats
+  static constexpr int kFixed = 256 /*barriers*/ + kRedBytes + 1024 /*alignment*/;
+  static constexpr int kStagesFit = (232448 - kFixed - 2 * kChunkBytes) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kChunkBytes + kFixed;
+};
+constexpr int kDeepMaxStages = 8;
+
+template <int BLOCK_N, int MODE, bool STATS, bool PAIR>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBh,
+                      const __grid_constant__ TmaSet tmAs, ConvArgs a, int n_tiles, int m_tiles) {
+  using Cfg = DeepCfg<BLOCK_N, PAIR>;
+  constexpr bool kBMn = mode_b_mn(MODE);
+  constexpr bool kTile = mode_tile(MODE);
+  constexpr int kStages = Cfg::kStages;
+  static_assert(!(PAIR && kBMn && BLOCK_N < 128), "MN-major pair tiles need 64-column halves");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg = smem + kStages * Cfg::kStageBytes;                   // two chunk staging buffers
+  uint64_t* full = reinterpret_cast<uint64_t*>(stg + 2 * Cfg::kChunkBytes);
+  uint64_t* empty = full + kDeepMaxStages;
+  uint64_t* acc_full = empty + kDeepMaxStages;  // [2]
+  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full) + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int KB = a.KB;
+  const int crank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const int m_items = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int total = n_tiles * m_items;
+  const int item0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int item_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1u);
+      mbar_init(&empty[s], 1u);
+    }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1u); mbar_init(&acc_empty[b], PAIR ? 2u : 1u); }
+    fence_mbar_init();
+  }
+  if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmBh);
+    tma_prefetch_desc(&tmAs.m[0]);
+  }
+  if (warp == 5) {
+    if (PAIR) tmem_alloc_pair<2 * BLOCK_N>(tmem_slot);
+    else tmem_alloc<2 * BLOCK_N>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();         // the peer's mbarriers exist before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_origin = [&](int t, int& n0, int& m0, int& tq0, int& tp0, int& tn0) -> bool {
+    const int nt = t % n_tiles;
+    int mt = t / n_tiles;
+    bool valid = true;
+    if (PAIR) {
+      mt = 2 * mt + crank;
+      valid = mt < m_tiles;
+      if (!valid) mt = m_tiles - 1;     // padding tile of an odd M-tile count: loads + MMAs in lock-step, no stores
+    }
+    n0 = nt * BLOCK_N;
+    m0 = mt * kBlockM;
+    tq0 = tp0 = tn0 = 0;
+    if (kTile) {
+      const int wb = mt % a.tiles_w; mt /= a.tiles_w;
+      const int hb = mt % a.tiles_h;
+      const int nb = mt / a.tiles_h;
+      tq0 = wb * a.tw; tp0 = hb * a.th; tn0 = nb * a.tn;
+      m0 = 0;
+    }
+    return valid;
+  };
+
+  if (warp < 4 || warp >= 6) {
+    // =================================== epilogue warps =======================================
+    const int egrp = warp < 4 ? 0 : 1;
+    const int qw = warp & 3;
+    const int row = qw * 32 + (threadIdx.x & 31);
+    const int etid = egrp * 128 + row;
+    const int ew = egrp * 4 + qw;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const uint32_t red_u32 = smem_u32(red);
+    const bool bias_relu = !STATS && (a.bias != nullptr || a.relu);
+    int it = 0;
+    uint32_t chunk_ctr = 0;             // staging buffer = chunk_ctr & 1 (identical sequence in every epilogue thread)
+    for (int t = item0; t < total; t += item_step, ++it) {
+      int n0, m0, tq0, tp0, tn0;
+      const bool valid = tile_origin(t, n0, m0, tq0, tp0, tn0);
+      const int buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      if (PAIR && !valid) {             // padding tile: keep the accumulator hand-shake going, write nothing
+        tc_fence_before();
+        named_bar_sync(1, kEpiThreads);
+        if (etid == 0) {
+          if (crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+          else mbar_arrive(&acc_empty[buf]);
+        }
+        continue;
+      }
+      int my_m;
+      if (kTile) {
+        const int wl = row % a.tw;
+        const int t2 = row / a.tw;
+        const int hl = t2 % a.th;
+        const int nl = t2 / a.th;
+        const bool ok = nl < a.tn && (tn0 + nl) < a.batch && (tp0 + hl) < a.dstH && (tq0 + wl) < a.dstW;
+        my_m = ok ? ((tn0 + nl) * a.outH + (tp0 + hl) * a.out_stride + a.out_pa) * a.outW +
+                        (tq0 + wl) * a.out_stride + a.out_pb
+                  : -1;
+      } else {
+        my_m = (m0 + row) < a.M ? (m0 + row) : -1;
+      }
+      const bool zero_row = kTile && my_m < 0;
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + buf * BLOCK_N;
+      constexpr int kChunks = BLOCK_N / Cfg::kChunk;
+#pragma unroll 1
+      for (int ch = 0; ch < kChunks; ++ch, ++chunk_ctr) {
+        const uint32_t sbuf = stg_u32 + (chunk_ctr & 1u) * Cfg::kChunkBytes;
+        const uint32_t stg_row = sbuf + row * Cfg::kChunkPitch;
+        // my 32 of the chunk's 64 columns: TMEM -> (bias, ReLU) -> bf16 -> staging row
+        if (bias_relu)
+          epi_tmem_to_stage<true>(taddr_row + ch * Cfg::kChunk, stg_row, egrp * 32, egrp * 32 + 32, a,
+                                  n0 + ch * Cfg::kChunk, zero_row);
+        else
+          epi_tmem_to_stage<false>(taddr_row + ch * Cfg::kChunk, stg_row, egrp * 32, egrp * 32 + 32, a,
+                                   n0 + ch * Cfg::kChunk, zero_row);
+        if (kTile && egrp == 0) sts32(stg_row + Cfg::kChunk * 2, static_cast<uint32_t>(my_m));
+        if (ch == kChunks - 1) tc_fence_before();
+        // all 256 threads: the chunk is staged; everybody has also left the buffer written two chunks ago
+        named_bar_sync(1, kEpiThreads);
+        if (ch == kChunks - 1 && etid == 0) {           // every epilogue thread has finished reading this TMEM buffer
+          if (PAIR && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));
+          else mbar_arrive(&acc_empty[buf]);
+        }
+        // (no trailing barrier: the next chunk stages into the OTHER buffer, and nobody rewrites the stats scratch or
+        //  this buffer before passing the next chunk's barrier, which everyone reaches only after leaving this call)
+        epi_stats_store<Cfg::kChunk, STATS, kTile>(sbuf, red_u32, etid, ew, a, n0 + ch * Cfg::kChunk, m0);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================================== TMA producer =======================================
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t a_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : kATileBytes;
+      for (int t = item0; t < total; t += item_step) {
+        int n0, m0, tq0, tp0, tn0;
+        tile_origin(t, n0, m0, tq0, tp0, tn0);
+        int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          uint8_t* sA = smem + stage * Cfg::kStageBytes;
+          const uint32_t sB = smem_u32(sA + kATileBytes);
+          const uint32_t pair_bar = PAIR ? mapa_shared(smem_u32(&full[stage]), 0) : 0u;
+          if (!PAIR) mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + a_bytes);
+          else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (Cfg::kBTileBytes + a_bytes));
+          int widx = tap, dh = 0, dw = 0, mapi = 0;
+          if (kTile) {
+            if (a.ntaps > 0) {
+              widx = a.tap_widx[tap]; dh = a.tap_dh[tap]; dw = a.tap_dw[tap]; mapi = a.tap_map[tap];
+            } else if (MODE == kConvTileFwd) {
+              dh = tap_r * a.dil - a.pad; dw = tap_s * a.dil - a.pad_w;
+            } else {
+              dh = a.pad - tap_r * a.dil; dw = a.pad_w - tap_s * a.dil;
+            }
+          }
+          const int kcoord = mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK;
+          const int nb0 = n0 + crank * Cfg::kBLoadRows;        // first weight row / column this CTA fetches
+          if (PAIR) {
+            if (kBMn) {
+#pragma unroll
+              for (int j = 0; j < Cfg::kBLoadRows / 64; ++j)
+                tma_load_2d_pair(sB + j * 8192, &tmB, widx * a.ldc + nb0 + j * 64, cc * 64, pair_bar);
+            } else if (Cfg::kBLoadRows == 128) {
+              tma_load_2d_pair(sB, &tmB, kcoord, nb0, pair_bar);           // the full map's box is 128 rows
+            } else {
+              tma_load_2d_pair(sB, &tmBh, kcoord, nb0, pair_bar);          // half-height box map
+            }
+            if (MODE == kConvStemTma) tma_load_5d_pair(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, pair_bar);
+            else if (kTile) tma_load_4d_pair(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, pair_bar);
+            else tma_load_2d_pair(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, pair_bar);
+          } else {
+            if (kBMn) {
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
+            } else {
+              constexpr int kBoxRows = BLOCK_N < 128 ? BLOCK_N : 128;      // the weight map's box height
+#pragma unroll
+              for (int h = 0; h < BLOCK_N / kBoxRows; ++h)
+                tma_load_2d(sB + h * kBoxRows * 128, &tmB, kcoord, n0 + h * kBoxRows, &full[stage]);
+            }
+            if (MODE == kConvStemTma) tma_load_5d(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, &full[stage]);
+            else if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
+            else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, &full[stage]);
+          }
+          if (++cc == a.cchunks) { cc = 0; ++tap; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ====================================== MMA issuer ========================================
+    constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    if (!(PAIR && crank != 0)) {        // the leader issues the MMAs of a pair
+      for (int t = item0; t < total; t += item_step, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);     // epilogue(s) have drained this TMEM buffer
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
+            const uint32_t sB = sA + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
+              const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+              if (PAIR) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0);
+              else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+            }
+            if (PAIR) {
+              umma_commit_pair_multicast(&empty[stage], 0x3);          // frees the stage in both CTAs
+              if (kb == KB - 1) umma_commit_pair_multicast(&acc_full[buf], 0x3);
+            } else {
+              umma_commit(&empty[stage]);
+              if (kb == KB - 1) umma_commit(&acc_full[buf]);
+            }
+          }
+          __syncwarp();
+          if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();         // no CTA leaves while its peer may still signal its barriers / read its smem
+  if (warp == 5) {
+    tc_fence_after();
+    if (PAIR) tmem_dealloc_pair<2 * BLOCK_N>(tmem_base);
+    else tmem_dealloc<2 * BLOCK_N>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // wgrad kernel: dW[co][k] += sum over a pixel range of dY[m][co] * im2col(X)[m][k]
 // ---------------------------------------------------------------------------------------------
 constexpr int kWgMaxStages = 3;
@@ -1254,6 +1534,77 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const CUtensorMap& tmBh,
   return cudaGetLastError();
 }
 
+template <int BLOCK_N, int MODE, bool STATS, bool PAIR>
+cudaError_t launch_deep_t(const CUtensorMap& tmB, const CUtensorMap& tmBh, const TmaSet& tmA, const ConvArgs& a,
+                          int n_total, int m_tiles, cudaStream_t stream) {
+  using Cfg = DeepCfg<BLOCK_N, PAIR>;
+  auto kern = conv_gemm_deep_kernel<BLOCK_N, MODE, STATS, PAIR>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int n_tiles = n_total / BLOCK_N;
+  const long long items = static_cast<long long>(n_tiles) * (PAIR ? (m_tiles + 1) / 2 : m_tiles);
+  long long grid = g_num_sms;                      // one CTA per SM
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    if (grid > 2 * items) grid = 2 * items;
+    grid &= ~1LL;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  } else if (grid > items) {
+    grid = items;
+  }
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
+  return cudaLaunchKernelEx(&cfg, kern, tmB, tmBh, tmA, a, n_tiles, m_tiles);
+}
+
+// Variant word (ConvArgs::variant; 0 = built-in policy).  The Python layer autotunes it per layer shape on first use
+// (ops/native.py: the analogue of the reference's `cudnn.benchmark = True`, pytorch_synthetic_benchmark.py:57).
+//   bits 0-3  kernel: 1 = one tile per CTA, 2 = persistent (2 CTAs/SM, 2-3 stage ring), 3 = deep ring (1 CTA/SM)
+//   bits 4-7  tile width: 0 = widest that divides Cout, 1 = 64, 2 = 128, 3 = 256 (deep only)
+//   bit  8    deep only: CTA pairs sharing one M = 256 MMA (cta_group::2)
+constexpr int kVarOneTile = 1, kVarPersistent = 2, kVarDeep = 3;
+
+template <int MODE>
+constexpr bool mode_deep(){ return MODE == kConvGemm || MODE == kConvTileFwd || MODE == kConvTileDgrad || MODE == kConvGemmDgrad; }
+
+template <int MODE>
+cudaError_t launch_deep_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, const TmaSet& tmA, const ConvArgs& a,
+                             int n_total, int m_tiles, bool stats, int bn, bool pair, cudaStream_t stream) {
+  if constexpr (!mode_deep<MODE>()) {
+    return cudaErrorInvalidValue;
+  } else {
+#define DDL_DEEP(BN, PR)                                                                                     \
+  return stats ? launch_deep_t<BN, MODE, true, PR>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)              \
+               : launch_deep_t<BN, MODE, false, PR>(tmB, tmBh, tmA, a, n_total, m_tiles, stream)
+    if (bn == 256) { if (pair) { DDL_DEEP(256, true); } else { DDL_DEEP(256, false); } }
+    if (bn == 128) { if (pair) { DDL_DEEP(128, true); } else { DDL_DEEP(128, false); } }
+    if (bn == 64) {
+      if constexpr (!mode_b_mn(MODE)) { if (pair) { DDL_DEEP(64, true); } }
+      DDL_DEEP(64, false);
+    }
+#undef DDL_DEEP
+    return cudaErrorInvalidValue;
+  }
+}
+
 // Pipeline-depth policy.  Short-K tiles are dominated by per-CTA fixed latency (TMEM alloc, first TMA
 // round trip, epilogue), so they get a shallow ring -> small shared-memory footprint -> 3-4 CTAs per SM whose
 // prologues/epilogues overlap.  Long-K tiles get the deep ring.  g_force_stages (tuning hook) overrides.
@@ -1261,6 +1612,7 @@ int g_force_stages = 0;
 int g_cluster = 0;          // tuning hook: 1 = CTA pairs with TMA-multicast weight tiles, 2 = cta_group::2 pair MMAs
 int g_bn256 = 0;            // tuning hook: 1 lets long-K layers use 128 x 256 persistent tiles (measured 1.7 % SLOWER on
                             // ResNet-50: one CTA per SM leaves the epilogue half the warps; kept for A/B runs)
+int g_deep = 1;             // tuning hook: 0 = never use the deep-ring kernel, 1 = policy, 2-4 = wherever it applies
 int g_wgrad_swap = 1;       // tuning hook: 0 disables the operand-role swap of narrow-output wgrad tiles
 
 template <int BLOCK_N, int MODE>
@@ -1279,19 +1631,41 @@ int pick_stages(int KB) {
 template <int MODE>
 cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, bool have_half_map, const TmaSet& tmA,
                             ConvArgs a, int n_total, int m_tiles, bool stats, cudaStream_t stream) {
+  const int var_kind = a.variant & 0xf, var_bn = (a.variant >> 4) & 0xf, var_pair = (a.variant >> 8) & 1;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const long long tiles128 = static_cast<long long>(n_total / ((n_total % 128 == 0) ? 128 : 64)) * m_tiles;
+  // ---- deep-ring kernel (one CTA / CTA pair per SM): long-K layers with at least a couple of waves of tiles -------
+  if (mode_deep<MODE>() && g_deep &&
+      (var_kind == kVarDeep || (var_kind == 0 && (g_deep >= 2 || (a.KB >= 8 && tiles128 >= 2LL * g_num_sms))))) {
+    int bn = (n_total % 256 == 0) ? 256 : ((n_total % 128 == 0) ? 128 : 64);
+    if (var_kind == kVarDeep && var_bn != 0) {
+      const int want = var_bn == 1 ? 64 : (var_bn == 2 ? 128 : 256);
+      if (n_total % want != 0) return cudaErrorInvalidValue;
+      bn = want;
+    }
+    // test hooks: g_deep = 2 forces the deep kernel with pairs wherever possible, 3 = without pairs, 4 = without pairs
+    // and without 256-wide tiles
+    bool pair = var_kind == kVarDeep ? var_pair != 0 : (g_deep != 3 && g_deep != 4);
+    if (var_kind != kVarDeep && g_deep == 4 && bn == 256) bn = 128;
+    // pairs need two M tiles, 64-column halves of an MN-major weight tile, and a loadable half of a K-major one
+    // (bn = 256: the full map's 128-row box; narrower: the half-height box map)
+    if (m_tiles < 2 || (mode_b_mn(MODE) && bn < 128) || (!mode_b_mn(MODE) && bn < 256 && !have_half_map)) pair = false;
+    return launch_deep_mode<MODE>(tmB, tmBh, tmA, a, n_total, m_tiles, stats, bn, pair, stream);
+  }
+  if (var_kind == kVarDeep) return cudaErrorInvalidValue;
   bool persistent = false;
   if (mode_a_tma(MODE) && g_persistent) {
-    if (g_num_sms == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-      if (g_num_sms <= 0) g_num_sms = 148;
-    }
     // persistence pays when every CTA gets several tiles (measured crossover ~3.5 tiles per resident CTA);
     // below that the one-tile-per-CTA kernel with 3 CTAs/SM wins.  g_persistent == 2 forces it (tuning).
-    const long long tiles = static_cast<long long>(n_total / ((n_total % 128 == 0) ? 128 : 64)) * m_tiles;
-    persistent = g_persistent == 2 || tiles * 2 >= 7LL * 2 * g_num_sms;
+    persistent = g_persistent == 2 || tiles128 * 2 >= 7LL * 2 * g_num_sms;
   }
+  if (mode_a_tma(MODE) && var_kind == kVarPersistent) persistent = true;
+  if (var_kind == kVarOneTile) persistent = false;
   // 128 x 256 tiles: only where the main loop (operand traffic) matters (K >= 256) — with one CTA per SM the epilogue
   // has half the warps to hide its latency, which would cost the short-K, store-bound layers
   if (persistent && g_bn256 && n_total % 256 == 0 && a.KB >= 4 &&
@@ -1346,6 +1720,7 @@ void set_conv_persistent(int on) { g_persistent = on; }
 void set_wgrad_swap(int on) { g_wgrad_swap = on; }
 void set_conv_bn256(int on) { g_bn256 = on; }
 void set_conv_cluster(int on) { g_cluster = on; }
+void set_conv_deep(int on) { g_deep = on; }
 
 // `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
 // `a_matrix`: the A operand for the TMA-A modes (2-D matrix [M][a_cols], or the NHWC tensor in tile modes).
@@ -1363,7 +1738,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
     tmBh = tmB;
   } else {
     if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, bn)) return cudaErrorUnknown;
-    have_half = g_cluster && make_map_2d(&tmBh, w, w_rows, w_cols, w_cols, 64, bn / 2);
+    have_half = make_map_2d(&tmBh, w, w_rows, w_cols, w_cols, 64, bn / 2);     // pair tiles / multicast halves
     if (!have_half) tmBh = tmB;
   }
   a.ntaps = 0;

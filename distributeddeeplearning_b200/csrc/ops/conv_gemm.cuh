@@ -59,6 +59,8 @@ struct ConvArgs {
   int relu;                   // apply ReLU in the epilogue (after bias)
   int n_valid;                // output channels that really exist (bias is read only below this)
   int stages;                 // pipeline depth actually used (<= compile-time maximum)
+  int variant;                // kernel variant word chosen by the caller's autotuner (0 = built-in policy); see
+                              //   launch_fwd_mode in conv_gemm.cu for the encoding
   // tile modes: the M tile is a tw x th x tn box of pixels of the dstH x dstW iteration grid (w fastest);
   // tw*th*tn <= 128.  Row (n, i, j) of the grid is written to out[n][out_stride*i + out_pa][out_stride*j + out_pb]
   // of an outH x outW image (dense output: out_stride = 1).

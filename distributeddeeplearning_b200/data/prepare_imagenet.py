@@ -3,8 +3,9 @@
 Parity: reference ``scripts/prepare_imagenet.py`` — SHA1 check of the two archives (``:18-35``),
 ``ILSVRC2012_img_train.tar`` is a tar of per-class tars -> ``train/<wnid>/*.JPEG`` (``:38-55``),
 ``ILSVRC2012_img_val.tar`` is flat -> ``validation/<wnid>/`` using the val filename->wnid map
-(``:58-71``; the map ships as ``scripts/imagenet_val_maps.csv`` in the reference — here the caller
-passes any ``filename,wnid`` CSV via ``--val-map`` or drops it next to the archives).
+(``:58-71``; the map ships as ``scripts/imagenet_val_maps.csv`` in the reference — here it comes from the
+packaged ``data/imagenet_meta`` lookup unless the caller passes a CSV via ``--val-map`` or drops one next to
+the archives).
 """
 from __future__ import annotations
 
@@ -58,8 +59,12 @@ def load_val_map(path: str) -> Dict[str, str]:
     m: Dict[str, str] = {}
     with open(path, newline="") as f:
         for row in csv.reader(f):
-            if len(row) >= 2 and row[0].lower() not in ("filename", "file"):
-                m[os.path.basename(row[0])] = row[1]
+            if len(row) < 2 or row[0].lower() in ("filename", "file", "class"):
+                continue
+            if row[0].upper().endswith((".JPEG", ".JPG", ".PNG")):
+                m[os.path.basename(row[0])] = row[1]            # filename,wnid
+            else:
+                m[os.path.basename(row[1])] = row[0]            # class,filename (the reference's column order)
     return m
 
 
@@ -94,8 +99,12 @@ def main(download_dir: str, target_dir: str, check: bool = True, val_map: Option
         if check:
             check_sha1(val_tar, SHA1[VAL_TAR])
         vm_path = val_map or os.path.join(download_dir, "imagenet_val_maps.csv")
-        if not os.path.isfile(vm_path):
-            raise FileNotFoundError(f"validation map CSV not found: {vm_path}")
-        counts["validation"] = extract_val(val_tar, target_dir, load_val_map(vm_path))
+        if os.path.isfile(vm_path):
+            vm = load_val_map(vm_path)          # a user-supplied ``filename,wnid`` / ``class,filename`` CSV wins
+        else:
+            from . import imagenet_meta
+
+            vm = imagenet_meta.val_map()        # the packaged ILSVRC2012 ground truth (reference: scripts/imagenet_val_maps.csv)
+        counts["validation"] = extract_val(val_tar, target_dir, vm)
     print(counts)
     return counts

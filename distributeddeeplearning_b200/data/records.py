@@ -108,3 +108,62 @@ class RecordDataset(torch.utils.data.IterableDataset):
                     y, n = _HDR.unpack(hdr)
                     img = Image.open(io.BytesIO(f.read(n))).convert("RGB")
                     yield (self.transform(img) if self.transform else img), y
+
+
+def count_records(path: str) -> int:
+    """Number of records in one shard (header walk with seeks: no image bytes are read)."""
+    n = 0
+    size = os.path.getsize(path)
+    with open(path, "rb") as f:
+        pos = 0
+        while pos + _HDR.size <= size:
+            f.seek(pos)
+            _, nbytes = _HDR.unpack(f.read(_HDR.size))
+            pos += _HDR.size + nbytes
+            n += 1
+    return n
+
+
+class RecordLoader:
+    """Batched loader over THIS rank's record shards — the trainer-facing end of the record path.
+
+    Parity: the reference's TF input functions give every rank a disjoint subset of the shard FILES
+    (``TensorFlow_imagenet/src/data/tfrecords.py:130-141``: ``dataset.shard(hvd.size(), hvd.rank())`` on the file list,
+    shuffled per epoch) and its tasks select them with ``--data_type tfrecords``
+    (``TensorFlow_imagenet/tensorflow_imagenet.py:110-151``).  Here ``RecordDataset`` does the file-level sharding
+    (rank r reads shards r, r+size, ...; DataLoader workers split those again), ``set_epoch`` reseeds the shard order,
+    and ``len()`` is the number of batches EVERY rank runs (the minimum over ranks, so collectives stay in step).
+    """
+
+    def __init__(self, directory: str, split: str, batch_size: int, train: bool, size: int = 224, num_workers: int = 4,
+                 rank: int = 0, world: int = 1, normalize_on_host: bool = True, seed: int = 0):
+        from .images import build_transforms
+
+        self.dataset = RecordDataset(directory, split, rank, world, build_transforms(train, size, normalize_on_host),
+                                     shuffle_seed=seed if train else None)
+        all_files = sorted(os.path.join(directory, f) for f in os.listdir(directory)
+                           if f.startswith(split + "-") and f.endswith(".rec"))
+        if not all_files:
+            raise FileNotFoundError(f"no {split}-*.rec shards in {directory}")
+        counts = [count_records(p) for p in all_files]
+        self.total = sum(counts)
+        per_rank = [sum(counts[r::world]) for r in range(world)]
+        self.per_rank = min(per_rank)                           # samples every rank is guaranteed to have
+        self.batch_size, self.train, self._seed = batch_size, train, seed
+        workers = min(num_workers, max(1, len(self.dataset.files)))
+        self._loader = torch.utils.data.DataLoader(self.dataset, batch_size=batch_size, num_workers=workers,
+                                                   pin_memory=torch.cuda.is_available(), drop_last=False)
+        self._batches = -(-self.per_rank // batch_size) if self.per_rank else 0
+
+    def set_epoch(self, epoch: int) -> None:
+        if self.train:
+            self.dataset.seed = self._seed + epoch
+
+    def __len__(self) -> int:
+        return self._batches
+
+    def __iter__(self):
+        for i, batch in enumerate(self._loader):
+            if i >= self._batches:
+                break                                            # ranks with more samples stop with the others
+            yield batch

@@ -30,7 +30,89 @@ def _C():
         C.set_conv_cluster(int(os.environ["DDL_CONV_CLUSTER"]))       #   weights, 2 = cta_group::2 pair MMAs
     if os.environ.get("DDL_CONV_BN256", "0") == "1":       # tuning hook (A/B runs): 128 x 256 persistent tiles
         C.set_conv_bn256(1)
+    if os.environ.get("DDL_CONV_DEEP", "") in ("0", "2", "3", "4"):   # 0 = never the deep-ring kernel; 2-4 = force it
+        C.set_conv_deep(int(os.environ["DDL_CONV_DEEP"]))            #   (with pairs / without / without + N <= 128)
     return C
+
+
+# ------------------------------------------------------------------------------------------------
+# per-shape kernel autotuning — the analogue of the reference's ``torch.backends.cudnn.benchmark = True``
+# (``PyTorch_benchmark/src/pytorch_synthetic_benchmark.py:57``, ``PyTorch_imagenet/src/imagenet_pytorch_horovod.py:378``)
+# ------------------------------------------------------------------------------------------------
+# The tcgen05 conv/GEMM launcher has several kernels for the same maths (one tile per CTA; persistent with two CTAs per
+# SM; deep-ring with one CTA or one cta_group::2 pair per SM, 64/128/256-wide tiles).  Which one wins depends on K, the
+# number of tiles and how memory-bound the epilogue is, so the first (eager) call of every distinct layer shape times
+# the applicable variants on the real operands and remembers the winner; CUDA-graph capture and all later calls use
+# the table.  ``DDL_CONV_AUTOTUNE=0`` keeps the launcher's built-in policy.
+VAR_ONE_TILE, VAR_PERSISTENT, VAR_DEEP = 1, 2, 3
+_TUNE = {"enabled": os.environ.get("DDL_CONV_AUTOTUNE", "1") == "1", "table": {}, "timings": {}}
+
+
+def conv_variants(n_total: int, m_rows: int, kb: int, b_mn_major: bool):
+    """Variant words worth timing for an ``m_rows`` x ``n_total`` x ``kb*64`` problem (see launch_fwd_mode)."""
+    out = [VAR_ONE_TILE, VAR_PERSISTENT]
+    if m_rows < 128 * 148:            # less than one wave of 128-row tiles: the persistent kernels cannot pay
+        return out[:1]
+    widths = [w for w in (256, 128, 64) if n_total % w == 0][:2]
+    for w in widths:
+        code = {64: 1, 128: 2, 256: 3}[w]
+        out.append(VAR_DEEP | (code << 4))
+        if not (b_mn_major and w < 128):
+            out.append(VAR_DEEP | (code << 4) | (1 << 8))
+    return out
+
+
+def force_variant(v: Optional[int]) -> None:
+    """Tools / tests: make every tunable conv launch use variant ``v`` (None = back to autotuning)."""
+    _TUNE["force"] = v
+
+
+def variant_name(v: int) -> str:
+    kind = {0: "policy", 1: "one-tile", 2: "persistent", 3: "deep"}[v & 0xf]
+    if (v & 0xf) == 3:
+        kind += "-N%d" % {0: 0, 1: 64, 2: 128, 3: 256}[(v >> 4) & 0xf] + ("-pair" if (v >> 8) & 1 else "")
+    return kind
+
+
+def autotune_table():
+    """{shape key: (chosen variant name, {variant name: microseconds})} — what the tuner decided so far."""
+    return {k: (variant_name(v), {variant_name(c): t for c, t in _TUNE["timings"].get(k, {}).items()})
+            for k, v in _TUNE["table"].items()}
+
+
+def _tuned(key, candidates, launch, accumulators=()):
+    """Run ``launch(variant)`` with the best known variant for ``key``; time the candidates on first sight."""
+    if _TUNE.get("force") is not None:                 # tools / tests: run exactly this variant
+        return launch(_TUNE["force"])
+    if not _TUNE["enabled"]:
+        return launch(0)
+    v = _TUNE["table"].get(key)
+    if v is not None:
+        return launch(v)
+    if torch.cuda.is_current_stream_capturing() or len(candidates) < 2:
+        return launch(candidates[0] if len(candidates) == 1 else 0)
+    times = {}
+    for c in candidates:
+        try:
+            launch(c)
+            launch(c)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(4):
+                launch(c)
+            b.record()
+            b.synchronize()
+            times[c] = a.elapsed_time(b) / 4 * 1e3
+        except RuntimeError:
+            continue                                   # variant not applicable to this shape
+    if not times:
+        return launch(0)
+    best = min(times, key=times.get)
+    _TUNE["table"][key] = best
+    _TUNE["timings"][key] = times
+    for t in accumulators:                             # the trial launches accumulated BN statistics: start over
+        t.zero_()
+    return launch(best)
 
 
 @functools.lru_cache(maxsize=None)
@@ -263,16 +345,21 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
     if Cin % 8 != 0:
         raise ValueError("conv_fwd: Cin must be a multiple of 8 (or an NHWC4 stem)")
     if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
-        C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, cch, Cout, H, W, Cin, P, Q,
-                    1, 1, 1, 0, 1, cch, int(relu), Cout, wp, wr, wc, n_total, x.data_ptr(), Cin, N, 0, 0, 0, 0,
-                    _stream(), 0, Cin)
+        _tuned(("fwd1x1", N, H, W, Cin, Cout, stats, bias is not None, relu), conv_variants(n_total, M, cch, False),
+               lambda v: C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, cch, Cout, H, W, Cin,
+                                     P, Q, 1, 1, 1, 0, 1, cch, int(relu), Cout, wp, wr, wc, n_total, x.data_ptr(), Cin,
+                                     N, 0, 0, 0, 0, _stream(), 0, Cin, variant=v),
+               (st,) if stats else ())
     elif USE_TILE_TMA and (stride == 1 or (stride == 2 and R * S <= 16 and USE_TILE_S2)):
         # window conv: the activation operand comes through ONE 4-D TMA box per filter tap (stride 2: the box is
         # taken from the matching 2x2 phase sub-image of x)
         tw, th, tn = tile_geometry(P, Q, N, 128)
-        C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * cch, Cout, H, W,
-                    Cin, P, Q, R, S, stride, ph, dil, cch, int(relu), Cout, wp, wr, wc, n_total, x.data_ptr(), Cin,
-                    N, tw, th, tn, 0, _stream(), pw, Cin)
+        _tuned(("fwd", N, H, W, Cin, Cout, R, S, stride, ph, pw, dil, stats, bias is not None, relu),
+               conv_variants(n_total, M, R * S * cch, False),
+               lambda v: C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * cch,
+                                     Cout, H, W, Cin, P, Q, R, S, stride, ph, dil, cch, int(relu), Cout, wp, wr, wc,
+                                     n_total, x.data_ptr(), Cin, N, tw, th, tn, 0, _stream(), pw, Cin, variant=v),
+               (st,) if stats else ())
     else:
         C.conv_gemm(C.CONV_FWD, x.data_ptr(), y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * cch,
                     Cout, H, W, Cin, P, Q, R, S, stride, ph, dil, cch, int(relu), Cout, wp, wr, wc, n_total, 0, 0,
@@ -330,20 +417,30 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
                    bnr_mean=bsave[0].data_ptr(), bnr_invstd=bsave[1].data_ptr())
         s1, s2 = bscr[1].data_ptr(), bscr[0].data_ptr()      # scratch layout of bn_act_bwd: [0] = dgamma, [1] = dbeta
     if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
-        C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, cch, Cin, P, Q, Cout, H,
-                    W, 1, 1, 1, 0, 1, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, 0, 0, 0, 0, _stream(),
-                    0, 0, _ptr(add_mask), **bnr)
+        _tuned(("dgrad1x1", N, H, W, Cin, Cout, add is not None, add_mask is not None, bn_reduce is not None),
+               conv_variants(n_total, N * H * W, cch, True),
+               lambda v: C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, cch, Cin, P, Q,
+                                     Cout, H, W, 1, 1, 1, 0, 1, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N,
+                                     0, 0, 0, 0, _stream(), 0, 0, _ptr(add_mask), variant=v, **bnr),
+               (bn_reduce[4],) if bn_reduce is not None else ())
     elif stride == 1 and USE_TILE_TMA:
         tw, th, tn = tile_geometry(H, W, N, 128)
-        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, R * S * cch, Cin, P, Q,
-                    Cout, H, W, R, S, 1, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, tw, th, tn,
-                    0, _stream(), pw, 0, _ptr(add_mask), **bnr)
+        _tuned(("dgrad", N, H, W, Cin, Cout, R, S, 1, ph, pw, dil, add is not None, add_mask is not None,
+                bn_reduce is not None), conv_variants(n_total, N * H * W, R * S * cch, True),
+               lambda v: C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, R * S * cch,
+                                     Cin, P, Q, Cout, H, W, R, S, 1, ph, dil, cch, 0, Cin, wp, wr, wc, n_total,
+                                     dy.data_ptr(), Cout, N, tw, th, tn, 0, _stream(), pw, 0, _ptr(add_mask), variant=v,
+                                     **bnr),
+               (bn_reduce[4],) if bn_reduce is not None else ())
     elif s2_tile:
         # four stride-1 phase problems (one launch each), tiles iterate the half-resolution phase grid
         tw, th, tn = tile_geometry((H + 1) // 2, (W + 1) // 2, N, 128)
-        C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, s1, s2, N * H * W, R * S * cch, Cin, P, Q,
-                    Cout, H, W, R, S, 2, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(), Cout, N, tw, th, tn,
-                    zfill, _stream(), pw, 0, 0, **bnr)
+        _tuned(("dgrad_s2", N, H, W, Cin, Cout, R, S, 2, ph, pw, dil, zfill, bn_reduce is not None),
+               conv_variants(n_total, N * ((H + 1) // 2) * ((W + 1) // 2), max(1, (R * S * cch) // 4), True),
+               lambda v: C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, s1, s2, N * H * W, R * S * cch, Cin, P,
+                                     Q, Cout, H, W, R, S, 2, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, dy.data_ptr(),
+                                     Cout, N, tw, th, tn, zfill, _stream(), pw, 0, 0, variant=v, **bnr),
+               (bn_reduce[4],) if bn_reduce is not None else ())
     else:
         C.conv_gemm(C.CONV_DGRAD, dy.data_ptr(), dx.data_ptr(), _ptr(add), 0, s1, s2, N * H * W, R * S * cch,
                     Cin, P, Q, Cout, H, W, R, S, stride, ph, dil, cch, 0, Cin, wp, wr, wc, n_total, 0, 0, N, 0, 0, 0, 0,

@@ -157,9 +157,13 @@ def validate(val_loader, model, criterion, device, classes, prepare=None):
 
 def main(training_data_path=None, validation_data_path=None, use_gpu=False, save_filepath=None, model="resnet50",
          epochs=_EPOCHS, batch_size=_BATCHSIZE, fp16_allreduce=False, base_lr=0.0125, warmup_epochs=5,
-         num_workers=5, host_data=False, cuda_graph=True):
+         num_workers=5, host_data=False, cuda_graph=True, data_type=None):
     """``cuda_graph``: on a GPU with the fused engine, replay the training step from a captured CUDA graph (the
-    reference's default batch of 64 per GPU is launch-bound: ~340 kernels per ResNet-50 step)."""
+    reference's default batch of 64 per GPU is launch-bound: ~340 kernels per ResNet-50 step).
+    ``data_type``: ``synthetic`` | ``images`` (class folders) | ``records`` / ``tfrecords`` (sharded record files
+    written by ``inv storage.tfrecords.generate-tf-records``; the data paths are then the shard directories) — the
+    switch of the reference's TF trainer tasks (``TensorFlow_imagenet/tensorflow_imagenet.py:110-151``).  Default:
+    synthetic without a training path, images with one."""
     logger = logging.getLogger(__name__)
     epochs = int(epochs)
     cuda_graph = _str_to_bool(cuda_graph) if isinstance(cuda_graph, str) else bool(cuda_graph)
@@ -193,7 +197,14 @@ def main(training_data_path=None, validation_data_path=None, use_gpu=False, save
     classes = getattr(net, "num_classes", 1000)
     prepare = None
     val_loader = None
-    if training_data_path is None:
+    data_type = (data_type or ("synthetic" if training_data_path is None else "images")).lower()
+    if data_type == "tfrecords":
+        data_type = "records"
+    if data_type not in ("synthetic", "images", "records"):
+        raise ValueError(f"data_type must be synthetic, images or records, got {data_type!r}")
+    if data_type != "synthetic" and training_data_path is None:
+        raise ValueError(f"--data_type {data_type} needs --training_data_path")
+    if data_type == "synthetic":
         logger.info("Setting up fake loaders")
         if use_gpu and not host_data:
             train_loader = DeviceSyntheticLoader(_data_length(), batch_size, size, classes, device, rank, world, _SEED)
@@ -203,6 +214,20 @@ def main(training_data_path=None, validation_data_path=None, use_gpu=False, save
             train_sampler = get_sampler(ds)
             train_loader = torch.utils.data.DataLoader(ds, batch_size=batch_size, sampler=train_sampler,
                                                        num_workers=num_workers if use_gpu else 0, pin_memory=use_gpu)
+    elif data_type == "records":
+        from ..data.images import DeviceNormalizer
+        from ..data.records import RecordLoader
+
+        logger.info("Setting up record loaders")
+        logger.info(f"Loading training shards from {training_data_path}")
+        train_loader = RecordLoader(training_data_path, "train", batch_size, True, size, num_workers, rank, world,
+                                    normalize_on_host=not use_gpu, seed=_SEED)
+        train_sampler = train_loader
+        prepare = DeviceNormalizer(device) if use_gpu else None
+        if validation_data_path is not None:
+            logger.info(f"Loading validation shards from {validation_data_path}")
+            val_loader = RecordLoader(validation_data_path, "validation", batch_size, False, size, num_workers, rank,
+                                      world, normalize_on_host=not use_gpu)
     else:
         from ..data.images import DeviceNormalizer, image_folder_loader
 

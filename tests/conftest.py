@@ -35,3 +35,12 @@ def _few_threads():
 
     torch.set_num_threads(2)
     yield
+
+
+@pytest.fixture(autouse=True)
+def _artefacts_outside_the_repo(tmp_path, monkeypatch):
+    """Run history, TensorBoard event files and checkpoints of anything a test launches go to the test's tmp dir
+    (child processes inherit the environment): the suite must not create or delete files inside the repository."""
+    monkeypatch.setenv("DDL_RUNS_DIR", str(tmp_path / "runs"))
+    monkeypatch.setenv("DDL_LOG_DIR", str(tmp_path / "logs"))
+    yield

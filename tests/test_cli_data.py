@@ -136,3 +136,97 @@ def test_prepare_imagenet_and_records(tmp_path):
     ds0 = list(records.RecordDataset(str(tmp_path / "rec" / "train"), "train", rank=0, world=2))
     ds1 = list(records.RecordDataset(str(tmp_path / "rec" / "train"), "train", rank=1, world=2))
     assert len(ds0) + len(ds1) == 4 and {y for _, y in ds0 + ds1} == {0, 1}
+
+
+def test_val_map_falls_back_to_packaged_lookup(tmp_path):
+    """Without a user CSV, prepare_imagenet sorts the validation images with the packaged ILSVRC2012 ground truth."""
+    from distributeddeeplearning_b200.data import imagenet_meta as meta
+
+    labels = meta.val_labels()
+    assert len(labels) == 50000 and min(labels) == 0 and max(labels) == 999
+    ci = meta.class_index()
+    assert ci["0"] == ("n01440764", "tench") and len(ci) == 1000 and meta.nounid_to_class()["n01443537"] == 1
+    # every class has exactly 50 validation images
+    counts = [0] * 1000
+    for c in labels:
+        counts[c] += 1
+    assert set(counts) == {50}
+    jpg = _tiny_jpeg()
+    dl = tmp_path / "dl"
+    dl.mkdir()
+    with tarfile.open(dl / prepare_imagenet.VAL_TAR, "w") as tf:
+        for i in (0, 1, 49999):
+            ti = tarfile.TarInfo(meta.val_filename(i))
+            ti.size = len(jpg)
+            tf.addfile(ti, io.BytesIO(jpg))
+    counts = prepare_imagenet.main(str(dl), str(tmp_path / "out"), check=False)
+    assert counts == {"validation": 3}
+    w = meta.wnids()
+    for i in (0, 1, 49999):
+        assert os.path.isfile(tmp_path / "out" / "validation" / w[labels[i]] / meta.val_filename(i))
+    files = meta.write_reference_files(str(tmp_path / "lookups"))
+    head = open(files[1]).read().splitlines()[:2]
+    assert head[0] == "class,filename" and head[1].endswith("ILSVRC2012_val_00000001.JPEG")
+    # the reference's column order (class,filename) is accepted as a user-supplied map too
+    assert prepare_imagenet.load_val_map(files[1])[meta.val_filename(0)] == w[labels[0]]
+
+
+def _class_folders(root, classes=2, per_class=6):
+    from PIL import Image
+
+    for split in ("train", "validation"):
+        for c in range(classes):
+            d = root / split / f"n{c:08d}"
+            d.mkdir(parents=True)
+            for i in range(per_class):
+                Image.new("RGB", (40, 36), (40 * c, 10 * i, 99)).save(d / f"img_{i}.JPEG")
+
+
+def test_record_loader_shards_files_across_ranks(tmp_path):
+    _class_folders(tmp_path / "data")
+    records.convert(str(tmp_path / "data"), str(tmp_path / "rec"), shards_train=4, shards_val=2)
+    loaders = [records.RecordLoader(str(tmp_path / "rec" / "train"), "train", batch_size=2, train=True, size=32,
+                                    num_workers=0, rank=r, world=2) for r in range(2)]
+    assert loaders[0].total == 12 and len(loaders[0]) == len(loaders[1]) == 3
+    assert not set(loaders[0].dataset.files) & set(loaders[1].dataset.files)          # disjoint FILE sets
+    for l in loaders:
+        l.set_epoch(1)
+        batches = list(l)
+        assert len(batches) == 3 and batches[0][0].shape == (2, 3, 32, 32)
+
+
+def test_imagenet_trainer_reads_record_shards(tmp_path):
+    """`--data_type records` (the reference's tfrecords tasks) trains from the sharded record files."""
+    from distributeddeeplearning_b200.cli import launcher
+
+    _class_folders(tmp_path / "data")
+    records.convert(str(tmp_path / "data"), str(tmp_path / "rec"), shards_train=2, shards_val=1)
+    out, err = io.StringIO(), io.StringIO()
+    res = launcher.launch("distributeddeeplearning_b200.workloads.imagenet",
+                          ["--epochs", "1", "--batch_size", "4", "--model", "squeezenet1_1", "--data_type", "tfrecords",
+                           "--training_data_path", str(tmp_path / "rec" / "train"),
+                           "--validation_data_path", str(tmp_path / "rec" / "validation"), "--num_workers", "0"],
+                          gpus=1, no_cuda=True, record=False, stdout=out, stderr=err, timeout=600,
+                          env={"PYTHONPATH": os.path.dirname(os.path.dirname(os.path.abspath(__file__)))})
+    text = out.getvalue() + err.getvalue()
+    assert res.returncode == 0, text[-3000:]
+    assert "Loading training shards" in text and "Total images/sec:" in text and "Data length:      12" in text
+
+
+def test_enabled_workloads_prunes_the_task_tree(tmp_path, monkeypatch):
+    from distributeddeeplearning_b200.cli import tasks
+
+    p = template.render_project(str(tmp_path / "proj"), type="pytorch_benchmark", _remove_unused_projects=True)
+    assert 'ENABLED_WORKLOADS="pytorch_benchmark"' in open(os.path.join(p, ".env")).read()
+    assert not os.path.exists(os.path.join(p, "experiment"))          # no skeleton for a non-template type
+    monkeypatch.chdir(p)
+    monkeypatch.delenv("ENABLED_WORKLOADS", raising=False)
+    names = set(tasks.build_namespace().task_names)
+    assert "pytorch-benchmark.submit.remote.synthetic" in names and "storage.create-container" in names
+    assert not any(n.startswith(("pytorch-imagenet", "tf-", "pytorch-hvd", "pytorch-experiment")) for n in names)
+    monkeypatch.setenv("ENABLED_WORKLOADS", "tensorflow_imagenet,pytorch_template")
+    names = set(tasks.build_namespace().task_names)
+    assert "tf-imagenet.submit.local.tfrecords" in names and "pytorch-experiment.submit.local.synthetic" in names
+    assert "pytorch-benchmark.submit.local.synthetic" not in names
+    q = template.render_project(str(tmp_path / "proj2"), type="pytorch_template", _remove_unused_projects=True)
+    assert os.path.isdir(os.path.join(q, "experiment"))

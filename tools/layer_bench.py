@@ -76,19 +76,36 @@ def main():
         gg, bg = torch.zeros(co, device=dev), torch.zeros(co, device=dev)
         C = nv._C()
         sweep = {}
-        if os.environ.get("LB_SWEEP", "1") == "1":
-            for st_ in (1, 2, 3, 4):
-                C.set_conv_force_stages(st_)
-                f_ = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), reps=3, flush=flush)
-                d_ = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), reps=3, flush=flush) if ci != 3 else 0.0
-                w_ = timeit(lambda: nv.conv_wgrad(x, dy, gw, (k, k), s, p), reps=3, flush=flush)
-                sweep[st_] = (round(f_, 4), round(d_, 4), round(w_, 4))
-            C.set_conv_force_stages(0)
-        C.set_conv_persistent(0)
-        np_f = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), reps=3, flush=flush)
-        np_d = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), reps=3, flush=flush) if ci != 3 else 0.0
-        C.set_conv_persistent(1)
-        sweep["nonpersistent"] = (round(np_f, 4), round(np_d, 4))
+        # every applicable kernel variant on this shape: time (L2 flushed) + max |difference| against the one-tile
+        # kernel's output (the variants share the k order, so their results must agree to bf16 rounding)
+        vt = {}
+        if ci != 3 and os.environ.get("LB_VARIANTS", "1") == "1":
+            M_f, M_d = B * P * P, B * hw * hw
+            kb_f = k * k * ((ci + 63) // 64)
+            kb_d = k * k * ((co + 63) // 64)
+            nt_f, nt_d = (co + 63) // 64 * 64, (ci + 63) // 64 * 64
+            for name, cands, run in (
+                    ("fwd", nv.conv_variants(nt_f, M_f, kb_f, False),
+                     lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co)[0]),
+                    ("dgrad", nv.conv_variants(nt_d, M_d if s == 1 else M_d // 4, kb_d if s == 1 else max(1, kb_d // 4), True),
+                     lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p))):
+                ref_out, res = None, {}
+                for v in cands:
+                    nv.force_variant(v)
+                    try:
+                        out = run()
+                        torch.cuda.synchronize()
+                    except RuntimeError as e:
+                        res[nv.variant_name(v)] = ("n/a", str(e).splitlines()[0][:40])
+                        continue
+                    if ref_out is None:
+                        ref_out = out.float()
+                    diff = float((out.float() - ref_out).abs().max())
+                    t_ = timeit(run, reps=3, flush=flush)
+                    res[nv.variant_name(v)] = (round(t_ * 1e3, 1), diff)
+                nv.force_variant(None)
+                vt[name] = res
+        sweep["variants_us_maxdiff"] = vt
         t_fwd = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), flush=flush)
         t_bn = timeit(lambda: nv.bn_act_fwd(y, st, gamma, beta, rm, rv, 1e-5, 0.1, True, None, True), flush=flush)
         t_dg = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), flush=flush) if ci != 3 else 0.0
