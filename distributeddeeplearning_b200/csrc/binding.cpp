@@ -39,6 +39,7 @@ void set_wgrad_swap(int on);
 void set_conv_bn256(int on);
 void set_conv_cluster(int on);
 void set_conv_deep(int on);
+cudaError_t conv_timeout_info(unsigned int out[8]);
 }  // namespace ddl
 
 namespace {
@@ -194,6 +195,11 @@ PYBIND11_MODULE(_C, m) {
   // ------------------------------------------------------------------ conv / GEMM
   m.def("set_conv_persistent", &ddl::set_conv_persistent, "tuning hook: 1 = persistent kernel for TMA-fed modes");
   m.def("set_conv_cluster", &ddl::set_conv_cluster, "tuning hook: 1 = CTA pairs with TMA-multicast weight tiles");
+  m.def("conv_timeout_info", []() {
+    unsigned int v[8];
+    check(ddl::conv_timeout_info(v), "conv_timeout_info");
+    return std::vector<unsigned int>(v, v + 8);
+  }, "post-mortem of the first timed-out mbarrier wait (flag, site, block, thread, parity); clears the record");
   m.def("set_conv_deep", &ddl::set_conv_deep, "tuning hook: 0 = never the deep-ring kernel, 1 = policy, 2 = always");
   m.def("set_conv_bn256", &ddl::set_conv_bn256, "tuning hook: 0 = no 128x256 persistent tiles");
   m.def("set_wgrad_swap", &ddl::set_wgrad_swap, "tuning hook: 0 = no operand-role swap for narrow-output wgrad tiles");
@@ -203,9 +209,11 @@ PYBIND11_MODULE(_C, m) {
            int srcH, int srcW, int srcC, int dstH, int dstW, int R, int Sx, int stride, int pad, int dil,
            int cchunks, int relu, int n_valid, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
            int batch, int tw, int th, int tn, int zfill, ptr_t stream, int pad_w, int kstride, ptr_t add_mask,
-           ptr_t bnr_y, ptr_t bnr_gamma, ptr_t bnr_beta, ptr_t bnr_mean, ptr_t bnr_invstd, int variant) {
+           ptr_t bnr_y, ptr_t bnr_gamma, ptr_t bnr_beta, ptr_t bnr_mean, ptr_t bnr_invstd, int variant, int fp8,
+           ptr_t deq_a, ptr_t deq_b) {
           ConvArgs a;
           a.variant = variant;
+          a.fp8 = fp8; a.deq_a = P<const float>(deq_a); a.deq_b = P<const float>(deq_b);
           a.bnr_y = P<const __nv_bfloat16>(bnr_y); a.bnr_gamma = P<const float>(bnr_gamma);
           a.bnr_beta = P<const float>(bnr_beta); a.bnr_mean = P<const float>(bnr_mean);
           a.bnr_invstd = P<const float>(bnr_invstd);
@@ -228,7 +236,8 @@ PYBIND11_MODULE(_C, m) {
         py::arg("a_matrix"), py::arg("a_cols"), py::arg("batch"), py::arg("tw"), py::arg("th"), py::arg("tn"),
         py::arg("zfill"), py::arg("stream"), py::arg("pad_w") = -1, py::arg("kstride") = 0, py::arg("add_mask") = 0,
         py::arg("bnr_y") = 0, py::arg("bnr_gamma") = 0, py::arg("bnr_beta") = 0, py::arg("bnr_mean") = 0,
-        py::arg("bnr_invstd") = 0, py::arg("variant") = 0);
+        py::arg("bnr_invstd") = 0, py::arg("variant") = 0, py::arg("fp8") = 0, py::arg("deq_a") = 0,
+        py::arg("deq_b") = 0);
   m.def("conv_wgrad",
         [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int dy_ld, int ldw, int ncols, int H, int W, int C, int Pq,
            int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, int batch, int tw, int th, int tn,
@@ -367,6 +376,18 @@ PYBIND11_MODULE(_C, m) {
   m.def("nhwc_u8_to_nhwc4", [](ptr_t in, ptr_t out, int64_t pixels, ptr_t mean, ptr_t stdv, ptr_t stream) {
     check(ddl::launch_nhwc_u8_to_nhwc4(P<const uint8_t>(in), P<__nv_bfloat16>(out), pixels, P<const float>(mean),
                                        P<const float>(stdv), S(stream)), "nhwc_u8_to_nhwc4");
+  });
+  // ------------------------------------------------------------------ fp8 operand preparation
+  m.attr("FP8_SLOT_BYTES") = static_cast<int>(sizeof(ddl::Fp8Slot));
+  m.def("fp8_quantize", [](ptr_t x, ptr_t out, int64_t n, ptr_t slot, bool e5m2, int sms, ptr_t stream) {
+    check(ddl::launch_fp8_quantize(P<const __nv_bfloat16>(x), P<uint8_t>(out), n, P<ddl::Fp8Slot>(slot), e5m2, sms,
+                                   S(stream)), "fp8_quantize");
+  });
+  m.def("fp8_amax", [](ptr_t x, int64_t n, ptr_t slot, int sms, ptr_t stream) {
+    check(ddl::launch_fp8_amax(P<const __nv_bfloat16>(x), n, P<ddl::Fp8Slot>(slot), sms, S(stream)), "fp8_amax");
+  });
+  m.def("fp8_update_scales", [](ptr_t slots, int n, ptr_t stream) {
+    check(ddl::launch_fp8_update_scales(P<ddl::Fp8Slot>(slots), n, S(stream)), "fp8_update_scales");
   });
   m.def("cast_f32_bf16", [](ptr_t in, ptr_t out, int64_t n, ptr_t stream) {
     check(ddl::launch_cast_f32_bf16(P<const float>(in), P<__nv_bfloat16>(out), n, S(stream)), "cast_f32_bf16");

@@ -107,7 +107,7 @@ DDL_DEVICE float lds_f32(uint32_t addr) { return __uint_as_float(lds32(addr)); }
 // `stg_row`: shared address of the row's staging line; `zero_row`: the row lies outside the image (tile modes).
 template <bool BIAS_RELU>
 DDL_DEVICE void epi_tmem_to_stage(uint32_t taddr_row, uint32_t stg_row, int c_begin, int c_end, const ConvArgs& a,
-                                  int n0, bool zero_row) {
+                                  int n0, bool zero_row, float deq = 1.0f) {
 #pragma unroll 1
   for (int c0 = c_begin; c0 < c_end; c0 += 32) {
     uint32_t v[32];
@@ -116,7 +116,7 @@ DDL_DEVICE void epi_tmem_to_stage(uint32_t taddr_row, uint32_t stg_row, int c_be
     uint32_t packed[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
+      float x0 = __uint_as_float(v[2 * j]) * deq, x1 = __uint_as_float(v[2 * j + 1]) * deq;
       if (BIAS_RELU) {
         if (a.bias) {
           const int cb = n0 + c0 + 2 * j;
@@ -371,7 +371,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_wait(&empty[stage], phase ^ 1u, 17);
         const uint32_t dst = smem_u32(smem + stage * Cfg::kStageBytes) + row_off;
         if (MODE == kConvStem) {
           // k-block = RPK filter rows x SP taps x 4 channels, SP = a.cchunks (padded taps per row)
@@ -446,7 +446,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
     } else {
       my_m = (m0 + row) < a.M ? (m0 + row) : -1;
     }
-    mbar_wait(acc_full, 0);
+    mbar_wait(acc_full, 0, 20);
     tc_fence_after();
     // pipeline buffers are free (every MMA that read them has completed): the tile is staged over them
     const uint32_t stg = smem_u32(smem);
@@ -471,7 +471,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
       uint32_t phase = 0;
       const uint32_t a_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : kATileBytes;
       for (int kb = 0; kb < KB; ++kb) {
-        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_wait(&empty[stage], phase ^ 1u, 17);
         uint8_t* sA = smem + stage * Cfg::kStageBytes;
         const uint32_t sB = smem_u32(sA + kATileBytes);
         mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + (kATma ? a_bytes : 0u));
@@ -511,7 +511,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < KB; ++kb) {
-      mbar_wait(&full[stage], phase);
+      mbar_wait(&full[stage], phase, 18);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -660,7 +660,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
       const bool valid = tile_origin(t, n0, m0, tq0, tp0, tn0);
       if (CLUSTER && !valid) {          // padding tile: keep the accumulator hand-shake going, write nothing
         const int pbuf = it & 1;
-        mbar_wait(&acc_full[pbuf], (it >> 1) & 1);
+        mbar_wait(&acc_full[pbuf], (it >> 1) & 1, 36);
         tc_fence_after();
         tc_fence_before();
         named_bar_sync(1, kEpiThreads);
@@ -684,7 +684,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         my_m = (m0 + row) < a.M ? (m0 + row) : -1;
       }
       const int buf = it & 1;
-      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      mbar_wait(&acc_full[buf], (it >> 1) & 1, 36);
       tc_fence_after();
       const uint32_t stg_row = stg_u32 + row * Cfg::kPitch;
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + buf * BLOCK_N;
@@ -714,7 +714,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         tile_origin(t, n0, m0, tq0, tp0, tn0);
         int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_wait(&empty[stage], phase ^ 1u, 33);
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           const uint32_t sB = smem_u32(sA + kATileBytes);
           // CTA pair: every load of BOTH CTAs completes on the LEADER's barrier (it alone waits for operands), which
@@ -782,11 +782,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     } else {
       for (int t = item0; t < total; t += item_step, ++it) {
         const int buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);     // epilogue(s) have drained this TMEM buffer
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u, 35);     // epilogue(s) have drained this TMEM buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stage], phase, 34);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -935,13 +935,14 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
     const uint32_t stg_u32 = smem_u32(stg);
     const uint32_t red_u32 = smem_u32(red);
     const bool bias_relu = !STATS && (a.bias != nullptr || a.relu);
+    const float deq = a.fp8 ? (*a.deq_a) * (*a.deq_b) : 1.0f;      // fp8 operands: undo both quantisation scales
     int it = 0;
     uint32_t chunk_ctr = 0;             // staging buffer = chunk_ctr & 1 (identical sequence in every epilogue thread)
     for (int t = item0; t < total; t += item_step, ++it) {
       int n0, m0, tq0, tp0, tn0;
       const bool valid = tile_origin(t, n0, m0, tq0, tp0, tn0);
       const int buf = it & 1;
-      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      mbar_wait(&acc_full[buf], (it >> 1) & 1, 52);
       tc_fence_after();
       if (PAIR && !valid) {             // padding tile: keep the accumulator hand-shake going, write nothing
         tc_fence_before();
@@ -975,10 +976,10 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
         // my 32 of the chunk's 64 columns: TMEM -> (bias, ReLU) -> bf16 -> staging row
         if (bias_relu)
           epi_tmem_to_stage<true>(taddr_row + ch * Cfg::kChunk, stg_row, egrp * 32, egrp * 32 + 32, a,
-                                  n0 + ch * Cfg::kChunk, zero_row);
+                                  n0 + ch * Cfg::kChunk, zero_row, deq);
         else
           epi_tmem_to_stage<false>(taddr_row + ch * Cfg::kChunk, stg_row, egrp * 32, egrp * 32 + 32, a,
-                                   n0 + ch * Cfg::kChunk, zero_row);
+                                   n0 + ch * Cfg::kChunk, zero_row, deq);
         if (kTile && egrp == 0) sts32(stg_row + Cfg::kChunk * 2, static_cast<uint32_t>(my_m));
         if (ch == kChunks - 1) tc_fence_before();
         // all 256 threads: the chunk is staged; everybody has also left the buffer written two chunks ago
@@ -998,12 +999,15 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t a_bytes = kTile ? static_cast<uint32_t>(a.tw * a.th * a.tn) * 128u : kATileBytes;
+      const int kElems = a.fp8 ? 128 : 64;            // elements in one 128-byte operand row = K extent of a k-block
+      const int mnBoxes = Cfg::kBLoadRows / kElems;   // MN-major B: boxes of kElems columns x kElems K-rows (128 B rows)
+      const uint32_t mnBoxBytes = 128u * static_cast<uint32_t>(kElems);
       for (int t = item0; t < total; t += item_step) {
         int n0, m0, tq0, tp0, tn0;
         tile_origin(t, n0, m0, tq0, tp0, tn0);
         int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1u);
+          mbar_wait(&empty[stage], phase ^ 1u, 49);
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           const uint32_t sB = smem_u32(sA + kATileBytes);
           const uint32_t pair_bar = PAIR ? mapa_shared(smem_u32(&full[stage]), 0) : 0u;
@@ -1019,35 +1023,31 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
               dh = a.pad - tap_r * a.dil; dw = a.pad_w - tap_s * a.dil;
             }
           }
-          const int kcoord = mode_stem(MODE) ? kb * kBlockK : widx * a.kstride + cc * kBlockK;
+          const int kcoord = widx * a.kstride + cc * kElems;
           const int nb0 = n0 + crank * Cfg::kBLoadRows;        // first weight row / column this CTA fetches
           if (PAIR) {
             if (kBMn) {
-#pragma unroll
-              for (int j = 0; j < Cfg::kBLoadRows / 64; ++j)
-                tma_load_2d_pair(sB + j * 8192, &tmB, widx * a.ldc + nb0 + j * 64, cc * 64, pair_bar);
+              for (int j = 0; j < mnBoxes; ++j)
+                tma_load_2d_pair(sB + j * mnBoxBytes, &tmB, widx * a.ldc + nb0 + j * kElems, cc * kElems, pair_bar);
             } else if (Cfg::kBLoadRows == 128) {
               tma_load_2d_pair(sB, &tmB, kcoord, nb0, pair_bar);           // the full map's box is 128 rows
             } else {
               tma_load_2d_pair(sB, &tmBh, kcoord, nb0, pair_bar);          // half-height box map
             }
-            if (MODE == kConvStemTma) tma_load_5d_pair(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, pair_bar);
-            else if (kTile) tma_load_4d_pair(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, pair_bar);
-            else tma_load_2d_pair(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, pair_bar);
+            if (kTile) tma_load_4d_pair(smem_u32(sA), &tmAs.m[mapi], cc * kElems, tq0 + dw, tp0 + dh, tn0, pair_bar);
+            else tma_load_2d_pair(smem_u32(sA), &tmAs.m[0], kb * kElems, m0, pair_bar);
           } else {
             if (kBMn) {
-#pragma unroll
-              for (int j = 0; j < BLOCK_N / 64; ++j)
-                tma_load_2d(sB + j * 8192, &tmB, widx * a.ldc + n0 + j * 64, cc * 64, &full[stage]);
+              for (int j = 0; j < mnBoxes; ++j)
+                tma_load_2d(sB + j * mnBoxBytes, &tmB, widx * a.ldc + n0 + j * kElems, cc * kElems, &full[stage]);
             } else {
               constexpr int kBoxRows = BLOCK_N < 128 ? BLOCK_N : 128;      // the weight map's box height
 #pragma unroll
               for (int h = 0; h < BLOCK_N / kBoxRows; ++h)
                 tma_load_2d(sB + h * kBoxRows * 128, &tmB, kcoord, n0 + h * kBoxRows, &full[stage]);
             }
-            if (MODE == kConvStemTma) tma_load_5d(smem_u32(sA), &tmAs.m[0], 0, kb, tq0, tp0, tn0, &full[stage]);
-            else if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * 64, tq0 + dw, tp0 + dh, tn0, &full[stage]);
-            else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kBlockK, m0, &full[stage]);
+            if (kTile) tma_load_4d(smem_u32(sA), &tmAs.m[mapi], cc * kElems, tq0 + dw, tp0 + dh, tn0, &full[stage]);
+            else tma_load_2d(smem_u32(sA), &tmAs.m[0], kb * kElems, m0, &full[stage]);
           }
           if (++cc == a.cchunks) { cc = 0; ++tap; if (++tap_s == a.S) { tap_s = 0; ++tap_r; } }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
@@ -1056,28 +1056,39 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
     }
   } else {
     // ====================================== MMA issuer ========================================
-    constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    constexpr int kMmaM = PAIR ? 2 * kBlockM : kBlockM;
+    const bool f8 = a.fp8 != 0;
+    const uint32_t idesc = f8 ? idesc_f8(kMmaM, BLOCK_N, a.fp8 == 2 ? 1 : 0, 0, 0, kBMn ? 1 : 0)
+                              : idesc_bf16(kMmaM, BLOCK_N, 0, kBMn ? 1 : 0);
+    // MN-major B: K rows of 128 bytes; one MMA consumes 16 (bf16) / 32 (fp8) K rows, chunks of 64 / 128 columns
+    const uint32_t mnKStep = f8 ? 4096u : 2048u, mnLbo = f8 ? 16384u : 8192u;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     if (!(PAIR && crank != 0)) {        // the leader issues the MMAs of a pair
       for (int t = item0; t < total; t += item_step, ++it) {
         const int buf = it & 1;
-        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u);     // epilogue(s) have drained this TMEM buffer
+        mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1u, 51);     // epilogue(s) have drained this TMEM buffer
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait(&full[stage], phase, 50);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
             const uint32_t sB = sA + kATileBytes;
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
+            for (int k = 0; k < 4; ++k) {                      // 4 x 32 bytes of K per 128-byte row
               const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
-              const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
-              if (PAIR) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0);
-              else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+              const uint64_t db = kBMn ? smem_desc_sw128(sB + k * mnKStep, mnLbo, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+              const bool acc = (kb | k) != 0;
+              if (f8) {
+                if (PAIR) umma_f8_pair(d_tmem, da, db, idesc, acc);
+                else umma_f8(d_tmem, da, db, idesc, acc);
+              } else {
+                if (PAIR) umma_bf16_pair(d_tmem, da, db, idesc, acc);
+                else umma_bf16(d_tmem, da, db, idesc, acc);
+              }
             }
             if (PAIR) {
               umma_commit_pair_multicast(&empty[stage], 0x3);          // frees the stage in both CTAs
@@ -1195,7 +1206,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < KB; ++i) {
-        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_wait(&empty[stage], phase ^ 1u, 65);
         const uint32_t dst = smem_u32(smem + stage * kWgStageBytes) + row_off;
         const int m = (kb_begin + i) * 64 + row;
         const bool m_ok = col_ok && m < a.M;
@@ -1247,7 +1258,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     }
 
     // epilogue: TMEM -> fp32 staging -> coalesced vector reductions into the gradient arena
-    mbar_wait(acc_full, 0);
+    mbar_wait(acc_full, 0, 68);
     tc_fence_after();
     float* stg = reinterpret_cast<float*>(smem);
     const int row = qw * 32 + (threadIdx.x & 31);
@@ -1311,7 +1322,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < KB; ++i) {
-        mbar_wait(&empty[stage], phase ^ 1u);
+        mbar_wait(&empty[stage], phase ^ 1u, 65);
         const uint32_t sA = smem_u32(smem + stage * kWgStageBytes);
         if (kTile) {
           int t = kb_begin + i;
@@ -1349,7 +1360,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < KB; ++i) {
-      mbar_wait(&full[stage], phase);
+      mbar_wait(&full[stage], phase, 66);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sDy = smem_u32(smem + stage * kWgStageBytes);
@@ -1394,31 +1405,35 @@ EncodeTiledFn encode_fn() {
 }
 
 // 2-D bf16 row-major matrix [rows][cols] (cols contiguous), box = {box_cols, box_rows}, 128B swizzle.
+// `esize` = element size in bytes: 2 = bf16, 1 = fp8 (maps over bytes; a 128-byte swizzle row is 128 elements then).
 bool make_map_2d(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
-                 uint32_t box_cols, uint32_t box_rows) {
+                 uint32_t box_cols, uint32_t box_rows, int esize = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {row_stride_elems * 2};
+  cuuint64_t strides[1] = {row_stride_elems * static_cast<uint64_t>(esize)};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
 // 4-D NHWC bf16 activation [N][H][W][C]; box = {64 channels, tw, th, tn}; out-of-bounds -> zeros.
-bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int tw, int th, int tn) {
+bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int tw, int th, int tn,
+                   int esize = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
+  const cuuint64_t es = static_cast<cuuint64_t>(esize);
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H),
                         static_cast<cuuint64_t>(N)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(W) * C * 2,
-                           static_cast<cuuint64_t>(H) * W * C * 2};
-  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tn)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(C) * es, static_cast<cuuint64_t>(W) * C * es,
+                           static_cast<cuuint64_t>(H) * W * C * es};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / esize), static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th),
+                       static_cast<cuuint32_t>(tn)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(map, esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -1426,19 +1441,21 @@ bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int 
 
 // Phase (pa, pb) sub-image of a stride-`st` NHWC source: X[n][st*i + pa][st*j + pb][c] as a dense 4-D map.
 bool make_map_nhwc_phase(CUtensorMap* map, const void* base, int N, int H, int W, int C, int st, int pa, int pb,
-                         int tw, int th, int tn) {
+                         int tw, int th, int tn, int esize = 2) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   const int Hp = (H - pa + st - 1) / st, Wp = (W - pb + st - 1) / st;
-  if (Hp <= 0 || Wp <= 0) return make_map_nhwc(map, base, N, H, W, C, tw, th, tn);   // never referenced
-  const char* b = static_cast<const char*>(base) + (static_cast<size_t>(pa) * W + pb) * C * 2;
+  if (Hp <= 0 || Wp <= 0) return make_map_nhwc(map, base, N, H, W, C, tw, th, tn, esize);   // never referenced
+  const cuuint64_t es = static_cast<cuuint64_t>(esize);
+  const char* b = static_cast<const char*>(base) + (static_cast<size_t>(pa) * W + pb) * C * es;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(Wp), static_cast<cuuint64_t>(Hp),
                         static_cast<cuuint64_t>(N)};
-  cuuint64_t strides[3] = {static_cast<cuuint64_t>(st) * C * 2, static_cast<cuuint64_t>(st) * W * C * 2,
-                           static_cast<cuuint64_t>(H) * W * C * 2};
-  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), static_cast<cuuint32_t>(tn)};
+  cuuint64_t strides[3] = {static_cast<cuuint64_t>(st) * C * es, static_cast<cuuint64_t>(st) * W * C * es,
+                           static_cast<cuuint64_t>(H) * W * C * es};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(128 / esize), static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th),
+                       static_cast<cuuint32_t>(tn)};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, estr,
+  CUresult r = fn(map, esize == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<char*>(b), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
@@ -1628,9 +1645,28 @@ int pick_stages(int KB) {
   return s < 1 ? 1 : s;
 }
 
+struct WeightDesc {       // what the B tensor maps are built from (their box height depends on the tile width chosen)
+  const void* w;
+  int rows, cols, esize;
+};
+
+// B-operand maps for a kernel whose N tile is `bn` wide: full box (min(bn, 128) weight rows) and half box (bn / 2 rows: one
+// CTA's share of a pair tile).  MN-major weights (data gradient) use square boxes of one swizzle row x as many K rows.
+bool make_b_maps(int mode, const WeightDesc& wd, int bn, CUtensorMap* full, CUtensorMap* half) {
+  const uint32_t kcols = 128u / wd.esize;
+  if (mode_b_mn(mode)) {
+    if (!make_map_2d(full, wd.w, wd.rows, wd.cols, wd.cols, kcols, kcols, wd.esize)) return false;
+    *half = *full;
+    return true;
+  }
+  if (!make_map_2d(full, wd.w, wd.rows, wd.cols, wd.cols, kcols, bn < 128 ? bn : 128, wd.esize)) return false;
+  if (!make_map_2d(half, wd.w, wd.rows, wd.cols, wd.cols, kcols, bn / 2 < 128 ? bn / 2 : 128, wd.esize)) *half = *full;
+  return true;
+}
+
 template <int MODE>
-cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, bool have_half_map, const TmaSet& tmA,
-                            ConvArgs a, int n_total, int m_tiles, bool stats, cudaStream_t stream) {
+cudaError_t launch_fwd_mode(const WeightDesc& wd, const CUtensorMap& tmB, const CUtensorMap& tmBh, bool have_half_map,
+                            const TmaSet& tmA, ConvArgs a, int n_total, int m_tiles, bool stats, cudaStream_t stream) {
   const int var_kind = a.variant & 0xf, var_bn = (a.variant >> 4) & 0xf, var_pair = (a.variant >> 8) & 1;
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1654,8 +1690,12 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, boo
     if (var_kind != kVarDeep && g_deep == 4 && bn == 256) bn = 128;
     // pairs need two M tiles, 64-column halves of an MN-major weight tile, and a loadable half of a K-major one
     // (bn = 256: the full map's 128-row box; narrower: the half-height box map)
-    if (m_tiles < 2 || (mode_b_mn(MODE) && bn < 128) || (!mode_b_mn(MODE) && bn < 256 && !have_half_map)) pair = false;
-    return launch_deep_mode<MODE>(tmB, tmBh, tmA, a, n_total, m_tiles, stats, bn, pair, stream);
+    if (m_tiles < 2 || (mode_b_mn(MODE) && bn < (a.fp8 ? 256 : 128))) pair = false;
+    if (a.fp8 && mode_b_mn(MODE) && bn < 128) return cudaErrorInvalidValue;
+    // the weight maps' box heights follow THIS kernel's tile width (not the widest tile Cout would allow)
+    CUtensorMap dB, dBh;
+    if (!make_b_maps(MODE, wd, bn, &dB, &dBh)) return cudaErrorUnknown;
+    return launch_deep_mode<MODE>(dB, dBh, tmA, a, n_total, m_tiles, stats, bn, pair, stream);
   }
   if (var_kind == kVarDeep) return cudaErrorInvalidValue;
   bool persistent = false;
@@ -1715,6 +1755,17 @@ cudaError_t launch_fwd_mode(const CUtensorMap& tmB, const CUtensorMap& tmBh, boo
 
 }  // namespace
 
+// {abort flag, site, block, thread, parity} of the first mbarrier wait that timed out since the last call; clears it.
+cudaError_t conv_timeout_info(unsigned int out[8]) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, tc::g_mbar_diag, sizeof(unsigned int) * 8);
+  if (e != cudaSuccess) return e;
+  if (out[0] != 0u) {
+    unsigned int zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    e = cudaMemcpyToSymbol(tc::g_mbar_diag, zero, sizeof(zero));
+  }
+  return e;
+}
+
 void set_conv_force_stages(int s) { g_force_stages = s; }
 void set_conv_persistent(int on) { g_persistent = on; }
 void set_wgrad_swap(int on) { g_wgrad_swap = on; }
@@ -1731,14 +1782,25 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
   TmaSet tmA;
   const int bn = (n_total % 128 == 0) ? 128 : 64;
   if (n_total % 64 != 0) return cudaErrorInvalidValue;
+  const int es = a.fp8 ? 1 : 2;                   // operand element size (bytes)
+  const uint32_t kcols = 128u / es;               // elements in a 128-byte swizzle row
+  if (a.fp8) {
+    // fp8 operands run on the deep-ring kernel only (GEMM / stride-1-or-2 tile modes), with 128-element k-blocks
+    if (!(mode == kConvGemm || mode == kConvTileFwd || mode == kConvTileDgrad || mode == kConvGemmDgrad))
+      return cudaErrorInvalidValue;
+    if (a.deq_a == nullptr || a.deq_b == nullptr) return cudaErrorInvalidValue;
+    if (mode_b_mn(mode) && n_total % 128 != 0) return cudaErrorInvalidValue;    // MN-major boxes are 128 columns wide
+    if ((a.variant & 0xf) == 0) a.variant = kVarDeep;
+    if ((a.variant & 0xf) != kVarDeep) return cudaErrorInvalidValue;
+  }
   CUtensorMap tmBh;                 // K-major weights: half-height box (one CTA's share of a multicast pair)
   bool have_half = false;
   if (mode_b_mn(mode)) {
-    if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, 64)) return cudaErrorUnknown;
+    if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, kcols, kcols, es)) return cudaErrorUnknown;
     tmBh = tmB;
   } else {
-    if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, 64, bn)) return cudaErrorUnknown;
-    have_half = make_map_2d(&tmBh, w, w_rows, w_cols, w_cols, 64, bn / 2);     // pair tiles / multicast halves
+    if (!make_map_2d(&tmB, w, w_rows, w_cols, w_cols, kcols, bn, es)) return cudaErrorUnknown;
+    have_half = make_map_2d(&tmBh, w, w_rows, w_cols, w_cols, kcols, bn / 2, es);     // pair tiles / multicast halves
     if (!have_half) tmBh = tmB;
   }
   a.ntaps = 0;
@@ -1747,21 +1809,22 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
   a.zfill = 0;
   int m_tiles = (a.M + kBlockM - 1) / kBlockM;
   const bool stats = a.sum != nullptr;
+  const WeightDesc wd{w, w_rows, w_cols, es};
   auto dispatch = [&](const ConvArgs& args, int tiles) -> cudaError_t {
     switch (mode) {
-      case kConvFwd: return launch_fwd_mode<kConvFwd>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
-      case kConvDgrad: return launch_fwd_mode<kConvDgrad>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
-      case kConvGemm: return launch_fwd_mode<kConvGemm>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
-      case kConvStem: return launch_fwd_mode<kConvStem>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
-      case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
-      case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
-      case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
-      case kConvStemTma: return launch_fwd_mode<kConvStemTma>(tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvFwd: return launch_fwd_mode<kConvFwd>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvDgrad: return launch_fwd_mode<kConvDgrad>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvGemm: return launch_fwd_mode<kConvGemm>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvStem: return launch_fwd_mode<kConvStem>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvTileFwd: return launch_fwd_mode<kConvTileFwd>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvTileDgrad: return launch_fwd_mode<kConvTileDgrad>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvGemmDgrad: return launch_fwd_mode<kConvGemmDgrad>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
+      case kConvStemTma: return launch_fwd_mode<kConvStemTma>(wd, tmB, tmBh, have_half, tmA, args, n_total, tiles, stats, stream);
       default: return cudaErrorInvalidValue;
     }
   };
   if (mode == kConvGemm || mode == kConvGemmDgrad) {
-    if (!make_map_2d(&tmA.m[0], a_matrix, a.M, a_cols, a_cols, 64, 128)) return cudaErrorUnknown;
+    if (!make_map_2d(&tmA.m[0], a_matrix, a.M, a_cols, a_cols, kcols, 128, es)) return cudaErrorUnknown;
     for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
     return dispatch(a, m_tiles);
   }
@@ -1788,7 +1851,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
     return dispatch(a, set_tiles(a));
   }
   if (st == 1) {
-    if (!make_map_nhwc(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+    if (!make_map_nhwc(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn, es)) return cudaErrorUnknown;
     for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
     return dispatch(a, set_tiles(a));
   }
@@ -1798,7 +1861,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
     for (int pa = 0; pa < 2; ++pa)
       for (int pb = 0; pb < 2; ++pb)
         if (!make_map_nhwc_phase(&tmA.m[pa * 2 + pb], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, 2, pa, pb, a.tw, a.th,
-                                 a.tn))
+                                 a.tn, es))
           return cudaErrorUnknown;
     a.ntaps = a.R * a.S;
     for (int r = 0; r < a.R; ++r)
@@ -1816,7 +1879,7 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
   // stride-2 data gradient: four stride-1 problems, one per output phase (pa, pb) of dx; each is a conv of dy
   // with the subset of taps of matching parity, scattered to dx[2i+pa][2j+pb].  Phases with no tap stay as the
   // caller initialised them (the Python wrapper zero-fills dx when such phases exist).
-  if (!make_map_nhwc(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn)) return cudaErrorUnknown;
+  if (!make_map_nhwc(&tmA.m[0], a_matrix, a.batch, a.srcH, a.srcW, a.srcC, a.tw, a.th, a.tn, es)) return cudaErrorUnknown;
   for (int i = 1; i < 4; ++i) tmA.m[i] = tmA.m[0];
   const int fullH = a.dstH, fullW = a.dstW;
   for (int pa = 0; pa < 2; ++pa)

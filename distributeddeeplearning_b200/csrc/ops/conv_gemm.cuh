@@ -59,6 +59,13 @@ struct ConvArgs {
   int relu;                   // apply ReLU in the epilogue (after bias)
   int n_valid;                // output channels that really exist (bias is read only below this)
   int stages;                 // pipeline depth actually used (<= compile-time maximum)
+  // FP8 operands (deep-ring kernel only): 0 = bf16; 1 = A and B are e4m3; 2 = A is e5m2 (gradients), B is e4m3.
+  // A k-block is still 128 BYTES per row (128 fp8 elements), so shared-memory images, swizzle and descriptors keep
+  // their geometry; tensor maps are built over bytes.  The epilogue multiplies the accumulator by *deq_a * *deq_b
+  // (the operands' inverse quantisation scales, device-resident: ops.h Fp8Slot::inv_scale).
+  int fp8;
+  const float* deq_a;
+  const float* deq_b;
   int variant;                // kernel variant word chosen by the caller's autotuner (0 = built-in policy); see
                               //   launch_fwd_mode in conv_gemm.cu for the encoding
   // tile modes: the M tile is a tw x th x tn box of pixels of the dstH x dstW iteration grid (w fastest);

@@ -137,4 +137,16 @@ cudaError_t launch_concat_channels(const CatArgs& a, bool scatter, cudaStream_t 
 cudaError_t launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv_bfloat16* y, int64_t n,
                             cudaStream_t stream);
 
+// ---- FP8 operand preparation (fp8.cu) ----------------------------------------------------------------
+struct Fp8Slot {       // one quantised tensor role; lives in a device-resident table (graph replays see live values)
+  float amax;          // running max |x| of the current step (cleared by update_scales)
+  float scale;         // multiply before the fp8 conversion (power of two)
+  float inv_scale;     // 1 / scale: folded into the consuming GEMM's epilogue
+  int e5m2;            // 0 = e4m3 (activations, weights), 1 = e5m2 (gradients)
+};
+cudaError_t launch_fp8_quantize(const __nv_bfloat16* x, uint8_t* out, int64_t n, Fp8Slot* slot, bool e5m2, int sms,
+                                cudaStream_t stream);
+cudaError_t launch_fp8_amax(const __nv_bfloat16* x, int64_t n, Fp8Slot* slot, int sms, cudaStream_t stream);
+cudaError_t launch_fp8_update_scales(Fp8Slot* slots, int n, cudaStream_t stream);
+
 }  // namespace ddl

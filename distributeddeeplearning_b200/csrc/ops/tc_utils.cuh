@@ -54,14 +54,33 @@ DDL_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (kills the launch) instead of hanging the GPU.  The bound is an iteration
-// count (each failed try_wait already suspends the thread for a hardware-defined window), which keeps the spin
-// loop at 4 instructions: the ncu source view showed the former clock64()-based loop of the TMA / MMA warps
+// Bounded wait with a post-mortem.  A protocol bug must neither hang the GPU nor kill the context without a trace:
+// the first waiter that exceeds the bound records WHERE it was stuck (site id, block, thread, parity) in a device-side
+// diagnostic block and raises an abort flag; every other waiter of this and later kernels then drains immediately, so
+// the launch terminates (with garbage results) and the host can read the record (conv_timeout_info) and raise.
+// `site` = 16 * kernel family (1 one-tile, 2 persistent, 3 deep-ring, 4 wgrad) + role (1 producer waits for a free
+// stage, 2 MMA waits for operands, 3 MMA waits for a drained accumulator, 4 epilogue waits for the accumulator).
+// The bound is an iteration count (each failed try_wait already suspends the thread for a hardware-defined window),
+// which keeps the spin loop short: the ncu source view showed the former clock64()-based loop of the TMA / MMA warps
 // taking ~25 % of all issued instructions in short-K kernels.
-DDL_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ unsigned int g_mbar_diag[8];     // [0] abort flag, [1] site, [2] blockIdx.x, [3] threadIdx.x, [4] parity
+
+DDL_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site = 0) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 0x3ffu) == 0) {
+      if (*reinterpret_cast<volatile unsigned int*>(&g_mbar_diag[0]) != 0u) return;     // somebody timed out: drain
+      if (spins > (1u << 24)) {
+        if (atomicCAS(&g_mbar_diag[0], 0u, 1u) == 0u) {
+          g_mbar_diag[1] = site;
+          g_mbar_diag[2] = blockIdx.x + gridDim.x * blockIdx.y;
+          g_mbar_diag[3] = threadIdx.x;
+          g_mbar_diag[4] = parity;
+          __threadfence();
+        }
+        return;
+      }
+    }
   }
 }
 
@@ -225,6 +244,28 @@ DDL_DEVICE void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uin
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+// fp8 operands (kind::f8f6f4, dense, fp32 accumulate): format codes 0 = e4m3, 1 = e5m2; K = 32 elements (32 bytes) per MMA
+__host__ __device__ constexpr uint32_t idesc_f8(int m, int n, int a_fmt, int b_fmt, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (static_cast<uint32_t>(a_fmt) << 7) | (static_cast<uint32_t>(b_fmt) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) | (static_cast<uint32_t>(b_mn_major) << 16) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+DDL_DEVICE void umma_f8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+DDL_DEVICE void umma_f8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
 // Arrive on `bar` when all previously issued MMAs of this thread have completed

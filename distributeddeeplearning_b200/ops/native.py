@@ -80,6 +80,25 @@ def autotune_table():
             for k, v in _TUNE["table"].items()}
 
 
+_SITES = {1: "producer waits for a free stage", 2: "MMA waits for operands", 3: "MMA waits for a drained accumulator",
+          4: "epilogue waits for the accumulator"}
+_FAMILIES = {1: "one-tile", 2: "persistent", 3: "deep-ring", 4: "wgrad"}
+
+
+def conv_timeouts(raise_error: bool = True):
+    """Post-mortem of the tcgen05 kernels' bounded mbarrier waits (tc_utils.cuh): None, or a description of the first
+    wait that timed out since the last call (the kernels drain instead of hanging / trapping; results are garbage)."""
+    info = _C().conv_timeout_info()
+    if not info[0]:
+        return None
+    site = int(info[1])
+    msg = (f"tcgen05 pipeline timeout in the {_FAMILIES.get(site >> 4, '?')} kernel: "
+           f"{_SITES.get(site & 15, 'site %d' % site)} (block {info[2]}, thread {info[3]}, parity {info[4]})")
+    if raise_error:
+        raise RuntimeError(msg)
+    return msg
+
+
 def _tuned(key, candidates, launch, accumulators=()):
     """Run ``launch(variant)`` with the best known variant for ``key``; time the candidates on first sight."""
     if _TUNE.get("force") is not None:                 # tools / tests: run exactly this variant
@@ -102,6 +121,10 @@ def _tuned(key, candidates, launch, accumulators=()):
                 launch(c)
             b.record()
             b.synchronize()
+            bad = conv_timeouts(raise_error=False)
+            if bad is not None:                        # a variant that dead-locks on this shape is never chosen
+                _TUNE.setdefault("rejected", {}).setdefault(key, {})[variant_name(c)] = bad
+                continue
             times[c] = a.elapsed_time(b) / 4 * 1e3
         except RuntimeError:
             continue                                   # variant not applicable to this shape
@@ -344,6 +367,34 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
         return (y, st) if stats else y
     if Cin % 8 != 0:
         raise ValueError("conv_fwd: Cin must be a multiple of 8 (or an NHWC4 stem)")
+    from . import fp8 as _fp8
+
+    one_by_one = R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0
+    tile_ok = USE_TILE_TMA and (stride == 1 or (stride == 2 and R * S <= 16 and USE_TILE_S2))
+    if _fp8.fwd_eligible(Cin, Cout) and (one_by_one or tile_ok) and M >= 2048:
+        # e4m3 operands: quantise x (delayed per-tensor scale) and take this step's e4m3 weights; a k-block is 128
+        # channels (128 bytes), the epilogue multiplies by inv_scale(x) * inv_scale(w)
+        xq, sx = _fp8.quantize(x, ("x", wp, N, H, W))
+        wq, sw = _fp8.quantize_weight(w_bf16)
+        cch8 = Cin // 128
+        fp8kw = dict(fp8=1, deq_a=_fp8.inv_scale_ptr(sx, x.device), deq_b=_fp8.inv_scale_ptr(sw, x.device))
+        cands = [v for v in conv_variants(n_total, M, R * S * cch8, False) if (v & 0xf) == VAR_DEEP]
+        _fp8.count("fwd")
+        if one_by_one:
+            _tuned(("fwd1x1_f8", N, H, W, Cin, Cout, stats, bias is not None, relu), cands,
+                   lambda v: C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, cch8, Cout, H, W,
+                                         Cin, P, Q, 1, 1, 1, 0, 1, cch8, int(relu), Cout, wq.data_ptr(), wr, wc, n_total,
+                                         xq.data_ptr(), Cin, N, 0, 0, 0, 0, _stream(), 0, Cin, variant=v, **fp8kw),
+                   (st,) if stats else ())
+        else:
+            tw, th, tn = tile_geometry(P, Q, N, 128)
+            _tuned(("fwd_f8", N, H, W, Cin, Cout, R, S, stride, ph, pw, dil, stats, bias is not None, relu), cands,
+                   lambda v: C.conv_gemm(C.CONV_TILE_FWD, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, R * S * cch8,
+                                         Cout, H, W, Cin, P, Q, R, S, stride, ph, dil, cch8, int(relu), Cout,
+                                         wq.data_ptr(), wr, wc, n_total, xq.data_ptr(), Cin, N, tw, th, tn, 0, _stream(),
+                                         pw, Cin, variant=v, **fp8kw),
+                   (st,) if stats else ())
+        return (y, st) if stats else y
     if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
         _tuned(("fwd1x1", N, H, W, Cin, Cout, stats, bias is not None, relu), conv_variants(n_total, M, cch, False),
                lambda v: C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, _ptr(bias), s_ptr, ss_ptr, M, cch, Cout, H, W, Cin,
@@ -416,6 +467,43 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
         bnr = dict(bnr_y=by.data_ptr(), bnr_gamma=bgam.data_ptr(), bnr_beta=bbeta.data_ptr(),
                    bnr_mean=bsave[0].data_ptr(), bnr_invstd=bsave[1].data_ptr())
         s1, s2 = bscr[1].data_ptr(), bscr[0].data_ptr()      # scratch layout of bn_act_bwd: [0] = dgamma, [1] = dbeta
+    from . import fp8 as _fp8
+
+    one_by_one = R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0
+    if _fp8.dgrad_eligible(Cin, Cout) and bn_reduce is None and N * H * W >= 2048 and \
+            (one_by_one or (stride == 1 and USE_TILE_TMA) or s2_tile):
+        # e5m2 output gradients x e4m3 weights (the forward's quantised copy, consumed MN-major): k-blocks of 128
+        # output channels; the epilogue (incl. the shortcut-gradient add) runs on the de-quantised fp32 accumulator
+        dyq, sd = _fp8.quantize(dy, ("dy", wp, N, P, Q), e5m2=True)
+        wq, sw = _fp8.quantize_weight(w_bf16)
+        cch8 = Cout // 128
+        fp8kw = dict(fp8=2, deq_a=_fp8.inv_scale_ptr(sd, dy.device), deq_b=_fp8.inv_scale_ptr(sw, dy.device))
+        _fp8.count("dgrad")
+        if one_by_one:
+            cands = [v for v in conv_variants(n_total, N * H * W, cch8, True) if (v & 0xf) == VAR_DEEP]
+            _tuned(("dgrad1x1_f8", N, H, W, Cin, Cout, add is not None, add_mask is not None), cands,
+                   lambda v: C.conv_gemm(C.CONV_GEMM_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W, cch8, Cin, P,
+                                         Q, Cout, H, W, 1, 1, 1, 0, 1, cch8, 0, Cin, wq.data_ptr(), wr, wc, n_total,
+                                         dyq.data_ptr(), Cout, N, 0, 0, 0, 0, _stream(), 0, 0, _ptr(add_mask), variant=v,
+                                         **fp8kw))
+        elif stride == 1:
+            tw, th, tn = tile_geometry(H, W, N, 128)
+            cands = [v for v in conv_variants(n_total, N * H * W, R * S * cch8, True) if (v & 0xf) == VAR_DEEP]
+            _tuned(("dgrad_f8", N, H, W, Cin, Cout, R, S, ph, pw, dil, add is not None, add_mask is not None), cands,
+                   lambda v: C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), _ptr(add), 0, 0, 0, N * H * W,
+                                         R * S * cch8, Cin, P, Q, Cout, H, W, R, S, 1, ph, dil, cch8, 0, Cin,
+                                         wq.data_ptr(), wr, wc, n_total, dyq.data_ptr(), Cout, N, tw, th, tn, 0,
+                                         _stream(), pw, 0, _ptr(add_mask), variant=v, **fp8kw))
+        else:
+            tw, th, tn = tile_geometry((H + 1) // 2, (W + 1) // 2, N, 128)
+            cands = [v for v in conv_variants(n_total, N * ((H + 1) // 2) * ((W + 1) // 2),
+                                              max(1, (R * S * cch8) // 4), True) if (v & 0xf) == VAR_DEEP]
+            _tuned(("dgrad_s2_f8", N, H, W, Cin, Cout, R, S, ph, pw, dil, zfill), cands,
+                   lambda v: C.conv_gemm(C.CONV_TILE_DGRAD, 0, dx.data_ptr(), 0, 0, 0, 0, N * H * W, R * S * cch8, Cin, P,
+                                         Q, Cout, H, W, R, S, 2, ph, dil, cch8, 0, Cin, wq.data_ptr(), wr, wc, n_total,
+                                         dyq.data_ptr(), Cout, N, tw, th, tn, zfill, _stream(), pw, 0, 0, variant=v,
+                                         **fp8kw))
+        return dx
     if R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0:
         _tuned(("dgrad1x1", N, H, W, Cin, Cout, add is not None, add_mask is not None, bn_reduce is not None),
                conv_variants(n_total, N * H * W, cch, True),

@@ -326,6 +326,9 @@ class FusedSGD(torch.optim.Optimizer):
         if self._scalars_pending and self.world == 1:
             self._scalars_out.copy_(self._scalars_in)
         self._scalars_last, self._scalars_pending = self._scalars_pending, 0
+        from ..ops import fp8 as _fp8
+
+        _fp8.end_of_step()          # fp8 mode: this step's amax values become next step's quantisation scales
         self._pending = list(self.plan["bucket_param_count"])
         self._ready_seen = [False] * len(self.params)
         self._next_bucket = 0

@@ -48,6 +48,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--momentum", type=float, default=0.0)
     p.add_argument("--json", type=str, default=None, help="also write a JSON summary to this path ('-' = stdout)")
     p.add_argument("--profile", action="store_true", help="wrap phases in NVTX ranges")
+    p.add_argument("--precision", choices=["bf16", "fp8"], default="bf16",
+                   help="tensor-core operand format of the forward / data-gradient convolutions")
     p.add_argument("--cuda-graph", action="store_true",
                    help="capture the training step into a CUDA graph after warm-up and replay it (small batches are "
                         "launch-bound: ~340 kernels per ResNet-50 step)")
@@ -186,6 +188,12 @@ def run(args) -> Dict:
 
         os.environ["DDL_NO_CUDA"] = "1"
     dist.init()
+    if getattr(args, "precision", "bf16") == "fp8":
+        if not cuda:
+            raise SystemExit("--precision fp8 needs a CUDA device")
+        from ..ops import fp8
+
+        fp8.enable(True)
     session = BenchmarkSession(args.model, args.batch_size, cuda, args.fp16_allreduce, args.lr, args.momentum,
                                profile=args.profile)
     device = "GPU" if cuda else "CPU"

@@ -157,13 +157,16 @@ def validate(val_loader, model, criterion, device, classes, prepare=None):
 
 def main(training_data_path=None, validation_data_path=None, use_gpu=False, save_filepath=None, model="resnet50",
          epochs=_EPOCHS, batch_size=_BATCHSIZE, fp16_allreduce=False, base_lr=0.0125, warmup_epochs=5,
-         num_workers=5, host_data=False, cuda_graph=True, data_type=None):
+         num_workers=5, host_data=False, cuda_graph=True, data_type=None, precision="bf16"):
     """``cuda_graph``: on a GPU with the fused engine, replay the training step from a captured CUDA graph (the
     reference's default batch of 64 per GPU is launch-bound: ~340 kernels per ResNet-50 step).
     ``data_type``: ``synthetic`` | ``images`` (class folders) | ``records`` / ``tfrecords`` (sharded record files
     written by ``inv storage.tfrecords.generate-tf-records``; the data paths are then the shard directories) — the
     switch of the reference's TF trainer tasks (``TensorFlow_imagenet/tensorflow_imagenet.py:110-151``).  Default:
-    synthetic without a training path, images with one."""
+    synthetic without a training path, images with one.
+    ``precision``: ``bf16`` (default) or ``fp8`` — e4m3 / e5m2 tensor-core operands for the forward and data-gradient
+    convolutions (``ops/fp8.py``; the analogue of the reference's ``--use_fp16``,
+    ``TensorFlow_benchmark/tensorflow_benchmark.py:51``)."""
     logger = logging.getLogger(__name__)
     epochs = int(epochs)
     cuda_graph = _str_to_bool(cuda_graph) if isinstance(cuda_graph, str) else bool(cuda_graph)
@@ -181,6 +184,16 @@ def main(training_data_path=None, validation_data_path=None, use_gpu=False, save
     if use_gpu:
         torch.cuda.manual_seed(_SEED)
     logger.info("PyTorch version {}".format(torch.__version__))
+    precision = str(precision).lower()
+    if precision not in ("bf16", "fp8"):
+        raise ValueError(f"precision must be bf16 or fp8, got {precision!r}")
+    if precision == "fp8":
+        if not use_gpu:
+            raise ValueError("--precision fp8 needs --use_gpu True (tcgen05 fp8 tensor cores)")
+        from ..ops import fp8
+
+        fp8.enable(True)
+        logger.info("Precision: fp8 operands (e4m3 activations/weights, e5m2 gradients), fp32 accumulate")
 
     run = writer = None
     if rank == 0:

@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Loss-curve parity of the FP8 training mode against bf16 (BASELINE config #3 acceptance test).
+
+Trains the same randomly initialised ResNet-50 (same seed, same cycling pool of synthetic batches, SGD momentum 0.9)
+for --steps steps twice — bf16 operands, then fp8 operands (e4m3 activations / weights, e5m2 gradients for the forward
+and data-gradient convolutions) — and compares the loss trajectories: the fp8 curve must track the bf16 curve (mean
+|difference| over the run and final-window means within --tol of each other) and both must actually learn.
+Each arm runs in its own process (clean kernel autotune / fp8 state).  Writes gpurun_out/fp8_parity.json and prints a
+markdown table (copy to profiles/fp8_parity.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def arm(precision, steps, batch, model, graph):
+    import torch
+
+    from distributeddeeplearning_b200.data import fixed_synthetic_batch
+    from distributeddeeplearning_b200.ops import fp8
+    from distributeddeeplearning_b200.parallel import dist
+    from distributeddeeplearning_b200.workloads.benchmark import BenchmarkSession
+
+    dist.init()
+    if precision == "fp8":
+        fp8.enable(True)
+    s = BenchmarkSession(model, batch, True, lr=0.02, momentum=0.9, seed=3)
+    pool = [fixed_synthetic_batch(batch, 224, 1000, s.device, seed=100 + i) for i in range(8)]
+    losses = []
+    for i in range(steps):
+        if graph and i == 8:
+            assert s.enable_graph(warmup=1), "graph capture failed"
+        x, y = pool[i % len(pool)]
+        l = s.step(x, y)
+        losses.append(l.detach().clone())
+    torch.cuda.synchronize()
+    out = {"precision": precision, "losses": [float(v) for v in losses], "fp8_launches": fp8.launches(),
+           "graph": bool(graph)}
+    print("ARM " + json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--model", default="resnet50")
+    ap.add_argument("--tol", type=float, default=0.08, help="allowed relative gap between the curves")
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--arm", default=None)
+    a = ap.parse_args()
+    if a.arm:
+        return arm(a.arm, a.steps, a.batch, a.model, a.graph)
+    res = {}
+    for p in ("bf16", "fp8"):
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--arm", p, "--steps", str(a.steps), "--batch",
+                            str(a.batch), "--model", a.model, "--graph", str(a.graph)], capture_output=True, text=True,
+                           timeout=1500)
+        line = [l for l in r.stdout.splitlines() if l.startswith("ARM ")]
+        if r.returncode != 0 or not line:
+            print(r.stdout[-2000:], r.stderr[-3000:])
+            return 1
+        res[p] = json.loads(line[-1][4:])
+    b, f = res["bf16"]["losses"], res["fp8"]["losses"]
+    n = len(b)
+    win = max(10, n // 10)
+    mean = lambda v: sum(v) / len(v)
+    gap = mean([abs(x - y) for x, y in zip(b, f)]) / mean(b)
+    tail_b, tail_f = mean(b[-win:]), mean(f[-win:])
+    learned = tail_b < 0.8 * mean(b[:win]) and tail_f < 0.8 * mean(f[:win])
+    ok = gap < a.tol and abs(tail_b - tail_f) / tail_b < a.tol and learned and res["fp8"]["fp8_launches"]["fwd"] > 0 \
+        and res["fp8"]["fp8_launches"]["dgrad"] > 0
+    print(f"| step | bf16 loss | fp8 loss |\n|---|---|---|")
+    for i in list(range(0, n, max(1, n // 10))) + [n - 1]:
+        print(f"| {i} | {b[i]:.4f} | {f[i]:.4f} |")
+    print(f"\nmean |bf16 - fp8| / mean bf16 = {gap:.4f}; last-{win}-step means: bf16 {tail_b:.4f}, fp8 {tail_f:.4f}; "
+          f"fp8 launches per run: {res['fp8']['fp8_launches']}; learned={learned}")
+    print("FP8 PARITY:", "ok" if ok else "FAIL")
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump({"ok": ok, "gap": gap, "tail_bf16": tail_b, "tail_fp8": tail_f, "arms": res},
+              open(os.path.join(ROOT, "gpurun_out", "fp8_parity.json"), "w"))
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

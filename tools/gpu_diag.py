@@ -15,7 +15,7 @@ import time
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 
-GROUPS = ["elementwise", "zoo", "graph", "zoograd", "gemm", "conv_generic", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
+GROUPS = ["fp8", "benchshape", "elementwise", "zoo", "graph", "zoograd", "gemm", "conv_generic", "conv_fwd", "conv_dgrad", "conv_wgrad", "linear", "bn", "sgd", "model"]
 RESULTS = []
 
 
@@ -44,6 +44,130 @@ def bf(t):
     import torch
 
     return t.to(torch.bfloat16)
+
+
+def report_abs(name, got, ref, rtol, atol):
+    """allclose-style check: |got - ref| <= atol + rtol * |ref| ELEMENT-WISE (small-magnitude errors are not hidden
+    behind max|ref| the way `report` normalises)."""
+    import torch
+
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    bound = atol + rtol * ref.abs()
+    bad = int((err > bound).sum().item())
+    worst = float((err / bound).max().item())
+    ok = bad == 0 and bool(torch.isfinite(got).all().item())
+    print(f"[{'ok' if ok else 'FAIL'}] {name:58s} violations={bad}/{err.numel()} worst={worst:.3f}x of (atol {atol:g} + rtol {rtol:g}*|ref|)",
+          flush=True)
+    RESULTS.append(ok)
+    return ok
+
+
+def g_fp8():
+    """FP8 operand path: quantisation kernels vs torch.float8 casts; e4m3 x e4m3 forward and e5m2 x e4m3 data-gradient
+    convolutions (tcgen05 kind::f8f6f4, deep-ring kernel) vs an fp32 convolution of the DE-QUANTISED operands (isolates
+    the kernel from the quantisation error) and vs the unquantised fp32 result (bounds the quantisation error)."""
+    import torch
+    import torch.nn.functional as F
+
+    from distributeddeeplearning_b200.ops import fp8
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = torch.device("cuda")
+    fp8.reset()
+    fp8.enable(True)
+    # ---- quantise: codes must equal torch's float8 cast of x * scale, scale must be a power of two covering amax
+    for e5m2, tdt, fmax in ((False, torch.float8_e4m3fn, 448.0), (True, torch.float8_e5m2, 57344.0)):
+        x = cl(bf(torch.randn(4, 128, 9, 9, device=dev) * 3.7))
+        q, idx = fp8.quantize(x, ("t", e5m2), e5m2=e5m2)
+        torch.cuda.synchronize()
+        slot = fp8._table(dev)[idx].tolist()
+        scale = slot[1]
+        amax = float(x.float().abs().max())
+        ok = scale > 0 and abs(scale * slot[2] - 1.0) < 1e-6 and (scale * amax <= fmax) and (2 * scale * amax > fmax)
+        import math
+        ok = ok and abs(math.log2(scale) - round(math.log2(scale))) < 1e-6
+        print(f"[{'ok' if ok else 'FAIL'}] fp8 slot e5m2={e5m2}: amax={amax:.3f} scale={scale:g} inv={slot[2]:g}")
+        RESULTS.append(ok)
+        ref = (x.float() * scale).clamp(-fmax, fmax).to(tdt).view(torch.uint8)
+        same = (q.reshape(-1) == ref.reshape(-1)).float().mean().item()
+        print(f"[{'ok' if same > 0.999 else 'FAIL'}] fp8 codes e5m2={e5m2}: {same * 100:.3f}% identical to torch cast")
+        RESULTS.append(same > 0.999)
+    # ---- forward convs (n, cin, h, w, cout, k, stride, pad): M >= one wave of 128-row tiles
+    for (n, ci, h, w_, co, k, s, p) in [(32, 128, 28, 28, 256, 1, 1, 0), (32, 256, 28, 28, 128, 3, 1, 1),
+                                        (32, 128, 56, 56, 128, 3, 2, 1), (40, 512, 28, 28, 1024, 1, 2, 0),
+                                        (32, 256, 28, 28, 64, 1, 1, 0), (128, 512, 14, 14, 512, 3, 1, 1)]:
+        x = cl(bf(torch.randn(n, ci, h, w_, device=dev).relu() * 1.5))
+        w = bf(torch.randn(co, ci, k, k, device=dev) * (1.0 / (ci * k * k) ** 0.5))
+        wb = _w_bf16(w)
+        before = fp8.launches()["fwd"]
+        y, st = nv.conv_fwd(x, wb, (k, k), s, p, stats=True)
+        torch.cuda.synchronize()
+        assert fp8.launches()["fwd"] == before + 1, "fp8 forward path not taken"
+        xq, sx = fp8.quantize(x, ("x", wb.data_ptr(), n, h, w_))
+        wq, sw = fp8.quantize_weight(wb)
+        tab = fp8._table(dev)
+        xd = xq.view(torch.float8_e4m3fn).float() * tab[sx, 2]
+        wd = (wq.view(torch.float8_e4m3fn).float() * tab[sw, 2]).view(co, k, k, ci).permute(0, 3, 1, 2)
+        ref_q = F.conv2d(xd, wd, None, s, p)
+        report(f"fp8 conv_fwd n{n} c{ci} {h}x{w_}->{co} k{k}s{s} vs dequantised", y, ref_q, 1e-2)
+        report("  vs unquantised fp32", y, _conv_ref(x, w, s, p), 8e-2)
+        report("  stats sum", st[0], y.float().sum((0, 2, 3)), 2e-3, atol=1e-1)
+        fp8.end_of_step()
+    # ---- data gradients
+    for (n, ci, h, w_, co, k, s, p) in [(32, 128, 28, 28, 256, 1, 1, 0), (32, 256, 28, 28, 128, 3, 1, 1),
+                                        (32, 128, 56, 56, 128, 3, 2, 1), (32, 256, 56, 56, 512, 1, 2, 0),
+                                        (128, 512, 14, 14, 512, 3, 1, 1)]:
+        w = bf(torch.randn(co, ci, k, k, device=dev) * (1.0 / (ci * k * k) ** 0.5))
+        wb = _w_bf16(w)
+        P = (h + 2 * p - k) // s + 1
+        dy = cl(bf(torch.randn(n, co, P, P, device=dev) * 1e-3))
+        xs = (n, ci, h, w_)
+        before = fp8.launches()["dgrad"]
+        dx = nv.conv_dgrad(dy, wb, xs, (k, k), s, p)
+        torch.cuda.synchronize()
+        assert fp8.launches()["dgrad"] == before + 1, "fp8 dgrad path not taken"
+        dq, sd = fp8.quantize(dy, ("dy", wb.data_ptr(), n, P, P), e5m2=True)
+        wq, sw = fp8.quantize_weight(wb)
+        tab = fp8._table(dev)
+        dd = dq.view(torch.float8_e5m2).float() * tab[sd, 2]
+        wd = (wq.view(torch.float8_e4m3fn).float() * tab[sw, 2]).view(co, k, k, ci).permute(0, 3, 1, 2)
+        ref_q = torch.nn.grad.conv2d_input(xs, wd, dd, s, p)
+        report(f"fp8 conv_dgrad n{n} c{ci} {h}x{w_}<-{co} k{k}s{s} vs dequantised", dx, ref_q, 1e-2)
+        ref = torch.nn.grad.conv2d_input(xs, w.float(), dy.float(), s, p)
+        report("  vs unquantised fp32", dx, ref, 1.5e-1)
+        fp8.end_of_step()
+    fp8.enable(False)
+
+
+def g_benchshape():
+    """Benchmark-shape cases (batch 256 layer1 / layer4 of ResNet-50; M = 802,816 and 12,544 rows) through EVERY
+    kernel variant the autotuner can pick, checked element-wise (atol + rtol*|ref|) against fp32."""
+    import torch
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    dev = "cuda"
+    for (n, ci, hw, co, k, s, p) in [(256, 64, 56, 64, 3, 1, 1), (256, 64, 56, 256, 1, 1, 0), (256, 512, 7, 512, 3, 1, 1),
+                                     (256, 2048, 7, 512, 1, 1, 0), (256, 256, 14, 256, 3, 1, 1)]:
+        x = cl(bf(torch.randn(n, ci, hw, hw, device=dev)))
+        w = bf(torch.randn(co, ci, k, k, device=dev) * (1.0 / (ci * k * k) ** 0.5))
+        wb = _w_bf16(w)
+        ref = _conv_ref(x, w, s, p)
+        P = (hw + 2 * p - k) // s + 1
+        dy = cl(bf(torch.randn(n, co, P, P, device=dev)))
+        ref_dx = torch.nn.grad.conv2d_input(x.shape, w.float(), dy.float(), s, p)
+        kb = k * k * ((ci + 63) // 64)
+        for v in nv.conv_variants((co + 63) // 64 * 64, n * P * P, kb, False):
+            nv.force_variant(v)
+            y, st = nv.conv_fwd(x, wb, (k, k), s, p, stats=True)
+            report_abs(f"fwd {ci}x{hw}->{co} k{k} [{nv.variant_name(v)}]", y, ref, 1.6e-2, 2e-2)
+            report("  stats sum", st[0], y.float().sum((0, 2, 3)), 2e-3, atol=2.0)
+        for v in nv.conv_variants((ci + 63) // 64 * 64, n * hw * hw, k * k * ((co + 63) // 64), True):
+            nv.force_variant(v)
+            dx = nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p)
+            report_abs(f"dgrad {ci}x{hw}<-{co} k{k} [{nv.variant_name(v)}]", dx, ref_dx, 1.6e-2, 3e-2)
+        nv.force_variant(None)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -668,6 +792,16 @@ def run_group(name):
     import torch
 
     torch.cuda.synchronize()
+    from distributeddeeplearning_b200.ops import native as _nv
+
+    stuck = _nv.conv_timeouts(raise_error=False)
+    if stuck is not None:
+        print("[FAIL]", stuck, flush=True)
+        RESULTS.append(False)
+    rejected = _nv._TUNE.get("rejected")
+    if rejected:
+        print("[FAIL] autotuner rejected dead-locking variants:", rejected, flush=True)
+        RESULTS.append(False)
     ok = all(RESULTS)
     print(f"== group {name}: {sum(RESULTS)}/{len(RESULTS)} checks passed ==", flush=True)
     return 0 if ok else 1
