@@ -451,6 +451,8 @@ class FusedSGD(torch.optim.Optimizer):
         groups = []
         for g in self.param_groups:
             d = {k: v for k, v in g.items() if k != "params"}
+            for k, v in (("maximize", False), ("foreach", None), ("differentiable", False), ("fused", None)):
+                d.setdefault(k, v)                 # keys torch.optim.SGD.step() expects after load_state_dict
             d["params"] = list(range(n))
             groups.append(d)
         return {"state": state, "param_groups": groups, "ddl": {"fused": True, "first_step": self._first_step}}

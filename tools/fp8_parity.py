@@ -29,8 +29,10 @@ def arm(precision, steps, batch, model, graph):
     dist.init()
     if precision == "fp8":
         fp8.enable(True)
-    s = BenchmarkSession(model, batch, True, lr=0.02, momentum=0.9, seed=3)
-    pool = [fixed_synthetic_batch(batch, 224, 1000, s.device, seed=100 + i) for i in range(8)]
+    s = BenchmarkSession(model, batch, True, lr=0.01, momentum=0.9, seed=3)
+    # 64 distinct batches (2,048 images, seen ~3 times in 200 steps): the loss falls steadily without collapsing to
+    # ~0, where relative differences stop meaning anything
+    pool = [fixed_synthetic_batch(batch, 224, 1000, s.device, seed=100 + i) for i in range(64)]
     losses = []
     for i in range(steps):
         if graph and i == 8:
@@ -69,15 +71,18 @@ def main():
     n = len(b)
     win = max(10, n // 10)
     mean = lambda v: sum(v) / len(v)
-    gap = mean([abs(x - y) for x, y in zip(b, f)]) / mean(b)
+    # smooth both curves over `win` steps (batches differ in difficulty), then compare point by point
+    sm = lambda v: [mean(v[max(0, i - win + 1): i + 1]) for i in range(len(v))]
+    sb, sf = sm(b), sm(f)
+    gap = max(abs(x - y) / x for x, y in zip(sb[win:], sf[win:]))
     tail_b, tail_f = mean(b[-win:]), mean(f[-win:])
-    learned = tail_b < 0.8 * mean(b[:win]) and tail_f < 0.8 * mean(f[:win])
+    learned = tail_b < 0.97 * mean(b[:win]) and tail_f < 0.97 * mean(f[:win])
     ok = gap < a.tol and abs(tail_b - tail_f) / tail_b < a.tol and learned and res["fp8"]["fp8_launches"]["fwd"] > 0 \
         and res["fp8"]["fp8_launches"]["dgrad"] > 0
     print(f"| step | bf16 loss | fp8 loss |\n|---|---|---|")
     for i in list(range(0, n, max(1, n // 10))) + [n - 1]:
         print(f"| {i} | {b[i]:.4f} | {f[i]:.4f} |")
-    print(f"\nmean |bf16 - fp8| / mean bf16 = {gap:.4f}; last-{win}-step means: bf16 {tail_b:.4f}, fp8 {tail_f:.4f}; "
+    print(f"\nmax relative gap of the {win}-step running means = {gap:.4f}; last-{win}-step means: bf16 {tail_b:.4f}, fp8 {tail_f:.4f}; "
           f"fp8 launches per run: {res['fp8']['fp8_launches']}; learned={learned}")
     print("FP8 PARITY:", "ok" if ok else "FAIL")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -1,11 +1,12 @@
 #!/bin/bash
-# Local helper (not for the GPU box): retry a gpurun call while the pod answers "busy / draining" (exit 3).
-#   bash tools/gpurun_retry.sh <out-file> [--gpus N] [--timeout S] -- '<command>'
-OUT=$1; shift
-for i in $(seq 1 12); do
-  /usr/local/graft/bin/gpurun "$@" > "$OUT" 2>&1
-  rc=$?
-  if [ $rc -ne 3 ] && ! grep -q "status=transient" "$OUT"; then exit $rc; fi
-  sleep 120
+# usage: gpurun_retry.sh <gpus> <timeout> <command...> ; retries while the pod answers busy/transient
+G=$1; T=$2; shift 2
+for i in $(seq 1 30); do
+  out=$(/usr/local/graft/bin/gpurun --gpus $G --timeout $T -- "$@" 2>&1)
+  if echo "$out" | grep -q "status=transient\|status=busy\|no box\|retry in a few minutes"; then
+    echo "[retry $i] busy"; sleep 150; continue
+  fi
+  echo "$out" | tail -220
+  exit 0
 done
-exit 3
+echo "gave up"
