@@ -508,18 +508,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
   } else {
     // =================================== MMA issuer =======================================
     constexpr uint32_t idesc = idesc_bf16(kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    const uint64_t odA0 = smem_desc_sw128(smem_u32(smem), 0, 1024);
+    const uint64_t odB0 = kBMn ? smem_desc_sw128(smem_u32(smem) + kATileBytes, 8192, 1024)
+                               : smem_desc_sw128(smem_u32(smem) + kATileBytes, 0, 1024);
+    const uint32_t oa_lo = static_cast<uint32_t>(odA0), oa_hi = static_cast<uint32_t>(odA0 >> 32);
+    const uint32_t ob_lo = static_cast<uint32_t>(odB0), ob_hi = static_cast<uint32_t>(odB0 >> 32);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < KB; ++kb) {
       mbar_wait(&full[stage], phase, 18);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t sB = sA + kATileBytes;
+        const uint32_t so = static_cast<uint32_t>(stage) * (Cfg::kStageBytes >> 4);
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
-          const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+          const uint64_t da = desc_join(oa_lo + so + 2u * k, oa_hi);
+          const uint64_t db = desc_join(ob_lo + so + (kBMn ? 128u : 2u) * k, ob_hi);
           umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
         }
         umma_commit(&empty[stage]);
@@ -774,6 +778,12 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
   } else {
     // ====================================== MMA issuer ========================================
     constexpr uint32_t idesc = idesc_bf16(PAIR ? 2 * kBlockM : kBlockM, BLOCK_N, 0, kBMn ? 1 : 0);
+    // stage-0 descriptors built once; stage / K-slice steps are 32-bit adds on the low word (see desc_join)
+    const uint64_t pdA0 = smem_desc_sw128(smem_u32(smem), 0, 1024);
+    const uint64_t pdB0 = kBMn ? smem_desc_sw128(smem_u32(smem) + kATileBytes, 8192, 1024)
+                               : smem_desc_sw128(smem_u32(smem) + kATileBytes, 0, 1024);
+    const uint32_t pa_lo = static_cast<uint32_t>(pdA0), pa_hi = static_cast<uint32_t>(pdA0 >> 32);
+    const uint32_t pb_lo = static_cast<uint32_t>(pdB0), pb_hi = static_cast<uint32_t>(pdB0 >> 32);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -789,12 +799,11 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
           mbar_wait(&full[stage], phase, 34);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint32_t sB = sA + kATileBytes;
+            const uint32_t so = static_cast<uint32_t>(stage) * (Cfg::kStageBytes >> 4);
 #pragma unroll
             for (int k = 0; k < kBlockK / 16; ++k) {
-              const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
-              const uint64_t db = kBMn ? smem_desc_sw128(sB + k * 2048, 8192, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+              const uint64_t da = desc_join(pa_lo + so + 2u * k, pa_hi);
+              const uint64_t db = desc_join(pb_lo + so + (kBMn ? 128u : 2u) * k, pb_hi);
               if (PAIR) umma_bf16_pair(d_tmem, da, db, idesc, (kb | k) != 0);
               else umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
             }
@@ -1062,6 +1071,14 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
                               : idesc_bf16(kMmaM, BLOCK_N, 0, kBMn ? 1 : 0);
     // MN-major B: K rows of 128 bytes; one MMA consumes 16 (bf16) / 32 (fp8) K rows, chunks of 64 / 128 columns
     const uint32_t mnKStep = f8 ? 4096u : 2048u, mnLbo = f8 ? 16384u : 8192u;
+    // descriptors of stage 0 / K slice 0, built once; stages and K slices are 32-bit adds on the low word
+    const uint32_t sA0 = smem_u32(smem), sB0 = sA0 + kATileBytes;
+    const uint64_t dA0 = smem_desc_sw128(sA0, 0, 1024);
+    const uint64_t dB0 = kBMn ? smem_desc_sw128(sB0, mnLbo, 1024) : smem_desc_sw128(sB0, 0, 1024);
+    const uint32_t a_lo = static_cast<uint32_t>(dA0), a_hi = static_cast<uint32_t>(dA0 >> 32);
+    const uint32_t b_lo = static_cast<uint32_t>(dB0), b_hi = static_cast<uint32_t>(dB0 >> 32);
+    constexpr uint32_t kStageStep = Cfg::kStageBytes >> 4;
+    const uint32_t bStep = kBMn ? (mnKStep >> 4) : 2u;         // K slice of one MMA in 16-byte units (A: always 2)
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -1075,12 +1092,11 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
           mbar_wait(&full[stage], phase, 50);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t sA = smem_u32(smem + stage * Cfg::kStageBytes);
-            const uint32_t sB = sA + kATileBytes;
+            const uint32_t so = static_cast<uint32_t>(stage) * kStageStep;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {                      // 4 x 32 bytes of K per 128-byte row
-              const uint64_t da = smem_desc_sw128(sA + k * 32, 0, 1024);
-              const uint64_t db = kBMn ? smem_desc_sw128(sB + k * mnKStep, mnLbo, 1024) : smem_desc_sw128(sB + k * 32, 0, 1024);
+              const uint64_t da = desc_join(a_lo + so + 2u * k, a_hi);
+              const uint64_t db = desc_join(b_lo + so + bStep * k, b_hi);
               const bool acc = (kb | k) != 0;
               if (f8) {
                 if (PAIR) umma_f8_pair(d_tmem, da, db, idesc, acc);

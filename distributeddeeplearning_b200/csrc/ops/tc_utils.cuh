@@ -230,6 +230,15 @@ DDL_DEVICE uint64_t smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint
   d |= 2ull << 61;                                                      // SWIZZLE_128B
   return d;
 }
+// The start-address field (16-byte units, bits [0,14)) sits in the descriptor's low word and never carries out of it for
+// addresses below 256 KB, so stepping through stages / K slices is ONE 32-bit add on a pre-built descriptor.  The MMA
+// thread issues 4 MMAs per k-block on its own: rebuilding two 64-bit descriptors per MMA (~25 dependent integer
+// instructions each) made that single thread, not the tensor core, the pacing resource of a one-CTA-per-SM kernel.
+DDL_DEVICE uint64_t desc_join(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 // Instruction descriptor: bf16 x bf16 -> fp32, M x N tile, operand major-ness (0 = K, 1 = MN).
 __host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, int a_mn_major, int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |

@@ -50,6 +50,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--profile", action="store_true", help="wrap phases in NVTX ranges")
     p.add_argument("--precision", choices=["bf16", "fp8"], default="bf16",
                    help="tensor-core operand format of the forward / data-gradient convolutions")
+    p.add_argument("--phase-times", action="store_true",
+                   help="after the benchmark, device-time forward / backward / optimizer join of a few eager steps and "
+                        "the per-bucket allreduce+SGD kernels (per-phase profile; reference has none)")
     p.add_argument("--cuda-graph", action="store_true",
                    help="capture the training step into a CUDA graph after warm-up and replay it (small batches are "
                         "launch-bound: ~340 kernels per ResNet-50 step)")
@@ -160,6 +163,54 @@ class BenchmarkSession:
             torch.cuda.synchronize()
 
 
+def phase_times(session: BenchmarkSession, steps: int = 5) -> Dict[str, float]:
+    """Device time (CUDA events, ms/step, max over ranks) of the phases of an EAGER step: forward + loss, backward (with
+    the bucket kernels it overlaps), the optimizer join, and the sum of the bucket kernels' own durations."""
+    if not session.cuda:
+        return {}
+    opt = session.optimizer
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    graph, session._graph = session._graph, None
+    bucket_ms = []
+    orig = getattr(opt, "_launch_bucket", None)
+    if orig is not None:
+        def timed(b):
+            st = opt._comm_stream or torch.cuda.current_stream()
+            cur = torch.cuda.current_stream()
+            if opt._comm_stream is not None:
+                r = ev(); r.record(cur); st.wait_event(r)
+            e0, e1 = ev(), ev()
+            e0.record(st)
+            orig(b)
+            e1.record(st)
+            bucket_ms.append((e0, e1))
+        opt._launch_bucket = timed
+    tot = {"forward": 0.0, "backward": 0.0, "step_join": 0.0, "bucket_kernels": 0.0}
+    try:
+        for _ in range(steps):
+            bucket_ms.clear()
+            a, b, c, d = ev(), ev(), ev(), ev()
+            a.record()
+            opt.zero_grad()
+            out = session.model(session.data)
+            loss = session.loss_fn(out, session.target)
+            b.record()
+            loss.backward()
+            c.record()
+            opt.step()
+            d.record()
+            torch.cuda.synchronize()
+            tot["forward"] += a.elapsed_time(b)
+            tot["backward"] += b.elapsed_time(c)
+            tot["step_join"] += c.elapsed_time(d)
+            tot["bucket_kernels"] += sum(x.elapsed_time(y) for x, y in bucket_ms)
+    finally:
+        if orig is not None:
+            opt._launch_bucket = orig
+        session._graph = graph
+    return {k: dist.allreduce_scalar(v / steps, op="max") for k, v in tot.items()}
+
+
 def timed_steps(session: BenchmarkSession, n: int) -> float:
     """Milliseconds for ``n`` steps: CUDA events on the launching stream (CPU: perf_counter), max over ranks."""
     import time
@@ -213,12 +264,15 @@ def run(args) -> Dict:
         img_secs.append(img_sec)
     if hasattr(session.optimizer, "check_errors"):
         session.optimizer.check_errors()
+    phases = phase_times(session) if getattr(args, "phase_times", False) else {}
+    if phases:
+        log("Phase ms/step (eager, device-timed): " + ", ".join(f"{k} {v:.3f}" for k, v in phases.items()))
     mean, conf = float(np.mean(img_secs)), float(1.96 * np.std(img_secs))
     log("Img/sec per %s: %.1f +-%.1f" % (device, mean, conf))
     log("Total img/sec on %d %s(s): %.1f +-%.1f" % (dist.size(), device, dist.size() * mean, dist.size() * conf))
     result = {"model": args.model, "batch_size": args.batch_size, "world_size": dist.size(), "device": device,
               "img_sec_per_device": mean, "img_sec_conf": conf, "total_img_sec": dist.size() * mean,
-              "iters": img_secs, "final_loss": float(session.last_loss) if session.last_loss is not None else None}
+              "iters": img_secs, "phase_ms": phases, "final_loss": float(session.last_loss) if session.last_loss is not None else None}
     if args.json and dist.rank() == 0:
         if args.json == "-":
             print(json.dumps(result))

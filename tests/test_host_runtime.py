@@ -105,3 +105,29 @@ def test_launch_accounting_table_matches_module(C):
     n0 = _ext.launch_count()
     _ext.add_launches(7)
     assert _ext.launch_count() == n0 + 7
+
+
+def test_tile_geometry_maximises_useful_rows():
+    """The TMA pixel box of the tile-mode convolutions: never more rows than the MMA tile, always covering the map, and
+    at least as many useful rows as the naive full-width choice (14x14 maps: 77 % -> 96 %)."""
+    import math
+
+    from distributeddeeplearning_b200.ops import native as nv
+
+    def eff(P, Q, N, rows, t):
+        tw, th, tn = t
+        return (tw * th * tn / rows) * (Q / (math.ceil(Q / tw) * tw)) * (P / (math.ceil(P / th) * th)) * \
+            (N / (math.ceil(N / tn) * tn))
+
+    for rows in (64, 128):
+        for hw in (7, 8, 13, 14, 17, 28, 35, 56, 112):
+            for n in (1, 2, 32, 256):
+                t = nv.tile_geometry(hw, hw, n, rows)
+                tw, th, tn = t
+                assert 1 <= tw <= hw and 1 <= th <= hw and 1 <= tn <= n and tw * th * tn <= rows
+                naive_th = max(1, min(hw, rows // hw)) if hw <= rows else 1
+                naive = (hw if hw <= rows else -(-hw // -(-hw // rows)), naive_th,
+                         max(1, min(n, rows // (hw * naive_th))) if (hw <= rows and naive_th == hw) else 1)
+                assert eff(hw, hw, n, rows, t) >= eff(hw, hw, n, rows, naive) - 1e-9, (hw, n, rows, t, naive)
+    assert eff(14, 14, 256, 128, nv.tile_geometry(14, 14, 256, 128)) > 0.95
+    assert eff(7, 7, 256, 128, nv.tile_geometry(7, 7, 256, 128)) > 0.9

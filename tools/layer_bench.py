@@ -106,6 +106,20 @@ def main():
                 nv.force_variant(None)
                 vt[name] = res
         sweep["variants_us_maxdiff"] = vt
+        f8 = {}
+        if os.environ.get("LB_FP8", "0") == "1" and ci % 128 == 0:
+            from distributeddeeplearning_b200.ops import fp8 as f8m
+
+            f8m.enable(True)
+            nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co)          # calibrate + autotune
+            f8["fwd_total"] = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), flush=flush) * 1e3
+            f8["quant_x"] = timeit(lambda: f8m.quantize(x, ("lbx", ci, hw)), flush=flush) * 1e3
+            if co % 128 == 0:
+                nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p)
+                f8["dgrad_total"] = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), flush=flush) * 1e3
+                f8["quant_dy"] = timeit(lambda: f8m.quantize(dy, ("lbdy", co, hw), e5m2=True), flush=flush) * 1e3
+            f8m.enable(False)
+        sweep["fp8_us"] = {k_: round(v_, 1) for k_, v_ in f8.items()}
         t_fwd = timeit(lambda: nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co), flush=flush)
         t_bn = timeit(lambda: nv.bn_act_fwd(y, st, gamma, beta, rm, rv, 1e-5, 0.1, True, None, True), flush=flush)
         t_dg = timeit(lambda: nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p), flush=flush) if ci != 3 else 0.0

@@ -28,6 +28,21 @@ if what == "conv":
             dy = torch.randn_like(y)
             nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p)
             nv.conv_wgrad(x, dy, gw, (k, k), s, p)
+elif what == "convlong":
+    # long-K layers through each kernel variant (forward + dgrad), one launch each: where does the time go?
+    for (ci, hw, co, k, s, p) in [(256, 14, 256, 3, 1, 1), (1024, 14, 256, 1, 1, 0)]:
+        x = torch.randn(B, ci, hw, hw, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
+        w = torch.randn(co, ci, k, k, device=dev) * 0.05
+        wb = w.permute(0, 2, 3, 1).reshape(co, -1).contiguous().to(torch.bfloat16)
+        P = (hw + 2 * p - k) // s + 1
+        dy = torch.randn(B, co, P, P, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
+        gw = torch.zeros(co, ci, k, k, device=dev).contiguous(memory_format=cl)
+        for v in (1, 2, 3 | (3 << 4), 3 | (3 << 4) | (1 << 8), 3 | (2 << 4)):
+            nv.force_variant(v)
+            nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co)
+            nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p)
+        nv.force_variant(None)
+        nv.conv_wgrad(x, dy, gw, (k, k), s, p)
 elif what == "bn":
     c, hw = 256, 56
     y = torch.randn(B, c, hw, hw, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
