@@ -137,7 +137,8 @@ def run_ours(a):
     # ---- multi-GPU correctness, visible to whoever reads the JSON line (N>1, before anything is timed) ------------
     # check_engine: per-rank DIFFERENT gradients through the fused allreduce+SGD kernels (NVLS and P2P transports, fp32
     # and bf16 wire, with and without artificial block skew) against the same maths in torch, replicas bit-identical.
-    # step_equivalence: one ResNet-50 step on N ranks holding identical data == one step of a single-rank engine.
+    # step_equivalence: a real ResNet-50 step (per-rank different batches): the engine's new weights == w - lr * mean_r(g_r)
+    # with the per-rank gradients gathered independently over NCCL; plus the run-to-run noise floor of a single-rank step.
     engine_check, equivalence = None, None
     if world > 1 and not a.no_selfcheck:
         from distributeddeeplearning_b200.parallel import Compression, selfcheck

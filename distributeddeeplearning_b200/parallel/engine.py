@@ -226,6 +226,7 @@ class FusedSGD(torch.optim.Optimizer):
         self._first_step = True
         self._comm_stream = torch.cuda.Stream(device=dev, priority=-1) if overlap else None
         self._steps = 0
+        self._hold_buckets = False
         if broadcast_root is not None and self.world > 1:
             self.broadcast_parameters(broadcast_root)
         self.refresh_bf16()
@@ -304,6 +305,8 @@ class FusedSGD(torch.optim.Optimizer):
         self._ready_seen[idx] = True
         b = int(self.plan["param_bucket"][idx])
         self._pending[b] -= 1
+        if self._hold_buckets:          # selfcheck: keep the gradients in the arena until step() (no overlap)
+            return
         # buckets are launched strictly in plan order so every rank issues the same kernel sequence
         while self._next_bucket < self.num_buckets and self._pending[self._next_bucket] == 0:
             self._launch_bucket(self._next_bucket)

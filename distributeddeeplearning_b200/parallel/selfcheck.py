@@ -140,51 +140,90 @@ def replica_checksum(optimizer) -> Dict[str, object]:
 
 
 def step_equivalence(model_name: str = "resnet50", batch_size: int = 32, lr: float = 0.01, wire=Compression.none,
-                     seed: int = 7) -> Dict[str, float]:
-    """One training step on ``dist.size()`` ranks that all hold the SAME batch must equal one step of a single-rank
-    engine: the allreduce-average of N identical gradients is that gradient, so
+                     seed: int = 7, noise_floor: bool = True) -> Dict[str, float]:
+    """Does one REAL training step on ``dist.size()`` ranks apply exactly the average of the ranks' gradients?
 
-        || (w_N - w_0) - (w_1 - w_0) || / || w_1 - w_0 ||
+    Every rank runs forward + backward of the same model on its OWN batch with the bucket kernels held back, so the
+    per-rank gradients sit complete in the arenas; they are gathered with a plain ``all_gather`` (NCCL — independent of
+    the kernels under test), and after ``step()`` the fused engine's new weights must equal ``w - lr * mean_r(g_r)``:
+    ``engine_rel_error = ||dw_engine - dw_expected|| / ||dw_expected||`` (fp32 wire: rounding only, bound 1e-5; bf16
+    wire: 1e-2).  That pins the averaging semantics of ``hvd.DistributedOptimizer`` on real model gradients.
 
-    measures nothing but the engine (wire rounding, dropped / doubled contributions, wrong scale).  The two models are
-    built from the same seed; kernels with fp32 atomics make the two gradients agree to rounding noise only, which
-    the bound (1e-3, bf16 wire: 1e-2) leaves room for.  Collective: every rank must call."""
+    ``noise_floor``: comparing an N-rank step with a separately executed 1-rank step says little, because two
+    executions of the SAME step do not agree: fp32 atomics make reduction orders run-dependent and bf16 rounding
+    amplifies the differences to rounding level in every layer of a randomly initialised (not zero-init-residual)
+    ResNet-50, whose step-0 gradient has a small signal-to-rounding-noise ratio.  Two single-rank executions of the
+    identical step are therefore compared too (``repeat_cosine`` / ``repeat_rel_error``): averaging N noisy copies of the
+    same gradient is WHY the loss of the fixed-batch benchmark falls faster with more ranks.  Collective call."""
+    import torch.distributed as td
+
     from .. import models, ops
     from ..data import fixed_synthetic_batch
     from .engine import FusedSGD
 
     dev = torch.device("cuda", torch.cuda.current_device())
+    world, rank = dist.size(), dist.rank()
+    size = models.input_size(models.get_model(model_name))
 
     def build(local: bool):
         torch.manual_seed(seed)
         m = models.get_model(model_name).cuda().train()
-        opt = FusedSGD(m.named_parameters(), lr=lr, compression=wire, local=local)
-        return m, opt
+        return m, FusedSGD(m.named_parameters(), lr=lr, compression=wire, local=local)
 
-    size = models.input_size(models.get_model(model_name))
-    data, target = fixed_synthetic_batch(batch_size, size, 1000, dev, seed=seed + 17)    # identical on every rank
-
-    def one_step(m, opt):
-        w0 = opt.W.detach().clone()
+    def fwd_bwd(m, data, target):
         out = m(data)
         if isinstance(out, tuple):
             loss = ops.softmax_cross_entropy(out[0], target, 1000) + 0.4 * ops.softmax_cross_entropy(out[1], target, 1000)
         else:
             loss = ops.softmax_cross_entropy(out, target, 1000)
         loss.backward()
-        opt.step()
-        torch.cuda.synchronize()
-        opt.check_errors()
-        return (opt.W.detach() - w0).double(), float(loss)
+        return float(loss.detach())
 
-    m1, o1 = build(local=True)
-    d1, loss1 = one_step(m1, o1)
-    mn, on = build(local=False)
-    dn, lossn = one_step(mn, on)
-    # the two engines lay parameters out identically (same plan for the same model)
-    rel = float((dn - d1).norm() / d1.norm().clamp_min(1e-30))
-    scale = float((dn * d1).sum() / (d1 * d1).sum().clamp_min(1e-30))      # least-squares step-size ratio
-    rel = dist.allreduce_scalar(rel, op="max")
-    return {"rel_delta_error": rel, "step_scale": scale, "loss_single": loss1, "loss_multi": lossn,
-            "world": dist.size(), "ok": bool(rel < (1e-2 if wire is not Compression.none else 1e-3)),
-            "replicas_identical": replica_checksum(on)["replicas_identical"]}
+    # ---- exact check of the engine on real gradients (per-rank different data) -------------------------------------
+    m, opt = build(local=False)
+    opt._hold_buckets = True
+    data, target = fixed_synthetic_batch(batch_size, size, 1000, dev, seed=seed + 17 + 1000 * rank)
+    loss = fwd_bwd(m, data, target)
+    torch.cuda.synchronize()
+    g = opt.G.detach().clone()
+    w0 = opt.W.detach().clone()
+    if world > 1:
+        gs = [torch.empty_like(g) for _ in range(world)]
+        td.all_gather(gs, g)
+    else:
+        gs = [g]
+    if wire is not Compression.none:
+        g_mean = sum((x / world).to(torch.bfloat16).float() for x in gs)
+    else:
+        g_mean = sum(gs) / world
+    opt.step()
+    torch.cuda.synchronize()
+    opt.check_errors()
+    expected = (-lr * g_mean).double()
+    got = (opt.W.detach() - w0).double()
+    err = float((got - expected).norm() / expected.norm().clamp_min(1e-30))
+    err = dist.allreduce_scalar(err, op="max")
+    cleared = float(opt.G.abs().max()) == 0.0
+    same = replica_checksum(opt)["replicas_identical"]
+    rank_spread = float(torch.stack([(x - g_mean).norm() for x in gs]).mean() / g_mean.norm().clamp_min(1e-30))
+    out = {"engine_rel_error": err, "world": world, "loss": loss, "grads_cleared": bool(cleared),
+           "replicas_identical": bool(same), "per_rank_grad_spread": rank_spread,
+           "bound": 1e-2 if wire is not Compression.none else 1e-5}
+    out["ok"] = bool(err < out["bound"] and cleared and same)
+    del m, opt, gs
+    # ---- how reproducible is a step at all?  two single-rank executions of the identical step -----------------------
+    if noise_floor:
+        deltas = []
+        for _ in range(2):
+            m1, o1 = build(local=True)
+            d1, t1 = fixed_synthetic_batch(batch_size, size, 1000, dev, seed=seed + 17)
+            w1 = o1.W.detach().clone()
+            fwd_bwd(m1, d1, t1)
+            o1.step()
+            torch.cuda.synchronize()
+            deltas.append((o1.W.detach() - w1).double())
+            del m1, o1
+        a, b = deltas
+        out["repeat_rel_error"] = float((a - b).norm() / a.norm().clamp_min(1e-30))
+        out["repeat_cosine"] = float((a * b).sum() / (a.norm() * b.norm()).clamp_min(1e-30))
+    return out
