@@ -78,17 +78,30 @@ def _imagenet_argv(epochs, use_gpu, train=None, val=None, extra=()):
     return argv + list(extra)
 
 
-@task
-def imagenet_synthetic_local(c, epochs=1, no_cuda=False):
+def _trainer_extra(batch_size, precision, fp16_allreduce=False):
+    extra = []
+    if batch_size:
+        extra += ["--batch_size", str(batch_size)]
+    if precision and precision != "bf16":
+        extra += ["--precision", str(precision)]
+    if fp16_allreduce:
+        extra += ["--fp16_allreduce", "True"]
+    return extra
+
+
+@task(help={"precision": "bf16 (default) or fp8 tensor-core operands", "batch_size": "per-GPU batch (script default 64)"})
+def imagenet_synthetic_local(c, epochs=1, no_cuda=False, batch_size=None, precision="bf16"):
     """ImageNet trainer, synthetic data, one rank."""
-    _submit(_IMAGENET, _imagenet_argv(epochs, not no_cuda), 1, "synthetic_images_local", no_cuda)
+    _submit(_IMAGENET, _imagenet_argv(epochs, not no_cuda, extra=_trainer_extra(batch_size, precision)), 1,
+            "synthetic_images_local", no_cuda)
 
 
-@task
-def imagenet_synthetic_remote(c, node_count=None, epochs=1, no_cuda=False):
+@task(help={"precision": "bf16 (default) or fp8 tensor-core operands", "batch_size": "per-GPU batch (script default 64)"})
+def imagenet_synthetic_remote(c, node_count=None, epochs=1, no_cuda=False, batch_size=None, precision="bf16",
+                              fp16_allreduce=False):
     """ImageNet trainer, synthetic data, --node-count ranks."""
-    _submit(_IMAGENET, _imagenet_argv(epochs, not no_cuda), int(node_count or _max_nodes()), "synthetic_images_remote",
-            no_cuda)
+    _submit(_IMAGENET, _imagenet_argv(epochs, not no_cuda, extra=_trainer_extra(batch_size, precision, fp16_allreduce)),
+            int(node_count or _max_nodes()), "synthetic_images_remote", no_cuda)
 
 
 @task

@@ -261,9 +261,10 @@ PYBIND11_MODULE(_C, m) {
   // ------------------------------------------------------------------ BN / activation
   m.def("bn_act_fwd", [](ptr_t x, ptr_t residual, ptr_t z, ptr_t sum, ptr_t sumsq, ptr_t gamma, ptr_t beta,
                          ptr_t mean, ptr_t invstd, ptr_t rmean, ptr_t rvar, float eps, float momentum, int M, int C,
-                         int relu, bool train, int sms, ptr_t stream, ptr_t mask) {
-    BnFwdArgs a;
+                         int relu, bool train, int sms, ptr_t stream, ptr_t mask, ptr_t zq, ptr_t zq_slot) {
+    BnFwdArgs a{};
     a.mask = P<uint8_t>(mask);
+    a.zq = P<uint8_t>(zq); a.zq_slot = P<ddl::Fp8Slot>(zq_slot);
     a.x = P<const __nv_bfloat16>(x); a.residual = P<const __nv_bfloat16>(residual); a.z = P<__nv_bfloat16>(z);
     a.sum = P<const float>(sum); a.sumsq = P<const float>(sumsq); a.gamma = P<const float>(gamma);
     a.beta = P<const float>(beta); a.mean = P<float>(mean); a.invstd = P<float>(invstd);
@@ -272,12 +273,15 @@ PYBIND11_MODULE(_C, m) {
     check(ddl::launch_bn_act_fwd(a, train, sms, S(stream)), "bn_act_fwd");
   }, py::arg("x"), py::arg("residual"), py::arg("z"), py::arg("sum"), py::arg("sumsq"), py::arg("gamma"), py::arg("beta"),
      py::arg("mean"), py::arg("invstd"), py::arg("rmean"), py::arg("rvar"), py::arg("eps"), py::arg("momentum"),
-     py::arg("M"), py::arg("C"), py::arg("relu"), py::arg("train"), py::arg("sms"), py::arg("stream"), py::arg("mask") = 0);
+     py::arg("M"), py::arg("C"), py::arg("relu"), py::arg("train"), py::arg("sms"), py::arg("stream"), py::arg("mask") = 0,
+     py::arg("zq") = 0, py::arg("zq_slot") = 0);
   m.def("bn_act_bwd", [](ptr_t dz, ptr_t z, ptr_t x, ptr_t dx, ptr_t dres, ptr_t mean, ptr_t invstd, ptr_t gamma,
                          ptr_t beta, ptr_t dgamma, ptr_t dbeta, ptr_t gamma_grad, ptr_t beta_grad, int M, int C,
-                         int relu, int mask_from_x, int sms, ptr_t stream, ptr_t zmask, bool skip_reduce) {
-    BnBwdArgs a;
+                         int relu, int mask_from_x, int sms, ptr_t stream, ptr_t zmask, bool skip_reduce, ptr_t dxq,
+                         ptr_t dxq_slot) {
+    BnBwdArgs a{};
     a.zmask = P<const uint8_t>(zmask);
+    a.dxq = P<uint8_t>(dxq); a.dxq_slot = P<ddl::Fp8Slot>(dxq_slot);
     a.dz = P<const __nv_bfloat16>(dz); a.z = P<const __nv_bfloat16>(z); a.x = P<const __nv_bfloat16>(x);
     a.dx = P<__nv_bfloat16>(dx); a.dres = P<__nv_bfloat16>(dres); a.mean = P<const float>(mean);
     a.invstd = P<const float>(invstd); a.gamma = P<const float>(gamma); a.dgamma = P<float>(dgamma);
@@ -287,11 +291,11 @@ PYBIND11_MODULE(_C, m) {
   }, py::arg("dz"), py::arg("z"), py::arg("x"), py::arg("dx"), py::arg("dres"), py::arg("mean"), py::arg("invstd"),
      py::arg("gamma"), py::arg("beta"), py::arg("dgamma"), py::arg("dbeta"), py::arg("gamma_grad"), py::arg("beta_grad"),
      py::arg("M"), py::arg("C"), py::arg("relu"), py::arg("mask_from_x"), py::arg("sms"), py::arg("stream"),
-     py::arg("zmask") = 0, py::arg("skip_reduce") = false);
+     py::arg("zmask") = 0, py::arg("skip_reduce") = false, py::arg("dxq") = 0, py::arg("dxq_slot") = 0);
   m.def("bn_relu_maxpool_fwd", [](ptr_t x, ptr_t pooled, ptr_t argmax, ptr_t sum, ptr_t sumsq, ptr_t gamma, ptr_t beta,
                                   ptr_t mean, ptr_t invstd, ptr_t rmean, ptr_t rvar, float eps, float momentum, int N, int H,
                                   int W, int C, int Pq, int Q, int k, int stride, int pad, int sms, ptr_t stream) {
-    BnFwdArgs a;
+    BnFwdArgs a{};
     a.x = P<const __nv_bfloat16>(x); a.residual = nullptr; a.z = nullptr; a.mask = nullptr;
     a.sum = P<const float>(sum); a.sumsq = P<const float>(sumsq); a.gamma = P<const float>(gamma);
     a.beta = P<const float>(beta); a.mean = P<float>(mean); a.invstd = P<float>(invstd);
@@ -303,7 +307,7 @@ PYBIND11_MODULE(_C, m) {
   m.def("bn_pool_bwd", [](ptr_t dy_pooled, ptr_t argmax, ptr_t x, ptr_t dx, ptr_t mean, ptr_t invstd, ptr_t gamma, ptr_t beta,
                           ptr_t dgamma, ptr_t dbeta, ptr_t gamma_grad, ptr_t beta_grad, int N, int H, int W, int C, int Pq,
                           int Q, int k, int stride, int pad, int sms, ptr_t stream) {
-    BnBwdArgs a;
+    BnBwdArgs a{};
     a.dz = nullptr; a.z = nullptr; a.x = P<const __nv_bfloat16>(x); a.dx = P<__nv_bfloat16>(dx); a.dres = nullptr;
     a.mean = P<const float>(mean); a.invstd = P<const float>(invstd); a.gamma = P<const float>(gamma);
     a.beta = P<const float>(beta); a.dgamma = P<float>(dgamma); a.dbeta = P<float>(dbeta);

@@ -36,6 +36,20 @@ DDL_DEVICE float warp_max(float v) {
   return v;
 }
 
+// four floats -> four fp8 codes (e4m3 or e5m2, round-to-nearest, saturating to the finite range), a at the lowest byte
+template <bool E5M2>
+DDL_DEVICE uint32_t fp8_cvt4(float a, float b, float c, float d) {
+  uint16_t lo, hi;
+  if (E5M2) {
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  } else {
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
+  }
+  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
+}
+
 // 16-byte global accesses with cache hints (streaming data: do not pollute L1)
 DDL_DEVICE uint4 ld_stream_u4(const void* p) {
   uint4 r;

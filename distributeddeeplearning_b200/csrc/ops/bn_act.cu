@@ -65,10 +65,20 @@ DDL_DEVICE bool bn_thread_map(int C, int& c0, int& row0, int& row_stride) {
   return true;
 }
 
-template <bool TRAIN, bool CHUNKED>
+// FP8: also emit the e4m3 twin of z (z * slot scale) and fold max|z| into the slot — the quantisation pass of the fp8
+// training mode rides in this kernel's streaming pass (+1 byte written per element) instead of re-reading z.
+DDL_DEVICE void fp8_fold_amax(Fp8Slot* slot, float amax) {
+  amax = warp_max(amax);
+  if ((threadIdx.x & 31) == 0 && amax > 0.f)
+    atomicMax(reinterpret_cast<unsigned int*>(&slot->amax), __float_as_uint(amax));    // one per warp, fire-and-forget
+}
+
+template <bool TRAIN, bool CHUNKED, bool FP8>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) {
   int c0, row0, row_stride;
   if (!bn_thread_map<CHUNKED>(a.C, c0, row0, row_stride)) return;
+  const float qscale = FP8 ? a.zq_slot->scale : 1.f;
+  float amax = 0.f;
   float scale[8], shift[8];
   {
     Vec8 gam = load8_f32(a.gamma + c0), bet = load8_f32(a.beta + c0);
@@ -126,6 +136,13 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
       for (int i = 0; i < 8; ++i) z[i] = fmaxf(z[i], 0.f);
     }
     store8_bf16(a.z + off, z);
+    if (FP8) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(z[i]));
+      *reinterpret_cast<uint2*>(a.zq + off) =
+          make_uint2(fp8_cvt4<false>(z[0] * qscale, z[1] * qscale, z[2] * qscale, z[3] * qscale),
+                     fp8_cvt4<false>(z[4] * qscale, z[5] * qscale, z[6] * qscale, z[7] * qscale));
+    }
   };
   int r = row0;
   for (; r + row_stride < a.M; r += 2 * row_stride) {
@@ -144,6 +161,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
     if (a.residual) r0 = ld_stream_u4(a.residual + off0);
     finish(x0, r0, off0);
   }
+  if (FP8) fp8_fold_amax(a.zq_slot, amax);
 }
 
 // ---- backward pass 1: per-channel reductions ----------------------------------------------------
@@ -243,10 +261,12 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
 
 // ---- backward pass 2: elementwise ----------------------------------------------------------------
 // dx = k1*dy + x*B + A   with k1 = gamma*invstd, B = -k1*invstd*dgamma/M, A = -k1*dbeta/M - mean*B
-template <int MASK, bool CHUNKED>
+template <int MASK, bool CHUNKED, bool FP8>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdArgs a) {
   int c0, row0, row_stride;
   if (!bn_thread_map<CHUNKED>(a.C, c0, row0, row_stride)) return;
+  const float qscale = FP8 ? a.dxq_slot->scale : 1.f;
+  float amax = 0.f;
   float k1[8], cA[8], cB[8], msh[8];
   {
     Vec8 mean = load8_f32(a.mean + c0), invstd = load8_f32(a.invstd + c0), gam = load8_f32(a.gamma + c0);
@@ -294,7 +314,15 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdAr
 #pragma unroll
     for (int i = 0; i < 8; ++i) x[i] = fmaf(dz[i], k1[i], fmaf(x[i], cB[i], cA[i]));
     store8_bf16(a.dx + off, x);
+    if (FP8) {       // e5m2 twin of the gradient for the data-gradient convolution (same rounding source: fp32 x[])
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(x[i]));
+      *reinterpret_cast<uint2*>(a.dxq + off) =
+          make_uint2(fp8_cvt4<true>(x[0] * qscale, x[1] * qscale, x[2] * qscale, x[3] * qscale),
+                     fp8_cvt4<true>(x[4] * qscale, x[5] * qscale, x[6] * qscale, x[7] * qscale));
+    }
   }
+  if (FP8) fp8_fold_amax(a.dxq_slot, amax);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -540,14 +568,17 @@ inline bool bn_flat_ok(int C) {
 
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream) {
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
+  const bool f8 = a.zq != nullptr && a.zq_slot != nullptr && train;
   if (bn_flat_ok(a.C)) {
     const int grid = bn_grid(a.M, a.C, sms);
-    if (train) bn_act_fwd_kernel<true, false><<<grid, kBnThreads, 0, stream>>>(a);
-    else bn_act_fwd_kernel<false, false><<<grid, kBnThreads, 0, stream>>>(a);
+    if (f8) bn_act_fwd_kernel<true, false, true><<<grid, kBnThreads, 0, stream>>>(a);
+    else if (train) bn_act_fwd_kernel<true, false, false><<<grid, kBnThreads, 0, stream>>>(a);
+    else bn_act_fwd_kernel<false, false, false><<<grid, kBnThreads, 0, stream>>>(a);
   } else {
     const dim3 grid = bn_chunk_grid(a.M, a.C, sms);
-    if (train) bn_act_fwd_kernel<true, true><<<grid, kBnThreads, 0, stream>>>(a);
-    else bn_act_fwd_kernel<false, true><<<grid, kBnThreads, 0, stream>>>(a);
+    if (f8) bn_act_fwd_kernel<true, true, true><<<grid, kBnThreads, 0, stream>>>(a);
+    else if (train) bn_act_fwd_kernel<true, true, false><<<grid, kBnThreads, 0, stream>>>(a);
+    else bn_act_fwd_kernel<false, true, false><<<grid, kBnThreads, 0, stream>>>(a);
   }
   return cudaGetLastError();
 }
@@ -564,20 +595,21 @@ cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream, 
   }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  const bool f8 = a.dxq != nullptr && a.dxq_slot != nullptr;
   if (bn_flat_ok(a.C)) {
     const int grid = bn_grid(a.M, a.C, sms);
     switch (mask) {
-      case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone, false><<<grid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ, false><<<grid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskBits: bn_act_bwd_apply_kernel<kMaskBits, false><<<grid, kBnThreads, 0, stream>>>(a); break;
-      default: bn_act_bwd_apply_kernel<kMaskX, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskNone: if (f8) bn_act_bwd_apply_kernel<kMaskNone, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskNone, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskZ: if (f8) bn_act_bwd_apply_kernel<kMaskZ, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskZ, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskBits: if (f8) bn_act_bwd_apply_kernel<kMaskBits, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskBits, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      default: if (f8) bn_act_bwd_apply_kernel<kMaskX, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskX, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
     }
   } else {
     switch (mask) {
-      case kMaskNone: bn_act_bwd_apply_kernel<kMaskNone, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskZ: bn_act_bwd_apply_kernel<kMaskZ, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskBits: bn_act_bwd_apply_kernel<kMaskBits, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-      default: bn_act_bwd_apply_kernel<kMaskX, true><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskNone: if (f8) bn_act_bwd_apply_kernel<kMaskNone, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskNone, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskZ: if (f8) bn_act_bwd_apply_kernel<kMaskZ, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskZ, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskBits: if (f8) bn_act_bwd_apply_kernel<kMaskBits, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskBits, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      default: if (f8) bn_act_bwd_apply_kernel<kMaskX, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskX, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
     }
   }
   return cudaGetLastError();

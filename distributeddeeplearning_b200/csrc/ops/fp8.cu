@@ -24,20 +24,6 @@ namespace {
 constexpr float kE4m3Max = 448.f;
 constexpr float kE5m2Max = 57344.f;
 
-template <bool E5M2>
-DDL_DEVICE uint32_t cvt4(float a, float b, float c, float d) {
-  // cvt.rn.satfinite.{e4m3x2,e5m2x2}.f32: two floats -> two fp8 (upper operand first)
-  uint16_t lo, hi;
-  if (E5M2) {
-    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
-    asm("cvt.rn.satfinite.e5m2x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
-  } else {
-    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(b), "f"(a));
-    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(d), "f"(c));
-  }
-  return static_cast<uint32_t>(lo) | (static_cast<uint32_t>(hi) << 16);
-}
-
 DDL_DEVICE float block_max(float v) {
   __shared__ float s[32];
   v = warp_max(v);
@@ -65,8 +51,8 @@ __global__ void __launch_bounds__(256) quantize_fp8_kernel(const __nv_bfloat16* 
     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))));
     amax = fmaxf(amax, fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(d.x), fabsf(d.y))));
     uint2 o;
-    o.x = cvt4<E5M2>(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
-    o.y = cvt4<E5M2>(c.x * scale, c.y * scale, d.x * scale, d.y * scale);
+    o.x = fp8_cvt4<E5M2>(a.x * scale, a.y * scale, b.x * scale, b.y * scale);
+    o.y = fp8_cvt4<E5M2>(c.x * scale, c.y * scale, d.x * scale, d.y * scale);
     reinterpret_cast<uint2*>(out)[i] = o;
   }
   amax = block_max(amax);

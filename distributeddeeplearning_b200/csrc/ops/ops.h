@@ -7,6 +7,12 @@
 
 namespace ddl {
 
+struct Fp8Slot {       // one quantised tensor role; lives in a device-resident table (graph replays see live values)
+  float amax;          // running max |x| of the current step (cleared by update_scales)
+  float scale;         // multiply before the fp8 conversion (power of two)
+  float inv_scale;     // 1 / scale: folded into the consuming GEMM's epilogue
+  int e5m2;            // 0 = e4m3 (activations, weights), 1 = e5m2 (gradients)
+};
 struct BnFwdArgs {
   const __nv_bfloat16* x;         // [M][C] conv output
   const __nv_bfloat16* residual;  // optional [M][C]
@@ -23,6 +29,8 @@ struct BnFwdArgs {
   int M, C, relu;
   uint8_t* mask;                  // optional [M][C/8]: bit i of byte (row, group) = (z[row][8*group + i] > 0).  Written
                                   //   for residual layers so that backward reads 1 bit instead of 16 bits per element
+  uint8_t* zq;                    // optional fp8 (e4m3) twin of z for the consuming convolution's tensor-core operand:
+  Fp8Slot* zq_slot;               //   z * slot->scale, amax(|z|) folded into the slot (ops/fp8.py: no separate quantise pass)
 };
 
 struct BnBwdArgs {
@@ -42,6 +50,8 @@ struct BnBwdArgs {
   int M, C, relu;
   int mask_from_x;                // no residual: z > 0  <=>  x*scale + shift > 0, so z is never read
   const uint8_t* zmask;           // residual layers: the bit mask written by the forward kernel (z is never read)
+  uint8_t* dxq;                   // optional fp8 (e5m2) twin of dx for the data-gradient convolution that consumes it
+  Fp8Slot* dxq_slot;
 };
 
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream);
@@ -138,12 +148,6 @@ cudaError_t launch_add_bf16(const __nv_bfloat16* a, const __nv_bfloat16* b, __nv
                             cudaStream_t stream);
 
 // ---- FP8 operand preparation (fp8.cu) ----------------------------------------------------------------
-struct Fp8Slot {       // one quantised tensor role; lives in a device-resident table (graph replays see live values)
-  float amax;          // running max |x| of the current step (cleared by update_scales)
-  float scale;         // multiply before the fp8 conversion (power of two)
-  float inv_scale;     // 1 / scale: folded into the consuming GEMM's epilogue
-  int e5m2;            // 0 = e4m3 (activations, weights), 1 = e5m2 (gradients)
-};
 cudaError_t launch_fp8_quantize(const __nv_bfloat16* x, uint8_t* out, int64_t n, Fp8Slot* slot, bool e5m2, int sms,
                                 cudaStream_t stream);
 cudaError_t launch_fp8_amax(const __nv_bfloat16* x, int64_t n, Fp8Slot* slot, int sms, cudaStream_t stream);

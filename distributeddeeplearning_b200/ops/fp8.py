@@ -95,6 +95,53 @@ def quantize(x: torch.Tensor, key, e5m2: bool = False) -> Tuple[torch.Tensor, in
     return out, idx
 
 
+# ---- producer-side quantisation ("twins") -------------------------------------------------------------------------
+# The BN-apply kernels can emit the fp8 copy of their output in the same streaming pass (bn_act.cu, FP8 variants): the
+# producer registers it here, the consuming convolution looks it up by tensor identity and skips its own quantise pass.
+# Entries hold a weak reference to the bf16 tensor (a recycled address can never alias) and die at the end of the step.
+import weakref
+
+_TWINS = {}
+_PRODUCED = {}        # id(bf16 tensor) -> (weakref, producer key): who wrote this tensor (this step)
+_WANTED = set()       # producer keys whose output an fp8 convolution actually consumes: only those emit a twin
+
+
+def note_producer(t: torch.Tensor, key) -> bool:
+    """Called by a kernel wrapper that COULD emit a twin of ``t``; returns whether a consumer asked for one."""
+    _PRODUCED[id(t)] = (weakref.ref(t), key)
+    return key in _WANTED
+
+
+def request_twin(t: torch.Tensor) -> None:
+    """Called by an fp8 convolution that had to quantise ``t`` itself: from the next step on its producer does it."""
+    e = _PRODUCED.get(id(t))
+    if e is not None and e[0]() is t:
+        _WANTED.add(e[1])
+
+
+def producer_slot(key, device, like: torch.Tensor, e5m2: bool = False):
+    """(slot index, fused) for a tensor role quantised by its producing kernel.  ``fused`` is False until the slot is
+    calibrated: the first time the producer runs plain and ``attach_by_quantize`` does the two-pass calibration."""
+    idx = _slot(key, device, e5m2)
+    return idx, idx in _STATE["calibrated"]
+
+
+def attach_twin(t: torch.Tensor, q: torch.Tensor, idx: int) -> None:
+    _TWINS[id(t)] = (weakref.ref(t), q, idx)
+
+
+def attach_by_quantize(t: torch.Tensor, key, e5m2: bool = False) -> None:
+    q, idx = quantize(t, key, e5m2)
+    attach_twin(t, q, idx)
+
+
+def twin_of(t: torch.Tensor):
+    e = _TWINS.get(id(t))
+    if e is None or e[0]() is not t:
+        return None
+    return e[1], e[2]
+
+
 def quantize_weight(w_bf16: torch.Tensor) -> Tuple[torch.Tensor, int]:
     """e4m3 copy of a bf16 weight matrix, quantised once per step and shared by forward and dgrad."""
     key = ("w", w_bf16.data_ptr(), tuple(w_bf16.shape))
@@ -113,16 +160,24 @@ def end_of_step(device=None) -> None:
     t = _STATE["table"]
     C = _ext.load()
     C.fp8_update_scales(t.data_ptr(), int(_STATE["n"]), torch.cuda.current_stream(t.device).cuda_stream)
+    _TWINS.clear()
+    _PRODUCED.clear()
     _STATE["step"] += 1          # next step quantises its weights again (a captured step never reuses an eager copy)
 
 
-def fwd_eligible(cin: int, cout: int) -> bool:
-    return _STATE["enabled"] and cin % 128 == 0 and cout % 64 == 0
+# fp8 pays where the main loop dominates: measured per layer (profiles/layer_bench_fp8.md), reductions of >= 512
+# elements run 1.5-1.9x faster than bf16, shorter ones are epilogue-bound and lose (the fp8 path exists on the
+# one-CTA-per-SM deep-ring kernel only, which trails the two-CTA persistent kernel on short-K layers).
+MIN_K = int(os.environ.get("DDL_FP8_MIN_K", "512"))
 
 
-def dgrad_eligible(cin: int, cout: int) -> bool:
+def fwd_eligible(cin: int, cout: int, taps: int = 1) -> bool:
+    return _STATE["enabled"] and cin % 128 == 0 and cout % 64 == 0 and cin * taps >= MIN_K
+
+
+def dgrad_eligible(cin: int, cout: int, taps: int = 1) -> bool:
     # reduction dim = Cout (k-blocks of 128), MN-major weight boxes are 128 input channels wide
-    return _STATE["enabled"] and cout % 128 == 0 and cin % 128 == 0
+    return _STATE["enabled"] and cout % 128 == 0 and cin % 128 == 0 and cout * taps >= MIN_K
 
 
 def count(kind: str) -> None:
@@ -132,3 +187,6 @@ def count(kind: str) -> None:
 def reset() -> None:
     """Forget all slots (tests)."""
     _STATE.update(table=None, n=0, slots={}, calibrated=set(), step=0, wcache={}, stats={"fwd": 0, "dgrad": 0})
+    _TWINS.clear()
+    _PRODUCED.clear()
+    _WANTED.clear()

@@ -391,10 +391,13 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
 
     one_by_one = R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0
     tile_ok = USE_TILE_TMA and (stride == 1 or (stride == 2 and R * S <= 16 and USE_TILE_S2))
-    if _fp8.fwd_eligible(Cin, Cout) and (one_by_one or tile_ok) and M >= 2048:
+    if _fp8.fwd_eligible(Cin, Cout, R * S) and (one_by_one or tile_ok) and M >= 2048:
         # e4m3 operands: quantise x (delayed per-tensor scale) and take this step's e4m3 weights; a k-block is 128
         # channels (128 bytes), the epilogue multiplies by inv_scale(x) * inv_scale(w)
-        xq, sx = _fp8.quantize(x, ("x", wp, N, H, W))
+        tw_ = _fp8.twin_of(x)                       # produced by the BN-apply kernel that wrote x, if any
+        if tw_ is None:
+            _fp8.request_twin(x)                    # from the next step on the producer emits the e4m3 copy itself
+        xq, sx = tw_ if tw_ is not None else _fp8.quantize(x, ("x", wp, N, H, W))
         wq, sw = _fp8.quantize_weight(w_bf16)
         cch8 = Cin // 128
         fp8kw = dict(fp8=1, deq_a=_fp8.inv_scale_ptr(sx, x.device), deq_b=_fp8.inv_scale_ptr(sw, x.device))
@@ -490,11 +493,15 @@ def conv_dgrad(dy: torch.Tensor, w_bf16: torch.Tensor, x_shape, kernel: Tuple[in
     from . import fp8 as _fp8
 
     one_by_one = R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0
-    if _fp8.dgrad_eligible(Cin, Cout) and bn_reduce is None and N * H * W >= 2048 and \
+    if _fp8.dgrad_eligible(Cin, Cout, R * S if stride == 1 else max(1, (R * S) // 4)) and bn_reduce is None \
+            and N * H * W >= 2048 and \
             (one_by_one or (stride == 1 and USE_TILE_TMA) or s2_tile):
         # e5m2 output gradients x e4m3 weights (the forward's quantised copy, consumed MN-major): k-blocks of 128
         # output channels; the epilogue (incl. the shortcut-gradient add) runs on the de-quantised fp32 accumulator
-        dyq, sd = _fp8.quantize(dy, ("dy", wp, N, P, Q), e5m2=True)
+        tw_ = _fp8.twin_of(dy)                      # produced by the BN-backward kernel that wrote dy, if any
+        if tw_ is None:
+            _fp8.request_twin(dy)
+        dyq, sd = tw_ if tw_ is not None else _fp8.quantize(dy, ("dy", wp, N, P, Q), e5m2=True)
         wq, sw = _fp8.quantize_weight(w_bf16)
         cch8 = Cout // 128
         fp8kw = dict(fp8=2, deq_a=_fp8.inv_scale_ptr(sd, dy.device), deq_b=_fp8.inv_scale_ptr(sw, dy.device))
@@ -686,10 +693,25 @@ def bn_act_fwd(y: torch.Tensor, stats: Optional[torch.Tensor], gamma, beta, runn
                             _stream())
         save = torch.empty((2, Ch), dtype=torch.float32, device=y.device)
         mask = torch.empty((M, Ch // 8), dtype=torch.uint8, device=y.device) if (want_mask and relu) else None
+        from . import fp8 as _fp8
+
+        zq = slot = None
+        key = ("act", gamma.data_ptr(), N, H, W)
+        # emit the e4m3 twin only when an fp8 convolution consumed this layer's output in an earlier step
+        twin = _fp8.enabled() and Ch % 128 == 0 and M >= 2048 and _fp8.note_producer(z, key)
+        if twin:
+            idx, fused = _fp8.producer_slot(key, y.device, z)
+            if fused:       # the e4m3 twin rides in this kernel's pass (+1 B/element) instead of a 3 B/element pass
+                zq, slot = torch.empty_like(z, dtype=torch.uint8), _fp8.slot_ptr(idx, y.device)
         C.bn_act_fwd(y.data_ptr(), _ptr(residual), z.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
                      gamma.data_ptr(), beta.data_ptr(), save[0].data_ptr(), save[1].data_ptr(), _ptr(running_mean),
                      _ptr(running_var), eps, momentum, M, Ch, int(relu), True, sm_count(y.device.index or 0), _stream(),
-                     _ptr(mask))
+                     _ptr(mask), _ptr(zq), slot or 0)
+        if twin:
+            if zq is not None:
+                _fp8.attach_twin(z, zq, idx)
+            else:
+                _fp8.attach_by_quantize(z, key)          # first sight of this layer: calibrate, then quantise
         return (z, save, mask) if want_mask else (z, save)
     C.bn_act_fwd(y.data_ptr(), _ptr(residual), z.data_ptr(), 0, 0, gamma.data_ptr(), beta.data_ptr(), 0, 0,
                  running_mean.data_ptr(), running_var.data_ptr(), eps, momentum, M, Ch, int(relu), False,
@@ -719,10 +741,25 @@ def bn_act_bwd(dz: torch.Tensor, z: Optional[torch.Tensor], y: torch.Tensor, sav
         raise ValueError("pre_reduced sums are only defined for BN+ReLU layers without residual")
     if relu and not mask_from_x and zmask is None and z is None:
         raise ValueError("bn_act_bwd: need z or zmask for the ReLU mask of a residual layer")
+    from . import fp8 as _fp8
+
+    dyq = slot = None
+    key = ("grad", gamma.data_ptr(), N, H, W)
+    twin = _fp8.enabled() and Ch % 128 == 0 and M >= 2048 and _fp8.note_producer(dy, key)   # an fp8 dgrad consumed it before
+    if twin:
+        idx, fused = _fp8.producer_slot(key, y.device, dy, e5m2=True)
+        if fused:
+            dyq, slot = torch.empty_like(dy, dtype=torch.uint8), _fp8.slot_ptr(idx, y.device)
     C.bn_act_bwd(dz.data_ptr(), _ptr(z), y.data_ptr(), dy.data_ptr(), _ptr(dres), save[0].data_ptr(),
                  save[1].data_ptr(), gamma.data_ptr(), _ptr(beta), scratch[0].data_ptr(), scratch[1].data_ptr(),
                  _ptr(gamma_grad), _ptr(beta_grad), M, Ch, int(relu), int(mask_from_x), sm_count(y.device.index or 0),
-                 _stream(), _ptr(zmask) if (relu and not mask_from_x) else 0, pre_reduced is not None)
+                 _stream(), _ptr(zmask) if (relu and not mask_from_x) else 0, pre_reduced is not None, _ptr(dyq),
+                 slot or 0)
+    if twin:
+        if dyq is not None:
+            _fp8.attach_twin(dy, dyq, idx)
+        else:
+            _fp8.attach_by_quantize(dy, key, e5m2=True)
     return dy, dres, scratch
 
 

@@ -137,6 +137,34 @@ def g_fp8():
         ref = torch.nn.grad.conv2d_input(xs, w.float(), dy.float(), s, p)
         report("  vs unquantised fp32", dx, ref, 1.5e-1)
         fp8.end_of_step()
+    # ---- producer-side twins: BN-apply forward (e4m3) and BN backward (e5m2) emit the fp8 copy in their own pass
+    ch, n, hw = 256, 16, 14
+    yb = cl(bf(torch.randn(n, ch, hw, hw, device=dev) * 2 + 0.3))
+    gamma, beta = torch.rand(ch, device=dev) + 0.5, torch.randn(ch, device=dev) * 0.1
+    rm, rv = torch.zeros(ch, device=dev), torch.ones(ch, device=dev)
+    for attempt in ("calibrating call", "fused call"):
+        fp8._WANTED.update({("act", gamma.data_ptr(), n, hw, hw), ("grad", gamma.data_ptr(), n, hw, hw)})
+        z, save = nv.bn_act_fwd(yb, None, gamma, beta, rm, rv, 1e-5, 0.1, True, None, True)
+        tw = fp8.twin_of(z)
+        assert tw is not None, "bn_act_fwd produced no fp8 twin"
+        zq, idx = tw
+        torch.cuda.synchronize()
+        sc = float(fp8._table(dev)[idx, 1])
+        # the fused kernel rounds the fp32 value once to e4m3 (the calibrating call rounds the bf16 tensor): compare the
+        # de-quantised twin with z at e4m3 resolution (3 mantissa bits: relative step 2^-3, half of it after rounding)
+        deq = zq.view(torch.float8_e4m3fn).float() / sc
+        report_abs(f"BN-apply e4m3 twin ({attempt}), scale {sc:g}", deq, z.float(), 0.0725, 2e-3 / sc * 64)
+        dz = cl(bf(torch.randn_like(z.float()) * 1e-3))
+        dy, _, _ = nv.bn_act_bwd(dz, z, yb, save, gamma, True, False, torch.zeros(ch, device=dev), torch.zeros(ch, device=dev),
+                                 beta=beta, had_residual=False)
+        tw = fp8.twin_of(dy)
+        assert tw is not None, "bn_act_bwd produced no fp8 twin"
+        dq, idx = tw
+        torch.cuda.synchronize()
+        sc = float(fp8._table(dev)[idx, 1])
+        deq = dq.view(torch.float8_e5m2).float() / sc
+        report(f"BN-backward e5m2 twin ({attempt}) vs bf16 dy, scale {sc:g}", deq, dy.float(), 0.14)
+        fp8.end_of_step()
     fp8.enable(False)
 
 
