@@ -3,28 +3,23 @@ mkdir -p gpurun_out/r2f
 O=gpurun_out/r2f
 TR8="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
 TR4="python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1"
-timeout 400 $TR8 --master-port 29801 tools/comm_test.py --no-sweep --model-check > $O/comm_N8.log 2>&1
-SWEEP_MAX=$((1<<28)) timeout 500 $TR4 --master-port 29802 tools/comm_test.py > $O/comm_N4.log 2>&1
+timeout 200 $TR8 --master-port 29801 tools/comm_test.py --no-sweep --model-check > $O/comm_N8.log 2>&1
+SWEEP_MAX=$((1<<26)) timeout 240 $TR4 --master-port 29802 tools/comm_test.py > $O/comm_N4.log 2>&1
 cp gpurun_out/comm_sweep_N4.json $O/ 2>/dev/null
-timeout 300 $TR8 --master-port 29803 tools/comm_timeline.py > $O/timeline_N8.log 2>&1
-timeout 400 $TR8 --master-port 29804 bench.py --gpus 8 --steps 20 --warmup 5 > $O/bench_N8.json 2> $O/bench_N8.err
-timeout 400 $TR4 --master-port 29805 bench.py --gpus 4 --steps 20 --warmup 5 --no-e2e > $O/bench_N4.json 2> $O/bench_N4.err
-timeout 400 $TR8 --master-port 29806 bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e --no-selfcheck --fp16-allreduce > $O/bench_N8_bf16wire.json 2> $O/bench_N8_bf16wire.err
-timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e > $O/bench_N1.json 2> $O/bench_N1.err
-timeout 400 $TR8 --master-port 29807 bench.py --impl reference --gpus 8 --steps 20 --warmup 5 > $O/ref_N8.json 2> $O/ref_N8.err
+timeout 120 $TR8 --master-port 29803 tools/comm_timeline.py --steps 4 > $O/timeline_N8.log 2>&1
+timeout 240 $TR8 --master-port 29804 bench.py --gpus 8 --steps 20 --warmup 5 > $O/bench_N8.json 2> $O/bench_N8.err
+timeout 200 $TR8 --master-port 29806 bench.py --gpus 8 --steps 20 --warmup 5 --no-e2e --no-selfcheck --fp16-allreduce > $O/bench_N8_bf16wire.json 2> $O/bench_N8_bf16wire.err
 for wire in "" "--fp16-allreduce"; do
-timeout 400 $TR8 --master-port 29808 -m distributeddeeplearning_b200.workloads.benchmark --model vgg16 --batch-size 128 --num-iters 3 --cuda-graph $wire > $O/vgg16_N8_${wire:-fp32}.log 2>&1
+timeout 200 $TR8 --master-port 29808 -m distributeddeeplearning_b200.workloads.benchmark --model vgg16 --batch-size 128 --num-iters 2 --num-warmup-batches 5 --cuda-graph $wire > $O/vgg16_N8_${wire:-fp32}.log 2>&1
 done
-timeout 400 $TR4 --master-port 29809 -m distributeddeeplearning_b200.workloads.benchmark --model vgg16 --batch-size 128 --num-iters 3 --cuda-graph > $O/vgg16_N4_fp32.log 2>&1
-timeout 400 $TR8 --master-port 29810 bench.py --impl reference --model vgg16 --batch-size 128 --gpus 8 --steps 10 --warmup 3 > $O/ref_vgg16_N8.json 2> $O/ref_vgg16_N8.err
-timeout 400 $TR8 --master-port 29811 -m distributeddeeplearning_b200.workloads.benchmark --model resnet152 --batch-size 128 --num-iters 3 --cuda-graph > $O/resnet152_N8.log 2>&1
-timeout 300 python -m distributeddeeplearning_b200.workloads.benchmark --model resnet152 --batch-size 128 --num-iters 3 --cuda-graph > $O/resnet152_N1.log 2>&1
-FAKE_DATA_LENGTH=163840 timeout 500 python -m invoke pytorch-imagenet.submit.remote.synthetic --node-count 8 --epochs 1 --batch-size 256 --precision fp8 > $O/imagenet_fp8_N8.log 2>&1
-FAKE_DATA_LENGTH=163840 timeout 500 python -m invoke pytorch-imagenet.submit.remote.synthetic --node-count 8 --epochs 1 --batch-size 256 > $O/imagenet_bf16_N8.log 2>&1
+timeout 200 $TR4 --master-port 29809 -m distributeddeeplearning_b200.workloads.benchmark --model vgg16 --batch-size 128 --num-iters 2 --num-warmup-batches 5 --cuda-graph > $O/vgg16_N4_fp32.log 2>&1
+timeout 240 $TR8 --master-port 29810 bench.py --impl reference --model vgg16 --batch-size 128 --gpus 8 --steps 10 --warmup 3 > $O/ref_vgg16_N8.json 2> $O/ref_vgg16_N8.err
+timeout 240 $TR8 --master-port 29811 -m distributeddeeplearning_b200.workloads.benchmark --model resnet152 --batch-size 128 --num-iters 2 --num-warmup-batches 5 --cuda-graph > $O/resnet152_N8.log 2>&1
+FAKE_DATA_LENGTH=122880 timeout 300 python -m invoke pytorch-imagenet.submit.remote.synthetic --node-count 8 --epochs 1 --batch-size 256 --precision fp8 > $O/imagenet_fp8_N8.log 2>&1
 echo "== comm8"; grep -E "ok\]|FAIL|EQUIV|ENGINE" $O/comm_N8.log | head -20
-echo "== comm4"; grep -E "KiB fp32|ENGINE" $O/comm_N4.log | tail -16
+echo "== comm4"; grep -E "KiB fp32|ENGINE" $O/comm_N4.log | tail -14
 echo "== timeline8"; tail -14 $O/timeline_N8.log
-echo "== bench"; for f in bench_N1 bench_N4 bench_N8 bench_N8_bf16wire ref_N8 ref_vgg16_N8; do echo $f; python - "$O/$f.json" <<'PY'
+echo "== bench"; for f in bench_N8 bench_N8_bf16wire ref_vgg16_N8; do echo $f; python - "$O/$f.json" <<'PY'
 import json,sys
 try:
     d=json.loads([l for l in open(sys.argv[1]) if l.startswith("{")][-1])
