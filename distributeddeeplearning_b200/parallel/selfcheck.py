@@ -146,8 +146,9 @@ def step_equivalence(model_name: str = "resnet50", batch_size: int = 32, lr: flo
     Every rank runs forward + backward of the same model on its OWN batch with the bucket kernels held back, so the
     per-rank gradients sit complete in the arenas; they are gathered with a plain ``all_gather`` (NCCL — independent of
     the kernels under test), and after ``step()`` the fused engine's new weights must equal ``w - lr * mean_r(g_r)``:
-    ``engine_rel_error = ||dw_engine - dw_expected|| / ||dw_expected||`` (fp32 wire: rounding only, bound 1e-5; bf16
-    wire: 1e-2).  That pins the averaging semantics of ``hvd.DistributedOptimizer`` on real model gradients.
+    ``engine_rel_error = ||dw_engine - dw_expected|| / ||dw_expected||`` (fp32 wire: summation-order rounding only —
+    measured 6e-6 at 2 ranks, 1.3e-5 at 8 ranks where the per-rank gradients differ by 2.6x their mean; bound 1e-4; a
+    dropped or doubled contribution would show as ~1/N.  bf16 wire: 1e-2).  That pins the averaging semantics of ``hvd.DistributedOptimizer`` on real model gradients.
 
     ``noise_floor``: comparing an N-rank step with a separately executed 1-rank step says little, because two
     executions of the SAME step do not agree: fp32 atomics make reduction orders run-dependent and bf16 rounding
@@ -208,7 +209,7 @@ def step_equivalence(model_name: str = "resnet50", batch_size: int = 32, lr: flo
     rank_spread = float(torch.stack([(x - g_mean).norm() for x in gs]).mean() / g_mean.norm().clamp_min(1e-30))
     out = {"engine_rel_error": err, "world": world, "loss": loss, "grads_cleared": bool(cleared),
            "replicas_identical": bool(same), "per_rank_grad_spread": rank_spread,
-           "bound": 1e-2 if wire is not Compression.none else 1e-5}
+           "bound": 1e-2 if wire is not Compression.none else 1e-4}
     out["ok"] = bool(err < out["bound"] and cleared and same)
     del m, opt, gs
     # ---- how reproducible is a step at all?  two single-rank executions of the identical step -----------------------
