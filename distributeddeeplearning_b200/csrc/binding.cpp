@@ -210,10 +210,11 @@ PYBIND11_MODULE(_C, m) {
            int cchunks, int relu, int n_valid, ptr_t w, int w_rows, int w_cols, int n_total, ptr_t a_matrix, int a_cols,
            int batch, int tw, int th, int tn, int zfill, ptr_t stream, int pad_w, int kstride, ptr_t add_mask,
            ptr_t bnr_y, ptr_t bnr_gamma, ptr_t bnr_beta, ptr_t bnr_mean, ptr_t bnr_invstd, int variant, int fp8,
-           ptr_t deq_a, ptr_t deq_b) {
+           ptr_t deq_a, ptr_t deq_b, ptr_t sfa, ptr_t sfb) {
           ConvArgs a;
           a.variant = variant;
           a.fp8 = fp8; a.deq_a = P<const float>(deq_a); a.deq_b = P<const float>(deq_b);
+          a.sfa = P<const uint8_t>(sfa); a.sfb = P<const uint8_t>(sfb);
           a.bnr_y = P<const __nv_bfloat16>(bnr_y); a.bnr_gamma = P<const float>(bnr_gamma);
           a.bnr_beta = P<const float>(bnr_beta); a.bnr_mean = P<const float>(bnr_mean);
           a.bnr_invstd = P<const float>(bnr_invstd);
@@ -237,7 +238,7 @@ PYBIND11_MODULE(_C, m) {
         py::arg("zfill"), py::arg("stream"), py::arg("pad_w") = -1, py::arg("kstride") = 0, py::arg("add_mask") = 0,
         py::arg("bnr_y") = 0, py::arg("bnr_gamma") = 0, py::arg("bnr_beta") = 0, py::arg("bnr_mean") = 0,
         py::arg("bnr_invstd") = 0, py::arg("variant") = 0, py::arg("fp8") = 0, py::arg("deq_a") = 0,
-        py::arg("deq_b") = 0);
+        py::arg("deq_b") = 0, py::arg("sfa") = 0, py::arg("sfb") = 0);
   m.def("conv_wgrad",
         [](int mode, ptr_t x, ptr_t dy, ptr_t dw, int M, int Cout, int dy_ld, int ldw, int ncols, int H, int W, int C, int Pq,
            int Q, int R, int Sx, int stride, int pad, int dil, int cchunks, int splits, int batch, int tw, int th, int tn,
@@ -387,6 +388,10 @@ PYBIND11_MODULE(_C, m) {
     check(ddl::launch_fp8_quantize(P<const __nv_bfloat16>(x), P<uint8_t>(out), n, P<ddl::Fp8Slot>(slot), e5m2, sms,
                                    S(stream)), "fp8_quantize");
   });
+  m.def("fp8_quantize_mx", [](ptr_t x, ptr_t out, ptr_t sf, int64_t rows, int64_t K, int sms, ptr_t stream) {
+    check(ddl::launch_fp8_quantize_mx(P<const __nv_bfloat16>(x), P<uint8_t>(out), P<uint8_t>(sf), rows, K, sms, S(stream)),
+          "fp8_quantize_mx");
+  }, "bf16 [rows][K] -> e4m3 [rows][K] + UE8M0 block scales (32 elements) in the tensor core's 512-byte atom order");
   m.def("fp8_amax", [](ptr_t x, int64_t n, ptr_t slot, int sms, ptr_t stream) {
     check(ddl::launch_fp8_amax(P<const __nv_bfloat16>(x), n, P<ddl::Fp8Slot>(slot), sms, S(stream)), "fp8_amax");
   });

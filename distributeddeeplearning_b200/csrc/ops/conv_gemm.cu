@@ -850,7 +850,8 @@ template <int BLOCK_N, bool PAIR>
 struct DeepCfg {
   static constexpr int kBLoadRows = PAIR ? BLOCK_N / 2 : BLOCK_N;   // weight rows (K-major) / columns (MN-major) per CTA
   static constexpr int kBTileBytes = kBLoadRows * 128;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kSfBytes = 1024;                              // MX scale atoms of a stage: SFA 512 B + SFB 512 B
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes + kSfBytes;
   static constexpr int kChunk = 64;                                  // accumulator columns drained per epilogue pass
   static constexpr int kChunkPitch = kChunk * 2 + 16;
   static constexpr int kChunkBytes = kBlockM * kChunkPitch;          // 18,432
@@ -902,9 +903,12 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
     tma_prefetch_desc(&tmBh);
     tma_prefetch_desc(&tmAs.m[0]);
   }
+  // single-CTA 128-wide tiles may run MX block-scaled operands: 8 more TMEM columns for the scale factors (the CTA owns
+  // the SM, so rounding the allocation up to the next power of two costs nothing)
+  constexpr int kTmemCols = (!PAIR && BLOCK_N == 128) ? 512 : 2 * BLOCK_N;
   if (warp == 5) {
-    if (PAIR) tmem_alloc_pair<2 * BLOCK_N>(tmem_slot);
-    else tmem_alloc<2 * BLOCK_N>(tmem_slot);
+    if (PAIR) tmem_alloc_pair<kTmemCols>(tmem_slot);
+    else tmem_alloc<kTmemCols>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
@@ -944,7 +948,7 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
     const uint32_t stg_u32 = smem_u32(stg);
     const uint32_t red_u32 = smem_u32(red);
     const bool bias_relu = !STATS && (a.bias != nullptr || a.relu);
-    const float deq = a.fp8 ? (*a.deq_a) * (*a.deq_b) : 1.0f;      // fp8 operands: undo both quantisation scales
+    const float deq = (a.fp8 == 1 || a.fp8 == 2) ? (*a.deq_a) * (*a.deq_b) : 1.0f;   // per-tensor fp8: undo both scales
     int it = 0;
     uint32_t chunk_ctr = 0;             // staging buffer = chunk_ctr & 1 (identical sequence in every epilogue thread)
     for (int t = item0; t < total; t += item_step, ++it) {
@@ -1020,8 +1024,14 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
           uint8_t* sA = smem + stage * Cfg::kStageBytes;
           const uint32_t sB = smem_u32(sA + kATileBytes);
           const uint32_t pair_bar = PAIR ? mapa_shared(smem_u32(&full[stage]), 0) : 0u;
-          if (!PAIR) mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + a_bytes);
+          const bool mx = !PAIR && a.fp8 == 3;
+          if (!PAIR) mbar_arrive_expect_tx(&full[stage], Cfg::kBTileBytes + a_bytes + (mx ? 1024u : 0u));
           else if (crank == 0) mbar_arrive_expect_tx(&full[stage], 2u * (Cfg::kBTileBytes + a_bytes));
+          if (mx) {      // this k-block's scale atoms (GEMM mode: tile = row block m0/128, weight block n0/128)
+            const uint32_t sSF = sB + Cfg::kBTileBytes;
+            bulk_load(sSF, a.sfa + (static_cast<size_t>(m0 / kBlockM) * KB + kb) * 512, 512, &full[stage]);
+            bulk_load(sSF + 512, a.sfb + (static_cast<size_t>(n0 / 128) * KB + kb) * 512, 512, &full[stage]);
+          }
           int widx = tap, dh = 0, dw = 0, mapi = 0;
           if (kTile) {
             if (a.ntaps > 0) {
@@ -1067,6 +1077,7 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
     // ====================================== MMA issuer ========================================
     constexpr int kMmaM = PAIR ? 2 * kBlockM : kBlockM;
     const bool f8 = a.fp8 != 0;
+    const bool mxk = !PAIR && BLOCK_N == 128 && !kBMn && a.fp8 == 3;      // MX block-scaled operands (K-major GEMM only)
     const uint32_t idesc = f8 ? idesc_f8(kMmaM, BLOCK_N, a.fp8 == 2 ? 1 : 0, 0, 0, kBMn ? 1 : 0)
                               : idesc_bf16(kMmaM, BLOCK_N, 0, kBMn ? 1 : 0);
     // MN-major B: K rows of 128 bytes; one MMA consumes 16 (bf16) / 32 (fp8) K rows, chunks of 64 / 128 columns
@@ -1093,12 +1104,21 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
           tc_fence_after();
           if (elect_one()) {
             const uint32_t so = static_cast<uint32_t>(stage) * kStageStep;
+            if (mxk) {
+              // scale atoms of this k-block: shared memory -> TMEM (4 columns each), in order with the MMAs that use them
+              const uint32_t sSF = sB0 + Cfg::kBTileBytes + static_cast<uint32_t>(stage) * Cfg::kStageBytes;
+              tmem_cp_32x128b_warpx4(tmem_base + 2 * BLOCK_N, smem_desc_nosw(sSF, 0, 128));
+              tmem_cp_32x128b_warpx4(tmem_base + 2 * BLOCK_N + 4, smem_desc_nosw(sSF + 512, 0, 128));
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {                      // 4 x 32 bytes of K per 128-byte row
               const uint64_t da = desc_join(a_lo + so + 2u * k, a_hi);
               const uint64_t db = desc_join(b_lo + so + bStep * k, b_hi);
               const bool acc = (kb | k) != 0;
-              if (f8) {
+              if (mxk) {
+                umma_mxf8(d_tmem, da, db, idesc_mxf8(kBlockM, BLOCK_N, 0, 0, k, k), acc, tmem_base + 2 * BLOCK_N,
+                          tmem_base + 2 * BLOCK_N + 4);
+              } else if (f8) {
                 if (PAIR) umma_f8_pair(d_tmem, da, db, idesc, acc);
                 else umma_f8(d_tmem, da, db, idesc, acc);
               } else {
@@ -1126,8 +1146,8 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
   if (PAIR) cluster_sync_all();         // no CTA leaves while its peer may still signal its barriers / read its smem
   if (warp == 5) {
     tc_fence_after();
-    if (PAIR) tmem_dealloc_pair<2 * BLOCK_N>(tmem_base);
-    else tmem_dealloc<2 * BLOCK_N>(tmem_base);
+    if (PAIR) tmem_dealloc_pair<kTmemCols>(tmem_base);
+    else tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -1804,7 +1824,13 @@ cudaError_t launch_conv_gemm(int mode, const ConvArgs& a_in, const void* w, int 
     // fp8 operands run on the deep-ring kernel only (GEMM / stride-1-or-2 tile modes), with 128-element k-blocks
     if (!(mode == kConvGemm || mode == kConvTileFwd || mode == kConvTileDgrad || mode == kConvGemmDgrad))
       return cudaErrorInvalidValue;
-    if (a.deq_a == nullptr || a.deq_b == nullptr) return cudaErrorInvalidValue;
+    if (a.fp8 == 3) {
+      // MX block-scaled operands: K-major GEMM, one 128-wide single-CTA tile per row block (scale atoms are per 128 rows)
+      if (mode != kConvGemm || n_total % 128 != 0 || a.sfa == nullptr || a.sfb == nullptr) return cudaErrorInvalidValue;
+      a.variant = kVarDeep | (2 << 4);
+    } else if (a.deq_a == nullptr || a.deq_b == nullptr) {
+      return cudaErrorInvalidValue;
+    }
     if (mode_b_mn(mode) && n_total % 128 != 0) return cudaErrorInvalidValue;    // MN-major boxes are 128 columns wide
     if ((a.variant & 0xf) == 0) a.variant = kVarDeep;
     if ((a.variant & 0xf) != kVarDeep) return cudaErrorInvalidValue;

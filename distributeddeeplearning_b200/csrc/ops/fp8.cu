@@ -92,7 +92,60 @@ __global__ void update_scales_kernel(Fp8Slot* slots, int n) {
   if (i < n) slot_update(slots[i]);
 }
 
+// MX quantisation: thread = 8 consecutive K elements; the 4 threads of a 32-element block agree on the block's amax
+// with two shuffles.  scale = 2^e with e = ceil(log2(amax / 448)) (so amax / scale <= 448), stored as UE8M0 (e + 127).
+__global__ void __launch_bounds__(256) quantize_mx_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ out,
+                                                          uint8_t* __restrict__ sf, int64_t rows, int64_t K) {
+  const int64_t vec_per_row = K / 8;
+  const int64_t total = rows * vec_per_row;
+  const int64_t kb128 = K / 128;
+  // the bound is a multiple of the warp size (as are the start and the stride): a warp is in the loop as a whole, which
+  // the full-mask shuffles below require
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < ((total + 31) / 32) * 32;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const bool live = i < total;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (live) v = ld_stream_u4(reinterpret_cast<const uint4*>(x) + i);
+    const float2 a = unpack_bf16x2(v.x), b = unpack_bf16x2(v.y), c = unpack_bf16x2(v.z), d = unpack_bf16x2(v.w);
+    float amax = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(b.x), fabsf(b.y))),
+                       fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(d.x), fabsf(d.y))));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 1));
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 2));
+    int e = 0;
+    if (amax > 0.f) {
+      int ex;
+      const float m = frexpf(amax / kE4m3Max, &ex);          // amax/448 = m * 2^ex, m in [0.5, 1)
+      e = (m == 0.5f) ? ex - 1 : ex;                          // smallest e with amax / 2^e <= 448
+      e = max(-127, min(127, e));
+    }
+    const float inv = ldexpf(1.0f, -e);
+    if (live) {
+      uint2 o;
+      o.x = fp8_cvt4<false>(a.x * inv, a.y * inv, b.x * inv, b.y * inv);
+      o.y = fp8_cvt4<false>(c.x * inv, c.y * inv, d.x * inv, d.y * inv);
+      reinterpret_cast<uint2*>(out)[i] = o;
+      if ((i & 3) == 0) {                                     // first thread of the 32-element block writes its scale
+        const int64_t row = i / vec_per_row;
+        const int64_t k32 = (i - row * vec_per_row) / 4;      // 32-element block index along K
+        const int64_t r = row & 127;
+        sf[((row >> 7) * kb128 + (k32 >> 2)) * 512 + (r & 31) * 16 + (r >> 5) * 4 + (k32 & 3)] =
+            static_cast<uint8_t>(e + 127);
+      }
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_fp8_quantize_mx(const __nv_bfloat16* x, uint8_t* out, uint8_t* sf, int64_t rows, int64_t K, int sms,
+                                   cudaStream_t stream) {
+  if (K % 128 != 0 || rows <= 0) return cudaErrorInvalidValue;
+  const int64_t total = rows * (K / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 8LL * sms) blocks = 8LL * sms;
+  quantize_mx_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, out, sf, rows, K);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_fp8_quantize(const __nv_bfloat16* x, uint8_t* out, int64_t n, Fp8Slot* slot, bool e5m2, int sms,
                                 cudaStream_t stream) {

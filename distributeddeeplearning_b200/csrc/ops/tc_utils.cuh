@@ -277,6 +277,41 @@ DDL_DEVICE void umma_f8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, 
       "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// ---- MX block-scaled fp8 (kind::mxf8f6f4.block_scale, scale vector = 32 elements, UE8M0 scales in TMEM) ------------
+// instruction descriptor of the block-scaled kinds: no C format field; scale format bit 23 (1 = E8M0); a_sf_id / b_sf_id
+// select WHICH of the 4 bytes of a scale column this MMA's K sub-block uses.
+__host__ __device__ constexpr uint32_t idesc_mxf8(int m, int n, int a_fmt, int b_fmt, int a_sf_id, int b_sf_id) {
+  return (static_cast<uint32_t>(b_sf_id) << 4) | (static_cast<uint32_t>(a_fmt) << 7) | (static_cast<uint32_t>(b_fmt) << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (1u << 23) | (static_cast<uint32_t>(m >> 4) << 24) |
+         (static_cast<uint32_t>(a_sf_id) << 29);
+}
+DDL_DEVICE void umma_mxf8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate,
+                          uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  const uint32_t acc = accumulate ? 1u : 0u;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+      :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(tmem_sfa), "r"(tmem_sfb) : "memory");
+}
+// shared memory -> TMEM copy of one 512-byte scale atom: 32 rows x 16 bytes, broadcast to the four 32-lane quarters
+DDL_DEVICE void tmem_cp_32x128b_warpx4(uint32_t dst_tmem, uint64_t src_desc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" :: "r"(dst_tmem), "l"(src_desc) : "memory");
+}
+// un-swizzled (interleave) K-major descriptor of a dense [rows][16 B] block: 8-row core matrices 128 bytes apart
+DDL_DEVICE uint64_t smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= 1ull << 46;
+  return d;
+}
+// plain (non-tensor) bulk copy global -> shared, completing on an mbarrier
+DDL_DEVICE void bulk_load(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // Arrive on `bar` when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 DDL_DEVICE void umma_commit(uint64_t* bar) {

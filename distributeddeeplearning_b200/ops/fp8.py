@@ -21,7 +21,7 @@ import torch
 
 from .. import _ext
 
-_STATE = {"enabled": os.environ.get("DDL_PRECISION", "bf16").lower() == "fp8", "table": None, "n": 0, "slots": {},
+_STATE = {"mx_launches": 0, "enabled": os.environ.get("DDL_PRECISION", "bf16").lower() == "fp8", "table": None, "n": 0, "slots": {},
           "calibrated": set(), "step": 0, "wcache": {}, "stats": {"fwd": 0, "dgrad": 0}}
 _MAX_SLOTS = 4096
 
@@ -140,6 +140,34 @@ def twin_of(t: torch.Tensor):
     if e is None or e[0]() is not t:
         return None
     return e[1], e[2]
+
+
+# ---- MX (OCP microscaling) block-scaled operands: one UE8M0 scale per 32 K elements of every row -----------------------
+MX = os.environ.get("DDL_FP8_MX", "0") == "1"      # 1x1 convolutions / GEMMs use kind::mxf8f6f4.block_scale
+
+
+def quantize_mx(x2d_bf16: torch.Tensor, rows: int, K: int):
+    """bf16 row-major [rows][K] (K % 128 == 0) -> (e4m3 codes uint8 [rows][K], scale atoms uint8): the scales are laid out
+    in the 512-byte atoms tcgen05 copies into TMEM (row block of 128 x K block of 128)."""
+    from . import native
+
+    C = _ext.load()
+    dev = x2d_bf16.device
+    out = torch.empty(rows * K, dtype=torch.uint8, device=dev)
+    sf = torch.zeros(((rows + 127) // 128) * (K // 128) * 512, dtype=torch.uint8, device=dev)
+    C.fp8_quantize_mx(x2d_bf16.data_ptr(), out.data_ptr(), sf.data_ptr(), rows, K, native.sm_count(dev.index or 0),
+                      torch.cuda.current_stream(dev).cuda_stream)
+    return out, sf
+
+
+def quantize_weight_mx(w_bf16: torch.Tensor):
+    key = ("wmx", w_bf16.data_ptr(), tuple(w_bf16.shape))
+    hit = _STATE["wcache"].get(key)
+    if hit is not None and hit[0] == _STATE["step"]:
+        return hit[1], hit[2]
+    q, sf = quantize_mx(w_bf16, w_bf16.shape[0], w_bf16.shape[1])
+    _STATE["wcache"][key] = (_STATE["step"], q, sf)
+    return q, sf
 
 
 def quantize_weight(w_bf16: torch.Tensor) -> Tuple[torch.Tensor, int]:

@@ -391,6 +391,19 @@ def conv_fwd(x: torch.Tensor, w_bf16: torch.Tensor, kernel: Tuple[int, int], str
 
     one_by_one = R == 1 and S == 1 and stride == 1 and ph == 0 and pw == 0
     tile_ok = USE_TILE_TMA and (stride == 1 or (stride == 2 and R * S <= 16 and USE_TILE_S2))
+    if _fp8.enabled() and _fp8.MX and one_by_one and Cin % 128 == 0 and Cout % 128 == 0 and M >= 2048 and bias is None \
+            and Cin >= _fp8.MIN_K:
+        # MX block-scaled e4m3 operands (kind::mxf8f6f4.block_scale): one UE8M0 scale per 32 channels of every pixel and
+        # of every filter, applied by the tensor core itself — no per-tensor scale, nothing to undo in the epilogue
+        xq, sfa = _fp8.quantize_mx(x, M, Cin)
+        wq, sfb = _fp8.quantize_weight_mx(w_bf16)
+        cch8 = Cin // 128
+        _fp8.count("fwd")
+        _fp8._STATE["mx_launches"] += 1
+        C.conv_gemm(C.CONV_GEMM, 0, y.data_ptr(), 0, 0, s_ptr, ss_ptr, M, cch8, Cout, H, W, Cin, P, Q, 1, 1, 1, 0, 1, cch8,
+                    int(relu), Cout, wq.data_ptr(), wr, wc, n_total, xq.data_ptr(), Cin, N, 0, 0, 0, 0, _stream(), 0, Cin,
+                    fp8=3, sfa=sfa.data_ptr(), sfb=sfb.data_ptr())
+        return (y, st) if stats else y
     if _fp8.fwd_eligible(Cin, Cout, R * S) and (one_by_one or tile_ok) and M >= 2048:
         # e4m3 operands: quantise x (delayed per-tensor scale) and take this step's e4m3 weights; a k-block is 128
         # channels (128 bytes), the epilogue multiplies by inv_scale(x) * inv_scale(w)
