@@ -27,8 +27,9 @@ def arm(precision, steps, batch, model, graph):
     from distributeddeeplearning_b200.workloads.benchmark import BenchmarkSession
 
     dist.init()
-    if precision == "fp8":
+    if precision in ("fp8", "mxfp8"):
         fp8.enable(True)
+        fp8.MX = precision == "mxfp8"
     s = BenchmarkSession(model, batch, True, lr=0.01, momentum=0.9, seed=3)
     # 64 distinct batches (2,048 images, seen ~3 times in 200 steps): the loss falls steadily without collapsing to
     # ~0, where relative differences stop meaning anything
@@ -42,7 +43,7 @@ def arm(precision, steps, batch, model, graph):
         losses.append(l.detach().clone())
     torch.cuda.synchronize()
     out = {"precision": precision, "losses": [float(v) for v in losses], "fp8_launches": fp8.launches(),
-           "graph": bool(graph)}
+           "mx_launches": fp8._STATE["mx_launches"], "graph": bool(graph)}
     print("ARM " + json.dumps(out), flush=True)
 
 
@@ -54,12 +55,13 @@ def main():
     ap.add_argument("--tol", type=float, default=0.08, help="allowed relative gap between the curves")
     ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--arm", default=None)
+    ap.add_argument("--fp8-mode", default="fp8", choices=["fp8", "mxfp8"], help="which 8-bit mode to compare with bf16")
     a = ap.parse_args()
     if a.arm:
         return arm(a.arm, a.steps, a.batch, a.model, a.graph)
     res = {}
     for p in ("bf16", "fp8"):
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--arm", p, "--steps", str(a.steps), "--batch",
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--arm", a.fp8_mode if p == "fp8" else p, "--steps", str(a.steps), "--batch",
                             str(a.batch), "--model", a.model, "--graph", str(a.graph)], capture_output=True, text=True,
                            timeout=1500)
         line = [l for l in r.stdout.splitlines() if l.startswith("ARM ")]
@@ -83,7 +85,7 @@ def main():
     for i in list(range(0, n, max(1, n // 10))) + [n - 1]:
         print(f"| {i} | {b[i]:.4f} | {f[i]:.4f} |")
     print(f"\nmax relative gap of the {win}-step running means = {gap:.4f}; last-{win}-step means: bf16 {tail_b:.4f}, fp8 {tail_f:.4f}; "
-          f"fp8 launches per run: {res['fp8']['fp8_launches']}; learned={learned}")
+          f"fp8 launches per run: {res['fp8']['fp8_launches']} (MX block-scaled: {res['fp8'].get('mx_launches', 0)}); learned={learned}")
     print("FP8 PARITY:", "ok" if ok else "FAIL")
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump({"ok": ok, "gap": gap, "tail_bf16": tail_b, "tail_fp8": tail_f, "arms": res},
