@@ -67,10 +67,23 @@ DDL_DEVICE bool bn_thread_map(int C, int& c0, int& row0, int& row_stride) {
 
 // FP8: also emit the e4m3 twin of z (z * slot scale) and fold max|z| into the slot — the quantisation pass of the fp8
 // training mode rides in this kernel's streaming pass (+1 byte written per element) instead of re-reading z.
+// BLOCK_WIDE: every thread of the block reaches this point (flat thread mapping): fold through shared memory and issue ONE
+// atomic per block — ~9.5k same-address atomics per launch (one per warp) were measured to cost ~10 us per BN kernel.
+template <bool BLOCK_WIDE>
 DDL_DEVICE void fp8_fold_amax(Fp8Slot* slot, float amax) {
   amax = warp_max(amax);
-  if ((threadIdx.x & 31) == 0 && amax > 0.f)
-    atomicMax(reinterpret_cast<unsigned int*>(&slot->amax), __float_as_uint(amax));    // one per warp, fire-and-forget
+  if (BLOCK_WIDE) {
+    __shared__ float s_amax[kBnThreads / 32];
+    if ((threadIdx.x & 31) == 0) s_amax[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < kBnThreads / 32 ? s_amax[threadIdx.x] : 0.f;
+      v = warp_max(v);
+      if (threadIdx.x == 0 && v > 0.f) atomicMax(reinterpret_cast<unsigned int*>(&slot->amax), __float_as_uint(v));
+    }
+  } else if ((threadIdx.x & 31) == 0 && amax > 0.f) {
+    atomicMax(reinterpret_cast<unsigned int*>(&slot->amax), __float_as_uint(amax));    // chunked mapping: idle threads left early
+  }
 }
 
 template <bool TRAIN, bool CHUNKED, bool FP8>
@@ -161,7 +174,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
     if (a.residual) r0 = ld_stream_u4(a.residual + off0);
     finish(x0, r0, off0);
   }
-  if (FP8) fp8_fold_amax(a.zq_slot, amax);
+  if (FP8) fp8_fold_amax<!CHUNKED>(a.zq_slot, amax);
 }
 
 // ---- backward pass 1: per-channel reductions ----------------------------------------------------
@@ -322,7 +335,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdAr
                      fp8_cvt4<true>(x[4] * qscale, x[5] * qscale, x[6] * qscale, x[7] * qscale));
     }
   }
-  if (FP8) fp8_fold_amax(a.dxq_slot, amax);
+  if (FP8) fp8_fold_amax<!CHUNKED>(a.dxq_slot, amax);
 }
 
 // ---------------------------------------------------------------------------------------------
