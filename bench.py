@@ -253,6 +253,12 @@ def run_ours(a):
 
         checksum = selfcheck.replica_checksum(session.optimizer)      # after ALL steps: replicas still bit-identical?
 
+    from distributeddeeplearning_b200.ops import fp8 as _fp8
+
+    dtype = "bf16"
+    if _fp8.enabled():          # DDL_PRECISION=fp8 experiment runs (the headline stays bf16)
+        dtype = "fp8 operands (e4m3/e5m2%s) for forward/dgrad convs with K >= %d, bf16 elsewhere" % (
+            ", MX block scales on 1x1 forward" if _fp8.MX else "", _fp8.MIN_K)
     if rank == 0:
         base = None
         try:
@@ -263,7 +269,7 @@ def run_ours(a):
             pass
         out = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": (value / base) if base else None, "dtype": "bf16", "data": "synthetic",
+               "vs_baseline": (value / base) if base else None, "dtype": dtype, "data": "synthetic",
                "impl": "ours", "final_loss": loss,
                "config": {"model": a.model, "global_batch": world * B, "per_gpu_batch": B, "image": "224x224x3",
                           "seq_len": None, "parallelism": f"dp{world}", "optimizer": "sgd lr=0.01 (fused allreduce+update)",
