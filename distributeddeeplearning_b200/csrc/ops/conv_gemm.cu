@@ -103,11 +103,18 @@ DDL_DEVICE uint32_t lds32(uint32_t addr) {
 }
 DDL_DEVICE float lds_f32(uint32_t addr) { return __uint_as_float(lds32(addr)); }
 
+// Attribution experiments (tools/epi_probe.py): bits 12-14 of the variant word switch epilogue phases OFF.  The results
+// are then wrong by construction; production launches never set them (native.py builds variant words from bits 0-8).
+constexpr int kDbgNoStats = 1 << 12;   // no statistics pass (and no atomics)
+constexpr int kDbgNoStore = 1 << 13;   // no global stores
+constexpr int kDbgNoDrain = 1 << 14;   // no TMEM -> staging copy
+
 // TMEM accumulator columns [c_begin, c_end) of this thread's row -> (bias, ReLU) -> bf16 -> staging row.
 // `stg_row`: shared address of the row's staging line; `zero_row`: the row lies outside the image (tile modes).
 template <bool BIAS_RELU>
 DDL_DEVICE void epi_tmem_to_stage(uint32_t taddr_row, uint32_t stg_row, int c_begin, int c_end, const ConvArgs& a,
                                   int n0, bool zero_row, float deq = 1.0f) {
+  if (a.variant & kDbgNoDrain) return;
 #pragma unroll 1
   for (int c0 = c_begin; c0 < c_end; c0 += 32) {
     uint32_t v[32];
@@ -133,128 +140,200 @@ DDL_DEVICE void epi_tmem_to_stage(uint32_t taddr_row, uint32_t stg_row, int c_be
   }
 }
 
-// BN statistics of the staged bf16 tile (+ one atomic per valid channel and statistic), then the coalesced
-// 16-byte global stores (optional `+= add`, optional zero-fill of the three stride-2 siblings).
-// Must be entered by all kEpiThreads epilogue threads after the staging writes were made visible (named barrier 1).
-template <int BLOCK_N, bool STATS, bool TILE>
-DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, const ConvArgs& a, int n0, int m0) {
+// ---- packed fp32 pairs (FADD2 / FFMA2: one issue slot for two lanes of statistics math) -----------------------------
+DDL_DEVICE uint64_t f2_pack(float lo, float hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+  return d;
+}
+DDL_DEVICE void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+DDL_DEVICE uint64_t f2_from_bf16x2(uint32_t u) {            // {bf16 lo, bf16 hi} -> {fp32, fp32}: two ALU ops
+  uint64_t d;
+  const uint32_t lo = u << 16, hi = u & 0xffff0000u;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+DDL_DEVICE uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+DDL_DEVICE uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// Per-thread partial BN statistics of 8 consecutive output channels (4 packed pairs each): they live in registers
+// ACROSS the tiles a persistent CTA walks (as long as the tiles share their first channel n0) and are flushed — warp
+// shuffles, one shared-memory fold, one atomic per channel and statistic — only when n0 changes or the CTA is done.
+struct StatAcc {
+  uint64_t s[4], q[4];
+  int n0;                       // first channel of the tile column these sums belong to; -1 = empty
+  DDL_DEVICE void clear() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { s[i] = 0ull; q[i] = 0ull; }
+    n0 = -1;
+  }
+};
+
+// Fold the staged bf16 tile (row pitch BLOCK_N*2+16) into `acc`.  Thread = (column group of 8, row slice); invalid rows
+// hold zeros.  Entered by all kEpiThreads epilogue threads after the staging writes were made visible (named barrier 1).
+template <int BLOCK_N, bool TILE>
+DDL_DEVICE void epi_stats_accum(uint32_t stg, int etid, const ConvArgs& a, int n0, int m0, StatAcc& acc) {
   constexpr int kPitch = BLOCK_N * 2 + 16;
-  if (STATS) {
-    // thread = (column group of 8, row slice): 16-byte shared loads, fp32 accumulation (invalid rows hold zeros)
-    constexpr int kColGroups = BLOCK_N / 8;                 // 16 (N=128) or 8 (N=64)
-    constexpr int kSlices = kEpiThreads / kColGroups;       // row slices
-    constexpr int kRowsPer = kBlockM / kSlices;             // rows per thread
-    const int cg = etid % kColGroups;
-    const int sl = etid / kColGroups;
-    float s[8], ss[8];
+  constexpr int kColGroups = BLOCK_N / 8;                 // 16 (N=128) or 8 (N=64)
+  constexpr int kSlices = kEpiThreads / kColGroups;       // row slices
+  constexpr int kRowsPer = kBlockM / kSlices;             // rows per thread
+  if (a.variant & kDbgNoStats) return;
+  const int cg = etid % kColGroups;
+  const int sl = etid / kColGroups;
+  const uint32_t p0 = stg + (sl * kRowsPer) * kPitch + cg * 16;
+  acc.n0 = n0;
+  if (a.bnr_y == nullptr) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { s[i] = 0.f; ss[i] = 0.f; }
-    const uint32_t p0 = stg + (sl * kRowsPer) * kPitch + cg * 16;
-    if (a.bnr_y == nullptr) {
+    for (int r = 0; r < kRowsPer; ++r) {
+      const uint4 u = lds128(p0 + r * kPitch);
+      uint64_t f;
+      f = f2_from_bf16x2(u.x); acc.s[0] = f2_add(acc.s[0], f); acc.q[0] = f2_fma(f, f, acc.q[0]);
+      f = f2_from_bf16x2(u.y); acc.s[1] = f2_add(acc.s[1], f); acc.q[1] = f2_fma(f, f, acc.q[1]);
+      f = f2_from_bf16x2(u.z); acc.s[2] = f2_add(acc.s[2], f); acc.q[2] = f2_fma(f, f, acc.q[2]);
+      f = f2_from_bf16x2(u.w); acc.s[3] = f2_add(acc.s[3], f); acc.q[3] = f2_fma(f, f, acc.q[3]);
+    }
+    return;
+  }
+  // fused BN-backward reduction (see ConvArgs::bnr_y): S1 = sum dm, S2 = sum dm * y with the ReLU mask of the BN
+  // recomputed from y.  The y tile is read with the same coalesced 16-byte accesses the stores use.
+  const int c0 = n0 + cg * 8;
+  if (c0 >= a.n_valid) return;
+  uint64_t sc[4], sh[4];
 #pragma unroll
-      for (int r = 0; r < kRowsPer; ++r) {
-        const uint4 u = lds128(p0 + r * kPitch);
-        float2 f;
-        f = unpack_bf16x2(u.x); s[0] += f.x; ss[0] = fmaf(f.x, f.x, ss[0]); s[1] += f.y; ss[1] = fmaf(f.y, f.y, ss[1]);
-        f = unpack_bf16x2(u.y); s[2] += f.x; ss[2] = fmaf(f.x, f.x, ss[2]); s[3] += f.y; ss[3] = fmaf(f.y, f.y, ss[3]);
-        f = unpack_bf16x2(u.z); s[4] += f.x; ss[4] = fmaf(f.x, f.x, ss[4]); s[5] += f.y; ss[5] = fmaf(f.y, f.y, ss[5]);
-        f = unpack_bf16x2(u.w); s[6] += f.x; ss[6] = fmaf(f.x, f.x, ss[6]); s[7] += f.y; ss[7] = fmaf(f.y, f.y, ss[7]);
-      }
-    } else {
-      // fused BN-backward reduction (see ConvArgs::bnr_y): S1 = sum dm, S2 = sum dm * y with the ReLU mask of the BN
-      // recomputed from y.  The y tile is read with the same coalesced 16-byte accesses the stores below use.
-      const int c0 = n0 + cg * 8;
-      const bool cols_ok = c0 < a.n_valid;
-      float sc[8], sh[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { sc[i] = 0.f; sh[i] = 0.f; }
-      if (cols_ok) {
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const float4 g4 = reinterpret_cast<const float4*>(a.bnr_gamma + c0)[q];
-          const float4 b4 = reinterpret_cast<const float4*>(a.bnr_beta + c0)[q];
-          const float4 m4 = reinterpret_cast<const float4*>(a.bnr_mean + c0)[q];
-          const float4 i4 = reinterpret_cast<const float4*>(a.bnr_invstd + c0)[q];
-          sc[4 * q + 0] = g4.x * i4.x; sh[4 * q + 0] = b4.x - m4.x * sc[4 * q + 0];
-          sc[4 * q + 1] = g4.y * i4.y; sh[4 * q + 1] = b4.y - m4.y * sc[4 * q + 1];
-          sc[4 * q + 2] = g4.z * i4.z; sh[4 * q + 2] = b4.z - m4.z * sc[4 * q + 2];
-          sc[4 * q + 3] = g4.w * i4.w; sh[4 * q + 3] = b4.w - m4.w * sc[4 * q + 3];
-        }
-      }
+  for (int qd = 0; qd < 2; ++qd) {
+    const float4 g4 = reinterpret_cast<const float4*>(a.bnr_gamma + c0)[qd];
+    const float4 b4 = reinterpret_cast<const float4*>(a.bnr_beta + c0)[qd];
+    const float4 m4 = reinterpret_cast<const float4*>(a.bnr_mean + c0)[qd];
+    const float4 i4 = reinterpret_cast<const float4*>(a.bnr_invstd + c0)[qd];
+    const float s0 = g4.x * i4.x, s1 = g4.y * i4.y, s2 = g4.z * i4.z, s3 = g4.w * i4.w;
+    sc[2 * qd] = f2_pack(s0, s1); sh[2 * qd] = f2_pack(b4.x - m4.x * s0, b4.y - m4.y * s1);
+    sc[2 * qd + 1] = f2_pack(s2, s3); sh[2 * qd + 1] = f2_pack(b4.z - m4.z * s2, b4.w - m4.w * s3);
+  }
 #pragma unroll 2
-      for (int r = 0; r < kRowsPer; ++r) {
-        const int row = sl * kRowsPer + r;
-        int m;
-        if (TILE) m = static_cast<int>(lds32(stg + row * kPitch + BLOCK_N * 2));
-        else m = (m0 + row) < a.M ? (m0 + row) : -1;
-        if (m < 0 || !cols_ok) continue;
-        const uint4 u = lds128(p0 + r * kPitch);
-        const uint4 yv = *reinterpret_cast<const uint4*>(a.bnr_y + static_cast<size_t>(m) * a.ldc + c0);
-        float2 d, y;
-        d = unpack_bf16x2(u.x); y = unpack_bf16x2(yv.x);
-        d.x = fmaf(y.x, sc[0], sh[0]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[1], sh[1]) > 0.f ? d.y : 0.f;
-        s[0] += d.x; ss[0] = fmaf(d.x, y.x, ss[0]); s[1] += d.y; ss[1] = fmaf(d.y, y.y, ss[1]);
-        d = unpack_bf16x2(u.y); y = unpack_bf16x2(yv.y);
-        d.x = fmaf(y.x, sc[2], sh[2]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[3], sh[3]) > 0.f ? d.y : 0.f;
-        s[2] += d.x; ss[2] = fmaf(d.x, y.x, ss[2]); s[3] += d.y; ss[3] = fmaf(d.y, y.y, ss[3]);
-        d = unpack_bf16x2(u.z); y = unpack_bf16x2(yv.z);
-        d.x = fmaf(y.x, sc[4], sh[4]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[5], sh[5]) > 0.f ? d.y : 0.f;
-        s[4] += d.x; ss[4] = fmaf(d.x, y.x, ss[4]); s[5] += d.y; ss[5] = fmaf(d.y, y.y, ss[5]);
-        d = unpack_bf16x2(u.w); y = unpack_bf16x2(yv.w);
-        d.x = fmaf(y.x, sc[6], sh[6]) > 0.f ? d.x : 0.f; d.y = fmaf(y.y, sc[7], sh[7]) > 0.f ? d.y : 0.f;
-        s[6] += d.x; ss[6] = fmaf(d.x, y.x, ss[6]); s[7] += d.y; ss[7] = fmaf(d.y, y.y, ss[7]);
-      }
+  for (int r = 0; r < kRowsPer; ++r) {
+    const int row = sl * kRowsPer + r;
+    int m;
+    if (TILE) m = static_cast<int>(lds32(stg + row * kPitch + BLOCK_N * 2));
+    else m = (m0 + row) < a.M ? (m0 + row) : -1;
+    if (m < 0) continue;
+    const uint4 u = lds128(p0 + r * kPitch);
+    const uint4 yv = *reinterpret_cast<const uint4*>(a.bnr_y + static_cast<size_t>(m) * a.ldc + c0);
+    const uint32_t du[4] = {u.x, u.y, u.z, u.w}, yu[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t y2 = f2_from_bf16x2(yu[j]);
+      float z0, z1, d0, d1;
+      f2_unpack(f2_fma(y2, sc[j], sh[j]), z0, z1);
+      f2_unpack(f2_from_bf16x2(du[j]), d0, d1);
+      const uint64_t dm = f2_pack(z0 > 0.f ? d0 : 0.f, z1 > 0.f ? d1 : 0.f);
+      acc.s[j] = f2_add(acc.s[j], dm);
+      acc.q[j] = f2_fma(dm, y2, acc.q[j]);
     }
-    // threads with the same column group inside a warp: lanes cg, cg+kColGroups, ... -> xor shuffles
+  }
+}
+
+// Publish `acc` (sums of tile column acc.n0) and clear it.  Contains one named barrier: must be reached by all
+// kEpiThreads epilogue threads together; `red` = [epi warps][2][BLOCK_N] floats of scratch.  A later flush may rewrite
+// the scratch only after another barrier of the same group (every caller has one per tile / chunk in between).
+template <int BLOCK_N>
+DDL_DEVICE void epi_stats_flush(uint32_t red, int etid, int ew, const ConvArgs& a, StatAcc& acc) {
+  constexpr int kColGroups = BLOCK_N / 8;
+  if (a.variant & kDbgNoStats) { acc.clear(); return; }
+  const int cg = etid % kColGroups;
+  const int n0 = acc.n0;
+  // threads with the same column group inside a warp: lanes cg, cg+kColGroups, ... -> xor shuffles
 #pragma unroll
-    for (int off = kColGroups; off < 32; off <<= 1) {
+  for (int off = kColGroups; off < 32; off <<= 1) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += __shfl_xor_sync(0xffffffffu, s[i], off);
-        ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], off);
-      }
+    for (int i = 0; i < 4; ++i) {
+      acc.s[i] = f2_add(acc.s[i], __shfl_xor_sync(0xffffffffu, acc.s[i], off));
+      acc.q[i] = f2_add(acc.q[i], __shfl_xor_sync(0xffffffffu, acc.q[i], off));
     }
-    // cross-warp fold in shared memory ([epi warp][2][BLOCK_N] floats), then ONE atomic per channel and statistic
-    if ((threadIdx.x & 31) < kColGroups) {
-      const uint32_t rb = red + ((ew * 2) * BLOCK_N + cg * 8) * 4;
-      sts128(rb, __float_as_uint(s[0]), __float_as_uint(s[1]), __float_as_uint(s[2]), __float_as_uint(s[3]));
-      sts128(rb + 16, __float_as_uint(s[4]), __float_as_uint(s[5]), __float_as_uint(s[6]), __float_as_uint(s[7]));
-      sts128(rb + BLOCK_N * 4, __float_as_uint(ss[0]), __float_as_uint(ss[1]), __float_as_uint(ss[2]), __float_as_uint(ss[3]));
-      sts128(rb + BLOCK_N * 4 + 16, __float_as_uint(ss[4]), __float_as_uint(ss[5]), __float_as_uint(ss[6]), __float_as_uint(ss[7]));
+  }
+  // cross-warp fold in shared memory ([epi warp][2][BLOCK_N] floats), then ONE atomic per channel and statistic
+  if ((threadIdx.x & 31) < kColGroups) {
+    const uint32_t rb = red + ((ew * 2) * BLOCK_N + cg * 8) * 4;
+    sts128(rb, static_cast<uint32_t>(acc.s[0]), static_cast<uint32_t>(acc.s[0] >> 32), static_cast<uint32_t>(acc.s[1]),
+           static_cast<uint32_t>(acc.s[1] >> 32));
+    sts128(rb + 16, static_cast<uint32_t>(acc.s[2]), static_cast<uint32_t>(acc.s[2] >> 32),
+           static_cast<uint32_t>(acc.s[3]), static_cast<uint32_t>(acc.s[3] >> 32));
+    sts128(rb + BLOCK_N * 4, static_cast<uint32_t>(acc.q[0]), static_cast<uint32_t>(acc.q[0] >> 32),
+           static_cast<uint32_t>(acc.q[1]), static_cast<uint32_t>(acc.q[1] >> 32));
+    sts128(rb + BLOCK_N * 4 + 16, static_cast<uint32_t>(acc.q[2]), static_cast<uint32_t>(acc.q[2] >> 32),
+           static_cast<uint32_t>(acc.q[3]), static_cast<uint32_t>(acc.q[3] >> 32));
+  }
+  acc.clear();
+  named_bar_sync(1, kEpiThreads);
+  if (a.bnr_y == nullptr) {
+    for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
+      const int which = c / BLOCK_N, col = c - which * BLOCK_N;
+      float v = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += lds_f32(red + ((wq * 2 + which) * BLOCK_N + col) * 4);
+      if (n0 + col < a.n_valid) atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
     }
-    named_bar_sync(1, kEpiThreads);
-    if (a.bnr_y == nullptr) {
-      for (int c = etid; c < 2 * BLOCK_N; c += kEpiThreads) {
-        const int which = c / BLOCK_N, col = c - which * BLOCK_N;
-        float v = 0.f;
+  } else {
+    for (int col = etid; col < BLOCK_N; col += kEpiThreads) {      // dbeta += S1, dgamma += invstd * (S2 - mean * S1)
+      float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-        for (int wq = 0; wq < 4 * kEpiGroups; ++wq) v += lds_f32(red + ((wq * 2 + which) * BLOCK_N + col) * 4);
-        if (n0 + col < a.n_valid) atomicAdd((which ? a.sumsq : a.sum) + n0 + col, v);
+      for (int wq = 0; wq < 4 * kEpiGroups; ++wq) {
+        t1 += lds_f32(red + ((wq * 2 + 0) * BLOCK_N + col) * 4);
+        t2 += lds_f32(red + ((wq * 2 + 1) * BLOCK_N + col) * 4);
       }
-    } else {
-      for (int col = etid; col < BLOCK_N; col += kEpiThreads) {      // dbeta += S1, dgamma += invstd * (S2 - mean * S1)
-        float t1 = 0.f, t2 = 0.f;
-#pragma unroll
-        for (int wq = 0; wq < 4 * kEpiGroups; ++wq) {
-          t1 += lds_f32(red + ((wq * 2 + 0) * BLOCK_N + col) * 4);
-          t2 += lds_f32(red + ((wq * 2 + 1) * BLOCK_N + col) * 4);
-        }
-        const int ch = n0 + col;
-        if (ch < a.n_valid) {
-          atomicAdd(a.sum + ch, t1);
-          atomicAdd(a.sumsq + ch, a.bnr_invstd[ch] * (t2 - a.bnr_mean[ch] * t1));
-        }
+      const int ch = n0 + col;
+      if (ch < a.n_valid) {
+        atomicAdd(a.sum + ch, t1);
+        atomicAdd(a.sumsq + ch, a.bnr_invstd[ch] * (t2 - a.bnr_mean[ch] * t1));
       }
     }
   }
-  // coalesced stores: thread = (16-byte column chunk, row phase); a tile row is BLOCK_N*2 contiguous bytes
+}
+
+// The coalesced 16-byte global stores of the staged tile (optional `+= add`, optional zero-fill of the three stride-2
+// siblings): thread = (16-byte column chunk, row phase); a tile row is BLOCK_N*2 contiguous bytes.
+template <int BLOCK_N, bool TILE>
+DDL_DEVICE void epi_store(uint32_t stg, int etid, const ConvArgs& a, int n0, int m0) {
+  constexpr int kPitch = BLOCK_N * 2 + 16;
   constexpr int kVecPerRow = BLOCK_N / 8;
   constexpr int kRowStep = kEpiThreads / kVecPerRow;
+  constexpr int kIters = kBlockM / kRowStep;
   const int ch = etid % kVecPerRow;
   const int r0 = etid / kVecPerRow;
   if (n0 + ch * 8 >= a.ldc) return;                       // channel padding of the last N tile (ldc = row width)
+  if (a.variant & kDbgNoStore) return;
   uint32_t sp = stg + r0 * kPitch + ch * 16;
   const size_t coff = static_cast<size_t>(n0 + ch * 8);
+  if (a.add == nullptr && !(TILE && a.zfill)) {
+    // plain stores (every forward launch): nothing but the shared load, the row's address and the store
+    if (!TILE) {
+      const int rows = a.M - m0;                            // valid rows of this tile (>= kBlockM except in the last one)
+      uint4* gp = reinterpret_cast<uint4*>(a.out + static_cast<size_t>(m0 + r0) * a.ldc + coff);
+      const size_t gstep = static_cast<size_t>(kRowStep) * a.ldc / 8;      // ldc % 8 == 0 (16-byte rows)
+      if (rows >= kBlockM) {
+#pragma unroll
+        for (int i = 0; i < kIters; ++i) gp[i * gstep] = lds128(sp + i * kRowStep * kPitch);
+      } else {
+#pragma unroll 1
+        for (int r = r0; r < rows; r += kRowStep, sp += kRowStep * kPitch, gp += gstep) *gp = lds128(sp);
+      }
+    } else {
+      __nv_bfloat16* gcol = a.out + coff;
+#pragma unroll
+      for (int i = 0; i < kIters; ++i) {
+        const int m = static_cast<int>(lds32(sp + i * kRowStep * kPitch - ch * 16 + BLOCK_N * 2));
+        if (m >= 0) *reinterpret_cast<uint4*>(gcol + static_cast<size_t>(m) * a.ldc) = lds128(sp + i * kRowStep * kPitch);
+      }
+    }
+    return;
+  }
 #pragma unroll 4
   for (int r = r0; r < kBlockM; r += kRowStep, sp += kRowStep * kPitch) {
     int m;
@@ -286,6 +365,19 @@ DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, co
       *reinterpret_cast<uint4*>(a.out + off + static_cast<size_t>(a.outW + 1) * a.ldc) = z;
     }
   }
+}
+
+// One-shot form (one tile per call: accumulate, publish, store) for the kernels that do not carry sums across tiles.
+template <int BLOCK_N, bool STATS, bool TILE>
+DDL_DEVICE void epi_stats_store(uint32_t stg, uint32_t red, int etid, int ew, const ConvArgs& a, int n0, int m0) {
+  if (STATS) {
+    StatAcc acc;
+    acc.clear();
+    epi_stats_accum<BLOCK_N, TILE>(stg, etid, a, n0, m0, acc);
+    acc.n0 = n0;
+    epi_stats_flush<BLOCK_N>(red, etid, ew, a, acc);
+  }
+  epi_store<BLOCK_N, TILE>(stg, etid, a, n0, m0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -659,6 +751,10 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
     const uint32_t stg_u32 = smem_u32(stg);
     const uint32_t red_u32 = smem_u32(red);
     int it = 0;
+    // BN statistics ride in registers across tiles: t advances by gridDim.x, so whenever the grid is a multiple of the
+    // number of N tiles (2 x 148 CTAs: 1, 2, 4 or 8 tiles) a CTA stays in ONE tile column and publishes its sums once
+    StatAcc acc;
+    acc.clear();
     for (int t = item0; t < total; t += item_step, ++it) {
       int n0, m0, tq0, tp0, tn0;
       const bool valid = tile_origin(t, n0, m0, tq0, tp0, tn0);
@@ -704,9 +800,14 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
         if (PAIR && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[buf]), 0));   // the leader issues the MMAs
         else mbar_arrive(&acc_empty[buf]);
       }
-      epi_stats_store<BLOCK_N, STATS, kTile>(stg_u32, red_u32, etid, ew, a, n0, m0);
-      named_bar_sync(1, kEpiThreads);      // staging (and the stats scratch) may be overwritten by the next tile
+      if (STATS) {
+        if (acc.n0 >= 0 && acc.n0 != n0) epi_stats_flush<BLOCK_N>(red_u32, etid, ew, a, acc);   // CTA-uniform branch
+        epi_stats_accum<BLOCK_N, kTile>(stg_u32, etid, a, n0, m0, acc);
+      }
+      epi_store<BLOCK_N, kTile>(stg_u32, etid, a, n0, m0);
+      named_bar_sync(1, kEpiThreads);      // staging may be overwritten by the next tile
     }
+    if (STATS && acc.n0 >= 0) epi_stats_flush<BLOCK_N>(red_u32, etid, ew, a, acc);
   } else if (warp == 4) {
     // ===================================== TMA producer =======================================
     if (elect_one()) {
@@ -951,6 +1052,19 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
     const float deq = (a.fp8 == 1 || a.fp8 == 2) ? (*a.deq_a) * (*a.deq_b) : 1.0f;   // per-tensor fp8: undo both scales
     int it = 0;
     uint32_t chunk_ctr = 0;             // staging buffer = chunk_ctr & 1 (identical sequence in every epilogue thread)
+    constexpr int kChunks = BLOCK_N / Cfg::kChunk;
+    // BN statistics stay in registers across the tiles of one tile column (see the persistent kernel); one accumulator
+    // set per 64-column chunk, published together when the column changes and at the end
+    StatAcc acc[kChunks];
+#pragma unroll
+    for (int ch = 0; ch < kChunks; ++ch) acc[ch].clear();
+    auto flush_all = [&]() {
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
+        if (acc[ch].n0 >= 0) epi_stats_flush<Cfg::kChunk>(red_u32, etid, ew, a, acc[ch]);
+        named_bar_sync(1, kEpiThreads);          // the next flush rewrites the scratch the fold above reads
+      }
+    };
     for (int t = item0; t < total; t += item_step, ++it) {
       int n0, m0, tq0, tp0, tn0;
       const bool valid = tile_origin(t, n0, m0, tq0, tp0, tn0);
@@ -981,8 +1095,8 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
       }
       const bool zero_row = kTile && my_m < 0;
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(qw * 32) << 16) + buf * BLOCK_N;
-      constexpr int kChunks = BLOCK_N / Cfg::kChunk;
-#pragma unroll 1
+      if (STATS && acc[0].n0 >= 0 && acc[0].n0 != n0) flush_all();      // CTA-uniform branch
+#pragma unroll
       for (int ch = 0; ch < kChunks; ++ch, ++chunk_ctr) {
         const uint32_t sbuf = stg_u32 + (chunk_ctr & 1u) * Cfg::kChunkBytes;
         const uint32_t stg_row = sbuf + row * Cfg::kChunkPitch;
@@ -1003,9 +1117,11 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
         }
         // (no trailing barrier: the next chunk stages into the OTHER buffer, and nobody rewrites the stats scratch or
         //  this buffer before passing the next chunk's barrier, which everyone reaches only after leaving this call)
-        epi_stats_store<Cfg::kChunk, STATS, kTile>(sbuf, red_u32, etid, ew, a, n0 + ch * Cfg::kChunk, m0);
+        if (STATS) epi_stats_accum<Cfg::kChunk, kTile>(sbuf, etid, a, n0 + ch * Cfg::kChunk, m0, acc[ch]);
+        epi_store<Cfg::kChunk, kTile>(sbuf, etid, a, n0 + ch * Cfg::kChunk, m0);
       }
     }
+    if (STATS) flush_all();
   } else if (warp == 4) {
     // ===================================== TMA producer =======================================
     if (elect_one()) {

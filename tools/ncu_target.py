@@ -43,6 +43,16 @@ elif what == "convlong":
             nv.conv_dgrad(dy, wb, x.shape, (k, k), s, p)
         nv.force_variant(None)
         nv.conv_wgrad(x, dy, gw, (k, k), s, p)
+elif what == "convwide":
+    # store-bound short-K forward layers through the persistent and the one-tile kernel
+    for (ci, hw, co, k, s, p) in [(64, 56, 256, 1, 1, 0), (64, 56, 64, 3, 1, 1)]:
+        x = torch.randn(B, ci, hw, hw, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
+        w = torch.randn(co, ci, k, k, device=dev) * 0.05
+        wb = w.permute(0, 2, 3, 1).reshape(co, -1).contiguous().to(torch.bfloat16)
+        for v in (2, 1):
+            nv.force_variant(v)
+            nv.conv_fwd(x, wb, (k, k), s, p, stats=True, cout=co)
+        nv.force_variant(None)
 elif what == "bn":
     c, hw = 256, 56
     y = torch.randn(B, c, hw, hw, device=dev, dtype=torch.bfloat16).contiguous(memory_format=cl)
