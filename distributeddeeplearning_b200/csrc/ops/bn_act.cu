@@ -16,6 +16,7 @@
 // 4 CTAs x 256 threads stay resident per SM (these kernels are pure HBM streams).
 #include "../common.cuh"
 #include "ops.h"
+#include "../launch.h"
 
 namespace ddl {
 
@@ -88,6 +89,8 @@ DDL_DEVICE void fp8_fold_amax(Fp8Slot* slot, float amax) {
 
 template <bool TRAIN, bool CHUNKED, bool FP8>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) {
+  pdl_trigger();
+  pdl_wait();      // nothing to prepare here: the gain is the launch latency and the block ramp-up
   int c0, row0, row_stride;
   if (!bn_thread_map<CHUNKED>(a.C, c0, row0, row_stride)) return;
   const float qscale = FP8 ? a.zq_slot->scale : 1.f;
@@ -185,6 +188,8 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
 // ~100 us floor that was measured to dominate the small layers.)
 template <int MASK>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdArgs a) {
+  pdl_trigger();
+  pdl_wait();      // nothing to prepare here: the gain is the launch latency and the block ramp-up
   const int cgl = threadIdx.x & 7;                 // channel group within the 64-channel chunk
   const int rl = threadIdx.x >> 3;                 // row lane 0..31
   const int c0 = blockIdx.y * 64 + cgl * 8;
@@ -276,6 +281,8 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
 // dx = k1*dy + x*B + A   with k1 = gamma*invstd, B = -k1*invstd*dgamma/M, A = -k1*dbeta/M - mean*B
 template <int MASK, bool CHUNKED, bool FP8>
 __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_apply_kernel(BnBwdArgs a) {
+  pdl_trigger();
+  pdl_wait();      // nothing to prepare here: the gain is the launch latency and the block ramp-up
   int c0, row0, row_stride;
   if (!bn_thread_map<CHUNKED>(a.C, c0, row0, row_stride)) return;
   const float qscale = FP8 ? a.dxq_slot->scale : 1.f;
@@ -579,53 +586,56 @@ inline bool bn_flat_ok(int C) {
   return (kBnThreads % groups == 0) || (groups % kBnThreads == 0);
 }
 
+void pdl_early_bn(int early) { cudaMemcpyToSymbol(c_pdl_early, &early, sizeof(int)); }
+
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream) {
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
   const bool f8 = a.zq != nullptr && a.zq_slot != nullptr && train;
+  cudaError_t e = cudaSuccess;
   if (bn_flat_ok(a.C)) {
     const int grid = bn_grid(a.M, a.C, sms);
-    if (f8) bn_act_fwd_kernel<true, false, true><<<grid, kBnThreads, 0, stream>>>(a);
-    else if (train) bn_act_fwd_kernel<true, false, false><<<grid, kBnThreads, 0, stream>>>(a);
-    else bn_act_fwd_kernel<false, false, false><<<grid, kBnThreads, 0, stream>>>(a);
+    if (f8) e = launch_pdl(bn_act_fwd_kernel<true, false, true>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a);
+    else if (train) e = launch_pdl(bn_act_fwd_kernel<true, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a);
+    else e = launch_pdl(bn_act_fwd_kernel<false, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a);
   } else {
     const dim3 grid = bn_chunk_grid(a.M, a.C, sms);
-    if (f8) bn_act_fwd_kernel<true, true, true><<<grid, kBnThreads, 0, stream>>>(a);
-    else if (train) bn_act_fwd_kernel<true, true, false><<<grid, kBnThreads, 0, stream>>>(a);
-    else bn_act_fwd_kernel<false, true, false><<<grid, kBnThreads, 0, stream>>>(a);
+    if (f8) e = launch_pdl(bn_act_fwd_kernel<true, true, true>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a);
+    else if (train) e = launch_pdl(bn_act_fwd_kernel<true, true, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a);
+    else e = launch_pdl(bn_act_fwd_kernel<false, true, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a);
   }
-  return cudaGetLastError();
+  return e;
 }
 
 cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream, bool skip_reduce) {
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
   const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : (a.zmask ? kMaskBits : kMaskZ));
   const dim3 rgrid = bn_chunk_grid(a.M, a.C, sms);
+  cudaError_t e = cudaSuccess;
   if (!skip_reduce) switch (mask) {
-    case kMaskNone: bn_act_bwd_reduce_kernel<kMaskNone><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-    case kMaskZ: bn_act_bwd_reduce_kernel<kMaskZ><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-    case kMaskBits: bn_act_bwd_reduce_kernel<kMaskBits><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-    default: bn_act_bwd_reduce_kernel<kMaskX><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+    case kMaskNone: e = launch_pdl(bn_act_bwd_reduce_kernel<kMaskNone>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
+    case kMaskZ: e = launch_pdl(bn_act_bwd_reduce_kernel<kMaskZ>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
+    case kMaskBits: e = launch_pdl(bn_act_bwd_reduce_kernel<kMaskBits>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
+    default: e = launch_pdl(bn_act_bwd_reduce_kernel<kMaskX>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
   }
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   const bool f8 = a.dxq != nullptr && a.dxq_slot != nullptr;
   if (bn_flat_ok(a.C)) {
     const int grid = bn_grid(a.M, a.C, sms);
     switch (mask) {
-      case kMaskNone: if (f8) bn_act_bwd_apply_kernel<kMaskNone, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskNone, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskZ: if (f8) bn_act_bwd_apply_kernel<kMaskZ, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskZ, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskBits: if (f8) bn_act_bwd_apply_kernel<kMaskBits, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskBits, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
-      default: if (f8) bn_act_bwd_apply_kernel<kMaskX, false, true><<<grid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskX, false, false><<<grid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskNone: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskNone, false, true>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskNone, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); break;
+      case kMaskZ: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskZ, false, true>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskZ, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); break;
+      case kMaskBits: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskBits, false, true>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskBits, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); break;
+      default: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskX, false, true>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskX, false, false>, dim3(grid), dim3(kBnThreads), 0, stream, 1, a); break;
     }
   } else {
     switch (mask) {
-      case kMaskNone: if (f8) bn_act_bwd_apply_kernel<kMaskNone, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskNone, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskZ: if (f8) bn_act_bwd_apply_kernel<kMaskZ, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskZ, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-      case kMaskBits: if (f8) bn_act_bwd_apply_kernel<kMaskBits, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskBits, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
-      default: if (f8) bn_act_bwd_apply_kernel<kMaskX, true, true><<<rgrid, kBnThreads, 0, stream>>>(a); else bn_act_bwd_apply_kernel<kMaskX, true, false><<<rgrid, kBnThreads, 0, stream>>>(a); break;
+      case kMaskNone: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskNone, true, true>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskNone, true, false>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
+      case kMaskZ: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskZ, true, true>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskZ, true, false>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
+      case kMaskBits: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskBits, true, true>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskBits, true, false>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
+      default: if (f8) e = launch_pdl(bn_act_bwd_apply_kernel<kMaskX, true, true>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); else e = launch_pdl(bn_act_bwd_apply_kernel<kMaskX, true, false>, dim3(rgrid), dim3(kBnThreads), 0, stream, 1, a); break;
     }
   }
-  return cudaGetLastError();
+  return e;
 }
 
 

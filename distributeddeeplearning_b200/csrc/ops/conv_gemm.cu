@@ -21,10 +21,14 @@
 // and one CTA's epilogue overlaps the others' loads).
 #include "conv_gemm.cuh"
 #include "tc_utils.cuh"
+#include "../launch.h"
 
 #include <dlfcn.h>
 
 namespace ddl {
+
+int g_pdl = 0;        // launch.h: opted-in kernels are launched with programmatic stream serialization
+
 using namespace tc;
 
 namespace {
@@ -433,6 +437,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();      // the next kernel in the stream may start its own preamble
+  pdl_wait();         // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp < 4 || warp >= 6) {
     const int egrp = warp < 4 ? 0 : 1;                 // epilogue group
@@ -715,6 +721,8 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
   if (CLUSTER) cluster_sync_all();      // the peer's mbarriers exist before any multicast can signal them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();         // preamble done; from here on the kernel reads and writes global memory
 
   // returns false for the padding tile of an odd M-tile count (its CTA still runs loads and MMAs in lock-step with
   // the peer, on the clamped last tile, but writes nothing)
@@ -1016,6 +1024,8 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
   if (PAIR) cluster_sync_all();         // the peer's mbarriers exist before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();         // preamble done; from here on the kernel reads and writes global memory
 
   auto tile_origin = [&](int t, int& n0, int& m0, int& tq0, int& tp0, int& tn0) -> bool {
     const int nt = t % n_tiles;
@@ -1653,8 +1663,7 @@ cudaError_t launch_fwd_t(const CUtensorMap& tmB, const TmaSet& tmA, const ConvAr
     configured = Cfg::smem_bytes(Cfg::kMaxStagesN);
   }
   dim3 grid(n_total / BLOCK_N, m_tiles);
-  kern<<<grid, kThreads, smem, stream>>>(tmB, tmA, a);
-  return cudaGetLastError();
+  return launch_pdl(kern, grid, dim3(kThreads), smem, stream, 1, tmB, tmA, a);
 }
 
 int g_persistent = 1;        // TMA-fed modes use the persistent kernel (tuning hook: set_conv_persistent)
@@ -1684,23 +1693,12 @@ cudaError_t launch_persistent_t(const CUtensorMap& tmB, const CUtensorMap& tmBh,
   if (CLUSTER) {
     if (grid > 2 * items) grid = 2 * items;
     grid &= ~1LL;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, tmB, tmBh, tmA, a, n_tiles, m_tiles);
+    return launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kThreads), Cfg::kSmemBytes, stream, 2, tmB, tmBh, tmA, a,
+                      n_tiles, m_tiles);
   }
   if (grid > items) grid = items;
-  kern<<<static_cast<unsigned>(grid), kThreads, Cfg::kSmemBytes, stream>>>(tmB, tmBh, tmA, a, n_tiles, m_tiles);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kThreads), Cfg::kSmemBytes, stream, 1, tmB, tmBh, tmA, a,
+                    n_tiles, m_tiles);
 }
 
 template <int BLOCK_N, int MODE, bool STATS, bool PAIR>
@@ -1723,25 +1721,14 @@ cudaError_t launch_deep_t(const CUtensorMap& tmB, const CUtensorMap& tmBh, const
   const int n_tiles = n_total / BLOCK_N;
   const long long items = static_cast<long long>(n_tiles) * (PAIR ? (m_tiles + 1) / 2 : m_tiles);
   long long grid = g_num_sms;                      // one CTA per SM
-  cudaLaunchConfig_t cfg = {};
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
   if (PAIR) {
     if (grid > 2 * items) grid = 2 * items;
     grid &= ~1LL;
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
   } else if (grid > items) {
     grid = items;
   }
-  cfg.gridDim = dim3(static_cast<unsigned>(grid));
-  return cudaLaunchKernelEx(&cfg, kern, tmB, tmBh, tmA, a, n_tiles, m_tiles);
+  return launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(kThreads), Cfg::kSmemBytes, stream, PAIR ? 2 : 1, tmB, tmBh,
+                    tmA, a, n_tiles, m_tiles);
 }
 
 // Variant word (ConvArgs::variant; 0 = built-in policy).  The Python layer autotunes it per layer shape on first use
@@ -1924,6 +1911,13 @@ void set_wgrad_swap(int on) { g_wgrad_swap = on; }
 void set_conv_bn256(int on) { g_bn256 = on; }
 void set_conv_cluster(int on) { g_cluster = on; }
 void set_conv_deep(int on) { g_deep = on; }
+void pdl_early_bn(int early);       // bn_act.cu's copy of c_pdl_early
+void set_pdl(int on) {
+  g_pdl = on;
+  const int early = on >= 2 ? 1 : 0;
+  cudaMemcpyToSymbol(c_pdl_early, &early, sizeof(int));
+  pdl_early_bn(early);
+}
 
 // `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
 // `a_matrix`: the A operand for the TMA-A modes (2-D matrix [M][a_cols], or the NHWC tensor in tile modes).

@@ -230,3 +230,20 @@ def test_enabled_workloads_prunes_the_task_tree(tmp_path, monkeypatch):
     assert "pytorch-benchmark.submit.local.synthetic" not in names
     q = template.render_project(str(tmp_path / "proj2"), type="pytorch_template", _remove_unused_projects=True)
     assert os.path.isdir(os.path.join(q, "experiment"))
+
+
+def test_control_image_recipe_builds_the_native_module(tmp_path):
+    """`make build` stages the framework into the docker context and the recipe compiles `_C.so` inside the image
+    (no docker daemon in CI: the staging step and the recipe's wiring are what can be checked here)."""
+    from distributeddeeplearning_b200.control import stage
+
+    p = template.render_project(str(tmp_path / "proj"))
+    mk = open(os.path.join(p, "Makefile")).read()
+    assert "control.stage control/Docker/framework" in mk and "docker build" in mk
+    df = open(os.path.join(p, "control", "Docker", "dockerfile")).read()
+    assert "COPY framework /opt/b200-ddl" in df and "distributeddeeplearning_b200._ext --force" in df
+    for f in ("tmux.conf", "bash.completion", "jupyter_notebook_config.py"):
+        assert f in df and os.path.isfile(os.path.join(p, "control", "Docker", f))
+    out = stage.stage(os.path.join(p, "control", "Docker", "framework"))
+    assert os.path.isfile(os.path.join(out, "csrc", "binding.cpp")) and os.path.isfile(os.path.join(out, "_ext.py"))
+    assert not [f for _, _, fs in os.walk(out) for f in fs if f.endswith(".so")]
