@@ -201,7 +201,7 @@ PYBIND11_MODULE(_C, m) {
     check(ddl::conv_timeout_info(v), "conv_timeout_info");
     return std::vector<unsigned int>(v, v + 8);
   }, "post-mortem of the first timed-out mbarrier wait (flag, site, block, thread, parity); clears the record");
-  m.def("set_pdl", &ddl::set_pdl, "0 = plain stream order (default), 1 = conv / BN kernels allow programmatic dependent launch, 2 = and trigger dependents early");
+  m.def("set_pdl", &ddl::set_pdl, "0 = plain stream order, 1 = conv / BN kernels allow programmatic dependent launch (default), 2 = + trigger at the last tile, 3 = + trigger at block start");
   m.def("set_conv_deep", &ddl::set_conv_deep, "tuning hook: 0 = never the deep-ring kernel, 1 = policy, 2 = always");
   m.def("set_conv_bn256", &ddl::set_conv_bn256, "tuning hook: 0 = no 128x256 persistent tiles");
   m.def("set_wgrad_swap", &ddl::set_wgrad_swap, "tuning hook: 0 = no operand-role swap for narrow-output wgrad tiles");

@@ -19,13 +19,21 @@ constexpr int kWarp = 32;
 // memory — it returns once the predecessor grid has completed and its writes are visible (no-op without the launch
 // attribute).  pdl_trigger() lets the NEXT kernel in the stream start its own preamble early.
 // ---------------------------------------------------------------------------------------------
-// Early triggering is opt-in per translation unit (c_pdl_early, set by set_pdl(2)): measured on ResNet-50 it LOSES 1.5 %
-// of the step — dependents that become resident while the predecessor drains land unevenly on the SMs, and every
-// kernel here assigns its tiles / rows statically to a grid sized for an even spread.  Without the explicit trigger the
-// dependent launches as the predecessor's last blocks exit and only skips the completion flush.
-__constant__ int c_pdl_early;
+// Triggering is a mode per translation unit (c_pdl_trigger, set_pdl): measured on ResNet-50 (bench.py, 1 GPU, same box)
+//   set_pdl(0) plain stream order                                   18.59 / 18.65 ms per step
+//   set_pdl(1) attribute only: dependents launch as the last blocks exit and skip the completion flush
+//                                                                    18.43 / 18.46 ms  (default)
+//   set_pdl(3) every block triggers at its start                    +0.3 ms: dependents that become resident while the
+//              predecessor drains land unevenly on the SMs, and every kernel here assigns its tiles / rows statically
+//              to a grid sized for an even spread
+//   set_pdl(2) the persistent conv kernels trigger when they start their LAST tile; everything else as (1):
+//              +0.10 / +0.21 ms against (1) on a second box (18.93 / 18.89 vs 19.03 / 19.10 ms) — also a loss
+__constant__ int c_pdl_trigger;       // 0 = never explicitly, 1 = at the last tile (conv), 2 = at block start
 DDL_DEVICE void pdl_trigger() {
-  if (c_pdl_early) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (c_pdl_trigger == 2) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+DDL_DEVICE void pdl_trigger_last_tile() {
+  if (c_pdl_trigger == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 DDL_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

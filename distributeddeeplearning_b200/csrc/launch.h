@@ -7,8 +7,8 @@
 
 namespace ddl {
 
-extern int g_pdl;        // set_pdl / DDL_PDL: 0 = plain stream order (default), 1 = opted-in kernels are launched with
-                         // programmaticStreamSerializationAllowed, 2 = and trigger their dependents early
+extern int g_pdl;        // set_pdl / DDL_PDL: 0 = plain stream order, 1 (default) = opted-in kernels are launched with
+                         // programmaticStreamSerializationAllowed, 2 / 3 = plus explicit triggers (common.cuh)
 
 // `cluster` > 1 launches thread-block clusters of that many CTAs along x.  Only kernels that execute pdl_wait() before
 // their first global-memory access may be launched through this helper.

@@ -586,7 +586,7 @@ inline bool bn_flat_ok(int C) {
   return (kBnThreads % groups == 0) || (groups % kBnThreads == 0);
 }
 
-void pdl_early_bn(int early) { cudaMemcpyToSymbol(c_pdl_early, &early, sizeof(int)); }
+void pdl_early_bn(int trig) { cudaMemcpyToSymbol(c_pdl_trigger, &trig, sizeof(int)); }
 
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream) {
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;

@@ -27,7 +27,7 @@
 
 namespace ddl {
 
-int g_pdl = 0;        // launch.h: opted-in kernels are launched with programmatic stream serialization
+int g_pdl = 1;        // launch.h: opted-in kernels are launched with programmatic stream serialization
 
 using namespace tc;
 
@@ -825,6 +825,7 @@ conv_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmB, const __gri
       for (int t = item0; t < total; t += item_step) {
         int n0, m0, tq0, tp0, tn0;
         tile_origin(t, n0, m0, tq0, tp0, tn0);
+        if (t + item_step >= total) pdl_trigger_last_tile();
         int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, 33);
@@ -1144,6 +1145,7 @@ conv_gemm_deep_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_cons
       for (int t = item0; t < total; t += item_step) {
         int n0, m0, tq0, tp0, tn0;
         tile_origin(t, n0, m0, tq0, tp0, tn0);
+        if (t + item_step >= total) pdl_trigger_last_tile();
         int tap = 0, cc = 0, tap_r = 0, tap_s = 0;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u, 49);
@@ -1914,9 +1916,9 @@ void set_conv_deep(int on) { g_deep = on; }
 void pdl_early_bn(int early);       // bn_act.cu's copy of c_pdl_early
 void set_pdl(int on) {
   g_pdl = on;
-  const int early = on >= 2 ? 1 : 0;
-  cudaMemcpyToSymbol(c_pdl_early, &early, sizeof(int));
-  pdl_early_bn(early);
+  const int trig = on == 2 ? 1 : (on >= 3 ? 2 : 0);
+  cudaMemcpyToSymbol(c_pdl_trigger, &trig, sizeof(int));
+  pdl_early_bn(trig);
 }
 
 // `w` is the bf16 weight matrix [n_total][KB*64] (fwd / gemm / stem) or [Cout][R*S*Cin] (dgrad modes).
