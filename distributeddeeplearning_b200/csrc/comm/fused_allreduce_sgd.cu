@@ -89,8 +89,12 @@ DDL_DEVICE uint32_t ld_acquire_sys(uint64_t addr) {
 // Signal pad layout (uint32), identical on every rank:  pad[channel][block][src_rank].
 // Block b of rank r stores `epoch` into pad[ch][b][r] of EVERY rank, then waits until its own
 // pad[ch][b][*] all reached `epoch`.  Epochs only grow, so a late reader never misses one.
+// The block-uniform verdict lives in a shared flag indexed by the epoch's parity: a kernel issues at most two barriers,
+// with consecutive epochs, so the thread that races ahead into the second barrier resets the OTHER slot while stragglers
+// still read the first one (compute-sanitizer racecheck flagged the single-flag version: profiles/sanitizer.md).
 DDL_DEVICE bool block_barrier(const CommCtx& c, int channel, uint32_t epoch) {
-  __shared__ int s_timed_out;
+  __shared__ int s_timed_out2[2];
+  int& s_timed_out = s_timed_out2[epoch & 1u];
   if (threadIdx.x == 0) s_timed_out = 0;
   __syncthreads();
   if (threadIdx.x < static_cast<unsigned>(c.world)) {

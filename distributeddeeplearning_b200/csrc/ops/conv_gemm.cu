@@ -1913,6 +1913,10 @@ void set_wgrad_swap(int on) { g_wgrad_swap = on; }
 void set_conv_bn256(int on) { g_bn256 = on; }
 void set_conv_cluster(int on) { g_cluster = on; }
 void set_conv_deep(int on) { g_deep = on; }
+void set_conv_wait_hint(int ns) {
+  const unsigned int v = ns > 0 ? static_cast<unsigned int>(ns) : 0u;
+  cudaMemcpyToSymbol(tc::c_wait_hint_ns, &v, sizeof(v));
+}
 void pdl_early_bn(int early);       // bn_act.cu's copy of c_pdl_early
 void set_pdl(int on) {
   g_pdl = on;

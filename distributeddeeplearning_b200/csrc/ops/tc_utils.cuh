@@ -45,13 +45,26 @@ DDL_DEVICE void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// c_wait_hint_ns != 0: pass that suspend-time hint to try_wait (the thread sleeps in hardware until the phase completes
+// or the time is up, instead of returning after the short system default and re-issuing the poll loop) — tuning hook
+// set_conv_wait_hint, A/B-measured in BASELINE.md
+__constant__ unsigned int c_wait_hint_ns;
 DDL_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  const unsigned int hint = c_wait_hint_ns;
+  if (hint != 0u) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint) : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
   return ok != 0;
 }
 // Bounded wait with a post-mortem.  A protocol bug must neither hang the GPU nor kill the context without a trace:
@@ -70,7 +83,7 @@ DDL_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t site = 0) {
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3ffu) == 0) {
       if (*reinterpret_cast<volatile unsigned int*>(&g_mbar_diag[0]) != 0u) return;     // somebody timed out: drain
-      if (spins > (1u << 24)) {
+      if (spins > (c_wait_hint_ns != 0u ? (1u << 21) : (1u << 24))) {     // hinted iterations last up to the hint
         if (atomicCAS(&g_mbar_diag[0], 0u, 1u) == 0u) {
           g_mbar_diag[1] = site;
           g_mbar_diag[2] = blockIdx.x + gridDim.x * blockIdx.y;

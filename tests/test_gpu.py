@@ -17,7 +17,8 @@ def _group(name, timeout=600, env=None):
     e.update(env or {})
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_diag.py"), "--group", name], cwd=ROOT,
                        capture_output=True, text=True, timeout=timeout, env=e)
-    tail = (r.stdout + r.stderr)[-4000:]
+    out = r.stdout + r.stderr
+    tail = "\n".join(l for l in out.splitlines() if "FAIL" in l or "Error" in l)[:3000] + "\n...\n" + out[-3000:]
     assert r.returncode == 0, tail
     assert "FAIL" not in r.stdout, tail
 
