@@ -122,7 +122,7 @@ def sanitizer():
         L.append(f"| memcheck | {what2} | final build | {r} |")
     r = summary(os.path.join(G, "r2t", "san_race_N2.log"), r"RACECHECK SUMMARY: [^\n]*")
     if r:
-        L.append(f"| racecheck | {what2} | before the fix below | {r}: ALL of them the read of `block_barrier`'s shared verdict flag "
+        L.append(f"| racecheck | {what2} | before the fix below | {r}: every displayed hazard is the read of `block_barrier`'s shared verdict flag "
                  "against thread 0 of the NEXT barrier resetting it (fused_allreduce_sgd.cu) |")
     r = summary(os.path.join(G, "r2u", "san_race_N2.log"), r"RACECHECK SUMMARY: [^\n]*")
     if r:
