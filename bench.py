@@ -58,7 +58,20 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int = 0):
-        self.gpu, self.proc, self.path = gpu_index, None, f"/tmp/ddl_clocks_{os.getpid()}.csv"
+        """``gpu_index`` is the CUDA ordinal; nvidia-smi wants the PHYSICAL GPU, which differs under CUDA_VISIBLE_DEVICES:
+        address it by UUID."""
+        self.gpu, self.proc, self.path = str(gpu_index), None, f"/tmp/ddl_clocks_{os.getpid()}.csv"
+        try:
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            probe = subprocess.run(["nvidia-smi", "-i", uuid, "--query-gpu=index", "--format=csv,noheader"],
+                                   capture_output=True, text=True, timeout=20)
+            if probe.returncode == 0 and probe.stdout.strip().isdigit():
+                self.gpu = uuid                      # else: keep the ordinal (right whenever no device remapping is active)
+        except Exception:
+            pass
         self.t0 = None
 
     def mark(self):
@@ -71,7 +84,7 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-lms", "200", "-i", self.gpu], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
