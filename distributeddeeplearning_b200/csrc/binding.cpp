@@ -5,6 +5,7 @@
 // dtype / contiguity checks live in the Python wrappers (ops/*.py, parallel/engine.py).  This keeps
 // the build to seconds and the module importable on a GPU-less box.
 #include <pybind11/pybind11.h>
+#include <pybind11/functional.h>
 #include <pybind11/stl.h>
 
 #include <cuda_runtime.h>
@@ -16,6 +17,7 @@
 #include "ops/conv_gemm.cuh"
 #include "ops/ops.h"
 #include "runtime/host_runtime.h"
+#include "runtime/step_launcher.h"
 
 namespace py = pybind11;
 using ddl::BnBwdArgs;
@@ -177,6 +179,48 @@ PYBIND11_MODULE(_C, m) {
      py::arg("use_mc"), py::arg("wire_bf16"), py::arg("blocks"), py::arg("stream"), py::arg("scalar_off") = 0,
      py::arg("scalar_out") = 0, py::arg("oneshot") = false, py::arg("closing") = true);
   m.attr("SCALAR_SLOTS") = ddl::kScalarSlots;
+
+  // ---- native hook -> bucket-launch sequencing (runtime/step_launcher.h) -------------------------------------------------
+  m.def("wgrad_note", [](ptr_t side) { ddl::wgrad_note(S(side)); }, "work was enqueued on the weight-gradient side stream");
+  m.def("wgrad_join", [](ptr_t consumer) { return ddl::wgrad_join(S(consumer)); },
+        "make `consumer` wait for the side-stream work noted since the last join (False: nothing pending)");
+  py::class_<ddl::StepLauncher>(m, "StepLauncher")
+      .def(py::init([](std::vector<int32_t> param_bucket, std::vector<int32_t> bucket_param_count,
+                       std::vector<int64_t> bucket_start, std::vector<int64_t> bucket_numel, const PyCommCtx& ctx, int world,
+                       ptr_t W, ptr_t G, ptr_t M, ptr_t Wb, ptr_t hyper_dev, int comm_blocks, int sms, bool use_mc,
+                       bool wire_bf16, int64_t oneshot_bytes, uint64_t scalars_off, ptr_t scalars_out, ptr_t comm_stream,
+                       py::function stream_fn, py::function hyper_fn) {
+             ddl::StepLauncherConfig c;
+             c.param_bucket = std::move(param_bucket);
+             c.bucket_param_count = std::move(bucket_param_count);
+             c.bucket_start = std::move(bucket_start);
+             c.bucket_numel = std::move(bucket_numel);
+             c.ctx = ctx.c;
+             c.world = world;
+             c.W = P<float>(W); c.G = P<float>(G); c.M = P<float>(M); c.Wb = P<void>(Wb);
+             c.hyper_dev = P<const SgdHyper>(hyper_dev);
+             c.comm_blocks = comm_blocks; c.sms = sms; c.use_mc = use_mc; c.wire_bf16 = wire_bf16;
+             c.oneshot_bytes = oneshot_bytes; c.scalars_off = scalars_off; c.scalars_out = P<float>(scalars_out);
+             c.comm_stream = S(comm_stream);
+             return new ddl::StepLauncher(
+                 std::move(c), [stream_fn]() { return S(stream_fn().cast<ptr_t>()); },
+                 [hyper_fn](cudaStream_t st) { hyper_fn(reinterpret_cast<ptr_t>(st)); });
+           }),
+           py::arg("param_bucket"), py::arg("bucket_param_count"), py::arg("bucket_start"), py::arg("bucket_numel"),
+           py::arg("ctx"), py::arg("world"), py::arg("W"), py::arg("G"), py::arg("M"), py::arg("Wb"), py::arg("hyper_dev"),
+           py::arg("comm_blocks"), py::arg("sms"), py::arg("use_mc"), py::arg("wire_bf16"), py::arg("oneshot_bytes"),
+           py::arg("scalars_off"), py::arg("scalars_out"), py::arg("comm_stream"), py::arg("stream_fn"), py::arg("hyper_fn"))
+      .def("on_ready", &ddl::StepLauncher::on_ready)
+      .def("hook", [](ddl::StepLauncher& s, int idx) {
+             // the autograd hook itself: a C++ callable (called as hook(param)); no Python frame on the per-parameter path
+             return py::cpp_function([&s, idx](py::args) { s.on_ready(idx); });
+           }, py::keep_alive<0, 1>())
+      .def("finish", &ddl::StepLauncher::finish)
+      .def("reset", &ddl::StepLauncher::reset)
+      .def("set_hold", &ddl::StepLauncher::set_hold)
+      .def("set_scalars_pending", &ddl::StepLauncher::set_scalars_pending)
+      .def_property_readonly("next_bucket", &ddl::StepLauncher::next_bucket)
+      .def_property_readonly("launches", &ddl::StepLauncher::launches);
   m.def("allreduce", [](const PyCommCtx& c, int channel, uint64_t off, int64_t numel, bool bf16, float scale,
                         bool use_mc, bool oneshot, int blocks, ptr_t stream) {
     check(ddl::launch_allreduce(c.c, channel, off, numel, bf16, scale, use_mc, oneshot, blocks, S(stream)), "allreduce");

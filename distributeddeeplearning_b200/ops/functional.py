@@ -47,7 +47,13 @@ def grad_buffer(p: torch.Tensor) -> torch.Tensor:
 # stream before it consumes a bucket) they are enqueued on a side stream so they overlap the dgrad -> BN-backward chain
 # of the earlier layers: the conv kernels are latency-bound per tile and the BN kernels are HBM-bound, so co-residency
 # fills otherwise idle issue slots.  DDL_ASYNC_WGRAD=0 restores single-stream execution.
-_WGRAD = {"stream": None, "enabled": os.environ.get("DDL_ASYNC_WGRAD", "1") != "0", "pending": False}
+_WGRAD = {"stream": None, "enabled": os.environ.get("DDL_ASYNC_WGRAD", "1") != "0", "pending": False, "native": False}
+
+
+def use_native_wgrad_join(on: bool) -> None:
+    """The engine's native StepLauncher joins the side stream itself (csrc/runtime/step_launcher.cpp): side-stream work
+    is then noted in the native module instead of the Python flag."""
+    _WGRAD["native"] = bool(on)
 
 
 def wgrad_stream() -> Optional["torch.cuda.Stream"]:
@@ -59,7 +65,11 @@ def wgrad_join(consumer: "torch.cuda.Stream") -> None:
     Skipped when nothing is pending: besides saving an event, that keeps CUDA-graph capture legal (a capturing stream
     must not wait on a stream that has not joined the capture yet)."""
     side = _WGRAD["stream"]
-    if side is not None and _WGRAD["pending"]:
+    if _WGRAD["native"]:
+        from .. import _ext
+
+        _ext.load().wgrad_join(consumer.cuda_stream)
+    elif side is not None and _WGRAD["pending"]:
         consumer.wait_stream(side)
         _WGRAD["pending"] = False
 
@@ -75,7 +85,12 @@ def run_wgrad(param: torch.Tensor, fn, *tensors: torch.Tensor) -> None:
     side.wait_stream(torch.cuda.current_stream(param.device))
     with torch.cuda.stream(side):
         fn()
-    _WGRAD["pending"] = True
+    if _WGRAD["native"]:
+        from .. import _ext
+
+        _ext.load().wgrad_note(side.cuda_stream)
+    else:
+        _WGRAD["pending"] = True
     if not torch.cuda.is_current_stream_capturing():
         for t in tensors:
             t.record_stream(side)

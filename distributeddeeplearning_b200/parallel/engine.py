@@ -123,6 +123,9 @@ def _bf16_operand_view(flat: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
     return flat.view(p.shape)
 
 
+_NATIVE_HOOKS_DEFAULT = "0"
+
+
 class FusedSGD(torch.optim.Optimizer):
     """SGD(+momentum, +weight decay, +nesterov) fused with the data-parallel gradient allreduce."""
 
@@ -216,8 +219,6 @@ class FusedSGD(torch.optim.Optimizer):
                 p.data = wv
                 p.grad = _param_view(self.G[o:o + n], p)
                 p._ddl_bf16 = _bf16_operand_view(self.Wb[o:o + n], p)
-                p._ddl_ready = (lambda idx=i: self._on_ready(idx))
-                p.register_post_accumulate_grad_hook(lambda _p, idx=i: self._on_ready(idx))
                 self._index[id(p)] = i
         self._pending = list(plan["bucket_param_count"])
         self._ready_seen = [False] * len(self.params)
@@ -226,7 +227,27 @@ class FusedSGD(torch.optim.Optimizer):
         self._first_step = True
         self._comm_stream = torch.cuda.Stream(device=dev, priority=-1) if overlap else None
         self._steps = 0
-        self._hold_buckets = False
+        self._hold = False
+        # ---- gradient-ready hooks ---------------------------------------------------------------------
+        # native (default): the per-parameter hook is a C++ callable of the StepLauncher (csrc/runtime/step_launcher.h):
+        # bucket accounting, stream joins and the bucket kernel launch happen without a Python frame; Python is called
+        # back once per step (current stream, hyper-parameter upload).  DDL_NATIVE_HOOKS=0: the same logic in Python.
+        self._launcher = None
+        self._launches_seen = 0
+        if os.environ.get("DDL_NATIVE_HOOKS", _NATIVE_HOOKS_DEFAULT) != "0":
+            from ..ops import functional as _F
+
+            self._launcher = self.C.StepLauncher(
+                [int(v) for v in plan["param_bucket"]], [int(v) for v in plan["bucket_param_count"]],
+                [int(v) for v in plan["bucket_start"]], [int(v) for v in plan["bucket_numel"]], self.ctx, self.world,
+                self.W.data_ptr(), self.G.data_ptr(), self.M.data_ptr(), self.Wb.data_ptr(), self._hyper_dev.data_ptr(),
+                self.comm_blocks, self._sms, bool(self.use_mc), bool(self.wire_bf16), self.oneshot_bytes,
+                self.arena.offsets["scalars"], self._scalars_out.data_ptr(),
+                self._comm_stream.cuda_stream if self._comm_stream is not None else 0,
+                lambda: torch.cuda.current_stream(self.device).cuda_stream, self._upload_hyper_handle)
+            _F.use_native_wgrad_join(True)
+        self._hook_handles = []
+        self._register_hooks()
         if broadcast_root is not None and self.world > 1:
             self.broadcast_parameters(broadcast_root)
         self.refresh_bf16()
@@ -267,6 +288,48 @@ class FusedSGD(torch.optim.Optimizer):
             self._hyper_dev.copy_(self._hyper_host, non_blocking=True)
         if not torch.cuda.is_current_stream_capturing():
             self.mark_hyper_consumed(stream)
+
+    def _register_hooks(self) -> None:
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles = []
+        for i, p in enumerate(self.params):
+            if self._launcher is not None:
+                hook = self._launcher.hook(i)
+                p._ddl_ready = hook
+                self._hook_handles.append(p.register_post_accumulate_grad_hook(hook))
+            else:
+                p._ddl_ready = (lambda idx=i: self._on_ready(idx))
+                self._hook_handles.append(p.register_post_accumulate_grad_hook(lambda _p, idx=i: self._on_ready(idx)))
+
+    def use_python_hooks(self) -> None:
+        """Switch this optimizer to the Python hook path (between steps): the timing tools that wrap ``_launch_bucket``
+        (``workloads.benchmark.phase_times``, ``tools/comm_timeline.py``) need a Python frame per bucket launch."""
+        if self._launcher is None:
+            return
+        from ..ops import functional as _F
+
+        self._launcher = None
+        _F.use_native_wgrad_join(False)
+        self._register_hooks()
+
+    @property
+    def _hold_buckets(self) -> bool:
+        return self._hold
+
+    @_hold_buckets.setter
+    def _hold_buckets(self, on: bool) -> None:          # selfcheck: keep the gradients in the arena until step()
+        self._hold = bool(on)
+        if self._launcher is not None:
+            self._launcher.set_hold(bool(on))
+
+    def _upload_hyper_handle(self, handle: int) -> None:
+        """StepLauncher callback (once per step, first bucket): upload the hyper-parameters on the raw stream ``handle``."""
+        if self._comm_stream is not None and handle == self._comm_stream.cuda_stream:
+            st = self._comm_stream
+        else:
+            st = torch.cuda.ExternalStream(handle, device=self.device)
+        self._upload_hyper(st)
 
     def _launch_bucket(self, b: int) -> None:
         cur = torch.cuda.current_stream(self.device)
@@ -319,13 +382,18 @@ class FusedSGD(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         # parameters that received no gradient this step still take part (their slots are zero)
-        while self._next_bucket < self.num_buckets:
-            self._launch_bucket(self._next_bucket)
-            self._next_bucket += 1
-        if self._comm_stream is not None:
-            ev = torch.cuda.Event()
-            ev.record(self._comm_stream)
-            torch.cuda.current_stream(self.device).wait_event(ev)
+        if self._launcher is not None:
+            self._launcher.finish()                      # ... and joins the communication stream into the current one
+            _ext.add_launches(self._launcher.launches - self._launches_seen)
+            self._launches_seen = self._launcher.launches
+        else:
+            while self._next_bucket < self.num_buckets:
+                self._launch_bucket(self._next_bucket)
+                self._next_bucket += 1
+            if self._comm_stream is not None:
+                ev = torch.cuda.Event()
+                ev.record(self._comm_stream)
+                torch.cuda.current_stream(self.device).wait_event(ev)
         if self._scalars_pending and self.world == 1:
             self._scalars_out.copy_(self._scalars_in)
         self._scalars_last, self._scalars_pending = self._scalars_pending, 0
@@ -336,6 +404,8 @@ class FusedSGD(torch.optim.Optimizer):
         self._ready_seen = [False] * len(self.params)
         self._next_bucket = 0
         self._hyper_uploaded = False
+        if self._launcher is not None:
+            self._launcher.reset()
         self._first_step = False
         self._steps += 1
         if self.debug:
@@ -373,6 +443,8 @@ class FusedSGD(torch.optim.Optimizer):
             raise ValueError(f"piggyback carries at most {self._scalars_in.numel()} scalars")
         self._scalars_in[:v.numel()].copy_(v)
         self._scalars_pending = int(v.numel())
+        if self._launcher is not None:
+            self._launcher.set_scalars_pending(True)
 
     def averaged_scalars(self) -> torch.Tensor:
         """Cross-rank means of the values passed to :meth:`piggyback` before the last ``step()`` (device tensor)."""

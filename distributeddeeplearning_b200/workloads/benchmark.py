@@ -172,6 +172,8 @@ def phase_times(session: BenchmarkSession, steps: int = 5) -> Dict[str, float]:
     ev = lambda: torch.cuda.Event(enable_timing=True)
     graph, session._graph = session._graph, None
     bucket_ms = []
+    if hasattr(opt, "use_python_hooks"):
+        opt.use_python_hooks()           # a Python frame per bucket launch is what gets timed here
     orig = getattr(opt, "_launch_bucket", None)
     if orig is not None:
         def timed(b):

@@ -131,3 +131,39 @@ def test_tile_geometry_maximises_useful_rows():
                 assert eff(hw, hw, n, rows, t) >= eff(hw, hw, n, rows, naive) - 1e-9, (hw, n, rows, t, naive)
     assert eff(14, 14, 256, 128, nv.tile_geometry(14, 14, 256, 128)) > 0.95
     assert eff(7, 7, 256, 128, nv.tile_geometry(7, 7, 256, 128)) > 0.9
+
+
+def test_step_launcher_accounting_without_a_gpu(C):
+    """The native hook -> bucket-launch sequencer (csrc/runtime/step_launcher.cpp): plan validation, per-parameter
+    accounting, the hook callable and reset — in `hold` mode, where nothing is launched (no GPU here)."""
+    plan = C.plan_buckets([4096, 64, 64, 8192, 128], 2048, 8192, 64, 2048)
+    ctx = C.CommCtx([0], 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 10 ** 9)
+    calls = {"stream": 0, "hyper": 0}
+
+    def stream_fn():
+        calls["stream"] += 1
+        return 0
+
+    def hyper_fn(handle):
+        calls["hyper"] += 1
+
+    def make(param_bucket):
+        return C.StepLauncher(param_bucket, list(plan["bucket_param_count"]), list(plan["bucket_start"]),
+                              list(plan["bucket_numel"]), ctx, 1, 0, 0, 0, 0, 0, 32, 148, False, False, 0, 0, 0, 0,
+                              stream_fn, hyper_fn)
+
+    with pytest.raises(ValueError):
+        make([99] * 5)                                        # bucket id out of range
+    sl = make(list(plan["param_bucket"]))
+    sl.set_hold(True)
+    hooks = [sl.hook(i) for i in range(5)]
+    assert sl.on_ready(0) == 0 and sl.on_ready(0) == 0        # second call for the same parameter is ignored
+    for h in hooks[1:]:
+        assert h("the parameter autograd passes in") is None  # the hook signature: hook(param)
+    assert sl.next_bucket == 0 and sl.launches == 0 and calls == {"stream": 0, "hyper": 0}
+    with pytest.raises(IndexError):
+        sl.on_ready(5)
+    sl.reset()
+    assert sl.on_ready(4) == 0 and sl.launches == 0
+    # the side-stream bookkeeping is module-wide: nothing noted -> nothing to join (and no CUDA call is made)
+    assert C.wgrad_join(0) is False

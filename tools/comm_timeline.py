@@ -37,6 +37,7 @@ def main():
     torch.cuda.synchronize()
     nb = opt.num_buckets
     rec = []
+    opt.use_python_hooks()              # the timeline wraps the Python bucket launch
     orig = opt._launch_bucket
 
     def timed_launch(b):
