@@ -21,6 +21,7 @@ With world_size == 1 the same class runs the local fused SGD kernel per bucket.
 from __future__ import annotations
 
 import os
+import weakref
 import secrets
 from typing import Dict, List, Optional, Tuple
 
@@ -123,7 +124,7 @@ def _bf16_operand_view(flat: torch.Tensor, p: torch.Tensor) -> torch.Tensor:
     return flat.view(p.shape)
 
 
-_NATIVE_HOOKS_DEFAULT = "0"
+_NATIVE_HOOKS_DEFAULT = "1"
 
 
 class FusedSGD(torch.optim.Optimizer):
@@ -244,7 +245,8 @@ class FusedSGD(torch.optim.Optimizer):
                 self.comm_blocks, self._sms, bool(self.use_mc), bool(self.wire_bf16), self.oneshot_bytes,
                 self.arena.offsets["scalars"], self._scalars_out.data_ptr(),
                 self._comm_stream.cuda_stream if self._comm_stream is not None else 0,
-                lambda: torch.cuda.current_stream(self.device).cuda_stream, self._upload_hyper_handle)
+                lambda d=dev: torch.cuda.current_stream(d).cuda_stream,
+                lambda handle, r=weakref.ref(self): r()._upload_hyper_handle(handle))      # no C++-held cycle
             _F.use_native_wgrad_join(True)
         self._hook_handles = []
         self._register_hooks()
