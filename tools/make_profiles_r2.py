@@ -88,7 +88,7 @@ def copy_text(src, dst, title, pre=""):
 
 
 def sanitizer():
-    L = ["# compute-sanitizer passes (tools/sanitize.sh <tool> <gpu_diag group>; round 2: tools/run_san.sh + 2-GPU comm memcheck)", "",
+    L = ["# compute-sanitizer passes (tools/sanitize.sh <tool> <gpu_diag group>; round 2: tools/runs/run_san.sh + 2-GPU comm memcheck)", "",
          "| tool | kernels | configuration | summary |", "|---|---|---|---|",
          "| memcheck | conv_generic | default (round 1) | ERROR SUMMARY: 0 errors |",
          "| racecheck | bn | default (round 1) | RACECHECK SUMMARY: 0 hazards displayed (0 errors, 0 warnings) |",
