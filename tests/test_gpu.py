@@ -165,9 +165,11 @@ def test_multi_rank_fused_engine():
     assert r.returncode == 0 and "ENGINE CHECKS: all ok" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
-def test_single_rank_local_engine_equals_torch_sgd():
+@pytest.mark.parametrize("native_hooks", ["1", "0"])
+def test_single_rank_local_engine_equals_torch_sgd(native_hooks):
     """One-GPU part of the engine contract: a FusedSGD step (world 1, `local` mode included) applies exactly
-    torch.optim.SGD's update, and its state_dict round-trips through torch.optim.SGD's loader and back."""
+    torch.optim.SGD's update, and its state_dict round-trips through torch.optim.SGD's loader and back — with the
+    native StepLauncher sequencing the bucket launches (default) and with the Python sequencing (DDL_NATIVE_HOOKS=0)."""
     code = ("import sys, torch; sys.path.insert(0, %r)\n"
             "from distributeddeeplearning_b200.parallel import dist\n"
             "from distributeddeeplearning_b200.parallel.engine import FusedSGD\n"
@@ -195,8 +197,10 @@ def test_single_rank_local_engine_equals_torch_sgd():
             "a2.load_state_dict(b.state_dict())                     # and the engine accepts torch's\n"
             "m = a2.state_dict()['state']\n"
             "for i in range(4): assert torch.allclose(m[i]['momentum_buffer'].cuda(), b.state[qs[i]]['momentum_buffer'], rtol=1e-5, atol=1e-6)\n"
-            "print('engine == torch.optim.SGD')\n" % ROOT)
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT)
+            "assert (a._launcher is not None) == (%r == '1')\n"
+            "print('engine == torch.optim.SGD')\n" % (ROOT, native_hooks))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                       env=dict(os.environ, DDL_NATIVE_HOOKS=native_hooks))
     assert r.returncode == 0 and "engine == torch.optim.SGD" in r.stdout, (r.stdout + r.stderr)[-3000:]
 
 
