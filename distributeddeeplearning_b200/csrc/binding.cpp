@@ -42,6 +42,7 @@ void set_conv_bn256(int on);
 void set_conv_cluster(int on);
 void set_conv_deep(int on);
 void set_pdl(int on);
+void set_bn_reverse(int on);
 void set_conv_wait_hint(int ns);
 cudaError_t conv_timeout_info(unsigned int out[8]);
 }  // namespace ddl
@@ -247,6 +248,7 @@ PYBIND11_MODULE(_C, m) {
     return std::vector<unsigned int>(v, v + 8);
   }, "post-mortem of the first timed-out mbarrier wait (flag, site, block, thread, parity); clears the record");
   m.def("set_conv_wait_hint", &ddl::set_conv_wait_hint, "tuning hook: suspend-time hint (ns) of the conv kernels' mbarrier waits, 0 = none");
+  m.def("set_bn_reverse", &ddl::set_bn_reverse, "1 (default) = BN forward / backward-reduce walk the rows from the end (L2 reuse of the producer's tail), 0 = front to back");
   m.def("set_pdl", &ddl::set_pdl, "0 = plain stream order, 1 = conv / BN kernels allow programmatic dependent launch (default), 2 = + trigger at the last tile, 3 = + trigger at block start");
   m.def("set_conv_deep", &ddl::set_conv_deep, "tuning hook: 0 = never the deep-ring kernel, 1 = policy, 2 = always");
   m.def("set_conv_bn256", &ddl::set_conv_bn256, "tuning hook: 0 = no 128x256 persistent tiles");

@@ -160,10 +160,13 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
                      fp8_cvt4<false>(z[4] * qscale, z[5] * qscale, z[6] * qscale, z[7] * qscale));
     }
   };
+  // logical row r -> physical row: mirrored when the tensor's tail is what the producer left in L2 (BnFwdArgs::reverse)
+  const int last = a.M - 1;
+  auto phys = [&](int rr) { return a.reverse ? last - rr : rr; };
   int r = row0;
   for (; r + row_stride < a.M; r += 2 * row_stride) {
-    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
-    const size_t off1 = static_cast<size_t>(r + row_stride) * a.C + c0;
+    const size_t off0 = static_cast<size_t>(phys(r)) * a.C + c0;
+    const size_t off1 = static_cast<size_t>(phys(r + row_stride)) * a.C + c0;
     const uint4 x0 = ld_stream_u4(a.x + off0), x1 = ld_stream_u4(a.x + off1);
     uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
     if (a.residual) { r0 = ld_stream_u4(a.residual + off0); r1 = ld_stream_u4(a.residual + off1); }
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_fwd_kernel(BnFwdArgs a) 
     finish(x1, r1, off1);
   }
   if (r < a.M) {
-    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
+    const size_t off0 = static_cast<size_t>(phys(r)) * a.C + c0;
     const uint4 x0 = ld_stream_u4(a.x + off0);
     uint4 r0 = make_uint4(0, 0, 0, 0);
     if (a.residual) r0 = ld_stream_u4(a.residual + off0);
@@ -227,10 +230,12 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
   };
   // two rows per iteration so that 4 (6 with the z mask) 16-byte loads are outstanding per thread
   const int rstep = gridDim.x * 32;
+  const int last = a.M - 1;
+  auto phys = [&](int rr) { return a.reverse ? last - rr : rr; };      // see BnBwdArgs::reverse
   int r = live ? blockIdx.x * 32 + rl : a.M;
   for (; r + rstep < a.M; r += 2 * rstep) {
-    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
-    const size_t off1 = static_cast<size_t>(r + rstep) * a.C + c0;
+    const size_t off0 = static_cast<size_t>(phys(r)) * a.C + c0;
+    const size_t off1 = static_cast<size_t>(phys(r + rstep)) * a.C + c0;
     const uint4 d0 = ld_stream_u4(a.dz + off0), d1 = ld_stream_u4(a.dz + off1);
     const uint4 x0 = ld_stream_u4(a.x + off0), x1 = ld_stream_u4(a.x + off1);
     uint4 z0 = make_uint4(0, 0, 0, 0), z1 = z0;
@@ -240,7 +245,7 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_act_bwd_reduce_kernel(BnBwdA
     accumulate(d1, x1, z1);
   }
   if (r < a.M) {
-    const size_t off0 = static_cast<size_t>(r) * a.C + c0;
+    const size_t off0 = static_cast<size_t>(phys(r)) * a.C + c0;
     const uint4 d0 = ld_stream_u4(a.dz + off0);
     const uint4 x0 = ld_stream_u4(a.x + off0);
     uint4 z0 = make_uint4(0, 0, 0, 0);
@@ -586,9 +591,14 @@ inline bool bn_flat_ok(int C) {
   return (kBnThreads % groups == 0) || (groups % kBnThreads == 0);
 }
 
+int g_bn_reverse = 1;        // tuning hook (set_bn_reverse / DDL_BN_REVERSE): BN forward and the backward reduce pass walk rows from the end
+void set_bn_reverse(int on) { g_bn_reverse = on; }
+
 void pdl_early_bn(int trig) { cudaMemcpyToSymbol(c_pdl_trigger, &trig, sizeof(int)); }
 
-cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream) {
+cudaError_t launch_bn_act_fwd(const BnFwdArgs& a_in, bool train, int sms, cudaStream_t stream) {
+  BnFwdArgs a = a_in;
+  a.reverse = g_bn_reverse;
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
   const bool f8 = a.zq != nullptr && a.zq_slot != nullptr && train;
   cudaError_t e = cudaSuccess;
@@ -606,7 +616,9 @@ cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStrea
   return e;
 }
 
-cudaError_t launch_bn_act_bwd(const BnBwdArgs& a, int sms, cudaStream_t stream, bool skip_reduce) {
+cudaError_t launch_bn_act_bwd(const BnBwdArgs& a_in, int sms, cudaStream_t stream, bool skip_reduce) {
+  BnBwdArgs a = a_in;
+  a.reverse = g_bn_reverse;
   if (a.C % 8 != 0 || a.C <= 0) return cudaErrorInvalidValue;
   const int mask = !a.relu ? kMaskNone : (a.mask_from_x ? kMaskX : (a.zmask ? kMaskBits : kMaskZ));
   const dim3 rgrid = bn_chunk_grid(a.M, a.C, sms);

@@ -31,6 +31,8 @@ struct BnFwdArgs {
                                   //   for residual layers so that backward reads 1 bit instead of 16 bits per element
   uint8_t* zq;                    // optional fp8 (e4m3) twin of z for the consuming convolution's tensor-core operand:
   Fp8Slot* zq_slot;               //   z * slot->scale, amax(|z|) folded into the slot (ops/fp8.py: no separate quantise pass)
+  int reverse;                    // walk the rows from the END: the producing conv wrote x front to back, so the tail of a
+                                  //   tensor larger than L2 is what is still cached (set by the launcher: set_bn_reverse)
 };
 
 struct BnBwdArgs {
@@ -52,6 +54,8 @@ struct BnBwdArgs {
   const uint8_t* zmask;           // residual layers: the bit mask written by the forward kernel (z is never read)
   uint8_t* dxq;                   // optional fp8 (e5m2) twin of dx for the data-gradient convolution that consumes it
   Fp8Slot* dxq_slot;
+  int reverse;                    // the REDUCE pass walks the rows from the end (dz was just written front to back; the apply
+                                  //   pass then walks forward and finds the rows the reduce pass read last)
 };
 
 cudaError_t launch_bn_act_fwd(const BnFwdArgs& a, bool train, int sms, cudaStream_t stream);

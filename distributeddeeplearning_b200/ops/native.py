@@ -30,6 +30,8 @@ def _C():
         C.set_conv_cluster(int(os.environ["DDL_CONV_CLUSTER"]))       #   weights, 2 = cta_group::2 pair MMAs
     if os.environ.get("DDL_CONV_BN256", "0") == "1":       # tuning hook (A/B runs): 128 x 256 persistent tiles
         C.set_conv_bn256(1)
+    if os.environ.get("DDL_BN_REVERSE", "") in ("0", "1"):             # BN row traversal order (A/B runs)
+        C.set_bn_reverse(int(os.environ["DDL_BN_REVERSE"]))
     if os.environ.get("DDL_CONV_WAIT_HINT", ""):                       # ns; suspend-time hint of the mbarrier waits (A/B runs)
         C.set_conv_wait_hint(int(os.environ["DDL_CONV_WAIT_HINT"]))
     if os.environ.get("DDL_PDL", "") in ("0", "1", "2", "3"):         # programmatic dependent launch (A/B runs, launch.h)
