@@ -73,6 +73,26 @@ def is_stale() -> bool:
         return True
 
 
+class _build_lock:
+    """Cross-process lock around the build (all ranks of a job import the package at once; if the module were stale they
+    would otherwise compile into the same build directory concurrently)."""
+
+    def __enter__(self):
+        import fcntl
+
+        os.makedirs(_BUILD, exist_ok=True)
+        self.f = open(os.path.join(_BUILD, ".lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+        return False
+
+
 def _pybind_include() -> str:
     import pybind11
 
@@ -91,7 +111,8 @@ def _run(cmd: List[str], verbose: bool) -> None:
 
 def build(verbose: bool = False, force: bool = False, ptxas_info: bool = False) -> str:
     """Compile and link ``_C.so``; returns its path."""
-    with _LOCK:
+    with _LOCK, _build_lock():
+        # (the file lock serialises the ranks of one job: whoever gets it first builds, the others find a fresh module)
         if not force and not is_stale():
             return _SO
         nvcc = os.path.join(CUDA_HOME, "bin", "nvcc")
