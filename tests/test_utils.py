@@ -124,3 +124,30 @@ def test_metric_skips_collective_when_values_are_already_averaged():
     assert m._global and float(m.avg) == 3.0
     m.update(torch.tensor(6.0))                 # a local value: the mean must go through the allreduce again
     assert not m._global and float(m.avg) == 4.0
+
+
+def test_fp8_parity_rule_tolerates_transient_noise_but_not_divergence():
+    """tools/fp8_parity.py::judge — the acceptance rule of the fp8-vs-bf16 loss-curve test: the chaotic first half only has
+    a blow-up guard, the settled second half and the final window are tight, both arms must learn."""
+    import importlib.util
+    import math
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "fp8_parity", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "fp8_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    n = 200
+    base = [7.0 + 1.5 * math.exp(-((i - 40) / 25.0) ** 2) - 0.2 * i / n for i in range(n)]      # overshoot, then decay
+    wiggle = lambda amp, ph: [x * (1 + amp * math.sin(i / 7.0 + ph)) for i, x in enumerate(base)]
+    b, b2 = wiggle(0.01, 0.0), wiggle(0.01, 1.0)
+    # fp8 runs 9 % below bf16 during the overshoot only (what a real run looked like): accepted
+    f = [x * (0.91 if 30 <= i < 90 else 1.0) for i, x in enumerate(wiggle(0.01, 2.0))]
+    v = mod.judge(b, b2, f, 0.08)
+    assert v["ok"] and 0.05 < v["gap_early"] < 0.12 and v["gap"] < 0.06 and v["learned"]
+    # a curve that stays 12 % off in the second half is rejected, and so is one that blows up early
+    assert not mod.judge(b, b2, [x * (1.12 if i >= 100 else 1.0) for i, x in enumerate(f)], 0.08)["ok"]
+    assert not mod.judge(b, b2, [x * (1.5 if 40 <= i < 80 else 1.0) for i, x in enumerate(f)], 0.08)["ok"]
+    # not learning (flat loss) is rejected even if the curves agree
+    flat = [7.0] * n
+    assert not mod.judge(flat, flat, flat, 0.08)["ok"]

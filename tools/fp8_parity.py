@@ -49,6 +49,32 @@ def arm(precision, steps, batch, model, graph):
     print("ARM " + json.dumps(out), flush=True)
 
 
+def judge(b, b2, f, tol):
+    """The acceptance rule, on three loss curves (bf16, bf16 again with the same seed, fp8).  Second half of the run: the
+    fp8 running mean stays within max(tol, 2 x what the two bf16 runs differ by) of the nearer bf16 run; first half (the
+    loss overshoots to ~8.5 and comes back; two bf16 runs differ by 1-10 % there): only a blow-up guard at 2.5 x tol;
+    final window: means within tol / 2 (or twice the bf16 spread); and both precisions must have learned."""
+    n = len(b)
+    win = max(10, n // 10)
+    mean = lambda v: sum(v) / len(v)
+    sm = lambda v: [mean(v[max(0, i - win + 1): i + 1]) for i in range(len(v))]     # batches differ in difficulty
+
+    def curve_gaps(u, v):
+        g = [abs(x - y) / x for x, y in zip(sm(u), sm(v))]
+        return max(g[win:n // 2]), max(g[n // 2:])
+
+    noise_early, noise = curve_gaps(b, b2)
+    cand = [curve_gaps(b, f), curve_gaps(b2, f)]             # distance to the nearer of the two bf16 runs
+    gap_early, gap = min(c[0] for c in cand), min(c[1] for c in cand)
+    tail_b, tail_f = 0.5 * (mean(b[-win:]) + mean(b2[-win:])), mean(f[-win:])
+    tail_noise = abs(mean(b[-win:]) - mean(b2[-win:])) / tail_b
+    learned = tail_b < 0.97 * mean(b[:win]) and tail_f < 0.97 * mean(f[:win])
+    ok = gap < max(tol, 2.0 * noise) and gap_early < max(2.5 * tol, 2.0 * noise_early) \
+        and abs(tail_b - tail_f) / tail_b < max(0.5 * tol, 2.0 * tail_noise) and learned
+    return {"ok": ok, "win": win, "gap": gap, "gap_early": gap_early, "noise": noise, "noise_early": noise_early,
+            "tail_bf16": tail_b, "tail_fp8": tail_f, "tail_noise": tail_noise, "learned": learned}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=200)
@@ -78,26 +104,10 @@ def main():
         res[p] = json.loads(line[-1][4:])
     b, b2, f = res["bf16"]["losses"], res["bf16_repeat"]["losses"], res["fp8"]["losses"]
     n = len(b)
-    win = max(10, n // 10)
-    mean = lambda v: sum(v) / len(v)
-    # smooth the curves over `win` steps (batches differ in difficulty), then compare point by point
-    sm = lambda v: [mean(v[max(0, i - win + 1): i + 1]) for i in range(len(v))]
-    def curve_gaps(u, v):
-        """(max gap over the chaotic first half, max gap over the settled second half) of the running means"""
-        g = [abs(x - y) / x for x, y in zip(sm(u), sm(v))]
-        return max(g[win:n // 2]), max(g[n // 2:])
-
-    noise_early, noise = curve_gaps(b, b2)
-    cand = [curve_gaps(b, f), curve_gaps(b2, f)]             # distance to the nearer of the two bf16 runs
-    gap_early, gap = min(c[0] for c in cand), min(c[1] for c in cand)
-    tail_b, tail_f = 0.5 * (mean(b[-win:]) + mean(b2[-win:])), mean(f[-win:])
-    tail_noise = abs(mean(b[-win:]) - mean(b2[-win:])) / tail_b
-    learned = tail_b < 0.97 * mean(b[:win]) and tail_f < 0.97 * mean(f[:win])
-    # second half: within --tol (or twice what bf16 does to itself); first half (loss overshoots to ~8.5 and comes back,
-    # two bf16 runs differ by 1-10 % there): only a blow-up guard; final window: within --tol / 2
-    ok = gap < max(a.tol, 2.0 * noise) and gap_early < max(2.5 * a.tol, 2.0 * noise_early) \
-        and abs(tail_b - tail_f) / tail_b < max(0.5 * a.tol, 2.0 * tail_noise) and learned \
-        and res["fp8"]["fp8_launches"]["fwd"] > 0 and res["fp8"]["fp8_launches"]["dgrad"] > 0
+    v = judge(b, b2, f, a.tol)
+    win, gap, gap_early, noise, noise_early = v["win"], v["gap"], v["gap_early"], v["noise"], v["noise_early"]
+    tail_b, tail_f, tail_noise, learned = v["tail_bf16"], v["tail_fp8"], v["tail_noise"], v["learned"]
+    ok = v["ok"] and res["fp8"]["fp8_launches"]["fwd"] > 0 and res["fp8"]["fp8_launches"]["dgrad"] > 0
     print(f"| step | bf16 loss | bf16 loss (same seed, second run) | fp8 loss |\n|---|---|---|---|")
     for i in list(range(0, n, max(1, n // 10))) + [n - 1]:
         print(f"| {i} | {b[i]:.4f} | {b2[i]:.4f} | {f[i]:.4f} |")
