@@ -133,7 +133,38 @@ def sanitizer():
     w("sanitizer.md", "\n".join(L))
 
 
+def bench_lines_r2():
+    """Every bench.py JSON line of round 2 (gpurun_out/r2*/bench*.json), oldest first: the progression of the build."""
+    import glob
+
+    L = ["# bench.py JSON lines of round 2 (`gpurun_out/r2*/bench*.json`, oldest first)", "",
+         "`value` = whole-job images/s, device-timed, max over ranks; `sm_mhz` = median SM clock sampled during the timed steps "
+         "(1965 = no cap; lower = `sw_power_cap`).  A/B pairs (pdl0/pdl1, rev0/rev1, hint0/hint2000) ran back to back on one box.", "",
+         "| run | file | GPUs | img/s | ms/step | end to end img/s | SM MHz | engine_check | note |", "|---|---|---|---|---|---|---|---|---|"]
+    files = sorted(glob.glob(os.path.join(G, "r2*", "bench*.json")), key=os.path.getmtime)
+    for p in files:
+        try:
+            line = [l for l in open(p).read().strip().splitlines() if l.startswith("{")][-1]
+            d = json.loads(line)
+        except Exception:
+            continue
+        if "value" not in d:
+            continue
+        e2e = (d.get("e2e") or {}).get("value")
+        clk = d.get("clocks") or {}
+        note = "reference script" if d.get("impl") == "reference" else ("fp8 operands" if "fp8" in str(d.get("dtype")) else "")
+        if (clk.get("sm_mhz") or 1e9) < 500:
+            note = "clock sampler read physical GPU 0 while the run used GPU 1 (CUDA_VISIBLE_DEVICES); fixed since: UUID"
+        L.append(f"| {os.path.basename(os.path.dirname(p))} | {os.path.basename(p)} | {d.get('n_gpus')} | {d['value']:,.0f} | "
+                 f"{d.get('ms_per_step'):.2f} | {e2e:,.0f} | {clk.get('sm_mhz')} | {d.get('engine_check', '')} | {note} |"
+                 if e2e else
+                 f"| {os.path.basename(os.path.dirname(p))} | {os.path.basename(p)} | {d.get('n_gpus')} | {d['value']:,.0f} | "
+                 f"{d.get('ms_per_step'):.2f} | - | {clk.get('sm_mhz')} | {d.get('engine_check', '')} | {note} |")
+    w("bench_lines_r2.md", "\n".join(L))
+
+
 def main():
+    bench_lines_r2()
     lb = os.path.join(G, "r2m", "layer_bench.json")           # latest full run (after the epilogue work)
     if not os.path.isfile(lb):
         lb = os.path.join(G, "r2b2", "layer_bench.json")
