@@ -167,3 +167,51 @@ def test_step_launcher_accounting_without_a_gpu(C):
     assert sl.on_ready(4) == 0 and sl.launches == 0
     # the side-stream bookkeeping is module-wide: nothing noted -> nothing to join (and no CUDA call is made)
     assert C.wgrad_join(0) is False
+
+
+def test_conv_variant_words_are_well_formed():
+    """The autotuner's candidate list (ops/native.py) only produces variant words the launcher understands
+    (conv_gemm.cu: bits 0-3 kernel, 4-7 tile width, 8 pair) — never the epilogue debug bits 12-14 of tools/epi_probe.py."""
+    from distributeddeeplearning_b200.ops import native
+
+    seen = set()
+    for n_total in (64, 128, 192, 256, 512, 1024, 2048):
+        for m_rows in (128, 128 * 148 - 1, 128 * 148, 802816):
+            for kb in (1, 4, 18, 36):
+                for mn in (False, True):
+                    cands = native.conv_variants(n_total, m_rows, kb, mn)
+                    assert cands[0] == native.VAR_ONE_TILE and len(set(cands)) == len(cands)
+                    if m_rows < 128 * 148:
+                        assert cands == [native.VAR_ONE_TILE]
+                    for v in cands:
+                        assert v >> 9 == 0, hex(v)                       # nothing above the pair bit
+                        kind, width, pair = v & 0xf, (v >> 4) & 0xf, (v >> 8) & 1
+                        assert kind in (1, 2, 3) and width in (0, 1, 2, 3)
+                        if kind != 3:
+                            assert width == 0 and pair == 0
+                        else:
+                            assert n_total % {1: 64, 2: 128, 3: 256}[width] == 0
+                        name = native.variant_name(v)
+                        assert name.startswith(("one-tile", "persistent", "deep"))
+                        seen.add(name)
+    assert {"one-tile", "persistent", "deep-N256-pair", "deep-N64"} <= seen
+
+
+def test_fp8_eligibility_rules():
+    """fp8 operands only where they pay and where the geometry allows (ops/fp8.py): reduction >= MIN_K elements, 128-channel
+    operand rows; everything else (stem, layer1's 64-channel convs, the classifier) stays bf16."""
+    from distributeddeeplearning_b200.ops import fp8
+
+    was = fp8.enabled()
+    try:
+        fp8.enable(False)
+        assert not fp8.fwd_eligible(512, 512, 9) and not fp8.dgrad_eligible(512, 512, 9)
+        fp8.enable(True)
+        assert fp8.MIN_K == 512
+        assert fp8.fwd_eligible(512, 128, 1) and fp8.fwd_eligible(128, 128, 9) and fp8.fwd_eligible(1024, 2048, 1)
+        assert not fp8.fwd_eligible(256, 64, 1)            # K = 256 < 512: epilogue-bound, bf16 is faster
+        assert not fp8.fwd_eligible(64, 64, 9)             # 64-channel rows are not a whole fp8 k-block
+        assert not fp8.fwd_eligible(3, 64, 49)             # stem
+        assert fp8.dgrad_eligible(128, 512, 1) and not fp8.dgrad_eligible(64, 256, 1) and not fp8.dgrad_eligible(512, 1000, 1)
+    finally:
+        fp8.enable(was)
